@@ -1,0 +1,167 @@
+"""ctypes binding of libarcflow_b200.so — mirrors include/arcflow_b200.h one to one.
+
+There is NO fallback: if the shared library is missing or an entry point fails, the caller gets an
+exception (`AfbError`), never a silent PyTorch path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libarcflow_b200.so"
+
+AFB_OK = 0
+AFB_EPI_BIAS, AFB_EPI_BIAS_GELU, AFB_EPI_BIAS_GATE_RES = 0, 1, 2
+AFB_SL_SILU_IN, AFB_SL_ACCUMULATE = 1, 2
+AFB_ARCH_FLUX, AFB_ARCH_QWEN = 0, 1
+AFB_ABI_VERSION = 1
+
+
+class AfbError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p * 3),
+        ("a_ld", C.c_int64 * 3),
+        ("a_batch_stride", C.c_int64 * 3),
+        ("a_k", C.c_int32 * 3),
+        ("batches", C.c_int32),
+        ("rows_per_batch", C.c_int32),
+        ("w", C.c_void_p),
+        ("w_ld", C.c_int64),
+        ("n", C.c_int32),
+        ("epilogue", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_ld", C.c_int64),
+        ("out_batch_stride", C.c_int64),
+        ("bias", C.c_void_p),
+        ("gate", C.c_void_p),
+        ("gate_batch_stride", C.c_int64),
+        ("res", C.c_void_p),
+        ("res_ld", C.c_int64),
+        ("res_batch_stride", C.c_int64),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("q_ld", C.c_int64), ("k_ld", C.c_int64), ("v_ld", C.c_int64), ("o_ld", C.c_int64),
+        ("q_batch_stride", C.c_int64), ("k_batch_stride", C.c_int64),
+        ("v_batch_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
+        ("scale", C.c_float),
+    ]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "arch", "num_double", "num_single", "dim", "heads", "mlp_dim", "in_channels", "txt_dim",
+        "pooled_dim", "guidance", "num_gaussians", "lora_rank", "head_mode")]
+
+
+_P = C.c_void_p
+
+
+class DoubleBlock(C.Structure):
+    _fields_ = [(n, _P) for n in (
+        "img_qkv_w", "img_qkv_b", "img_nq", "img_nk", "img_out_w", "img_out_b",
+        "img_up_w", "img_up_b", "img_up_la", "img_down_w", "img_down_b", "img_down_la",
+        "txt_qkv_w", "txt_qkv_b", "txt_nq", "txt_nk", "txt_out_w", "txt_out_b",
+        "txt_up_w", "txt_up_b", "txt_up_la", "txt_down_w", "txt_down_b", "txt_down_la")] + [
+        ("img_mod_off", C.c_int64), ("txt_mod_off", C.c_int64)]
+
+
+class SingleBlock(C.Structure):
+    _fields_ = [(n, _P) for n in (
+        "qkv_w", "qkv_b", "nq", "nk", "mlp_w", "mlp_b", "mlp_la", "out_w", "out_b", "out_la")] + [
+        ("mod_off", C.c_int64)]
+
+
+class Weights(C.Structure):
+    _fields_ = [(n, _P) for n in (
+        "x_emb_w", "x_emb_b", "ctx_w", "ctx_b", "txt_norm_w",
+        "t1_w", "t1_b", "t1_la", "t1_lb", "t2_w", "t2_b", "t2_la", "t2_lb",
+        "g1_w", "g1_b", "g2_w", "g2_b", "p1_w", "p1_b", "p2_w", "p2_b",
+        "mod_w", "mod_b")] + [
+        ("mod_total", C.c_int64), ("norm_out_mod_off", C.c_int64),
+        ("head_w", _P), ("head_b", _P), ("head_n", C.c_int32),
+        ("dbl", C.POINTER(DoubleBlock)), ("sgl", C.POINTER(SingleBlock))]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("txt_len", C.c_int32), ("img_len", C.c_int32),
+        ("latents", _P), ("txt", _P), ("pooled", _P),
+        ("timestep", _P), ("guidance", _P), ("rope_cos", _P), ("rope_sin", _P),
+        ("head_out", _P),
+    ]
+
+
+class DenoiseArgs(C.Structure):
+    _fields_ = [
+        ("fwd", ForwardArgs),
+        ("nfe", C.c_int32),
+        ("sigmas", C.POINTER(C.c_float)),
+        ("timesteps", C.POINTER(C.c_float)),
+        ("x", _P),
+        ("eps", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/arcflow_b200.h declares
+SIGNATURES = {
+    "afb_abi_version": (C.c_int, []),
+    "afb_last_error": (C.c_char_p, []),
+    "afb_launch_count": (C.c_uint64, []),
+    "afb_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
+    "afb_attention": (C.c_int, [C.POINTER(AttnDesc), _P]),
+    "afb_ln_modulate": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_float, _P]),
+    "afb_rmsnorm_rope": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P,
+                                   C.c_float, _P]),
+    "afb_small_linear": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, _P]),
+    "afb_timestep_embed": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "afb_sampler_step": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int32, C.c_float,
+                                   C.c_float, C.c_float, C.c_float, _P]),
+    "afb_cast_f32_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "afb_engine_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_P)]),
+    "afb_engine_destroy": (None, [_P]),
+    "afb_engine_bind": (C.c_int, [_P, C.POINTER(Weights)]),
+    "afb_engine_set_lora_scale": (C.c_int, [_P, C.c_float]),
+    "afb_engine_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "afb_engine_reserve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "afb_engine_forward": (C.c_int, [_P, C.POINTER(ForwardArgs), _P]),
+    "afb_engine_denoise": (C.c_int, [_P, C.POINTER(DenoiseArgs), _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the shared library (building is `__graft_entry__.build()`'s job). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise AfbError(
+            f"{LIB_PATH} not found — run `python -m arcflow_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: that is the point
+        fn.restype = res
+        fn.argtypes = args
+    if lib.afb_abi_version() != AFB_ABI_VERSION:
+        raise AfbError("libarcflow_b200.so ABI version mismatch — rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != AFB_OK:
+        msg = load().afb_last_error().decode(errors="replace")
+        raise AfbError(f"{what} failed (code {rc}): {msg}")

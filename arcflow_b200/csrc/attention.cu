@@ -1,0 +1,332 @@
+// arcflow_b200 — joint text+image attention forward (non-causal, head_dim 128) on tcgen05 / TMEM.
+//
+// Replaces F.scaled_dot_product_attention as reached through the diffusers attention processors the
+// reference's blocks use (reference call sites: lakonlab/models/architecture/arcflow/arcflux.py:180-230,
+// arcqwen.py:136-155; semantics SURVEY.md Appendix A.1/A.4: scale 1/sqrt(128), no mask, no dropout,
+// text tokens first in the joint sequence).
+//
+// One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that share every K/V tile.
+//   warp 0        TMA producer : Q once, then K_j / V_j into 2-stage rings (128 x 128 bf16, SW128)
+//   warp 1        MMA issuer   : S_t = Q_t K_j^T  (SS, M128 N128 K16 x8)  -> TMEM
+//                                O_t += P_t V_j   (TS: P read from TMEM, V MN-major from smem)
+//   warps 2..5    softmax WG 0 : one query row per thread; S from TMEM -> exp2 -> P (bf16) back into
+//   warps 6..9    softmax WG 1   the same TMEM columns; lazy O rescale; final O / l -> global
+// The MMA order  PV_A(j), QK_A(j+1), PV_B(j), QK_B(j+1)  keeps the tensor pipe busy on one tile while
+// the other tile's warpgroup is in its softmax (ping-pong).  TMEM: S_A S_B O_A O_B = 4 x 128 columns.
+#include <math.h>
+
+#include "common.cuh"
+#include "../../include/arcflow_b200.h"
+
+namespace afb {
+void count_launch(int n);
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int QT = 128;
+constexpr int NQT = 2;
+constexpr int KT = 128;
+constexpr int KV_STAGES = 2;
+constexpr int HALF_BYTES = 128 * 64 * 2;    // one 64-column SW128 half of a 128 x 128 tile
+constexpr int TILE_BYTES = 2 * HALF_BYTES;  // 32 KiB
+constexpr int ATT_THREADS = 32 * (2 + 4 * NQT);
+constexpr size_t ATT_SMEM_BYTES = 1024 + size_t(NQT + 2 * KV_STAGES) * TILE_BYTES + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: skip O rescale while max grows < 2^8
+
+struct AttnParams {
+  int seq, heads, batch;
+  float scale_log2;  // softmax scale * log2(e)
+  __nv_bfloat16* o;
+  long long o_ld, o_batch_stride;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + NQT * TILE_BYTES;
+  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;             // [1]
+  uint64_t* k_full = bars + 1;         // [2]
+  uint64_t* k_empty = bars + 3;        // [2]
+  uint64_t* v_full = bars + 5;         // [2]
+  uint64_t* v_empty = bars + 7;        // [2]
+  uint64_t* s_full = bars + 9;         // [NQT]  MMA -> softmax : S_t(j) ready
+  uint64_t* p_full = bars + 11;        // [NQT]  softmax -> MMA : P_t(j) written
+  uint64_t* o_done = bars + 13;        // [NQT]  MMA -> softmax : PV_t(j) retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (NQT * QT);
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_kv = (p.seq + KT - 1) / KT;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < NQT; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);  // one arrive per softmax warp
+      mbar_init(&o_done[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(q_full, NQT * TILE_BYTES);
+      for (int t = 0; t < NQT; ++t)
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_3d(sQ + t * TILE_BYTES + hf * HALF_BYTES, &tmQ, q_full, h * HD + hf * 64,
+                      q0 + t * QT, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_3d(sK + st * TILE_BYTES + hf * HALF_BYTES, &tmK, &k_full[st], h * HD + hf * 64,
+                      j * KT, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_3d(sV + st * TILE_BYTES + hf * HALF_BYTES, &tmV, &v_full[st], h * HD + hf * 64,
+                      j * KT, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KT, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(QT, HD, false, true);  // V is MN-major
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+
+      auto issue_qk = [&](int t, int st) {
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
+          umma_ss(tmem_base + t * KT, make_sw128_desc(q_addr + t * TILE_BYTES + off, 16, 1024),
+                  make_sw128_desc(k_addr + st * TILE_BYTES + off, 16, 1024), idesc_qk, kk > 0);
+        }
+      };
+      auto issue_pv = [&](int t, int st, bool acc) {
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          // A = P_t (bf16, TMEM, 8 columns per K=16); B = V rows [16 kk, 16 kk + 16) of the stage
+          umma_ts(tmem_base + NQT * KT + t * HD, tmem_base + t * KT + kk * 8,
+                  make_sw128_desc(v_addr + st * TILE_BYTES + kk * 2048, HALF_BYTES, 1024), idesc_pv,
+                  (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < NQT; ++t) {
+        issue_qk(t, 0);
+        tc_commit(&s_full[t]);
+      }
+      tc_commit(&k_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const bool has_next = (j + 1) < n_kv;
+        const int nst = (j + 1) & 1;
+        const uint32_t nph = ((j + 1) >> 1) & 1;
+        mbar_wait(&v_full[st], ph);
+        if (has_next) mbar_wait(&k_full[nst], nph);
+        for (int t = 0; t < NQT; ++t) {
+          mbar_wait(&p_full[t], j & 1);
+          tc_fence_after();
+          issue_pv(t, st, j > 0);
+          tc_commit(&o_done[t]);
+          if (has_next) {
+            issue_qk(t, nst);
+            tc_commit(&s_full[t]);
+          }
+        }
+        tc_commit(&v_empty[st]);
+        if (has_next) tc_commit(&k_empty[nst]);
+      }
+    }
+  } else {
+    // ------------------------------- softmax warpgroups -------------------------------------
+    const int t = (warp - 2) >> 2;  // which Q tile
+    const int qd = warp & 3;        // TMEM lane quarter
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * KT;
+    const uint32_t tO = tmem_base + lane_base + NQT * KT + t * HD;
+    const float c = p.scale_log2;
+    float m = -INFINITY;
+    float l = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[KT];
+#pragma unroll
+      for (int i = 0; i < KT / 32; ++i)
+        tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
+      tmem_ld_wait();
+
+      const int valid = p.seq - j * KT;
+      if (valid < KT) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < KT; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+      if (j == 0) {
+        m = mx;
+      } else {
+        const bool need = (mx - m) * c > RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? fast_exp2((m - mx) * c) : 1.0f;
+          if (need) m = mx;
+          l *= f;
+          mbar_wait(&o_done[t], (j - 1) & 1);  // PV_t(j-1) must have retired before O is touched
+          tc_fence_after();
+#pragma unroll 1
+          for (int i = 0; i < HD / 32; ++i) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + i * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tmem_st_32x32(tO + i * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+
+      const float neg_mc = -m * c;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < KT; i += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), c, neg_mc));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), c, neg_mc));
+        l0 += p0;
+        l1 += p1;
+        s[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      l += l0 + l1;
+#pragma unroll
+      for (int i = 0; i < KT / 32; ++i)
+        tmem_st_32x16(tS + i * 16, reinterpret_cast<const uint32_t(&)[16]>(s[i * 16]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+
+    // final: O / l -> bf16 -> global
+    mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int qrow = q0 + t * QT + row;
+    const bool valid_row = qrow < p.seq;
+    __nv_bfloat16* orow =
+        p.o + (long long)b * p.o_batch_stride + (long long)qrow * p.o_ld + h * HD;
+#pragma unroll 1
+    for (int i = 0; i < HD / 32; ++i) {
+      uint32_t o[32];
+      tmem_ld_32x32(tO + i * 32, o);
+      tmem_ld_wait();
+      if (valid_row) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + i * 32 + g * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
+  AFB_REQUIRE(d != nullptr, "attention: null descriptor");
+  AFB_REQUIRE(d->q && d->k && d->v && d->o, "attention: null operand pointer");
+  AFB_REQUIRE(d->batch >= 1 && d->seq >= 1 && d->heads >= 1, "attention: empty problem");
+  AFB_REQUIRE(d->o_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->o) & 15) == 0,
+              "attention: o must be 16-byte aligned with ld %% 8 == 0");
+  CUtensorMap tm[3];
+  const void* ptr[3] = {d->q, d->k, d->v};
+  const int64_t ld[3] = {d->q_ld, d->k_ld, d->v_ld};
+  const int64_t bs[3] = {d->q_batch_stride, d->k_batch_stride, d->v_batch_stride};
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t dims[3] = {uint64_t(d->heads) * HD, uint64_t(d->seq), uint64_t(d->batch)};
+    const uint64_t bstride = d->batch > 1 ? uint64_t(bs[i]) : uint64_t(d->seq) * uint64_t(ld[i]);
+    const uint64_t strides[2] = {uint64_t(ld[i]) * 2, bstride * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = make_tmap_bf16(&tm[i], ptr[i], 3, dims, strides, box);
+    if (rc != AFB_OK) return rc;
+  }
+  AttnParams p{};
+  p.seq = d->seq;
+  p.heads = d->heads;
+  p.batch = d->batch;
+  const float scale = d->scale > 0.f ? d->scale : 1.0f / sqrtf(float(HD));
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.o = static_cast<__nv_bfloat16*>(d->o);
+  p.o_ld = d->o_ld;
+  p.o_batch_stride = d->o_batch_stride;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(ATT_SMEM_BYTES)));
+    attr_set = true;
+  }
+  dim3 grid((d->seq + NQT * QT - 1) / (NQT * QT), d->heads, d->batch);
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], p);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+}  // namespace afb

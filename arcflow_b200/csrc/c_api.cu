@@ -1,0 +1,75 @@
+// arcflow_b200 — extern "C" surface (see include/arcflow_b200.h). Nothing but argument forwarding:
+// errors become return codes, never exceptions.
+#include "common.cuh"
+#include "../../include/arcflow_b200.h"
+
+namespace afb {
+uint64_t launch_count();
+void count_launch(int n);
+int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream);
+int attention_launch(const afb_attn_desc* d, cudaStream_t stream);
+int ln_modulate_launch(const void* x, int64_t x_bs, void* y, int64_t y_bs, const void* scale,
+                       const void* shift, int64_t mod_bs, int batches, int rows_per_batch, int dim,
+                       float eps, cudaStream_t stream);
+int rmsnorm_rope_launch(void* qkv, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
+                        int heads, int txt_rows, const void* wq_txt, const void* wk_txt,
+                        const void* wq_img, const void* wk_img, const float* cos_tab,
+                        const float* sin_tab, float eps, cudaStream_t stream);
+int small_linear_launch(const void* x, int64_t x_ld, const void* w, int64_t w_ld, const void* bias,
+                        void* y, int64_t y_ld, int m, int n, int k, int flags, cudaStream_t stream);
+int timestep_embed_launch(const float* t, void* out, int m, cudaStream_t stream);
+int sampler_step_launch(const void* head, int64_t head_ld, const float* x_in, float* x_out,
+                        void* x_out_bf16, int64_t tokens, int num_gaussians, float sigma_src,
+                        float sigma_start, float sigma_end, float eps, cudaStream_t stream);
+int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t stream);
+}  // namespace afb
+
+extern "C" {
+
+int afb_abi_version(void) { return AFB_ABI_VERSION; }
+const char* afb_last_error(void) { return afb::get_last_error(); }
+uint64_t afb_launch_count(void) { return afb::launch_count(); }
+
+int afb_gemm(const afb_gemm_desc* desc, void* stream) {
+  int rc = afb::gemm_launch(desc, static_cast<cudaStream_t>(stream));
+  if (rc == AFB_OK) afb::count_launch(1);
+  return rc;
+}
+int afb_attention(const afb_attn_desc* desc, void* stream) {
+  return afb::attention_launch(desc, static_cast<cudaStream_t>(stream));
+}
+int afb_ln_modulate(const void* x, int64_t x_batch_stride, void* y, int64_t y_batch_stride,
+                    const void* scale, const void* shift, int64_t mod_batch_stride, int32_t batches,
+                    int32_t rows_per_batch, int32_t dim, float eps, void* stream) {
+  return afb::ln_modulate_launch(x, x_batch_stride, y, y_batch_stride, scale, shift, mod_batch_stride,
+                                 batches, rows_per_batch, dim, eps, static_cast<cudaStream_t>(stream));
+}
+int afb_rmsnorm_rope(void* qkv, int64_t ld, int64_t batch_stride, int32_t q_off, int32_t k_off,
+                     int32_t batches, int32_t seq, int32_t heads, int32_t txt_rows, const void* wq_txt,
+                     const void* wk_txt, const void* wq_img, const void* wk_img, const float* cos_tab,
+                     const float* sin_tab, float eps, void* stream) {
+  return afb::rmsnorm_rope_launch(qkv, ld, batch_stride, q_off, k_off, batches, seq, heads, txt_rows,
+                                  wq_txt, wk_txt, wq_img, wk_img, cos_tab, sin_tab, eps,
+                                  static_cast<cudaStream_t>(stream));
+}
+int afb_small_linear(const void* x, int64_t x_ld, const void* w, int64_t w_ld, const void* bias,
+                     void* y, int64_t y_ld, int32_t m, int32_t n, int32_t k, int32_t flags,
+                     void* stream) {
+  return afb::small_linear_launch(x, x_ld, w, w_ld, bias, y, y_ld, m, n, k, flags,
+                                  static_cast<cudaStream_t>(stream));
+}
+int afb_timestep_embed(const float* t, void* out, int32_t m, void* stream) {
+  return afb::timestep_embed_launch(t, out, m, static_cast<cudaStream_t>(stream));
+}
+int afb_sampler_step(const void* head, int64_t head_ld, const float* x_in, float* x_out,
+                     void* x_out_bf16, int64_t tokens, int32_t num_gaussians, float sigma_src,
+                     float sigma_start, float sigma_end, float eps, void* stream) {
+  return afb::sampler_step_launch(head, head_ld, x_in, x_out, x_out_bf16, tokens, num_gaussians,
+                                  sigma_src, sigma_start, sigma_end, eps,
+                                  static_cast<cudaStream_t>(stream));
+}
+int afb_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
+  return afb::cast_f32_bf16_launch(in, out, n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,465 @@
+// arcflow_b200 — the HBM-bound kernels around the tensor-core tiles: AdaLN modulate, per-head
+// RMSNorm + RoPE, the batch-row ("small-M") Linear used for every AdaLN modulation vector and the
+// time/text embedders, the sinusoidal timestep embedding and the fused ArcFlow sampler step.
+// All are one-warp-per-row streaming kernels with 16-byte vector accesses.
+#include <math.h>
+
+#include "common.cuh"
+#include "../../include/arcflow_b200.h"
+
+namespace afb {
+void count_launch(int n);
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdaLN: y = LN(x) * (1 + scale[b]) + shift[b].   Reference: diffusers AdaLayerNormZero /
+// AdaLayerNormZeroSingle / AdaLayerNormContinuous as used by the blocks built at
+// lakonlab/models/architecture/arcflow/arcflux.py:63-85.
+// One warp per row, the row lives in registers (NCH chunks of 8 bf16 per lane).
+// ------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, __nv_bfloat16* __restrict__ y,
+                   long long y_bs, const __nv_bfloat16* __restrict__ scale,
+                   const __nv_bfloat16* __restrict__ shift, long long mod_bs, int batches,
+                   int rows_per_batch, float eps) {
+  constexpr int DIM = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)batches * rows_per_batch;
+  if (row >= total) return;
+  const int b = int(row / rows_per_batch);
+  const int r = int(row - (long long)b * rows_per_batch);
+  const __nv_bfloat16* xr = x + (long long)b * x_bs + (long long)r * DIM;
+  __nv_bfloat16* yr = y + (long long)b * y_bs + (long long)r * DIM;
+
+  float v[NCH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
+    unpack8(u, v[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += v[c][i];
+  }
+  const float mean = warp_sum(sum) * (1.0f / DIM);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = v[c][i] - mean;
+      sq += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / DIM) + eps);
+  const __nv_bfloat16* sc = scale + (long long)b * mod_bs;
+  const __nv_bfloat16* sh = shift + (long long)b * mod_bs;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float s[8], t[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(sc + c * 256 + lane * 8), s);
+    unpack8(*reinterpret_cast<const uint4*>(sh + c * 256 + lane * 8), t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = (v[c][i] - mean) * rstd * (1.0f + s[i]) + t[i];
+    *reinterpret_cast<uint4*>(yr + c * 256 + lane * 8) = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-head RMSNorm(q, k) + rotary embedding, in place on the fused QKV buffer.
+// Reference semantics: diffusers RMSNorm (fp32 variance, cast to bf16, * weight) then apply_rotary_emb
+// (fp32 math on adjacent pairs, cast back) — SURVEY.md Appendix A.1, A.3, A.5; rope tables are the
+// ones built at arcflux.py:171-173.  One warp per token row, 4 elements per lane per head.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, long long bs, int q_off, int k_off,
+                    int batches, int seq, int heads, int txt_rows,
+                    const __nv_bfloat16* __restrict__ wq_txt, const __nv_bfloat16* __restrict__ wk_txt,
+                    const __nv_bfloat16* __restrict__ wq_img, const __nv_bfloat16* __restrict__ wk_img,
+                    const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)batches * seq) return;
+  const int b = int(row / seq);
+  const int s = int(row - (long long)b * seq);
+  __nv_bfloat16* base = qkv + (long long)b * bs + (long long)s * ld;
+  const bool is_txt = s < txt_rows;
+  const float4 cs = *reinterpret_cast<const float4*>(cos_tab + (long long)s * 128 + lane * 4);
+  const float4 sn = *reinterpret_cast<const float4*>(sin_tab + (long long)s * 128 + lane * 4);
+  float wq[4], wk[4];
+  {
+    const uint2 a = *reinterpret_cast<const uint2*>((is_txt ? wq_txt : wq_img) + lane * 4);
+    const uint2 c = *reinterpret_cast<const uint2*>((is_txt ? wk_txt : wk_img) + lane * 4);
+    wq[0] = bf16_lo(a.x); wq[1] = bf16_hi(a.x); wq[2] = bf16_lo(a.y); wq[3] = bf16_hi(a.y);
+    wk[0] = bf16_lo(c.x); wk[1] = bf16_hi(c.x); wk[2] = bf16_lo(c.y); wk[3] = bf16_hi(c.y);
+  }
+  for (int slot = 0; slot < 2 * heads; ++slot) {
+    const bool is_k = slot >= heads;
+    const int h = is_k ? slot - heads : slot;
+    __nv_bfloat16* ptr = base + (is_k ? k_off : q_off) + h * 128 + lane * 4;
+    const uint2 u = *reinterpret_cast<const uint2*>(ptr);
+    float x[4] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)};
+    const float ss = warp_sum(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    const float rs = rsqrtf(ss * (1.0f / 128.0f) + eps);
+    const float* w = is_k ? wk : wq;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = round_bf16(round_bf16(x[i] * rs) * w[i]);
+    float o[4];
+    o[0] = x[0] * cs.x - x[1] * sn.x;
+    o[1] = x[1] * cs.y + x[0] * sn.y;
+    o[2] = x[2] * cs.z - x[3] * sn.z;
+    o[3] = x[3] * cs.w + x[2] * sn.w;
+    uint2 w2;
+    w2.x = pack_bf16x2(o[0], o[1]);
+    w2.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(ptr) = w2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small-M Linear: y[m, n] (+)= act(x[m, :]) . W[n, :] + bias[n],  m <= 8.  HBM-bound on W: every
+// warp streams 4 weight rows at a time with 16-byte loads; x (<= 8 rows) sits in shared memory.
+// Used for all AdaLN modulation Linears of a forward in ONE launch (weights concatenated along n) and
+// for the time / guidance / pooled-text embedder MLPs.
+// ------------------------------------------------------------------------------------------------
+constexpr int SL_ROWS = 8;
+constexpr int SL_COLS = 4;
+
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld,
+                    const __nv_bfloat16* __restrict__ w, long long w_ld,
+                    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                    long long y_ld, int m, int n, int k, int flags) {
+  extern __shared__ __align__(16) uint8_t sl_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(sl_smem);  // [SL_ROWS][k]
+  for (int i = threadIdx.x; i < SL_ROWS * k; i += blockDim.x) {
+    const int r = i / k, c = i - r * k;
+    float v = 0.f;
+    if (r < m) {
+      v = __bfloat162float(x[(long long)r * x_ld + c]);
+      if (flags & AFB_SL_SILU_IN) v = silu(v);
+    }
+    xs[i] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int groups = (n + SL_COLS - 1) / SL_COLS;
+  for (int g = blockIdx.x * warps_per_block + (threadIdx.x >> 5); g < groups;
+       g += gridDim.x * warps_per_block) {
+    const int n0 = g * SL_COLS;
+    float acc[SL_COLS][SL_ROWS];
+#pragma unroll
+    for (int c = 0; c < SL_COLS; ++c)
+#pragma unroll
+      for (int r = 0; r < SL_ROWS; ++r) acc[c][r] = 0.f;
+    for (int kc = lane * 8; kc < k; kc += 256) {
+      float wv[SL_COLS][8];
+#pragma unroll
+      for (int c = 0; c < SL_COLS; ++c) {
+        const int col = n0 + c < n ? n0 + c : n - 1;
+        unpack8(*reinterpret_cast<const uint4*>(w + (long long)col * w_ld + kc), wv[c]);
+      }
+#pragma unroll
+      for (int r = 0; r < SL_ROWS; ++r) {
+        float xv[8];
+        unpack8(*reinterpret_cast<const uint4*>(xs + r * k + kc), xv);
+#pragma unroll
+        for (int c = 0; c < SL_COLS; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[c][r] = fmaf(wv[c][i], xv[i], acc[c][r]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < SL_COLS; ++c)
+#pragma unroll
+      for (int r = 0; r < SL_ROWS; ++r) acc[c][r] = warp_sum(acc[c][r]);
+    if (lane < SL_COLS * SL_ROWS) {
+      const int c = lane / SL_ROWS, r = lane - c * SL_ROWS;
+      // select acc[c][r] without dynamic register indexing
+      float v = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < SL_COLS; ++cc)
+#pragma unroll
+        for (int rr = 0; rr < SL_ROWS; ++rr)
+          if (cc == c && rr == r) v = acc[cc][rr];
+      const int col = n0 + c;
+      if (col < n && r < m) {
+        if (bias) v += __bfloat162float(bias[col]);
+        __nv_bfloat16* yp = y + (long long)r * y_ld + col;
+        if (flags & AFB_SL_ACCUMULATE) v += __bfloat162float(*yp);
+        *yp = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin] halves.
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out,
+                                      int m) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * 128) return;
+  const int r = i / 128, j = i - r * 128;
+  const float freq = expf(-9.210340371976184f * float(j) / 128.0f);  // ln(10000)
+  const float a = t[r] * freq;
+  out[r * 256 + j] = __float2bfloat16_rn(cosf(a));
+  out[r * 256 + 128 + j] = __float2bfloat16_rn(sinf(a));
+}
+
+// ------------------------------------------------------------------------------------------------
+// ArcFlow sampler step, K = 16 components, packed-token layout (one warp per token).
+// Fuses what the reference does in ~30 launches + 4 layout copies per NFE:
+//   _unpack_latents / _unpack_mp      lakonlab/pipelines/arcflux_pipeline.py:135-193, :482-487
+//   log_softmax over K (bf16)         lakonlab/models/architecture/arcflow/arcflux.py:246-247
+//   ArcFlowPolicy                     lakonlab/models/diffusions/policies/arcflow.py:25-50
+//   momentum_integration              lakonlab/pipelines/arcflux_pipeline.py:195-249
+//   _pack_latents                     lakonlab/pipelines/arcflux_pipeline.py:506-510
+// Token layout: output channel o = c*4 + ph*2 + pw; mixture weights / rates are per (k, j = o % 4).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float group_max(float v) {  // over lanes sharing lane % 4
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+  return v;
+}
+__device__ __forceinline__ float group_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+__device__ __forceinline__ float phi_expm1(float z, float eps) {
+  const float sgn = z < 0.f ? -1.f : 1.f;  // sign(0) := +1 as in the reference
+  const float zs = sgn * fmaxf(fabsf(z), eps);
+  return expm1f(zs) / zs;
+}
+
+__global__ void __launch_bounds__(256)
+sampler_step_k16_kernel(const __nv_bfloat16* __restrict__ head, long long head_ld,
+                        const float* __restrict__ x_in, float* __restrict__ x_out,
+                        __nv_bfloat16* __restrict__ x_out_bf16, long long tokens, float dt_past,
+                        float dt_step, float eps) {
+  constexpr int K = 16;
+  __shared__ float sF[8][K * 4];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long tok = (long long)blockIdx.x * 8 + wib;
+  if (tok >= tokens) return;
+  const __nv_bfloat16* hrow = head + tok * head_ld;
+  const __nv_bfloat16* logit = hrow + K * 64;
+  const __nv_bfloat16* lgam = logit + K * 4;
+
+  // entries e0 = lane (k 0..7), e1 = lane + 32 (k 8..15); j = lane % 4
+  const float a0 = __bfloat162float(logit[lane]);
+  const float a1 = __bfloat162float(logit[lane + 32]);
+  // log_softmax over k in fp32, result rounded to bf16 (the network emits bf16)
+  const float mx = group_max(fmaxf(a0, a1));
+  const float se = group_sum(expf(a0 - mx) + expf(a1 - mx));
+  const float lse = mx + logf(se);
+  const float b0 = round_bf16(a0 - lse);
+  const float b1 = round_bf16(a1 - lse);
+  // softmax over k in fp32 (sampler side)
+  const float mx2 = group_max(fmaxf(b0, b1));
+  const float e0 = expf(b0 - mx2), e1 = expf(b1 - mx2);
+  const float inv = 1.0f / group_sum(e0 + e1);
+  const float w0 = e0 * inv, w1 = e1 * inv;
+  // rates: component 0 has lambda == 0 (decay 1, phi 1)
+  const float lam0 = lane >= 4 ? __bfloat162float(lgam[lane - 4]) : 0.f;
+  const float lam1 = __bfloat162float(lgam[lane + 28]);
+  float f0 = w0 * dt_step;
+  if (lane >= 4) f0 *= expf(lam0 * dt_past) * phi_expm1(lam0 * dt_step, eps);
+  const float f1 = w1 * dt_step * expf(lam1 * dt_past) * phi_expm1(lam1 * dt_step, eps);
+  sF[wib][lane] = f0;
+  sF[wib][lane + 32] = f1;
+  __syncwarp();
+
+  const int j0 = (2 * lane) & 3;  // channels 2*lane, 2*lane + 1 -> j0, j0 + 1
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t mv = *reinterpret_cast<const uint32_t*>(hrow + k * 64 + 2 * lane);
+    acc0 = fmaf(bf16_lo(mv), sF[wib][k * 4 + j0], acc0);
+    acc1 = fmaf(bf16_hi(mv), sF[wib][k * 4 + j0 + 1], acc1);
+  }
+  const float2 xi = *reinterpret_cast<const float2*>(x_in + tok * 64 + 2 * lane);
+  const float2 xo = make_float2(xi.x - acc0, xi.y - acc1);
+  *reinterpret_cast<float2*>(x_out + tok * 64 + 2 * lane) = xo;
+  if (x_out_bf16)
+    *reinterpret_cast<uint32_t*>(x_out_bf16 + tok * 64 + 2 * lane) = pack_bf16x2(xo.x, xo.y);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                     long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (long long e = i; e < n; ++e) out[e] = __float2bfloat16_rn(in[e]);
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+int ln_modulate_launch(const void* x, int64_t x_bs, void* y, int64_t y_bs, const void* scale,
+                       const void* shift, int64_t mod_bs, int batches, int rows_per_batch, int dim,
+                       float eps, cudaStream_t stream) {
+  AFB_REQUIRE(x && y && scale && shift, "ln_modulate: null pointer");
+  AFB_REQUIRE(batches >= 1 && rows_per_batch >= 1, "ln_modulate: empty input");
+  AFB_REQUIRE(dim % 256 == 0, "ln_modulate: dim=%d must be a multiple of 256", dim);
+  const long long rows = (long long)batches * rows_per_batch;
+  const int wpb = 8;
+  const unsigned grid = unsigned((rows + wpb - 1) / wpb);
+#define AFB_LN_CASE(NCH)                                                                          \
+  case NCH:                                                                                       \
+    ln_modulate_kernel<NCH><<<grid, wpb * 32, 0, stream>>>(                                       \
+        static_cast<const __nv_bfloat16*>(x), x_bs, static_cast<__nv_bfloat16*>(y), y_bs,         \
+        static_cast<const __nv_bfloat16*>(scale), static_cast<const __nv_bfloat16*>(shift),       \
+        mod_bs, batches, rows_per_batch, eps);                                                    \
+    break;
+  switch (dim / 256) {
+    AFB_LN_CASE(1)
+    AFB_LN_CASE(2)
+    AFB_LN_CASE(4)
+    AFB_LN_CASE(8)
+    AFB_LN_CASE(12)
+    AFB_LN_CASE(16)
+    default:
+      set_last_error("ln_modulate: unsupported dim %d", dim);
+      return AFB_ERR_UNSUPPORTED;
+  }
+#undef AFB_LN_CASE
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int rmsnorm_rope_launch(void* qkv, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
+                        int heads, int txt_rows, const void* wq_txt, const void* wk_txt,
+                        const void* wq_img, const void* wk_img, const float* cos_tab,
+                        const float* sin_tab, float eps, cudaStream_t stream) {
+  AFB_REQUIRE(qkv && wq_img && wk_img && cos_tab && sin_tab, "rmsnorm_rope: null pointer");
+  AFB_REQUIRE(txt_rows == 0 || (wq_txt && wk_txt), "rmsnorm_rope: text norm weights missing");
+  AFB_REQUIRE(ld % 4 == 0 && q_off % 4 == 0 && k_off % 4 == 0, "rmsnorm_rope: misaligned layout");
+  AFB_REQUIRE(batches >= 1 && seq >= 1 && heads >= 1, "rmsnorm_rope: empty input");
+  const long long rows = (long long)batches * seq;
+  const int wpb = 8;
+  const unsigned grid = unsigned((rows + wpb - 1) / wpb);
+  rmsnorm_rope_kernel<<<grid, wpb * 32, 0, stream>>>(
+      static_cast<__nv_bfloat16*>(qkv), ld, bs, q_off, k_off, batches, seq, heads, txt_rows,
+      static_cast<const __nv_bfloat16*>(wq_txt ? wq_txt : wq_img),
+      static_cast<const __nv_bfloat16*>(wk_txt ? wk_txt : wk_img),
+      static_cast<const __nv_bfloat16*>(wq_img), static_cast<const __nv_bfloat16*>(wk_img), cos_tab,
+      sin_tab, eps);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int small_linear_launch(const void* x, int64_t x_ld, const void* w, int64_t w_ld, const void* bias,
+                        void* y, int64_t y_ld, int m, int n, int k, int flags, cudaStream_t stream) {
+  AFB_REQUIRE(x && w && y, "small_linear: null pointer");
+  AFB_REQUIRE(m >= 1 && m <= SL_ROWS, "small_linear: m=%d must be in [1, %d]", m, SL_ROWS);
+  AFB_REQUIRE(n >= 1, "small_linear: n=%d", n);
+  AFB_REQUIRE(k >= 256 && k % 256 == 0 && k <= 4096, "small_linear: k=%d must be a multiple of 256 <= 4096", k);
+  AFB_REQUIRE(w_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+              "small_linear: W must be 16-byte aligned with ld %% 8 == 0");
+  const size_t smem = size_t(SL_ROWS) * k * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(small_linear_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 2));
+    attr_set = true;
+  }
+  const int groups = (n + SL_COLS - 1) / SL_COLS;
+  int grid = (groups + 7) / 8;
+  const int max_grid = device_sm_count() * 3;
+  if (grid > max_grid) grid = max_grid;
+  small_linear_kernel<<<grid, 256, smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<const __nv_bfloat16*>(w), w_ld,
+      static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), y_ld, m, n, k, flags);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int timestep_embed_launch(const float* t, void* out, int m, cudaStream_t stream) {
+  AFB_REQUIRE(t && out && m >= 1, "timestep_embed: bad arguments");
+  timestep_embed_kernel<<<(m * 128 + 127) / 128, 128, 0, stream>>>(
+      t, static_cast<__nv_bfloat16*>(out), m);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int sampler_step_launch(const void* head, int64_t head_ld, const float* x_in, float* x_out,
+                        void* x_out_bf16, int64_t tokens, int num_gaussians, float sigma_src,
+                        float sigma_start, float sigma_end, float eps, cudaStream_t stream) {
+  AFB_REQUIRE(head && x_in && x_out, "sampler_step: null pointer");
+  AFB_REQUIRE(tokens >= 1, "sampler_step: no tokens");
+  if (num_gaussians != 16) {
+    set_last_error("sampler_step: only K=16 mixture components are built (got %d)", num_gaussians);
+    return AFB_ERR_UNSUPPORTED;
+  }
+  AFB_REQUIRE(head_ld >= 16 * 64 + 16 * 4 + 15 * 4 && head_ld % 2 == 0, "sampler_step: head_ld=%lld too small",
+              (long long)head_ld);
+  const unsigned grid = unsigned((tokens + 7) / 8);
+  sampler_step_k16_kernel<<<grid, 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(head), head_ld, x_in, x_out,
+      static_cast<__nv_bfloat16*>(x_out_bf16), tokens, sigma_src - sigma_start,
+      sigma_start - sigma_end, eps);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t stream) {
+  AFB_REQUIRE(in && out && n >= 1, "cast: bad arguments");
+  const long long thr = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<unsigned((thr + 255) / 256), 256, 0, stream>>>(
+      in, static_cast<__nv_bfloat16*>(out), n);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int fill_f32_launch(float* p, float v, int n, cudaStream_t stream) {
+  fill_f32_kernel<<<(n + 127) / 128, 128, 0, stream>>>(p, v, n);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+}  // namespace afb

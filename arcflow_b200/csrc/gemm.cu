@@ -1,0 +1,338 @@
+// arcflow_b200 — persistent warp-specialised tcgen05 GEMM for the MMDiT linears.
+//
+//   out[b, r, n] = epilogue( sum_k A[b, r, k] * W[n, k] )        bf16 x bf16 -> fp32 (TMEM) -> bf16
+//
+// Replaces what the reference dispatches to cuBLASLt through torch.nn.Linear inside the diffusers
+// blocks it instantiates (reference: lakonlab/models/architecture/arcflow/arcflux.py:60-88 builds the
+// Linears; :180-249 calls them) plus the peft LoRA branch, which is folded in
+// as a K-extension: A may be given as up to three K-segments (e.g. [y | y·A_lora^T] against
+// [W | B_lora]), so "base + LoRA" is ONE accumulation in TMEM and no separate add kernel exists.
+//
+// Layout / roles (one CTA per SM, persistent over output tiles, 128 x 256 x 64 tiles):
+//   warp 0      TMA producer   : A tile (3-D map: k, row, batch) + W tile into a 4-stage smem ring
+//   warp 1      MMA issuer     : one lane issues tcgen05.mma (M128 N256 K16, SS), commits to mbarriers
+//   warps 2..5  epilogue       : tcgen05.ld accumulator -> bias / GELU-tanh / gate*y+residual -> bf16
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+#include "common.cuh"
+#include "../../include/arcflow_b200.h"
+
+namespace afb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr size_t GEMM_SMEM_BYTES =
+    1024 /*align slack*/ + size_t(STAGES) * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/;
+
+struct GemmParams {
+  int batches, rows_per_batch, tiles_per_batch;
+  int N;
+  int nk_end[3];  // cumulative K-block (64) boundaries of the A segments
+  int num_m_tiles, num_n_tiles;
+  int epi;
+  __nv_bfloat16* out;
+  long long out_ld, out_batch_stride;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* gate;
+  long long gate_batch_stride;
+  const __nv_bfloat16* res;
+  long long res_ld, res_batch_stride;
+};
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanh_approx(inner));
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;        // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmA2);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int nk = p.nk_end[2];
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int b = m_tile / p.tiles_per_batch;
+        const int r0 = (m_tile - b * p.tiles_per_batch) * BM;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          const CUtensorMap* am;
+          int kk;
+          if (kb < p.nk_end[0]) {
+            am = &tmA0;
+            kk = kb;
+          } else if (kb < p.nk_end[1]) {
+            am = &tmA1;
+            kk = kb - p.nk_end[0];
+          } else {
+            am = &tmA2;
+            kk = kb - p.nk_end[1];
+          }
+          tma_load_3d(sA + stage * A_STAGE_BYTES, am, &full_bar[stage], kk * BK, r0, b);
+          tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -----------------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int b = m_tile / p.tiles_per_batch;
+      const int r = (m_tile - b * p.tiles_per_batch) * BM + row;
+      const bool valid = r < p.rows_per_batch;
+      __nv_bfloat16* out_row = p.out + (long long)b * p.out_batch_stride + (long long)r * p.out_ld;
+      const __nv_bfloat16* res_row =
+          p.res ? p.res + (long long)b * p.res_batch_stride + (long long)r * p.res_ld : nullptr;
+      const __nv_bfloat16* gate_b = p.gate ? p.gate + (long long)b * p.gate_batch_stride : nullptr;
+
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_tile * BN + c * 32;
+        if (n0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(t_base + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            if (n < p.N) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+              if (p.bias) {
+                const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n);
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[2 * i] += bf16_lo(bw[i]);
+                  f[2 * i + 1] += bf16_hi(bw[i]);
+                }
+              }
+              if (p.epi == AFB_EPI_BIAS_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_fast(f[i]);
+              } else if (p.epi == AFB_EPI_BIAS_GATE_RES) {
+                const uint4 gv = *reinterpret_cast<const uint4*>(gate_b + n);
+                const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
+                const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[2 * i] = bf16_lo(rw[i]) + bf16_lo(gw[i]) * f[2 * i];
+                  f[2 * i + 1] = bf16_hi(rw[i]) + bf16_hi(gw[i]) * f[2 * i + 1];
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(out_row + n) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
+  AFB_REQUIRE(d != nullptr, "gemm: null descriptor");
+  AFB_REQUIRE(d->w && d->out && d->a[0], "gemm: null operand pointer");
+  AFB_REQUIRE(d->batches >= 1 && d->rows_per_batch >= 1, "gemm: empty M (batches=%d rows=%d)",
+              d->batches, d->rows_per_batch);
+  AFB_REQUIRE(d->n >= 8 && d->n % 8 == 0, "gemm: N=%d must be a positive multiple of 8", d->n);
+  AFB_REQUIRE(d->epilogue >= AFB_EPI_BIAS && d->epilogue <= AFB_EPI_BIAS_GATE_RES,
+              "gemm: unknown epilogue %d", d->epilogue);
+  if (d->epilogue == AFB_EPI_BIAS_GATE_RES)
+    AFB_REQUIRE(d->gate && d->res, "gemm: gate/residual epilogue needs gate and res pointers");
+  AFB_REQUIRE(d->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+              "gemm: out must be 16-byte aligned with ld %% 8 == 0");
+
+  GemmParams p{};
+  CUtensorMap tmA[3];
+  int ktot = 0;
+  int nseg = 0;
+  for (int s = 0; s < 3; ++s) {
+    const int ks = d->a_k[s];
+    if (ks == 0) {
+      AFB_REQUIRE(s > 0, "gemm: first A segment has K=0");
+      tmA[s] = tmA[s - 1];
+      p.nk_end[s] = p.nk_end[s - 1];
+      continue;
+    }
+    AFB_REQUIRE(nseg == s, "gemm: A segments must be contiguous");
+    AFB_REQUIRE(ks % BK == 0, "gemm: segment %d K=%d not a multiple of %d", s, ks, BK);
+    AFB_REQUIRE(d->a[s] != nullptr, "gemm: segment %d null", s);
+    const uint64_t dims[3] = {uint64_t(ks), uint64_t(d->rows_per_batch), uint64_t(d->batches)};
+    const uint64_t bstride = d->batches > 1 ? uint64_t(d->a_batch_stride[s])
+                                            : uint64_t(d->rows_per_batch) * uint64_t(d->a_ld[s]);
+    const uint64_t strides[2] = {uint64_t(d->a_ld[s]) * 2, bstride * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_bf16(&tmA[s], d->a[s], 3, dims, strides, box);
+    if (rc != AFB_OK) return rc;
+    ktot += ks;
+    p.nk_end[s] = ktot / BK;
+    ++nseg;
+  }
+  CUtensorMap tmB;
+  {
+    const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->n)};
+    const uint64_t strides[1] = {uint64_t(d->w_ld) * 2};
+    const uint32_t box[2] = {BK, BN};
+    AFB_REQUIRE(d->w_ld >= ktot, "gemm: w_ld=%lld < total K=%d", (long long)d->w_ld, ktot);
+    int rc = make_tmap_bf16(&tmB, d->w, 2, dims, strides, box);
+    if (rc != AFB_OK) return rc;
+  }
+
+  p.batches = d->batches;
+  p.rows_per_batch = d->rows_per_batch;
+  p.tiles_per_batch = (d->rows_per_batch + BM - 1) / BM;
+  p.N = d->n;
+  p.num_m_tiles = p.tiles_per_batch * d->batches;
+  p.num_n_tiles = (d->n + BN - 1) / BN;
+  p.epi = d->epilogue;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_ld = d->out_ld;
+  p.out_batch_stride = d->out_batch_stride;
+  p.bias = static_cast<const __nv_bfloat16*>(d->bias);
+  p.gate = static_cast<const __nv_bfloat16*>(d->gate);
+  p.gate_batch_stride = d->gate_batch_stride;
+  p.res = static_cast<const __nv_bfloat16*>(d->res);
+  p.res_ld = d->res_ld;
+  p.res_batch_stride = d->res_batch_stride;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(GEMM_SMEM_BYTES)));
+    attr_set = true;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int sms = device_sm_count();
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  return AFB_OK;
+}
+
+}  // namespace afb

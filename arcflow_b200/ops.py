@@ -1,0 +1,226 @@
+"""Tensor-level wrappers over the C ABI (torch is used only for device memory and the stream).
+
+These are the reference-facing operators of the hot path; each takes CUDA tensors, validates them,
+and enqueues exactly one kernel of libarcflow_b200.so on the current stream. A CPU tensor or a missing
+library is an error — the oracle under `oracle/` is test infrastructure and is never reached from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import AfbError, AttnDesc, GemmDesc
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise AfbError(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise AfbError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rows3(t: torch.Tensor, name: str):
+    """View a [batches, rows, cols] (or [rows, cols]) tensor as (ptr, ld, batch_stride, batches, rows, cols)."""
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise AfbError(f"{name}: need [batches, rows, cols] with contiguous last dim, got {tuple(t.shape)} "
+                       f"strides {t.stride()}")
+    return t.data_ptr(), t.stride(1), t.stride(0), t.shape[0], t.shape[1], t.shape[2]
+
+
+def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.Tensor,
+         bias: Optional[torch.Tensor] = None, epilogue: int = _lib.AFB_EPI_BIAS,
+         gate: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b, r, :] = epi(sum_s a_s[b, r, :] @ w[:, koff_s : koff_s + K_s].T).
+
+    `a` is one tensor or up to three K-segments sharing [batches, rows]; `w` is [N, sum K_s] (torch
+    Linear layout); `gate` is [batches, N]; `res` has the shape of `out` and may alias it.
+    """
+    lib = _lib.load()
+    segs = [a] if isinstance(a, torch.Tensor) else list(a)
+    if not 1 <= len(segs) <= 3:
+        raise AfbError("gemm: 1..3 A segments")
+    d = GemmDesc()
+    batches = rows = None
+    for i, s in enumerate(segs):
+        _chk(s, BF16, f"gemm a[{i}]")
+        ptr, ld, bs, nb, nr, k = _rows3(s, f"gemm a[{i}]")
+        if batches is None:
+            batches, rows = nb, nr
+        elif (nb, nr) != (batches, rows):
+            raise AfbError("gemm: A segments disagree on [batches, rows]")
+        d.a[i], d.a_ld[i], d.a_batch_stride[i], d.a_k[i] = ptr, ld, bs, k
+    _chk(w, BF16, "gemm w")
+    _chk(out, BF16, "gemm out")
+    if w.dim() != 2 or w.stride(1) != 1:
+        raise AfbError("gemm: w must be [N, K] with contiguous K")
+    optr, old, obs, ob, orows, on = _rows3(out, "gemm out")
+    if (ob, orows) != (batches, rows) or on != w.shape[0]:
+        raise AfbError(f"gemm: out shape {tuple(out.shape)} does not match [{batches}, {rows}, {w.shape[0]}]")
+    if w.shape[1] != sum(s.shape[-1] for s in segs):
+        raise AfbError("gemm: w K does not match the A segments")
+    d.batches, d.rows_per_batch = batches, rows
+    d.w, d.w_ld, d.n = w.data_ptr(), w.stride(0), w.shape[0]
+    d.epilogue = epilogue
+    d.out, d.out_ld, d.out_batch_stride = optr, old, obs
+    if bias is not None:
+        _chk(bias, BF16, "gemm bias")
+        d.bias = bias.data_ptr()
+    if gate is not None:
+        _chk(gate, BF16, "gemm gate")
+        if gate.dim() != 2 or gate.stride(1) != 1 or gate.shape[0] != batches:
+            raise AfbError("gemm: gate must be [batches, N]")
+        d.gate, d.gate_batch_stride = gate.data_ptr(), gate.stride(0)
+    if res is not None:
+        _chk(res, BF16, "gemm res")
+        rptr, rld, rbs, rb, rr, rn = _rows3(res, "gemm res")
+        if (rb, rr, rn) != (batches, rows, on):
+            raise AfbError("gemm: res shape mismatch")
+        d.res, d.res_ld, d.res_batch_stride = rptr, rld, rbs
+    _lib.check(lib.afb_gemm(C.byref(d), _stream()), "afb_gemm")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None,
+              scale: float = 0.0) -> torch.Tensor:
+    """Joint non-causal attention. q/k/v: [batch, seq, heads*128] views (last dim contiguous)."""
+    lib = _lib.load()
+    d = AttnDesc()
+    shp = None
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _chk(t, BF16, f"attention {name}")
+        ptr, ld, bs, nb, ns, nc = _rows3(t, f"attention {name}")
+        if shp is None:
+            shp = (nb, ns, nc)
+        elif shp != (nb, ns, nc):
+            raise AfbError("attention: q/k/v shapes differ")
+        setattr(d, name, ptr)
+        setattr(d, f"{name}_ld", ld)
+        setattr(d, f"{name}_batch_stride", bs)
+    nb, ns, nc = shp
+    if nc % 128:
+        raise AfbError("attention: last dim must be heads*128")
+    if out is None:
+        out = torch.empty((nb, ns, nc), dtype=BF16, device=q.device)
+    _chk(out, BF16, "attention out")
+    optr, old, obs, ob, os_, oc = _rows3(out, "attention out")
+    if (ob, os_, oc) != shp:
+        raise AfbError("attention: out shape mismatch")
+    d.o, d.o_ld, d.o_batch_stride = optr, old, obs
+    d.batch, d.seq, d.heads = nb, ns, nc // 128
+    d.scale = scale
+    _lib.check(lib.afb_attention(C.byref(d), _stream()), "afb_attention")
+    return out
+
+
+def ln_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                out: Optional[torch.Tensor] = None, eps: float = 1e-6) -> torch.Tensor:
+    """LayerNorm(x) * (1 + scale[b]) + shift[b]; x: [batches, rows, dim] (rows contiguous), scale/shift: [batches, dim] views."""
+    lib = _lib.load()
+    _chk(x, BF16, "ln_modulate x")
+    xptr, xld, xbs, nb, nr, dim = _rows3(x, "ln_modulate x")
+    if xld != dim:
+        raise AfbError("ln_modulate: x rows must be contiguous")
+    if out is None:
+        out = torch.empty_like(x)
+    _chk(out, BF16, "ln_modulate out")
+    optr, old, obs, ob, orr, od = _rows3(out, "ln_modulate out")
+    if (ob, orr, od) != (nb, nr, dim) or old != dim:
+        raise AfbError("ln_modulate: out shape mismatch")
+    for name, t in (("scale", scale), ("shift", shift)):
+        _chk(t, BF16, f"ln_modulate {name}")
+        if t.dim() != 2 or t.shape != (nb, dim) or t.stride(1) != 1:
+            raise AfbError(f"ln_modulate: {name} must be [batches, dim]")
+    if scale.stride(0) != shift.stride(0):
+        raise AfbError("ln_modulate: scale/shift must share a batch stride")
+    _lib.check(lib.afb_ln_modulate(xptr, xbs, optr, obs, scale.data_ptr(), shift.data_ptr(),
+                                   scale.stride(0), nb, nr, dim, eps, _stream()), "afb_ln_modulate")
+    return out
+
+
+def rmsnorm_rope(qkv: torch.Tensor, q_off: int, k_off: int, heads: int, txt_rows: int,
+                 wq_img: torch.Tensor, wk_img: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
+                 wq_txt: Optional[torch.Tensor] = None, wk_txt: Optional[torch.Tensor] = None,
+                 eps: float = 1e-6) -> torch.Tensor:
+    """In-place per-head RMSNorm + RoPE on the q and k thirds of a fused [batch, seq, ld] buffer."""
+    lib = _lib.load()
+    _chk(qkv, BF16, "rmsnorm_rope qkv")
+    ptr, ld, bs, nb, ns, _ = _rows3(qkv, "rmsnorm_rope qkv")
+    for name, t in (("cos", cos), ("sin", sin)):
+        _chk(t, torch.float32, f"rmsnorm_rope {name}")
+        if tuple(t.shape) != (ns, 128) or not t.is_contiguous():
+            raise AfbError(f"rmsnorm_rope: {name} must be contiguous [seq, 128] fp32")
+    for t in (wq_img, wk_img, wq_txt, wk_txt):
+        if t is not None:
+            _chk(t, BF16, "rmsnorm_rope weight")
+    _lib.check(lib.afb_rmsnorm_rope(
+        ptr, ld, bs, q_off, k_off, nb, ns, heads, txt_rows,
+        wq_txt.data_ptr() if wq_txt is not None else None,
+        wk_txt.data_ptr() if wk_txt is not None else None,
+        wq_img.data_ptr(), wk_img.data_ptr(), cos.data_ptr(), sin.data_ptr(), eps, _stream()),
+        "afb_rmsnorm_rope")
+    return qkv
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None, silu_in: bool = False,
+                 accumulate: bool = False) -> torch.Tensor:
+    """y[m, n] (+)= act(x) @ w.T + bias for m <= 8 rows (HBM-bound weight streaming)."""
+    lib = _lib.load()
+    _chk(x, BF16, "small_linear x")
+    _chk(w, BF16, "small_linear w")
+    m, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        if accumulate:
+            raise AfbError("small_linear: accumulate needs `out`")
+        out = torch.empty((m, n), dtype=BF16, device=x.device)
+    _chk(out, BF16, "small_linear out")
+    if bias is not None:
+        _chk(bias, BF16, "small_linear bias")
+    flags = (_lib.AFB_SL_SILU_IN if silu_in else 0) | (_lib.AFB_SL_ACCUMULATE if accumulate else 0)
+    _lib.check(lib.afb_small_linear(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0),
+                                    bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                    out.stride(0), m, n, k, flags, _stream()), "afb_small_linear")
+    return out
+
+
+def timestep_embed(t: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(t, torch.float32, "timestep_embed t")
+    out = torch.empty((t.numel(), 256), dtype=BF16, device=t.device)
+    _lib.check(lib.afb_timestep_embed(t.data_ptr(), out.data_ptr(), t.numel(), _stream()),
+               "afb_timestep_embed")
+    return out
+
+
+def sampler_step(head: torch.Tensor, x: torch.Tensor, sigma_src: float, sigma_start: float,
+                 sigma_end: float, num_gaussians: int = 16, eps: float = 1e-4,
+                 want_bf16: bool = False):
+    """One analytic momentum-integration step in packed token layout (see arcflow_b200.h)."""
+    lib = _lib.load()
+    _chk(head, BF16, "sampler_step head")
+    _chk(x, torch.float32, "sampler_step x")
+    if head.dim() != 2 or head.stride(1) != 1:
+        raise AfbError("sampler_step: head must be [tokens, head_ld]")
+    x2 = x.reshape(-1, 64)
+    if not x2.is_contiguous() or x2.shape[0] != head.shape[0]:
+        raise AfbError("sampler_step: x must be contiguous [tokens, 64]")
+    out = torch.empty_like(x2)
+    out_bf = torch.empty(x2.shape, dtype=BF16, device=x.device) if want_bf16 else None
+    _lib.check(lib.afb_sampler_step(head.data_ptr(), head.stride(0), x2.data_ptr(), out.data_ptr(),
+                                    out_bf.data_ptr() if want_bf16 else None, x2.shape[0],
+                                    num_gaussians, sigma_src, sigma_start, sigma_end, eps, _stream()),
+               "afb_sampler_step")
+    out = out.reshape(x.shape)
+    return (out, out_bf.reshape(x.shape)) if want_bf16 else out

@@ -1,0 +1,266 @@
+/* arcflow_b200 — C ABI of the B200-native ArcFlow denoising hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types, no exceptions across it.
+ * Every entry point returns 0 (AFB_OK) or a negative error code; afb_last_error() gives the message.
+ * All work is enqueued asynchronously on the caller's CUDA stream (passed as void* = cudaStream_t);
+ * no entry point allocates device memory except afb_engine_create / afb_engine_reserve.
+ * All device buffers are bf16 unless stated, row-major, and owned by the caller.
+ *
+ * What each entry replaces in the reference (paths relative to the upstream repo root):
+ *   afb_gemm            torch.nn.Linear (+ peft LoRA branch) inside the diffusers MMDiT blocks built at
+ *                       lakonlab/models/architecture/arcflow/arcflux.py:60-88 and called at :158-249
+ *   afb_attention       F.scaled_dot_product_attention reached through FluxAttention /
+ *                       QwenDoubleStreamAttnProcessor2_0 (arcflux.py:180-230, arcqwen.py:136-155)
+ *   afb_ln_modulate     AdaLayerNormZero / ZeroSingle / Continuous (arcflux.py:85, blocks' norm1/norm2)
+ *   afb_rmsnorm_rope    per-head RMSNorm(q,k) + apply_rotary_emb (pos_embed: arcflux.py:171-173)
+ *   afb_small_linear    the M = batch Linears: time_text_embed MLPs (arcflux.py:163-168) and every
+ *                       AdaLN modulation Linear (one batched call per forward)
+ *   afb_timestep_embed  diffusers Timesteps(256, flip_sin_to_cos=True)
+ *   afb_sampler_step    _unpack_mp + ArcFlowPolicy + momentum_integration + _pack_latents
+ *                       (lakonlab/pipelines/arcflux_pipeline.py:135-249, :482-510;
+ *                        lakonlab/models/diffusions/policies/arcflow.py:25-50)
+ *   afb_engine_*        _ArcFluxTransformer2DModel.forward (arcflux.py:134-257) /
+ *                       _ArcQwenImageTransformer2DModel.forward (arcqwen.py:106-174) and the denoising
+ *                       loop of ArcFluxPipeline.__call__ (arcflux_pipeline.py:453-524)
+ */
+#ifndef ARCFLOW_B200_H_
+#define ARCFLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFB_OK 0
+#define AFB_ERR_INVALID (-1)
+#define AFB_ERR_CUDA (-2)
+#define AFB_ERR_UNSUPPORTED (-3)
+
+/* ABI version; bumped on any incompatible change of the structs below. */
+#define AFB_ABI_VERSION 1
+int afb_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* afb_last_error(void);
+/* Number of kernels this library has launched in this process (all entry points). */
+uint64_t afb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM: out[b, r, n] = epi( sum_s sum_k A_s[b, r, k] * W[n, koff_s + k] )
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  AFB_EPI_BIAS = 0,          /* y + bias                                   (bias may be NULL)        */
+  AFB_EPI_BIAS_GELU = 1,     /* gelu_tanh(y + bias)                                                   */
+  AFB_EPI_BIAS_GATE_RES = 2  /* res + gate[b, n] * (y + bias)              (AdaLN-Zero gate+residual) */
+};
+
+typedef struct afb_gemm_desc {
+  /* A operand as up to 3 K-segments (LoRA / concat folded in as extra K). a_k[s] == 0 ends the list.
+   * Each segment: bf16 [batches, rows_per_batch, a_k[s]] with leading dim a_ld[s] (elements) and
+   * batch stride a_batch_stride[s] (elements). K of every segment must be a multiple of 64. */
+  const void* a[3];
+  int64_t a_ld[3];
+  int64_t a_batch_stride[3];
+  int32_t a_k[3];
+  int32_t batches;
+  int32_t rows_per_batch;
+  /* W: bf16 [n, sum(a_k)] K-major (torch Linear.weight layout), leading dim w_ld. */
+  const void* w;
+  int64_t w_ld;
+  int32_t n; /* multiple of 8 */
+  int32_t epilogue;
+  /* out: bf16 [batches, rows_per_batch, n], leading dim out_ld, batch stride out_batch_stride. */
+  void* out;
+  int64_t out_ld;
+  int64_t out_batch_stride;
+  const void* bias; /* bf16 [n] or NULL */
+  const void* gate; /* bf16, gate[b * gate_batch_stride + n] (AFB_EPI_BIAS_GATE_RES) */
+  int64_t gate_batch_stride;
+  const void* res; /* bf16, same shape as out; may alias out */
+  int64_t res_ld;
+  int64_t res_batch_stride;
+} afb_gemm_desc;
+
+int afb_gemm(const afb_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Joint (text+image) non-causal attention, head_dim 128:
+ *   o[b, s, h, :] = softmax(q[b, s, h, :] . k[b, :, h, :] / sqrt(128)) v[b, :, h, :]
+ * q/k/v: bf16 [batch, seq, heads*128] views with leading dim *_ld and batch stride *_batch_stride
+ * (they may live interleaved in one fused QKV buffer). o: bf16 [batch, seq, heads*128].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct afb_attn_desc {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int64_t q_ld, k_ld, v_ld, o_ld;
+  int64_t q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride;
+  int32_t batch, seq, heads;
+  float scale; /* 0 -> 1/sqrt(128) */
+} afb_attn_desc;
+
+int afb_attention(const afb_attn_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * y[b, r, :] = LayerNorm(x[b, r, :]; eps, no affine) * (1 + scale[b, :]) + shift[b, :]
+ * x, y: bf16 [batches, rows_per_batch, dim] (ld = dim, batch stride given); scale/shift: bf16 vectors
+ * addressed as ptr[b * mod_batch_stride + j]. dim must be a multiple of 256 and <= 8192.
+ * ---------------------------------------------------------------------------------------------- */
+int afb_ln_modulate(const void* x, int64_t x_batch_stride, void* y, int64_t y_batch_stride,
+                    const void* scale, const void* shift, int64_t mod_batch_stride,
+                    int32_t batches, int32_t rows_per_batch, int32_t dim, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * In place on a fused QKV buffer [batches, seq, ld]: for every head of q (cols q_off + h*128) and
+ * k (cols k_off + h*128): x <- RoPE(RMSNorm(x; eps) * w). Rows s < txt_rows use (wq_txt, wk_txt),
+ * the rest (wq_img, wk_img) (bf16 [128] each). cos/sin: fp32 [seq, 128] (adjacent-pair convention:
+ * out[2j] = x[2j]*cos[2j] - x[2j+1]*sin[2j]; out[2j+1] = x[2j+1]*cos[2j+1] + x[2j]*sin[2j+1]).
+ * ---------------------------------------------------------------------------------------------- */
+int afb_rmsnorm_rope(void* qkv, int64_t ld, int64_t batch_stride, int32_t q_off, int32_t k_off,
+                     int32_t batches, int32_t seq, int32_t heads, int32_t txt_rows,
+                     const void* wq_txt, const void* wk_txt, const void* wq_img, const void* wk_img,
+                     const float* cos_tab, const float* sin_tab, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small-M Linear (M = batch <= 8): y[m, n] (+)= sum_k act(x[m, k]) * W[n, k] + bias[n]
+ * x: bf16 [m, k] (ld x_ld); W: bf16 [n, k] (ld w_ld); y: bf16 [m, n] (ld y_ld). HBM-bound on W.
+ * flags: bit0 = apply SiLU to x on load; bit1 = accumulate into existing y. k % 256 == 0, k <= 4096.
+ * ---------------------------------------------------------------------------------------------- */
+#define AFB_SL_SILU_IN 1
+#define AFB_SL_ACCUMULATE 2
+int afb_small_linear(const void* x, int64_t x_ld, const void* w, int64_t w_ld, const void* bias,
+                     void* y, int64_t y_ld, int32_t m, int32_t n, int32_t k, int32_t flags,
+                     void* stream);
+
+/* out[m, 0:128] = cos(t[m] * f_j), out[m, 128:256] = sin(t[m] * f_j), f_j = exp(-ln(1e4) j / 128).
+ * t: fp32 [m] (already in the units the embedder sees, e.g. 1000*sigma); out: bf16 [m, 256]. */
+int afb_timestep_embed(const float* t, void* out, int32_t m, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One analytic momentum-integration step in packed token layout.
+ * head: bf16 [tokens, head_ld] = [means K*64 | logit K*4 | loggamma (K-1)*4 | pad], the raw output of
+ * the three ArcFlow heads (logits NOT yet log-softmaxed). x_in/x_out: fp32 [tokens, 64] packed latents
+ * (channel index c*4 + ph*2 + pw); x_out_bf16 (optional): bf16 copy for the next network call.
+ *   x_out = x_in - sum_k softmax_k(bf16(log_softmax_k(logit))) * mean_k * exp(lam_k * dt_past)
+ *                        * dt_step * phi(lam_k * dt_step),   lam_0 = 0, phi(z) = expm1(z~)/z~
+ * dt_past = sigma_src - sigma_start, dt_step = sigma_start - sigma_end, eps = 1e-4 clamp on |z|.
+ * ---------------------------------------------------------------------------------------------- */
+int afb_sampler_step(const void* head, int64_t head_ld, const float* x_in, float* x_out,
+                     void* x_out_bf16, int64_t tokens, int32_t num_gaussians, float sigma_src,
+                     float sigma_start, float sigma_end, float eps, void* stream);
+
+/* fp32 -> bf16 cast of a contiguous buffer. */
+int afb_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Engine: whole-transformer forward + 2-NFE denoise loop over packed weights.
+ * ---------------------------------------------------------------------------------------------- */
+#define AFB_ARCH_FLUX 0
+#define AFB_ARCH_QWEN 1
+
+typedef struct afb_model_desc {
+  int32_t arch;         /* AFB_ARCH_FLUX | AFB_ARCH_QWEN */
+  int32_t num_double;   /* FLUX 19, Qwen 60 */
+  int32_t num_single;   /* FLUX 38, Qwen 0 */
+  int32_t dim;          /* 3072 */
+  int32_t heads;        /* 24 (head_dim fixed at 128) */
+  int32_t mlp_dim;      /* 12288 */
+  int32_t in_channels;  /* 64 */
+  int32_t txt_dim;      /* FLUX 4096, Qwen 3584 */
+  int32_t pooled_dim;   /* FLUX 768, Qwen 0 */
+  int32_t guidance;     /* FLUX.1-dev: 1 */
+  int32_t num_gaussians; /* 16 */
+  int32_t lora_rank;    /* 256; 0 = no adapter branches (teacher trunk) */
+  int32_t head_mode;    /* 0 = ArcFlow 3 heads (means|logits|loggamma), 1 = stock proj_out (teacher) */
+} afb_model_desc;
+
+/* Packed per-block weights. All bf16. W*: [out, in(+rank)] K-major with the LoRA B matrix appended
+ * along K when lora_rank > 0 (so ld = in + rank); la_*: LoRA A matrices [rank, in]. NULL la_* = no LoRA
+ * on that Linear (then ld = in). */
+typedef struct afb_double_block {
+  /* image stream */
+  const void *img_qkv_w, *img_qkv_b;         /* [3D, D], [3D] */
+  const void *img_nq, *img_nk;               /* RMSNorm weights [128] */
+  const void *img_out_w, *img_out_b;         /* [D, D] */
+  const void *img_up_w, *img_up_b, *img_up_la;       /* [M, D(+r)], [M], [r, D] */
+  const void *img_down_w, *img_down_b, *img_down_la; /* [D, M(+r)], [D], [r, M] */
+  /* text stream */
+  const void *txt_qkv_w, *txt_qkv_b;
+  const void *txt_nq, *txt_nk;
+  const void *txt_out_w, *txt_out_b;
+  const void *txt_up_w, *txt_up_b, *txt_up_la;
+  const void *txt_down_w, *txt_down_b, *txt_down_la;
+  int64_t img_mod_off, txt_mod_off; /* column offset of this block's 6*D modulation chunk */
+} afb_double_block;
+
+typedef struct afb_single_block {
+  const void *qkv_w, *qkv_b;              /* [3D, D] */
+  const void *nq, *nk;
+  const void *mlp_w, *mlp_b, *mlp_la;     /* [M, D(+r)], [M], [r, D] */
+  const void *out_w, *out_b, *out_la;     /* [D, D+M(+r)], [D], [r, D+M] */
+  int64_t mod_off;                        /* 3*D chunk */
+} afb_single_block;
+
+typedef struct afb_weights {
+  const void *x_emb_w, *x_emb_b;          /* [D, in_channels] */
+  const void *ctx_w, *ctx_b;              /* [D, txt_dim] */
+  const void *txt_norm_w;                 /* Qwen: RMSNorm(txt_dim) weight, else NULL */
+  /* timestep / guidance / pooled-text embedders: Linear(256->D), Linear(D->D) each */
+  const void *t1_w, *t1_b, *t1_la, *t1_lb;   /* LoRA kept separate here: la [r,256], lb [D,r] */
+  const void *t2_w, *t2_b, *t2_la, *t2_lb;
+  const void *g1_w, *g1_b, *g2_w, *g2_b;
+  const void *p1_w, *p1_b, *p2_w, *p2_b;
+  /* all AdaLN modulation Linears of the model concatenated along the output dim */
+  const void *mod_w, *mod_b;              /* [mod_total, D], [mod_total] */
+  int64_t mod_total;
+  int64_t norm_out_mod_off;               /* 2*D chunk (scale, shift) */
+  const void *head_w, *head_b;            /* [head_n, D], [head_n]; head_n padded to a multiple of 8 */
+  int32_t head_n;
+  const afb_double_block* dbl;
+  const afb_single_block* sgl;
+} afb_weights;
+
+typedef struct afb_engine afb_engine;
+
+int afb_engine_create(const afb_model_desc* desc, afb_engine** out);
+void afb_engine_destroy(afb_engine* e);
+/* Borrows the packed weight pointers (caller keeps the storage alive). */
+int afb_engine_bind(afb_engine* e, const afb_weights* w);
+/* Runtime LoRA scale (joint_attention_kwargs['scale'] in the reference); 1.0 by default. The packed
+ * [W | B] weights assume scale 1; other values are applied by scaling the A-projection output. */
+int afb_engine_set_lora_scale(afb_engine* e, float scale);
+/* Bytes of workspace the engine needs for (batch, txt_len, img_len); afb_engine_reserve allocates it. */
+size_t afb_engine_workspace_bytes(const afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
+int afb_engine_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
+
+typedef struct afb_forward_args {
+  int32_t batch, txt_len, img_len;
+  const void* latents;        /* bf16 [batch, img_len, in_channels] packed tokens */
+  const void* txt;            /* bf16 [batch, txt_len, txt_dim] */
+  const void* pooled;         /* bf16 [batch, pooled_dim] or NULL */
+  const float* timestep;      /* fp32 [batch]: value the time embedder sees (FLUX: bf16(bf16(sigma)*1000)) */
+  const float* guidance;      /* fp32 [batch] or NULL (FLUX: bf16(bf16(g)*1000)) */
+  const float* rope_cos;      /* fp32 [txt_len + img_len, 128] */
+  const float* rope_sin;
+  void* head_out;             /* bf16 [batch*img_len, head_n] raw heads (means | logits | loggamma) */
+} afb_forward_args;
+
+int afb_engine_forward(afb_engine* e, const afb_forward_args* args, void* stream);
+
+typedef struct afb_denoise_args {
+  afb_forward_args fwd;       /* latents / head_out fields are ignored (engine-internal buffers) */
+  int32_t nfe;
+  const float* sigmas;        /* host fp32 [nfe + 1]: sigma at each network call, then the final sigma (0) */
+  const float* timesteps;     /* host fp32 [nfe]: value fed to the time embedder at each call */
+  float* x;                   /* fp32 [batch, img_len, 64] packed latents, updated in place */
+  float eps;                  /* 1e-4 */
+} afb_denoise_args;
+
+int afb_engine_denoise(afb_engine* e, const afb_denoise_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARCFLOW_B200_H_ */
