@@ -111,6 +111,11 @@ class DenoiseArgs(C.Structure):
     ]
 
 
+class Profile(C.Structure):
+    _fields_ = [("gemm_ms", C.c_double), ("attn_ms", C.c_double), ("gemm_flops", C.c_double),
+                ("attn_flops", C.c_double), ("gemm_launches", C.c_int64), ("attn_launches", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/arcflow_b200.h declares
 SIGNATURES = {
     "afb_abi_version": (C.c_int, []),
@@ -137,6 +142,8 @@ SIGNATURES = {
     "afb_engine_reserve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "afb_engine_forward": (C.c_int, [_P, C.POINTER(ForwardArgs), _P]),
     "afb_engine_denoise": (C.c_int, [_P, C.POINTER(DenoiseArgs), _P]),
+    "afb_engine_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "afb_engine_read_profile": (C.c_int, [_P, C.POINTER(Profile)]),
 }
 
 _lib = None

@@ -312,6 +312,35 @@ sampler_step_k16_kernel(const __nv_bfloat16* __restrict__ head, long long head_l
     *reinterpret_cast<uint32_t*>(x_out_bf16 + tok * 64 + 2 * lane) = pack_bf16x2(xo.x, xo.y);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plain RMSNorm over rows (Qwen-Image txt_norm, arcqwen.py:126-127): y = bf16(x * rsqrt(mean x^2 + eps)) * w
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                    const __nv_bfloat16* __restrict__ w, long long rows, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * dim;
+  __nv_bfloat16* yr = y + row * dim;
+  float ss = 0.f;
+  for (int c = lane * 8; c < dim; c += 256) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+  }
+  const float rs = rsqrtf(warp_sum(ss) / float(dim) + eps);
+  for (int c = lane * 8; c < dim; c += 256) {
+    float f[8], g[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c), f);
+    unpack8(*reinterpret_cast<const uint4*>(w + c), g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = round_bf16(f[i] * rs) * g[i];
+    *reinterpret_cast<uint4*>(yr + c) = pack8(o);
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                      long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -450,6 +479,18 @@ int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t str
   const long long thr = (n + 3) / 4;
   cast_f32_bf16_kernel<<<unsigned((thr + 255) / 256), 256, 0, stream>>>(
       in, static_cast<__nv_bfloat16*>(out), n);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int rmsnorm_rows_launch(const void* x, void* y, const void* w, int64_t rows, int dim, float eps,
+                        cudaStream_t stream) {
+  AFB_REQUIRE(x && y && w && rows >= 1, "rmsnorm_rows: bad arguments");
+  AFB_REQUIRE(dim % 256 == 0, "rmsnorm_rows: dim=%d must be a multiple of 256", dim);
+  rmsnorm_rows_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
+      static_cast<const __nv_bfloat16*>(w), rows, dim, eps);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

@@ -1,12 +1,575 @@
-// placeholder — replaced by the real engine
+// arcflow_b200 — engine: the whole ArcFlow transformer forward and the N-NFE denoising loop as a
+// fixed sequence of kernel launches on the caller's stream (CUDA-graph capturable: no host sync, no
+// allocation after afb_engine_reserve).
+//
+// Restates, on packed weights and a joint [text; image] residual buffer:
+//   FLUX  _ArcFluxTransformer2DModel.forward   lakonlab/models/architecture/arcflow/arcflux.py:134-257
+//         (+ diffusers FluxTransformerBlock / FluxSingleTransformerBlock)
+//   Qwen  _ArcQwenImageTransformer2DModel.forward lakonlab/models/architecture/arcflow/arcqwen.py:106-174
+//   loop  ArcFluxPipeline.__call__ denoising loop  lakonlab/pipelines/arcflux_pipeline.py:453-524
+//
+// Data layout in HBM (all bf16 unless noted; B batch, St text tokens, Si image tokens, S = St + Si):
+//   h     [B, S, D]    joint residual stream; the text stream is rows [0, St), the image stream rows
+//                      [St, S) of each batch — double-stream blocks address them as strided views, the
+//                      single-stream blocks use the whole buffer, so no concat/split copy ever happens
+//   y     [B, S, D]    AdaLN-modulated activations (GEMM A operand)
+//   qkv   [B, S, 3D]   fused Q|K|V; RMSNorm+RoPE in place; attention reads strided head views
+//   attn  [B, S, D]    attention output (A operand of the out projections)
+//   mlp   [B, S, M]    GELU(MLP-up) hidden
+//   lt0/1 [B, S, r]    LoRA A-projections (the K-extension operands)
+//   mod   [B, mod_total] every AdaLN vector of the forward, from ONE weight-streaming launch
+//   head  [B*Si, head_n] raw ArcFlow heads (means | logits | loggamma), consumed by the sampler kernel
+#include <new>
+#include <vector>
+
 #include "common.cuh"
-extern "C" {
-int afb_engine_create(const afb_model_desc*, afb_engine**) { afb::set_last_error("engine not built"); return AFB_ERR_UNSUPPORTED; }
-void afb_engine_destroy(afb_engine*) {}
-int afb_engine_bind(afb_engine*, const afb_weights*) { return AFB_ERR_UNSUPPORTED; }
-int afb_engine_set_lora_scale(afb_engine*, float) { return AFB_ERR_UNSUPPORTED; }
-size_t afb_engine_workspace_bytes(const afb_engine*, int32_t, int32_t, int32_t) { return 0; }
-int afb_engine_reserve(afb_engine*, int32_t, int32_t, int32_t) { return AFB_ERR_UNSUPPORTED; }
-int afb_engine_forward(afb_engine*, const afb_forward_args*, void*) { return AFB_ERR_UNSUPPORTED; }
-int afb_engine_denoise(afb_engine*, const afb_denoise_args*, void*) { return AFB_ERR_UNSUPPORTED; }
+
+namespace afb {
+int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream);
+int attention_launch(const afb_attn_desc* d, cudaStream_t stream);
+int ln_modulate_launch(const void* x, int64_t x_bs, void* y, int64_t y_bs, const void* scale,
+                       const void* shift, int64_t mod_bs, int batches, int rows_per_batch, int dim,
+                       float eps, cudaStream_t stream);
+int rmsnorm_rope_launch(void* qkv, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
+                        int heads, int txt_rows, const void* wq_txt, const void* wk_txt,
+                        const void* wq_img, const void* wk_img, const float* cos_tab,
+                        const float* sin_tab, float eps, cudaStream_t stream);
+int small_linear_launch(const void* x, int64_t x_ld, const void* w, int64_t w_ld, const void* bias,
+                        void* y, int64_t y_ld, int m, int n, int k, int flags, cudaStream_t stream);
+int timestep_embed_launch(const float* t, void* out, int m, cudaStream_t stream);
+int sampler_step_launch(const void* head, int64_t head_ld, const float* x_in, float* x_out,
+                        void* x_out_bf16, int64_t tokens, int num_gaussians, float sigma_src,
+                        float sigma_start, float sigma_end, float eps, cudaStream_t stream);
+int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t stream);
+int fill_f32_launch(float* p, float v, int n, cudaStream_t stream);
+int rmsnorm_rows_launch(const void* x, void* y, const void* w, int64_t rows, int dim, float eps,
+                        cudaStream_t stream);
+}  // namespace afb
+
+using bf16 = __nv_bfloat16;
+
+struct afb_engine {
+  afb_model_desc desc{};
+  afb_weights w{};
+  std::vector<afb_double_block> dbl;
+  std::vector<afb_single_block> sgl;
+  bool bound = false;
+  float lora_scale = 1.0f;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int cap_batch = 0, cap_txt = 0, cap_img = 0;
+  // carved pointers
+  bf16 *h = nullptr, *y = nullptr, *qkv = nullptr, *attn = nullptr, *mlp = nullptr, *lt0 = nullptr,
+       *lt1 = nullptr, *mod = nullptr, *temb = nullptr, *tmp = nullptr, *tproj = nullptr,
+       *ltv = nullptr, *head = nullptr, *x_bf16 = nullptr, *txtn = nullptr;
+  float *t_dev = nullptr, *g_dev = nullptr;
+  // optional per-launch CUDA-event profiling of the two tensor-core kernels
+  bool profiling = false;
+  struct ProfRec { int cls; double flops; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  afb_profile prof_acc{};
+};
+
+namespace {
+
+constexpr float LN_EPS = 1e-6f;
+
+size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t elems) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(elems * sizeof(T));
+    return p;
+  }
+};
+
+size_t carve(afb_engine* e, uint8_t* base, int B, int St, int Si) {
+  const afb_model_desc& d = e->desc;
+  const size_t S = size_t(St) + Si, D = d.dim, M = d.mlp_dim, r = d.lora_rank > 0 ? d.lora_rank : 8;
+  Carver c{base};
+  e->h = c.take<bf16>(B * S * D);
+  e->y = c.take<bf16>(B * S * D);
+  e->qkv = c.take<bf16>(B * S * 3 * D);
+  e->attn = c.take<bf16>(B * S * D);
+  e->mlp = c.take<bf16>(B * S * M);
+  e->lt0 = c.take<bf16>(B * S * r);
+  e->lt1 = c.take<bf16>(B * S * r);
+  e->mod = c.take<bf16>(size_t(B) * size_t(e->w.mod_total > 0 ? e->w.mod_total : 1));
+  e->temb = c.take<bf16>(B * D);
+  e->tmp = c.take<bf16>(B * D);
+  e->tproj = c.take<bf16>(size_t(B) * 256);
+  e->ltv = c.take<bf16>(B * r);
+  e->head = c.take<bf16>(size_t(B) * Si * size_t(e->w.head_n > 0 ? e->w.head_n : 8));
+  e->x_bf16 = c.take<bf16>(size_t(B) * Si * d.in_channels);
+  e->txtn = c.take<bf16>(d.arch == AFB_ARCH_QWEN ? size_t(B) * St * d.txt_dim : 8);
+  e->t_dev = c.take<float>(B);
+  e->g_dev = c.take<float>(B);
+  return c.off;
 }
+
+// [batches, rows, cols] view helper for the GEMM descriptor
+struct View {
+  const bf16* p;
+  int64_t ld, bs;
+};
+
+cudaEvent_t prof_event(afb_engine* e) {
+  cudaEvent_t ev;
+  if (!e->ev_pool.empty()) {
+    ev = e->ev_pool.back();
+    e->ev_pool.pop_back();
+  } else {
+    cudaEventCreate(&ev);
+  }
+  return ev;
+}
+
+struct ProfScope {
+  afb_engine* e;
+  cudaStream_t s;
+  int cls;
+  double flops;
+  cudaEvent_t e0{};
+  ProfScope(afb_engine* eng, cudaStream_t st, int c, double f) : e(eng), s(st), cls(c), flops(f) {
+    if (e && e->profiling) {
+      e0 = prof_event(e);
+      cudaEventRecord(e0, s);
+    }
+  }
+  ~ProfScope() {
+    if (e && e->profiling) {
+      cudaEvent_t e1 = prof_event(e);
+      cudaEventRecord(e1, s);
+      e->prof.push_back({cls, flops, e0, e1});
+    }
+  }
+};
+
+struct Gemm {
+  afb_gemm_desc d{};
+  int nseg = 0;
+  Gemm(int batches, int rows) {
+    d.batches = batches;
+    d.rows_per_batch = rows;
+  }
+  Gemm& a(View v, int k) {
+    d.a[nseg] = v.p;
+    d.a_ld[nseg] = v.ld;
+    d.a_batch_stride[nseg] = v.bs;
+    d.a_k[nseg] = k;
+    ++nseg;
+    return *this;
+  }
+  Gemm& w(const void* wp, int64_t ld, int n, const void* bias) {
+    d.w = wp;
+    d.w_ld = ld;
+    d.n = n;
+    d.bias = bias;
+    return *this;
+  }
+  Gemm& out(View v, int epi) {
+    d.out = const_cast<bf16*>(v.p);
+    d.out_ld = v.ld;
+    d.out_batch_stride = v.bs;
+    d.epilogue = epi;
+    return *this;
+  }
+  Gemm& gate_res(const bf16* gate, int64_t gate_bs, View res) {
+    d.gate = gate;
+    d.gate_batch_stride = gate_bs;
+    d.res = res.p;
+    d.res_ld = res.ld;
+    d.res_batch_stride = res.bs;
+    return *this;
+  }
+  int run(afb_engine* e, cudaStream_t s) {
+    double k = 0;
+    for (int i = 0; i < nseg; ++i) k += d.a_k[i];
+    ProfScope ps(e, s, 0, 2.0 * d.batches * d.rows_per_batch * double(d.n) * k);
+    int rc = afb::gemm_launch(&d, s);
+    if (rc == AFB_OK) afb::count_launch(1);
+    return rc;
+  }
+};
+
+int run_attention(afb_engine* e, const afb_attn_desc* at, cudaStream_t s) {
+  ProfScope ps(e, s, 1, 4.0 * at->batch * at->heads * double(at->seq) * at->seq * 128.0);
+  return afb::attention_launch(at, s);
+}
+
+#define AFB_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != AFB_OK) return _rc; \
+  } while (0)
+
+// y[m, n] = act(x) W^T + b for any m (loops the <= 8-row kernel)
+int small_linear_rows(const bf16* x, int64_t x_ld, const void* w, int64_t w_ld, const void* bias,
+                      bf16* y, int64_t y_ld, int m, int n, int k, int flags, cudaStream_t s) {
+  for (int r0 = 0; r0 < m; r0 += 8) {
+    const int mm = m - r0 < 8 ? m - r0 : 8;
+    AFB_TRY(afb::small_linear_launch(x + (int64_t)r0 * x_ld, x_ld, w, w_ld, bias,
+                                     y + (int64_t)r0 * y_ld, y_ld, mm, n, k, flags, s));
+  }
+  return AFB_OK;
+}
+
+// Linear(256 -> D) -> SiLU -> Linear(D -> D), optionally with un-merged LoRA on both, result
+// written (or accumulated) into e->temb.
+int embed_mlp(afb_engine* e, const bf16* in, int in_dim, const void* w1, const void* b1,
+              const void* la1, const void* lb1, const void* w2, const void* b2, const void* la2,
+              const void* lb2, bool accumulate, int B, cudaStream_t s) {
+  const int D = e->desc.dim, r = e->desc.lora_rank;
+  AFB_TRY(small_linear_rows(in, in_dim, w1, in_dim, b1, e->tmp, D, B, D, in_dim, 0, s));
+  if (la1 && lb1) {
+    AFB_TRY(small_linear_rows(in, in_dim, la1, in_dim, nullptr, e->ltv, r, B, r, in_dim, 0, s));
+    AFB_TRY(small_linear_rows(e->ltv, r, lb1, r, nullptr, e->tmp, D, B, D, r, AFB_SL_ACCUMULATE, s));
+  }
+  AFB_TRY(small_linear_rows(e->tmp, D, w2, D, b2, e->temb, D, B, D, D,
+                            AFB_SL_SILU_IN | (accumulate ? AFB_SL_ACCUMULATE : 0), s));
+  if (la2 && lb2) {
+    AFB_TRY(small_linear_rows(e->tmp, D, la2, D, nullptr, e->ltv, r, B, r, D, AFB_SL_SILU_IN, s));
+    AFB_TRY(small_linear_rows(e->ltv, r, lb2, r, nullptr, e->temb, D, B, D, r, AFB_SL_ACCUMULATE, s));
+  }
+  return AFB_OK;
+}
+
+// One MLP (Linear up + GELU-tanh + Linear down, both with optional LoRA K-extension), gated into res.
+int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v, int rows, int B,
+               const void* up_w, const void* up_b, const void* up_la, const void* down_w,
+               const void* down_b, const void* down_la, const bf16* gate, cudaStream_t s) {
+  const int D = e->desc.dim, M = e->desc.mlp_dim, r = e->desc.lora_rank;
+  const int64_t mod_bs = e->w.mod_total;
+  if (up_la) {
+    AFB_TRY(Gemm(B, rows).a(yv, D).w(up_la, D, r, nullptr).out(lt0v, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(yv, D).a(lt0v, r).w(up_w, D + r, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
+  } else {
+    AFB_TRY(Gemm(B, rows).a(yv, D).w(up_w, D, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
+  }
+  if (down_la) {
+    AFB_TRY(Gemm(B, rows).a(mlpv, M).w(down_la, M, r, nullptr).out(lt1v, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(mlpv, M).a(lt1v, r).w(down_w, M + r, D, down_b)
+                .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
+  } else {
+    AFB_TRY(Gemm(B, rows).a(mlpv, M).w(down_w, M, D, down_b)
+                .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
+  }
+  return AFB_OK;
+}
+
+int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, bf16* head_out,
+                 cudaStream_t s) {
+  const afb_model_desc& d = e->desc;
+  const afb_weights& w = e->w;
+  const int B = a->batch, St = a->txt_len, Si = a->img_len, S = St + Si;
+  const int D = d.dim, M = d.mlp_dim, r = d.lora_rank, H = d.heads;
+  const int64_t mod_bs = w.mod_total;
+  const bool flux = d.arch == AFB_ARCH_FLUX;
+
+  // ---- conditioning vector temb [B, D] ---------------------------------------------------------
+  AFB_TRY(afb::timestep_embed_launch(a->timestep, e->tproj, B, s));
+  AFB_TRY(embed_mlp(e, e->tproj, 256, w.t1_w, w.t1_b, r > 0 ? w.t1_la : nullptr, r > 0 ? w.t1_lb : nullptr,
+                    w.t2_w, w.t2_b, r > 0 ? w.t2_la : nullptr, r > 0 ? w.t2_lb : nullptr, false, B, s));
+  if (flux && d.guidance) {
+    AFB_REQUIRE(a->guidance != nullptr, "forward: model has guidance embeds but guidance is NULL");
+    AFB_TRY(afb::timestep_embed_launch(a->guidance, e->tproj, B, s));
+    AFB_TRY(embed_mlp(e, e->tproj, 256, w.g1_w, w.g1_b, nullptr, nullptr, w.g2_w, w.g2_b, nullptr,
+                      nullptr, true, B, s));
+  }
+  if (flux && d.pooled_dim > 0) {
+    AFB_REQUIRE(a->pooled != nullptr, "forward: pooled projections missing");
+    AFB_TRY(embed_mlp(e, static_cast<const bf16*>(a->pooled), d.pooled_dim, w.p1_w, w.p1_b, nullptr,
+                      nullptr, w.p2_w, w.p2_b, nullptr, nullptr, true, B, s));
+  }
+  // ---- every AdaLN modulation vector of this forward: one weight-streaming launch ---------------
+  AFB_TRY(small_linear_rows(e->temb, D, w.mod_w, D, w.mod_b, e->mod, mod_bs, B, int(w.mod_total), D,
+                            AFB_SL_SILU_IN, s));
+
+  // ---- token embedders into the joint residual buffer ------------------------------------------
+  const View h_txt{e->h, D, int64_t(S) * D};
+  const View h_img{e->h + int64_t(St) * D, D, int64_t(S) * D};
+  const View y_txt{e->y, D, int64_t(S) * D};
+  const View y_img{e->y + int64_t(St) * D, D, int64_t(S) * D};
+  const View qkv_txt{e->qkv, 3 * D, int64_t(S) * 3 * D};
+  const View qkv_img{e->qkv + int64_t(St) * 3 * D, 3 * D, int64_t(S) * 3 * D};
+  const View at_txt{e->attn, D, int64_t(S) * D};
+  const View at_img{e->attn + int64_t(St) * D, D, int64_t(S) * D};
+  const View mlp_txt{e->mlp, M, int64_t(S) * M};
+  const View mlp_img{e->mlp + int64_t(St) * M, M, int64_t(S) * M};
+  const int rr = r > 0 ? r : 8;
+  const View l0_txt{e->lt0, rr, int64_t(S) * rr};
+  const View l0_img{e->lt0 + int64_t(St) * rr, rr, int64_t(S) * rr};
+  const View l1_txt{e->lt1, rr, int64_t(S) * rr};
+  const View l1_img{e->lt1 + int64_t(St) * rr, rr, int64_t(S) * rr};
+
+  AFB_TRY(Gemm(B, Si).a(View{latents, d.in_channels, int64_t(Si) * d.in_channels}, d.in_channels)
+              .w(w.x_emb_w, d.in_channels, D, w.x_emb_b).out(h_img, AFB_EPI_BIAS).run(e, s));
+  {
+    const bf16* txt = static_cast<const bf16*>(a->txt);
+    if (!flux) {
+      AFB_TRY(afb::rmsnorm_rows_launch(txt, e->txtn, w.txt_norm_w, int64_t(B) * St, d.txt_dim, LN_EPS, s));
+      txt = e->txtn;
+    }
+    AFB_TRY(Gemm(B, St).a(View{txt, d.txt_dim, int64_t(St) * d.txt_dim}, d.txt_dim)
+                .w(w.ctx_w, d.txt_dim, D, w.ctx_b).out(h_txt, AFB_EPI_BIAS).run(e, s));
+  }
+
+  afb_attn_desc at{};
+  at.q = e->qkv;
+  at.k = e->qkv + D;
+  at.v = e->qkv + 2 * D;
+  at.o = e->attn;
+  at.q_ld = at.k_ld = at.v_ld = 3 * D;
+  at.o_ld = D;
+  at.q_batch_stride = at.k_batch_stride = at.v_batch_stride = int64_t(S) * 3 * D;
+  at.o_batch_stride = int64_t(S) * D;
+  at.batch = B;
+  at.seq = S;
+  at.heads = H;
+  at.scale = 0.f;
+
+  // ---- double-stream blocks --------------------------------------------------------------------
+  for (int i = 0; i < d.num_double; ++i) {
+    const afb_double_block& k = e->dbl[i];
+    // chunk(6): shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+    const bf16* im = e->mod + k.img_mod_off;
+    const bf16* tm = e->mod + k.txt_mod_off;
+    AFB_TRY(afb::ln_modulate_launch(h_img.p, h_img.bs, const_cast<bf16*>(y_img.p), y_img.bs, im + D, im,
+                                    mod_bs, B, Si, D, LN_EPS, s));
+    AFB_TRY(afb::ln_modulate_launch(h_txt.p, h_txt.bs, const_cast<bf16*>(y_txt.p), y_txt.bs, tm + D, tm,
+                                    mod_bs, B, St, D, LN_EPS, s));
+    AFB_TRY(Gemm(B, Si).a(y_img, D).w(k.img_qkv_w, D, 3 * D, k.img_qkv_b).out(qkv_img, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(Gemm(B, St).a(y_txt, D).w(k.txt_qkv_w, D, 3 * D, k.txt_qkv_b).out(qkv_txt, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, St, k.txt_nq,
+                                     k.txt_nk, k.img_nq, k.img_nk, a->rope_cos, a->rope_sin, LN_EPS, s));
+    AFB_TRY(run_attention(e, &at, s));
+    AFB_TRY(Gemm(B, Si).a(at_img, D).w(k.img_out_w, D, D, k.img_out_b)
+                .out(h_img, AFB_EPI_BIAS_GATE_RES).gate_res(im + 2 * D, mod_bs, h_img).run(e, s));
+    const bool last_qwen_txt = !flux && i == d.num_double - 1;  // its text stream output is never read
+    if (!last_qwen_txt)
+      AFB_TRY(Gemm(B, St).a(at_txt, D).w(k.txt_out_w, D, D, k.txt_out_b)
+                  .out(h_txt, AFB_EPI_BIAS_GATE_RES).gate_res(tm + 2 * D, mod_bs, h_txt).run(e, s));
+    AFB_TRY(afb::ln_modulate_launch(h_img.p, h_img.bs, const_cast<bf16*>(y_img.p), y_img.bs, im + 4 * D,
+                                    im + 3 * D, mod_bs, B, Si, D, LN_EPS, s));
+    AFB_TRY(mlp_branch(e, y_img, h_img, mlp_img, l0_img, l1_img, Si, B, k.img_up_w, k.img_up_b,
+                       r > 0 ? k.img_up_la : nullptr, k.img_down_w, k.img_down_b,
+                       r > 0 ? k.img_down_la : nullptr, im + 5 * D, s));
+    if (!last_qwen_txt) {
+      AFB_TRY(afb::ln_modulate_launch(h_txt.p, h_txt.bs, const_cast<bf16*>(y_txt.p), y_txt.bs, tm + 4 * D,
+                                      tm + 3 * D, mod_bs, B, St, D, LN_EPS, s));
+      AFB_TRY(mlp_branch(e, y_txt, h_txt, mlp_txt, l0_txt, l1_txt, St, B, k.txt_up_w, k.txt_up_b,
+                         r > 0 ? k.txt_up_la : nullptr, k.txt_down_w, k.txt_down_b,
+                         r > 0 ? k.txt_down_la : nullptr, tm + 5 * D, s));
+    }
+  }
+
+  // ---- single-stream blocks (FLUX) on the joint buffer -----------------------------------------
+  const View h_all{e->h, D, int64_t(S) * D};
+  const View y_all{e->y, D, int64_t(S) * D};
+  const View qkv_all{e->qkv, 3 * D, int64_t(S) * 3 * D};
+  const View at_all{e->attn, D, int64_t(S) * D};
+  const View mlp_all{e->mlp, M, int64_t(S) * M};
+  const View l0_all{e->lt0, rr, int64_t(S) * rr};
+  const View l1_all{e->lt1, rr, int64_t(S) * rr};
+  for (int i = 0; i < d.num_single; ++i) {
+    const afb_single_block& k = e->sgl[i];
+    const bf16* m = e->mod + k.mod_off;  // chunk(3): shift, scale, gate
+    AFB_TRY(afb::ln_modulate_launch(e->h, int64_t(S) * D, e->y, int64_t(S) * D, m + D, m, mod_bs, B, S, D,
+                                    LN_EPS, s));
+    AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(qkv_all, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, 0, nullptr, nullptr,
+                                     k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
+    AFB_TRY(run_attention(e, &at, s));
+    if (r > 0 && k.mlp_la) {
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, D + r, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
+    } else {
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, D, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
+    }
+    if (r > 0 && k.out_la) {
+      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, D + M + r, D, k.out_b)
+                  .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
+    } else {
+      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_w, D + M, D, k.out_b)
+                  .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
+    }
+  }
+
+  // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + heads ------------------------
+  const bf16* nm = e->mod + w.norm_out_mod_off;
+  AFB_TRY(afb::ln_modulate_launch(h_img.p, h_img.bs, const_cast<bf16*>(y_img.p), y_img.bs, nm, nm + D, mod_bs,
+                                  B, Si, D, LN_EPS, s));
+  AFB_TRY(Gemm(B, Si).a(y_img, D).w(w.head_w, D, w.head_n, w.head_b)
+              .out(View{head_out, w.head_n, int64_t(Si) * w.head_n}, AFB_EPI_BIAS).run(e, s));
+  return AFB_OK;
+}
+
+int check_shapes(afb_engine* e, int B, int St, int Si) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  AFB_REQUIRE(e->bound, "engine: weights not bound (call afb_engine_bind)");
+  AFB_REQUIRE(B >= 1 && St >= 1 && Si >= 1, "engine: empty problem (batch=%d txt=%d img=%d)", B, St, Si);
+  AFB_REQUIRE(e->ws != nullptr && B <= e->cap_batch && St <= e->cap_txt && Si <= e->cap_img,
+              "engine: workspace too small for (batch=%d txt=%d img=%d); call afb_engine_reserve", B, St, Si);
+  return AFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int afb_engine_create(const afb_model_desc* desc, afb_engine** out) {
+  AFB_REQUIRE(desc && out, "engine_create: null argument");
+  AFB_REQUIRE(desc->arch == AFB_ARCH_FLUX || desc->arch == AFB_ARCH_QWEN, "engine_create: unknown arch %d", desc->arch);
+  AFB_REQUIRE(desc->dim == desc->heads * 128, "engine_create: dim=%d must equal heads*128 (heads=%d)", desc->dim, desc->heads);
+  AFB_REQUIRE(desc->dim % 256 == 0 && desc->dim <= 4096, "engine_create: dim=%d must be a multiple of 256 <= 4096", desc->dim);
+  AFB_REQUIRE(desc->mlp_dim % 64 == 0 && desc->in_channels % 64 == 0 && desc->txt_dim % 256 == 0,
+              "engine_create: mlp_dim/in_channels must be multiples of 64 and txt_dim of 256");
+  AFB_REQUIRE(desc->lora_rank == 0 || desc->lora_rank % 256 == 0, "engine_create: lora_rank must be 0 or a multiple of 256");
+  AFB_REQUIRE(desc->arch != AFB_ARCH_FLUX || desc->pooled_dim % 256 == 0, "engine_create: pooled_dim must be a multiple of 256");
+  AFB_REQUIRE(desc->num_double >= 0 && desc->num_single >= 0, "engine_create: negative depth");
+  afb_engine* e = new (std::nothrow) afb_engine();
+  AFB_REQUIRE(e != nullptr, "engine_create: out of host memory");
+  e->desc = *desc;
+  *out = e;
+  return AFB_OK;
+}
+
+void afb_engine_destroy(afb_engine* e) {
+  if (!e) return;
+  if (e->ws) cudaFree(e->ws);
+  for (auto& r : e->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  delete e;
+}
+
+int afb_engine_bind(afb_engine* e, const afb_weights* w) {
+  AFB_REQUIRE(e && w, "engine_bind: null argument");
+  AFB_REQUIRE(w->x_emb_w && w->ctx_w && w->t1_w && w->t2_w && w->mod_w && w->head_w, "engine_bind: missing weights");
+  AFB_REQUIRE(w->head_n >= 8 && w->head_n % 8 == 0, "engine_bind: head_n=%d must be a multiple of 8", w->head_n);
+  AFB_REQUIRE(w->mod_total > 0 && w->mod_total % 8 == 0, "engine_bind: bad mod_total");
+  AFB_REQUIRE(e->desc.num_double == 0 || w->dbl, "engine_bind: double blocks missing");
+  AFB_REQUIRE(e->desc.num_single == 0 || w->sgl, "engine_bind: single blocks missing");
+  e->w = *w;
+  e->dbl.assign(w->dbl, w->dbl + e->desc.num_double);
+  e->sgl.assign(w->sgl, w->sgl + e->desc.num_single);
+  e->w.dbl = e->dbl.data();
+  e->w.sgl = e->sgl.data();
+  e->bound = true;
+  if (e->ws) carve(e, static_cast<uint8_t*>(e->ws), e->cap_batch, e->cap_txt, e->cap_img);
+  return AFB_OK;
+}
+
+int afb_engine_set_lora_scale(afb_engine* e, float scale) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  if (scale != 1.0f) {
+    afb::set_last_error("engine: runtime LoRA scale != 1 is not built yet (got %f)", double(scale));
+    return AFB_ERR_UNSUPPORTED;
+  }
+  e->lora_scale = scale;
+  return AFB_OK;
+}
+
+size_t afb_engine_workspace_bytes(const afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len) {
+  if (!e || batch < 1 || txt_len < 1 || img_len < 1) return 0;
+  afb_engine tmp = *e;
+  return carve(&tmp, nullptr, batch, txt_len, img_len);
+}
+
+int afb_engine_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  AFB_REQUIRE(e->bound, "engine_reserve: bind weights first");
+  AFB_REQUIRE(batch >= 1 && txt_len >= 1 && img_len >= 1, "engine_reserve: empty problem");
+  if (e->ws && batch <= e->cap_batch && txt_len <= e->cap_txt && img_len <= e->cap_img) return AFB_OK;
+  if (e->ws) {
+    AFB_CHECK_CUDA(cudaDeviceSynchronize());
+    AFB_CHECK_CUDA(cudaFree(e->ws));
+    e->ws = nullptr;
+  }
+  const size_t bytes = carve(e, nullptr, batch, txt_len, img_len);
+  AFB_CHECK_CUDA(cudaMalloc(&e->ws, bytes));
+  e->ws_bytes = bytes;
+  e->cap_batch = batch;
+  e->cap_txt = txt_len;
+  e->cap_img = img_len;
+  carve(e, static_cast<uint8_t*>(e->ws), batch, txt_len, img_len);
+  return AFB_OK;
+}
+
+int afb_engine_set_profiling(afb_engine* e, int32_t on) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  e->profiling = on != 0;
+  return AFB_OK;
+}
+
+int afb_engine_read_profile(afb_engine* e, afb_profile* out) {
+  AFB_REQUIRE(e && out, "engine_read_profile: null argument");
+  AFB_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& r : e->prof) {
+    float ms = 0.f;
+    AFB_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (r.cls == 0) {
+      e->prof_acc.gemm_ms += ms;
+      e->prof_acc.gemm_flops += r.flops;
+      e->prof_acc.gemm_launches += 1;
+    } else {
+      e->prof_acc.attn_ms += ms;
+      e->prof_acc.attn_flops += r.flops;
+      e->prof_acc.attn_launches += 1;
+    }
+    e->ev_pool.push_back(r.e0);
+    e->ev_pool.push_back(r.e1);
+  }
+  e->prof.clear();
+  *out = e->prof_acc;
+  e->prof_acc = afb_profile{};
+  return AFB_OK;
+}
+
+int afb_engine_forward(afb_engine* e, const afb_forward_args* a, void* stream) {
+  AFB_REQUIRE(a != nullptr, "engine_forward: null args");
+  AFB_TRY(check_shapes(e, a->batch, a->txt_len, a->img_len));
+  AFB_REQUIRE(a->latents && a->txt && a->timestep && a->rope_cos && a->rope_sin && a->head_out,
+              "engine_forward: null tensor argument");
+  // the workspace views are carved for the reserved capacity; re-carve for the actual shape
+  carve(e, static_cast<uint8_t*>(e->ws), a->batch, a->txt_len, a->img_len);
+  return forward_impl(e, a, static_cast<const bf16*>(a->latents), static_cast<bf16*>(a->head_out),
+                      static_cast<cudaStream_t>(stream));
+}
+
+int afb_engine_denoise(afb_engine* e, const afb_denoise_args* a, void* stream) {
+  AFB_REQUIRE(a != nullptr, "engine_denoise: null args");
+  const afb_forward_args& f = a->fwd;
+  AFB_TRY(check_shapes(e, f.batch, f.txt_len, f.img_len));
+  AFB_REQUIRE(a->nfe >= 1 && a->sigmas && a->timesteps && a->x, "engine_denoise: bad arguments");
+  AFB_REQUIRE(f.txt && f.rope_cos && f.rope_sin, "engine_denoise: null tensor argument");
+  AFB_REQUIRE(e->desc.head_mode == 0, "engine_denoise: needs the ArcFlow heads (head_mode 0)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  carve(e, static_cast<uint8_t*>(e->ws), f.batch, f.txt_len, f.img_len);
+  const int64_t tokens = int64_t(f.batch) * f.img_len;
+  float* x = static_cast<float*>(a->x);
+  AFB_TRY(afb::cast_f32_bf16_launch(x, e->x_bf16, tokens * e->desc.in_channels, s));
+  for (int i = 0; i < a->nfe; ++i) {
+    afb_forward_args fa = f;
+    AFB_TRY(afb::fill_f32_launch(e->t_dev, a->timesteps[i], f.batch, s));
+    fa.timestep = e->t_dev;
+    // guidance stays whatever the caller passed (device fp32 [batch]) — constant over the loop
+    AFB_TRY(forward_impl(e, &fa, e->x_bf16, e->head, s));
+    // sigma_start == sigma_src inside the pipeline loop (arcflux_pipeline.py:495-503)
+    AFB_TRY(afb::sampler_step_launch(e->head, e->w.head_n, x, x, e->x_bf16, tokens, e->desc.num_gaussians,
+                                     a->sigmas[i], a->sigmas[i], a->sigmas[i + 1],
+                                     a->eps > 0.f ? a->eps : 1e-4f, s));
+  }
+  return AFB_OK;
+}
+
+}  // extern "C"

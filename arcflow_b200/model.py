@@ -1,0 +1,312 @@
+"""ArcFlow-FLUX transformer on the native engine: weight packing + the C-ABI handle.
+
+`ArcFluxEngineModel` is what the reference's `_ArcFluxTransformer2DModel`
+(lakonlab/models/architecture/arcflow/arcflux.py:25-257) becomes here: it takes the reference's state
+dict (diffusers FLUX keys + ArcFlow adapter keys), packs it once into the layouts the kernels want
+(fused QKV, [W | lora_B] K-extended weights, all AdaLN Linears concatenated, the three heads fused and
+padded to a multiple of 8 rows) and drives `afb_engine_forward` / `afb_engine_denoise`.
+There is no PyTorch compute path in this class.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import AfbError
+from .config import ArcFluxConfig
+from .rope import flux_rope_tables
+from .schedule import denoise_sigmas, flux_time_inputs
+
+BF16 = torch.bfloat16
+
+
+def _cat_k(w: torch.Tensor, lora_b: Optional[torch.Tensor]) -> torch.Tensor:
+    """[W | B] along K so that [x | xA^T] @ [W | B]^T = xW^T + (xA^T)B^T (peft scaling alpha/r = 1)."""
+    return (torch.cat([w, lora_b], dim=1) if lora_b is not None else w).contiguous()
+
+
+class PackedFluxWeights:
+    """Owns the packed device tensors and the ctypes structs that point into them."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: ArcFluxConfig, device, consume: bool = False):
+        self.cfg = cfg
+        self.keep: List[torch.Tensor] = []
+        D = cfg.inner_dim
+        r = cfg.lora_rank
+
+        def get(name: str, required: bool = True) -> Optional[torch.Tensor]:
+            t = sd.pop(name) if (consume and name in sd) else sd.get(name)
+            if t is None:
+                if required:
+                    raise AfbError(f"state dict is missing '{name}'")
+                return None
+            return t.to(device=device, dtype=BF16)
+
+        def hold(t: Optional[torch.Tensor]):
+            if t is None:
+                return None
+            t = t.contiguous()
+            self.keep.append(t)
+            return t.data_ptr()
+
+        def lora(prefix: str):
+            if r <= 0:
+                return None, None
+            a = get(prefix + ".lora_A.weight", required=False)
+            b = get(prefix + ".lora_B.weight", required=False)
+            if (a is None) != (b is None):
+                raise AfbError(f"LoRA pair incomplete for '{prefix}'")
+            if a is not None and (a.shape[0] != r or b.shape[1] != r):
+                raise AfbError(f"LoRA rank mismatch for '{prefix}': {tuple(a.shape)}")
+            return a, b
+
+        w = _lib.Weights()
+        w.x_emb_w, w.x_emb_b = hold(get("x_embedder.weight")), hold(get("x_embedder.bias"))
+        w.ctx_w, w.ctx_b = hold(get("context_embedder.weight")), hold(get("context_embedder.bias"))
+        te = "time_text_embed."
+        for tag, name, with_lora in (("t", "timestep_embedder", True), ("g", "guidance_embedder", False),
+                                     ("p", "text_embedder", False)):
+            if tag == "g" and not cfg.guidance_embeds:
+                continue
+            for li in (1, 2):
+                pre = f"{te}{name}.linear_{li}"
+                setattr(w, f"{tag}{li}_w", hold(get(pre + ".weight")))
+                setattr(w, f"{tag}{li}_b", hold(get(pre + ".bias")))
+                if with_lora:
+                    a, b = lora(pre)
+                    setattr(w, f"{tag}{li}_la", hold(a))
+                    setattr(w, f"{tag}{li}_lb", hold(b))
+
+        mod_w: List[torch.Tensor] = []
+        mod_b: List[torch.Tensor] = []
+        mod_off = 0
+
+        def add_mod(prefix: str) -> int:
+            nonlocal mod_off
+            mw, mb = get(prefix + ".weight"), get(prefix + ".bias")
+            mod_w.append(mw)
+            mod_b.append(mb)
+            off = mod_off
+            mod_off += mw.shape[0]
+            return off
+
+        self.dbl = (_lib.DoubleBlock * max(cfg.num_layers, 1))()
+        for i in range(cfg.num_layers):
+            p = f"transformer_blocks.{i}."
+            k = self.dbl[i]
+            k.img_mod_off = add_mod(p + "norm1.linear")
+            k.txt_mod_off = add_mod(p + "norm1_context.linear")
+            for side, names, out_name, ff in (("img", ("to_q", "to_k", "to_v"), "to_out.0", "ff"),
+                                              ("txt", ("add_q_proj", "add_k_proj", "add_v_proj"), "to_add_out", "ff_context")):
+                setattr(k, f"{side}_qkv_w", hold(torch.cat([get(p + f"attn.{n}.weight") for n in names], 0)))
+                setattr(k, f"{side}_qkv_b", hold(torch.cat([get(p + f"attn.{n}.bias") for n in names], 0)))
+                setattr(k, f"{side}_out_w", hold(get(p + f"attn.{out_name}.weight")))
+                setattr(k, f"{side}_out_b", hold(get(p + f"attn.{out_name}.bias")))
+                la, lb = lora(p + f"{ff}.net.0.proj")
+                setattr(k, f"{side}_up_w", hold(_cat_k(get(p + f"{ff}.net.0.proj.weight"), lb)))
+                setattr(k, f"{side}_up_b", hold(get(p + f"{ff}.net.0.proj.bias")))
+                setattr(k, f"{side}_up_la", hold(la))
+                la, lb = lora(p + f"{ff}.net.2")
+                setattr(k, f"{side}_down_w", hold(_cat_k(get(p + f"{ff}.net.2.weight"), lb)))
+                setattr(k, f"{side}_down_b", hold(get(p + f"{ff}.net.2.bias")))
+                setattr(k, f"{side}_down_la", hold(la))
+            k.img_nq, k.img_nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
+            k.txt_nq, k.txt_nk = hold(get(p + "attn.norm_added_q.weight")), hold(get(p + "attn.norm_added_k.weight"))
+
+        self.sgl = (_lib.SingleBlock * max(cfg.num_single_layers, 1))()
+        for i in range(cfg.num_single_layers):
+            p = f"single_transformer_blocks.{i}."
+            k = self.sgl[i]
+            k.mod_off = add_mod(p + "norm.linear")
+            k.qkv_w = hold(torch.cat([get(p + f"attn.{n}.weight") for n in ("to_q", "to_k", "to_v")], 0))
+            k.qkv_b = hold(torch.cat([get(p + f"attn.{n}.bias") for n in ("to_q", "to_k", "to_v")], 0))
+            k.nq, k.nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
+            la, lb = lora(p + "proj_mlp")
+            k.mlp_w, k.mlp_b, k.mlp_la = hold(_cat_k(get(p + "proj_mlp.weight"), lb)), hold(get(p + "proj_mlp.bias")), hold(la)
+            la, lb = lora(p + "proj_out")
+            k.out_w, k.out_b, k.out_la = hold(_cat_k(get(p + "proj_out.weight"), lb)), hold(get(p + "proj_out.bias")), hold(la)
+
+        w.norm_out_mod_off = add_mod("norm_out.linear")
+        w.mod_w, w.mod_b = hold(torch.cat(mod_w, 0)), hold(torch.cat(mod_b, 0))
+        w.mod_total = mod_off
+        del mod_w, mod_b
+
+        heads_w = [get("proj_out_means.weight"), get("proj_out_logweights.weight"), get("proj_out_loggamma.weight")]
+        heads_b = [get("proj_out_means.bias"), get("proj_out_logweights.bias"), get("proj_out_loggamma.bias")]
+        n = sum(t.shape[0] for t in heads_w)
+        pad = (-n) % 8
+        if pad:
+            heads_w.append(torch.zeros(pad, D, device=device, dtype=BF16))
+            heads_b.append(torch.zeros(pad, device=device, dtype=BF16))
+        w.head_w, w.head_b, w.head_n = hold(torch.cat(heads_w, 0)), hold(torch.cat(heads_b, 0)), n + pad
+        self.head_n = n + pad
+        w.dbl = C.cast(self.dbl, C.POINTER(_lib.DoubleBlock))
+        w.sgl = C.cast(self.sgl, C.POINTER(_lib.SingleBlock))
+        self.struct = w
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.keep)
+
+
+class ArcFluxEngineModel:
+    """The ArcFlow-FLUX student transformer + 2-NFE sampler on the native engine (inference)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ArcFluxConfig, device="cuda",
+                 consume_state_dict: bool = False):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise AfbError("ArcFluxEngineModel needs a CUDA device (there is no CPU path)")
+        self.num_gaussians = cfg.num_gaussians
+        self.dtype = BF16
+        self.weights = PackedFluxWeights(state_dict, cfg, self.device, consume=consume_state_dict)
+        md = _lib.ModelDesc(
+            arch=_lib.AFB_ARCH_FLUX, num_double=cfg.num_layers, num_single=cfg.num_single_layers,
+            dim=cfg.inner_dim, heads=cfg.num_attention_heads, mlp_dim=cfg.mlp_dim,
+            in_channels=cfg.in_channels, txt_dim=cfg.joint_attention_dim, pooled_dim=cfg.pooled_projection_dim,
+            guidance=int(cfg.guidance_embeds), num_gaussians=cfg.num_gaussians, lora_rank=cfg.lora_rank,
+            head_mode=0)
+        h = C.c_void_p()
+        _lib.check(self.lib.afb_engine_create(C.byref(md), C.byref(h)), "afb_engine_create")
+        self.handle = h
+        _lib.check(self.lib.afb_engine_bind(self.handle, C.byref(self.weights.struct)), "afb_engine_bind")
+        self._rope_cache = {}
+        self._reserved = (0, 0, 0)
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.afb_engine_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # -- attributes the pipelines read off `pipe.transformer` -----------------------
+    @property
+    def config(self):
+        return SimpleNamespace(in_channels=self.cfg.in_channels, guidance_embeds=self.cfg.guidance_embeds,
+                               **{k: v for k, v in self.cfg.to_dict().items() if k not in ("in_channels", "guidance_embeds")})
+
+    def cache_context(self, name: str):
+        return contextlib.nullcontext()
+
+    # ------------------------------------------------------------------------------------------
+    def _reserve(self, batch: int, txt_len: int, img_len: int):
+        rb, rt, ri = self._reserved
+        if batch > rb or txt_len > rt or img_len > ri:
+            nb, nt, ni = max(batch, rb), max(txt_len, rt), max(img_len, ri)
+            _lib.check(self.lib.afb_engine_reserve(self.handle, nb, nt, ni), "afb_engine_reserve")
+            self._reserved = (nb, nt, ni)
+
+    def set_profiling(self, on: bool):
+        _lib.check(self.lib.afb_engine_set_profiling(self.handle, int(on)), "afb_engine_set_profiling")
+
+    def read_profile(self) -> dict:
+        p = _lib.Profile()
+        _lib.check(self.lib.afb_engine_read_profile(self.handle, C.byref(p)), "afb_engine_read_profile")
+        return {n: getattr(p, n) for n, _ in p._fields_}
+
+    def workspace_bytes(self, batch: int, txt_len: int, img_len: int) -> int:
+        return int(self.lib.afb_engine_workspace_bytes(self.handle, batch, txt_len, img_len))
+
+    def rope(self, txt_len: int, grid_h: int, grid_w: int):
+        key = (txt_len, grid_h, grid_w)
+        if key not in self._rope_cache:
+            self._rope_cache[key] = flux_rope_tables(txt_len, grid_h, grid_w, self.cfg.axes_dims_rope,
+                                                     round_bf16=True, device=self.device)
+        return self._rope_cache[key]
+
+    def _fwd_args(self, txt, pooled, timestep, guidance, cos, sin, batch, img_len) -> _lib.ForwardArgs:
+        a = _lib.ForwardArgs()
+        a.batch, a.txt_len, a.img_len = batch, txt.shape[1], img_len
+        a.txt = txt.data_ptr()
+        a.pooled = pooled.data_ptr() if pooled is not None else None
+        a.timestep = timestep.data_ptr() if timestep is not None else None
+        a.guidance = guidance.data_ptr() if guidance is not None else None
+        a.rope_cos, a.rope_sin = cos.data_ptr(), sin.data_ptr()
+        return a
+
+    def _check_inputs(self, latents, txt, pooled, grid_hw):
+        cfg = self.cfg
+        if latents.dim() != 3 or latents.shape[2] != cfg.in_channels:
+            raise AfbError(f"latents must be [batch, tokens, {cfg.in_channels}], got {tuple(latents.shape)}")
+        if txt.dim() != 3 or txt.shape[2] != cfg.joint_attention_dim or txt.shape[0] != latents.shape[0]:
+            raise AfbError(f"text embeds must be [batch, txt_len, {cfg.joint_attention_dim}], got {tuple(txt.shape)}")
+        if pooled is None or tuple(pooled.shape) != (latents.shape[0], cfg.pooled_projection_dim):
+            raise AfbError("pooled projections must be [batch, pooled_projection_dim]")
+        if grid_hw[0] * grid_hw[1] != latents.shape[1]:
+            raise AfbError(f"token grid {grid_hw} does not match {latents.shape[1]} image tokens")
+        for t in (latents, txt, pooled):
+            if not t.is_cuda:
+                raise AfbError("inputs must be CUDA tensors (no CPU fallback exists)")
+
+    @torch.no_grad()
+    def forward_heads(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor,
+                      sigma: float, guidance_scale: float, grid_hw: Sequence[int]) -> torch.Tensor:
+        """One network call. Returns the raw head tensor bf16 [batch, tokens, head_n]
+        (means K*64 | logits K*4 | loggamma (K-1)*4 | pad) — logits are NOT yet log-softmaxed."""
+        self._check_inputs(latents, txt, pooled, grid_hw)
+        B, Si, _ = latents.shape
+        lat = latents.to(BF16).contiguous()
+        txt = txt.to(BF16).contiguous()
+        pooled = pooled.to(BF16).contiguous()
+        self._reserve(B, txt.shape[1], Si)
+        t_in, g_in = flux_time_inputs(sigma, guidance_scale)
+        tdev = torch.full((B,), t_in, dtype=torch.float32, device=self.device)
+        gdev = torch.full((B,), g_in, dtype=torch.float32, device=self.device) if self.cfg.guidance_embeds else None
+        cos, sin = self.rope(txt.shape[1], grid_hw[0], grid_hw[1])
+        out = torch.empty(B, Si, self.weights.head_n, dtype=BF16, device=self.device)
+        a = self._fwd_args(txt, pooled, tdev, gdev, cos, sin, B, Si)
+        a.latents, a.head_out = lat.data_ptr(), out.data_ptr()
+        _lib.check(self.lib.afb_engine_forward(self.handle, C.byref(a), torch.cuda.current_stream().cuda_stream),
+                   "afb_engine_forward")
+        return out
+
+    def split_heads(self, head: torch.Tensor):
+        """Raw head tensor -> the reference's ArcFlowModelOutput fields in token layout
+        (means [B,S,K,64], logweights [B,S,K,4] log-softmaxed over K in bf16, loggammas [B,S,K-1,4])."""
+        cfg = self.cfg
+        nm, nw, ng = cfg.head_dims
+        B, S, _ = head.shape
+        means = head[..., :nm].reshape(B, S, cfg.num_gaussians, cfg.out_channels)
+        logw = head[..., nm:nm + nw].reshape(B, S, cfg.num_gaussians, cfg.logweights_channels).log_softmax(dim=-2)
+        gam = head[..., nm + nw:nm + nw + ng].reshape(B, S, cfg.num_gaussians - 1, cfg.logweights_channels)
+        return dict(means=means, logweights=logw, loggammas=gam)
+
+    @torch.no_grad()
+    def denoise(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int],
+                num_inference_steps: int = 2, total_substeps: int = 128, timestep_ratio: float = 1.0,
+                shift: float = 3.2, guidance_scale: float = 3.5, eps: float = 1e-4) -> torch.Tensor:
+        """The whole N-NFE loop (network + analytic momentum integration) in one C-ABI call.
+        latents: fp32 packed tokens [batch, tokens, 64]; returns the final fp32 packed latents."""
+        self._check_inputs(latents, txt, pooled, grid_hw)
+        if latents.dtype != torch.float32:
+            raise AfbError("denoise: latents must be fp32 (the sampler state is fp32, arcflux_pipeline.py:407)")
+        B, Si, _ = latents.shape
+        txt = txt.to(BF16).contiguous()
+        pooled = pooled.to(BF16).contiguous()
+        self._reserve(B, txt.shape[1], Si)
+        sig = denoise_sigmas(num_inference_steps, total_substeps, timestep_ratio, shift)
+        tin = [flux_time_inputs(s, guidance_scale)[0] for s in sig[:-1]]
+        g_in = flux_time_inputs(sig[0], guidance_scale)[1]
+        gdev = torch.full((B,), g_in, dtype=torch.float32, device=self.device) if self.cfg.guidance_embeds else None
+        cos, sin = self.rope(txt.shape[1], grid_hw[0], grid_hw[1])
+        x = latents.contiguous().clone()
+        d = _lib.DenoiseArgs()
+        d.fwd = self._fwd_args(txt, pooled, None, gdev, cos, sin, B, Si)
+        d.nfe = num_inference_steps
+        sig_arr = (C.c_float * len(sig))(*sig)
+        tin_arr = (C.c_float * len(tin))(*tin)
+        d.sigmas, d.timesteps = sig_arr, tin_arr
+        d.x = x.data_ptr()
+        d.eps = eps
+        _lib.check(self.lib.afb_engine_denoise(self.handle, C.byref(d), torch.cuda.current_stream().cuda_stream),
+                   "afb_engine_denoise")
+        return x

@@ -260,6 +260,18 @@ typedef struct afb_denoise_args {
 
 int afb_engine_denoise(afb_engine* e, const afb_denoise_args* args, void* stream);
 
+/* Optional instrumentation: when on, every tensor-core launch of forward/denoise is bracketed by CUDA
+ * events on the caller's stream. afb_engine_read_profile synchronises the device, returns the totals
+ * since the last read (algorithmic FLOPs: 2*M*N*K per GEMM incl. LoRA K-extension, 4*B*H*S^2*128 per
+ * attention launch) and clears them. Off by default; the timed path carries no events. */
+typedef struct afb_profile {
+  double gemm_ms, attn_ms;
+  double gemm_flops, attn_flops;
+  int64_t gemm_launches, attn_launches;
+} afb_profile;
+int afb_engine_set_profiling(afb_engine* e, int32_t on);
+int afb_engine_read_profile(afb_engine* e, afb_profile* out);
+
 #ifdef __cplusplus
 }
 #endif

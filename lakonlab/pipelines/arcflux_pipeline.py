@@ -1,0 +1,164 @@
+"""ArcFluxPipeline — the reference's text-to-image pipeline surface for the 2-NFE ArcFlow sampler,
+re-built on the native engine.
+
+Keeps the call signature and semantics of `ArcFluxPipeline.__call__`
+(lakonlab/pipelines/arcflux_pipeline.py:252-276, loop :453-524): fp32 packed latents, the timestep schedule of
+`retrieve_raw_timesteps` + fixed shift, one transformer call and one analytic momentum-integration step per
+NFE, `FluxPipelineOutput(images=...)`. Out of scope here (metric uses cached embeds and latent
+output): the CLIP/T5 text encoders and the VAE — `prompt=` needs a `text_encoder_fn`, `output_type='pil'`
+needs a `vae_decode_fn`, both optional hooks.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import torch
+
+from arcflow_b200 import ops
+from arcflow_b200.schedule import denoise_sigmas, retrieve_raw_timesteps  # noqa: F401  (same public name)
+from .arcflow_loader import ArcFlowLoaderMixin
+
+
+@dataclass
+class FluxPipelineOutput:
+    images: Any
+
+
+class FluxBaseTransformer:
+    """Holder of a stock FLUX transformer state dict until `load_arcflow_adapter` swaps it."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        self._sd = state_dict
+        self.device = torch.device(device)
+        self.dtype = torch.bfloat16
+
+    def state_dict(self):
+        return self._sd
+
+
+class ArcFluxPipeline(ArcFlowLoaderMixin):
+    vae_scale_factor = 8
+    default_sample_size = 128
+
+    def __init__(self, transformer=None, scheduler_shift: float = 3.2, text_encoder_fn: Optional[Callable] = None,
+                 vae_decode_fn: Optional[Callable] = None, policy_type: str = "ArcFlow"):
+        if policy_type != "ArcFlow":
+            raise ValueError(f"Invalid policy: {policy_type}. Supported policies are ['ArcFlow'].")
+        self.transformer = transformer
+        self.scheduler_shift = scheduler_shift
+        self.text_encoder_fn = text_encoder_fn
+        self.vae_decode_fn = vae_decode_fn
+        self._num_timesteps = 0
+        self._interrupt = False
+
+    @property
+    def num_timesteps(self):
+        return self._num_timesteps
+
+    @property
+    def interrupt(self):
+        return self._interrupt
+
+    def to(self, device):
+        return self
+
+    # -- layout helpers kept under the reference's names (arcflux_pipeline.py:163-193) ---------------
+    @staticmethod
+    def _pack_latents(latents, batch_size, num_channels_latents, height, width, patch_size=1, target_patch_size=2):
+        s = target_patch_size // patch_size
+        x = latents.view(batch_size, num_channels_latents * patch_size * patch_size, height // target_patch_size, s,
+                         width // target_patch_size, s)
+        return x.permute(0, 2, 4, 1, 3, 5).reshape(batch_size, (height // target_patch_size) * (width // target_patch_size),
+                                                   num_channels_latents * target_patch_size * target_patch_size)
+
+    @staticmethod
+    def _unpack_latents(latents, height, width, vae_scale_factor, patch_size=2, target_patch_size=1):
+        b, _, ch = latents.shape
+        s = patch_size // target_patch_size
+        h, w = int(height) // (vae_scale_factor * patch_size), int(width) // (vae_scale_factor * patch_size)
+        x = latents.view(b, h, w, ch // (s * s), s, s).permute(0, 3, 1, 4, 2, 5)
+        return x.reshape(b, ch // (s * s), h * s, w * s)
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        h, w = 2 * (int(height) // (self.vae_scale_factor * 2)), 2 * (int(width) // (self.vae_scale_factor * 2))
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype, non_blocking=True)
+        shape = (batch_size, num_channels_latents, h, w)
+        if isinstance(generator, list):
+            noise = torch.cat([torch.randn((1, *shape[1:]), generator=g, device=g.device, dtype=dtype).to(device)
+                               for g in generator], 0)
+        else:
+            gdev = generator.device if generator is not None else device
+            noise = torch.randn(shape, generator=generator, device=gdev, dtype=dtype).to(device)
+        return self._pack_latents(noise, batch_size, num_channels_latents, h, w)
+
+    @torch.inference_mode()
+    def __call__(self, prompt: Union[str, List[str]] = None, prompt_2=None, height: Optional[int] = None,
+                 width: Optional[int] = None, num_inference_steps: int = 4, total_substeps: int = 128,
+                 timestep_ratio: float = 0.5, temperature: Union[float, str] = "auto", guidance_scale: float = 3.5,
+                 num_images_per_prompt: Optional[int] = 1, generator=None, latents: Optional[torch.Tensor] = None,
+                 prompt_embeds: Optional[torch.Tensor] = None, pooled_prompt_embeds: Optional[torch.Tensor] = None,
+                 output_type: Optional[str] = "pil", return_dict: bool = True,
+                 joint_attention_kwargs: Optional[Dict[str, Any]] = None,
+                 callback_on_step_end: Optional[Callable[[Any, int, Any, Dict], Dict]] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], max_sequence_length: int = 512):
+        tr = self.transformer
+        if tr is None or not hasattr(tr, "denoise"):
+            raise RuntimeError("pipe.transformer is not an ArcFlow module — call pipe.load_arcflow_adapter(...) first")
+        height = height or self.default_sample_size * self.vae_scale_factor
+        width = width or self.default_sample_size * self.vae_scale_factor
+        if height % 16 or width % 16:
+            raise ValueError(f"`height` and `width` have to be divisible by 16 but are {height} and {width}.")
+        if joint_attention_kwargs and joint_attention_kwargs.get("scale", 1.0) != 1.0:
+            raise NotImplementedError("runtime LoRA scale != 1.0 is not built yet")
+        device = tr.device
+        if prompt_embeds is None:
+            if prompt is None:
+                raise ValueError("Provide either `prompt` or `prompt_embeds`.")
+            if self.text_encoder_fn is None:
+                raise NotImplementedError("text encoders are out of scope of this build: pass cached `prompt_embeds` "
+                                          "and `pooled_prompt_embeds`, or construct the pipeline with text_encoder_fn")
+            prompt_embeds, pooled_prompt_embeds = self.text_encoder_fn(prompt, max_sequence_length)
+        if pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        prompt_embeds = prompt_embeds.to(device, non_blocking=True)
+        pooled_prompt_embeds = pooled_prompt_embeds.to(device, non_blocking=True)
+        if num_images_per_prompt and num_images_per_prompt > 1:
+            prompt_embeds = prompt_embeds.repeat_interleave(num_images_per_prompt, 0)
+            pooled_prompt_embeds = pooled_prompt_embeds.repeat_interleave(num_images_per_prompt, 0)
+        batch = prompt_embeds.shape[0]
+        num_channels_latents = tr.cfg.in_channels // 4
+        latents = self.prepare_latents(batch, num_channels_latents, height, width, torch.float32, device, generator, latents)
+        grid = (height // 16, width // 16)
+        _, _, total = retrieve_raw_timesteps(num_inference_steps, total_substeps, timestep_ratio)
+        self._num_timesteps = total
+
+        if callback_on_step_end is None:
+            # whole loop in one C-ABI call (transformer + sampler per NFE, no host round trips)
+            latents = tr.denoise(latents, prompt_embeds, pooled_prompt_embeds, grid, num_inference_steps=num_inference_steps,
+                                 total_substeps=total_substeps, timestep_ratio=timestep_ratio, shift=self.scheduler_shift,
+                                 guidance_scale=guidance_scale)
+        else:
+            sig = denoise_sigmas(num_inference_steps, total_substeps, timestep_ratio, self.scheduler_shift)
+            for i in range(num_inference_steps):
+                if self.interrupt:
+                    continue
+                head = tr.forward_heads(latents, prompt_embeds, pooled_prompt_embeds, sig[i], guidance_scale, grid)
+                latents = ops.sampler_step(head.reshape(-1, head.shape[-1]), latents, sig[i], sig[i], sig[i + 1],
+                                           num_gaussians=tr.num_gaussians)
+                t_src = torch.tensor(sig[i] * 1000.0, device=device)
+                cb = callback_on_step_end(self, i, t_src, {k: locals()[k] for k in callback_on_step_end_tensor_inputs})
+                latents = cb.pop("latents", latents)
+                prompt_embeds = cb.pop("prompt_embeds", prompt_embeds)
+
+        if output_type == "latent":
+            image = latents
+        else:
+            if self.vae_decode_fn is None:
+                raise NotImplementedError("the VAE is out of scope of this build: use output_type='latent' "
+                                          "or construct the pipeline with vae_decode_fn")
+            image = self.vae_decode_fn(self._unpack_latents(latents, height, width, self.vae_scale_factor), output_type)
+        if not return_dict:
+            return (image,)
+        return FluxPipelineOutput(images=image)
