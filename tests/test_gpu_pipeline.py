@@ -1,0 +1,104 @@
+"""GPU: the reference-facing plugin surface — load_arcflow_adapter from the on-disk adapter format and
+ArcFluxPipeline.__call__ — end to end through the C ABI, checked against the oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import arcflow_oracle as O  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+@pytest.fixture(scope="module")
+def setup(lib, tmp_path_factory):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from arcflow_b200.config import flux_tiny
+    from arcflow_b200.synthetic import make_flux_state_dict, make_flux_inputs
+    from lakonlab.pipelines.arcflow_loader import split_adapter_keys, write_adapter_folder
+    cfg = flux_tiny(2, 2, 2)
+    sd = make_flux_state_dict(cfg, seed=77, device="cpu")
+    # split into "stock FLUX" base (has a proj_out, no heads/LoRA) and the ArcFlow adapter on disk
+    adapter_keys = [k for k in sd if "lora" in k or k.startswith(("proj_out_", "norm_out."))]
+    adapter = {k: sd[k] for k in adapter_keys}
+    base = {k: v for k, v in sd.items() if k not in adapter or k.startswith("norm_out.")}
+    base["norm_out.linear.weight"] = torch.zeros_like(sd["norm_out.linear.weight"])  # adapter must overwrite these
+    base["norm_out.linear.bias"] = torch.zeros_like(sd["norm_out.linear.bias"])
+    base["proj_out.weight"] = torch.zeros(64, cfg.inner_dim, dtype=torch.bfloat16)
+    base["proj_out.bias"] = torch.zeros(64, dtype=torch.bfloat16)
+    root = tmp_path_factory.mktemp("adapter")
+    write_adapter_folder(root / "arcflow-flux-2steps", cfg, adapter)
+    x, txt, pooled = make_flux_inputs(cfg, 2, 64, 64, txt_len=32, seed=5)
+    return cfg, sd, base, root, x, txt, pooled
+
+
+def test_load_arcflow_adapter_and_call(setup):
+    from lakonlab.pipelines.arcflux_pipeline import ArcFluxPipeline, FluxBaseTransformer
+    cfg, sd, base, root, x, txt, pooled = setup
+    pipe = ArcFluxPipeline(transformer=FluxBaseTransformer(base, device="cuda"))
+    name = pipe.load_arcflow_adapter(str(root), subfolder="arcflow-flux-2steps", target_module_name="transformer")
+    assert name == "transformer_arcflow"
+    assert pipe.transformer.num_gaussians == 16 and pipe.transformer.config.in_channels == 64
+    out = pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, height=64, width=64,
+               num_inference_steps=2, timestep_ratio=1.0, output_type="latent").images
+    ref = O.flux_denoise(sd, cfg, x, txt, pooled, (4, 4), num_inference_steps=2, timestep_ratio=1.0)
+    assert out.shape == x.shape and out.dtype == torch.float32
+    assert rel(out, ref) < 2e-2
+
+
+def test_adapter_without_lora_returns_none(setup, tmp_path):
+    from lakonlab.pipelines.arcflow_loader import write_adapter_folder
+    from lakonlab.pipelines.arcflux_pipeline import ArcFluxPipeline, FluxBaseTransformer
+    cfg, sd, base, root, *_ = setup
+    write_adapter_folder(tmp_path / "nolora", cfg, {"proj_out_means.bias": sd["proj_out_means.bias"]})
+    pipe = ArcFluxPipeline(transformer=FluxBaseTransformer(base, device="cuda"))
+    with pytest.warns(UserWarning, match="No LoRA"):
+        assert pipe.load_arcflow_adapter(str(tmp_path / "nolora")) is None
+    assert isinstance(pipe.transformer, FluxBaseTransformer)   # nothing swapped
+    with pytest.raises(RuntimeError, match="load_arcflow_adapter"):
+        pipe(prompt_embeds=torch.zeros(1, 8, 256), pooled_prompt_embeds=torch.zeros(1, 256), height=64, width=64)
+
+
+def test_callback_path_equals_fused_loop(setup):
+    """callback_on_step_end forces the per-step path (afb_engine_forward + afb_sampler_step); it must give the
+    same latents as the single afb_engine_denoise call, and the callback sees every step."""
+    from arcflow_b200.model import ArcFluxEngineModel
+    from lakonlab.pipelines.arcflux_pipeline import ArcFluxPipeline
+    cfg, sd, base, root, x, txt, pooled = setup
+    pipe = ArcFluxPipeline(transformer=ArcFluxEngineModel(sd, cfg, device="cuda"))
+    kw = dict(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, height=64, width=64,
+              num_inference_steps=4, timestep_ratio=0.5, output_type="latent")
+    fused = pipe(**kw).images
+    seen = []
+
+    def cb(p, i, t, tensors):
+        seen.append((i, float(t)))
+        return {}
+
+    stepped = pipe(callback_on_step_end=cb, **kw).images
+    assert [i for i, _ in seen] == [0, 1, 2, 3] and seen[0][1] == pytest.approx(1000.0)
+    assert torch.equal(fused, stepped)
+    ref = O.flux_denoise(sd, cfg, x, txt, pooled, (4, 4), num_inference_steps=4, timestep_ratio=0.5)
+    assert rel(fused, ref) < 2e-2
+
+
+def test_generator_latents_and_errors(setup):
+    from arcflow_b200.model import ArcFluxEngineModel
+    from lakonlab.pipelines.arcflux_pipeline import ArcFluxPipeline
+    cfg, sd, base, root, x, txt, pooled = setup
+    pipe = ArcFluxPipeline(transformer=ArcFluxEngineModel(sd, cfg, device="cuda"))
+    kw = dict(prompt_embeds=txt[:1], pooled_prompt_embeds=pooled[:1], height=64, width=64, num_inference_steps=2,
+              timestep_ratio=1.0, output_type="latent")
+    a = pipe(generator=torch.Generator("cuda").manual_seed(42), **kw).images
+    b = pipe(generator=torch.Generator("cuda").manual_seed(42), **kw).images
+    assert a.shape == (1, 16, 64) and torch.equal(a, b) and torch.isfinite(a).all()
+    with pytest.raises(NotImplementedError, match="text encoders"):
+        pipe(prompt="a kangaroo", height=64, width=64)
+    with pytest.raises(NotImplementedError, match="VAE"):
+        pipe(**{**kw, "output_type": "pil"})
+    with pytest.raises(ValueError, match="divisible by 16"):
+        pipe(**{**kw, "height": 72})
