@@ -123,6 +123,7 @@ SIGNATURES = {
     "afb_launch_count": (C.c_uint64, []),
     "afb_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "afb_attention": (C.c_int, [C.POINTER(AttnDesc), _P]),
+    "afb_debug_attention_trace": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
     "afb_ln_modulate": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_float, _P]),
     "afb_rmsnorm_rope": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -9,11 +9,18 @@
 //   warp 0        TMA producer : Q once, then K_j / V_j into 2-stage rings (128 x 128 bf16, SW128)
 //   warp 1        MMA issuer   : S_t = Q_t K_j^T  (SS, M128 N128 K16 x8)  -> TMEM
 //                                O_t += P_t V_j   (TS: P read from TMEM, V MN-major from smem)
-//   warps 2..5    softmax WG 0 : one query row per thread; S from TMEM -> exp2 -> P (bf16) back into
-//   warps 6..9    softmax WG 1   the same TMEM columns; lazy O rescale; final O / l -> global
+//   warps 2..3    idle (pad the producer warpgroup so setmaxnreg applies per warpgroup)
+//   warps 4..7    softmax WG 0 : one query row per thread; S from TMEM -> exp2 -> P (bf16) back into
+//   warps 8..11   softmax WG 1   the same TMEM columns; lazy O rescale; final O / l -> global
 // The MMA order  PV_A(j), QK_A(j+1), PV_B(j), QK_B(j+1)  keeps the tensor pipe busy on one tile while
 // the other tile's warpgroup is in its softmax (ping-pong).  TMEM: S_A S_B O_A O_B = 4 x 128 columns.
+// The exp phase is MUFU-bound (128 ex2 per row per tile = the tensor time of one tile), so
+//   * the two warpgroups take turns in it (named-barrier hand-off) instead of halving each other's rate,
+//   * one pair in four is evaluated on the FMA pipe (Cody-Waite split + cubic minimax for 2^frac),
+//   * scale/subtract, the polynomial and the row sum use packed f32x2 instructions,
+//   * registers move from the producer warpgroup to the softmax warpgroups (setmaxnreg).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/arcflow_b200.h"
@@ -27,11 +34,18 @@ constexpr int HD = 128;
 constexpr int QT = 128;
 constexpr int NQT = 2;
 constexpr int KT = 128;
-constexpr int KV_STAGES = 2;
+constexpr int K_STAGES = 3;
+constexpr int V_STAGES = 2;
 constexpr int HALF_BYTES = 128 * 64 * 2;    // one 64-column SW128 half of a 128 x 128 tile
 constexpr int TILE_BYTES = 2 * HALF_BYTES;  // 32 KiB
-constexpr int ATT_THREADS = 32 * (2 + 4 * NQT);
-constexpr size_t ATT_SMEM_BYTES = 1024 + size_t(NQT + 2 * KV_STAGES) * TILE_BYTES + 256;
+constexpr int ATT_THREADS = 32 * (4 + 4 * NQT);
+constexpr int SOFTMAX_REGS = 208;
+constexpr int PRODUCER_REGS = 88;
+// setmaxnreg draws from the registers this CTA released: (SOFTMAX - 168) * 256 <= (168 - PRODUCER) * 128
+static_assert((SOFTMAX_REGS - 168) * 256 <= (168 - PRODUCER_REGS) * 128, "register hand-off does not balance");
+constexpr int BAR_TURN_A = 1;  // named barriers: "warpgroup A may enter its exp phase" / same for B
+constexpr int BAR_TURN_B = 2;
+constexpr size_t ATT_SMEM_BYTES = 1024 + size_t(NQT + K_STAGES + V_STAGES) * TILE_BYTES + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: skip O rescale while max grows < 2^8
 
 struct AttnParams {
@@ -39,7 +53,40 @@ struct AttnParams {
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* o;
   long long o_ld, o_batch_stride;
+  int debug_mode;  // 0 = normal. Developer timing probes (results invalid): 1 = no exp, 2 = barriers only
 };
+
+// Developer trace (debug_mode 7): per-iteration clock stamps of one softmax thread per warpgroup of CTA 0.
+__device__ long long g_attn_trace[2][64][8];
+__device__ __forceinline__ void trace_stamp(bool on, int t, int j, int slot) {
+  if (on && j < 64) g_attn_trace[t][j][slot] = clock64();
+}
+
+template <int ID>
+__device__ __forceinline__ void named_bar_sync() {
+  asm volatile("bar.sync %0, 256;" ::"n"(ID) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void named_bar_arrive() {
+  asm volatile("bar.arrive %0, 256;" ::"n"(ID) : "memory");
+}
+
+// 2^x for a pair, on the FMA/ALU pipes: x = floor(x) + f, 2^f by a cubic minimax on [0, 1)
+// (max rel. error ~9e-5, far below the bf16 rounding of P), exponent patched in by integer add.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float magic = 12582912.0f;  // 1.5 * 2^23: float add with round-down leaves floor(x) in the low mantissa bits
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 sh = __fadd2_rd(x, make_float2(magic, magic));
+  const float2 fl = __fadd2_rn(sh, make_float2(-magic, -magic));
+  const float2 f = __fadd2_rn(x, make_float2(-fl.x, -fl.y));
+  float2 p = __ffma2_rn(make_float2(0.07711909f, 0.07711909f), f, make_float2(0.22756439f, 0.22756439f));
+  p = __ffma2_rn(p, f, make_float2(0.69514614f, 0.69514614f));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(sh.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(sh.y) << 23));
+  return p;
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -49,17 +96,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                              ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + NQT * TILE_BYTES;
-  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * TILE_BYTES);
-  uint64_t* q_full = bars;             // [1]
-  uint64_t* k_full = bars + 1;         // [2]
-  uint64_t* k_empty = bars + 3;        // [2]
-  uint64_t* v_full = bars + 5;         // [2]
-  uint64_t* v_empty = bars + 7;        // [2]
-  uint64_t* s_full = bars + 9;         // [NQT]  MMA -> softmax : S_t(j) ready
-  uint64_t* p_full = bars + 11;        // [NQT]  softmax -> MMA : P_t(j) written
-  uint64_t* o_done = bars + 13;        // [NQT]  MMA -> softmax : PV_t(j) retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint8_t* sV = sK + K_STAGES * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + V_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;                   // [1]
+  uint64_t* k_full = q_full + 1;             // [K_STAGES]
+  uint64_t* k_empty = k_full + K_STAGES;     // [K_STAGES]
+  uint64_t* v_full = k_empty + K_STAGES;     // [V_STAGES]
+  uint64_t* v_empty = v_full + V_STAGES;     // [V_STAGES]
+  uint64_t* s_full = v_empty + V_STAGES;     // [NQT]  MMA -> softmax : S_t(j) ready
+  uint64_t* p_full = s_full + NQT;           // [NQT]  softmax -> MMA : P_t(j) written
+  uint64_t* o_done = p_full + NQT;           // [NQT]  MMA -> softmax : PV_t(j) retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + NQT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,9 +120,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
+    for (int s = 0; s < K_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < V_STAGES; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
@@ -92,6 +141,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------------------
     if (lane == 0) {
@@ -101,43 +152,62 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tma_load_3d(sQ + t * TILE_BYTES + hf * HALF_BYTES, &tmQ, q_full, h * HD + hf * 64,
                       q0 + t * QT, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        const int ks = j % K_STAGES, vs = j % V_STAGES;
+        const uint32_t kph = (j / K_STAGES) & 1, vph = (j / V_STAGES) & 1;
+        mbar_wait(&k_empty[ks], kph ^ 1);
+        mbar_expect_tx(&k_full[ks], TILE_BYTES);
         for (int hf = 0; hf < 2; ++hf)
-          tma_load_3d(sK + st * TILE_BYTES + hf * HALF_BYTES, &tmK, &k_full[st], h * HD + hf * 64,
+          tma_load_3d(sK + ks * TILE_BYTES + hf * HALF_BYTES, &tmK, &k_full[ks], h * HD + hf * 64,
                       j * KT, b);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        mbar_wait(&v_empty[vs], vph ^ 1);
+        mbar_expect_tx(&v_full[vs], TILE_BYTES);
         for (int hf = 0; hf < 2; ++hf)
-          tma_load_3d(sV + st * TILE_BYTES + hf * HALF_BYTES, &tmV, &v_full[st], h * HD + hf * 64,
+          tma_load_3d(sV + vs * TILE_BYTES + hf * HALF_BYTES, &tmV, &v_full[vs], h * HD + hf * 64,
                       j * KT, b);
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------------------
-    if (lane == 0) {
+    // The whole warp runs this loop converged; one elected lane issues the tcgen05 instructions.
+    {
       constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KT, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(QT, HD, false, true);  // V is MN-major
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
+      const uint64_t k_desc = make_sw128_desc(smem_u32(sK), 16, 1024);
+      const uint64_t v_desc = make_sw128_desc(smem_u32(sV), HALF_BYTES, 1024);
 
+      const bool skip_qk = p.debug_mode == 4 || p.debug_mode == 6, skip_pv = p.debug_mode == 3 || p.debug_mode == 5 || p.debug_mode == 6;
+      const bool free_run = p.debug_mode == 5 || p.debug_mode == 6;  // probes 5/6: no softmax hand-shake at all
+      // descriptor start addresses are in 16-byte units, so advancing is an add on the low word
       auto issue_qk = [&](int t, int st) {
+        if (skip_qk) return;
+        const uint64_t a0 = q_desc + uint64_t((t * TILE_BYTES) >> 4);
+        const uint64_t b0 = k_desc + uint64_t((st * TILE_BYTES) >> 4);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
-          umma_ss(tmem_base + t * KT, make_sw128_desc(q_addr + t * TILE_BYTES + off, 16, 1024),
-                  make_sw128_desc(k_addr + st * TILE_BYTES + off, 16, 1024), idesc_qk, kk > 0);
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint32_t off = ((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4;
+            umma_ss(tmem_base + t * KT, a0 + off, b0 + off, idesc_qk, kk > 0);
+          }
         }
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int st, bool acc) {
+        if (skip_pv) return;
+        const uint64_t b0 = v_desc + uint64_t((st * TILE_BYTES) >> 4);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk) {
-          // A = P_t (bf16, TMEM, 8 columns per K=16); B = V rows [16 kk, 16 kk + 16) of the stage
-          umma_ts(tmem_base + NQT * KT + t * HD, tmem_base + t * KT + kk * 8,
-                  make_sw128_desc(v_addr + st * TILE_BYTES + kk * 2048, HALF_BYTES, 1024), idesc_pv,
-                  (acc || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < KT / 16; ++kk) {
+            // A = P_t (bf16, TMEM, 8 columns per K=16); B = V rows [16 kk, 16 kk + 16) of the stage
+            umma_ts(tmem_base + NQT * KT + t * HD, tmem_base + t * KT + kk * 8, b0 + uint64_t((kk * 2048) >> 4),
+                    idesc_pv, (acc || kk > 0) ? 1u : 0u);
+          }
         }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one_sync()) tc_commit(bar);
+        __syncwarp();
       };
 
       mbar_wait(q_full, 0);
@@ -145,34 +215,36 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       for (int t = 0; t < NQT; ++t) {
         issue_qk(t, 0);
-        tc_commit(&s_full[t]);
+        commit(&s_full[t]);
       }
-      tc_commit(&k_empty[0]);
+      commit(&k_empty[0]);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % V_STAGES;
+        const uint32_t ph = (j / V_STAGES) & 1;
         const bool has_next = (j + 1) < n_kv;
-        const int nst = (j + 1) & 1;
-        const uint32_t nph = ((j + 1) >> 1) & 1;
+        const int nst = (j + 1) % K_STAGES;
+        const uint32_t nph = ((j + 1) / K_STAGES) & 1;
         mbar_wait(&v_full[st], ph);
         if (has_next) mbar_wait(&k_full[nst], nph);
         for (int t = 0; t < NQT; ++t) {
-          mbar_wait(&p_full[t], j & 1);
+          if (!free_run) mbar_wait(&p_full[t], j & 1);
           tc_fence_after();
           issue_pv(t, st, j > 0);
-          tc_commit(&o_done[t]);
+          commit(&o_done[t]);
           if (has_next) {
             issue_qk(t, nst);
-            tc_commit(&s_full[t]);
+            commit(&s_full[t]);
           }
         }
-        tc_commit(&v_empty[st]);
-        if (has_next) tc_commit(&k_empty[nst]);
+        commit(&v_empty[st]);
+        if (has_next) commit(&k_empty[nst]);
       }
     }
+  }
   } else {
     // ------------------------------- softmax warpgroups -------------------------------------
-    const int t = (warp - 2) >> 2;  // which Q tile
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SOFTMAX_REGS));
+    const int t = (warp - 4) >> 2;  // which Q tile
     const int qd = warp & 3;        // TMEM lane quarter
     const int row = qd * 32 + lane;
     const uint32_t lane_base = uint32_t(qd * 32) << 16;
@@ -182,9 +254,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float m = -INFINITY;
     float l = 0.f;
 
-    for (int j = 0; j < n_kv; ++j) {
+    const bool use_turns = p.debug_mode != 8;
+    const bool tr = (p.debug_mode == 7 || p.debug_mode == 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0;
+    for (int j = 0; j < ((p.debug_mode == 5 || p.debug_mode == 6) ? 0 : n_kv); ++j) {
+      trace_stamp(tr, t, j, 0);
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      trace_stamp(tr, t, j, 1);
+      if (p.debug_mode >= 2 && p.debug_mode < 7) {  // timing probe: MMA/TMA pipeline alone
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        continue;
+      }
       uint32_t s[KT];
 #pragma unroll
       for (int i = 0; i < KT / 32; ++i)
@@ -230,17 +312,41 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
 
-      const float neg_mc = -m * c;
-      float l0 = 0.f, l1 = 0.f;
+      // ---- exp phase: the two warpgroups alternate (MUFU is the shared, saturated resource) ----
+      trace_stamp(tr, t, j, 2);
+      if (use_turns) {
+        if (t == 0) {
+          if (j > 0) named_bar_sync<BAR_TURN_A>();
+        } else {
+          named_bar_sync<BAR_TURN_B>();
+        }
+      }
+      trace_stamp(tr, t, j, 3);
+      const float2 c2 = make_float2(c, c);
+      const float2 nm2 = make_float2(-m * c, -m * c);
+      float2 lsum = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < KT; i += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), c, neg_mc));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), c, neg_mc));
-        l0 += p0;
-        l1 += p1;
-        s[i >> 1] = pack_bf16x2(p0, p1);
+        float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
+        float2 pv;
+        if (((i >> 1) & 3) == 3) {
+          pv = exp2_poly2(x);
+        } else {
+          pv.x = fast_exp2(x.x);
+          pv.y = fast_exp2(x.y);
+        }
+        lsum = __fadd2_rn(lsum, pv);
+        s[i >> 1] = pack_bf16x2(pv.x, pv.y);
       }
-      l += l0 + l1;
+      trace_stamp(tr, t, j, 4);
+      if (use_turns) {
+        if (t == 0) {
+          named_bar_arrive<BAR_TURN_B>();
+        } else {
+          named_bar_arrive<BAR_TURN_A>();
+        }
+      }
+      l += lsum.x + lsum.y;
 #pragma unroll
       for (int i = 0; i < KT / 32; ++i)
         tmem_st_32x16(tS + i * 16, reinterpret_cast<const uint32_t(&)[16]>(s[i * 16]));
@@ -248,10 +354,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
+      trace_stamp(tr, t, j, 5);
     }
 
+    if (t == 0 && (p.debug_mode < 2 || p.debug_mode == 7)) named_bar_sync<BAR_TURN_A>();  // consume warpgroup B's last hand-off
+
     // final: O / l -> bf16 -> global
-    mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    if (p.debug_mode < 5 || p.debug_mode >= 7) mbar_wait(&o_done[t], (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int qrow = q0 + t * QT + row;
@@ -287,6 +396,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 }  // namespace
 
+int attention_read_trace(long long* out, int n) {
+  long long host[2 * 64 * 8];
+  AFB_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(host)));
+  for (int i = 0; i < n && i < 2 * 64 * 8; ++i) out[i] = host[i];
+  return AFB_OK;
+}
+
 int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
   AFB_REQUIRE(d != nullptr, "attention: null descriptor");
   AFB_REQUIRE(d->q && d->k && d->v && d->o, "attention: null operand pointer");
@@ -314,6 +430,14 @@ int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
   p.o = static_cast<__nv_bfloat16*>(d->o);
   p.o_ld = d->o_ld;
   p.o_batch_stride = d->o_batch_stride;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("AFB_ATTN_DEBUG_MODE");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug_mode = dbg;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {

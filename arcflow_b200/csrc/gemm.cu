@@ -137,37 +137,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    // Whole warp converged; one elected lane issues (keeps descriptors in uniform registers).
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+    const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 16, 1024);
+    const uint64_t b_desc0 = make_sw128_desc(smem_u32(sB), 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < nk; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+        const uint64_t adesc = a_desc0 + uint64_t((stage * A_STAGE_BYTES) >> 4);
+        const uint64_t bdesc = b_desc0 + uint64_t((stage * B_STAGE_BYTES) >> 4);
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one_sync()) tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ------------------------------- epilogue warps -----------------------------------------

@@ -102,6 +102,9 @@ typedef struct afb_attn_desc {
 } afb_attn_desc;
 
 int afb_attention(const afb_attn_desc* desc, void* stream);
+/* Developer instrumentation: with env AFB_ATTN_DEBUG_MODE=7 the kernel records SM-clock stamps of the softmax
+ * hand-shake of CTA 0 ([warpgroup 2][iteration 64][stamp 8] int64); this copies them out. Not a product path. */
+int afb_debug_attention_trace(int64_t* out, int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * y[b, r, :] = LayerNorm(x[b, r, :]; eps, no affine) * (1 + scale[b, :]) + shift[b, :]
