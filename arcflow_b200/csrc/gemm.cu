@@ -8,12 +8,22 @@
 // as a K-extension: A may be given as up to three K-segments (e.g. [y | y·A_lora^T] against
 // [W | B_lora]), so "base + LoRA" is ONE accumulation in TMEM and no separate add kernel exists.
 //
-// Layout / roles (one CTA per SM, persistent over output tiles, 128 x 256 x 64 tiles):
-//   warp 0      TMA producer   : A tile (3-D map: k, row, batch) + W tile into a 4-stage smem ring
-//   warp 1      MMA issuer     : one lane issues tcgen05.mma (M128 N256 K16, SS), commits to mbarriers
-//   warps 2..5  epilogue       : tcgen05.ld accumulator -> bias / GELU-tanh / gate*y+residual -> bf16
-// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
-// the main loop of tile i+1.
+// Two kernels share one epilogue:
+//  * gemm_bf16_2cta_kernel (default): a CTA PAIR (cluster of 2, one TPC) owns a 256 x 256 output tile.
+//    tcgen05.mma.cta_group::2 (M256 N256 K16) is issued by the leader CTA only; each CTA stages its own
+//    128 rows of A and its own 128-row half of the W tile (6-stage TMA ring, 32 KiB / stage / CTA), so the
+//    UMMA shared-memory operand traffic per SM is 8 KiB per 128-cycle MMA (64 B/clk) instead of 12 KiB for
+//    a 1-CTA 128 x 256 tile — measured on B200: the SS operand path saturates near 64 B/clk/SM, which
+//    capped the 1-CTA kernel at ~70 % of the clock-limited peak. Both CTAs' TMA loads complete on the
+//    leader's mbarrier; the leader's tcgen05.commit is multicast to both CTAs' "slot free" and
+//    "accumulator full" barriers; the peer's epilogue warps release the accumulator with a remote arrive.
+//  * gemm_bf16_kernel (AFB_GEMM_1CTA=1, or tiny problems): one CTA per 128 x 256 tile, 4-stage ring.
+// Roles per CTA: warp 0 TMA producer, warp 1 MMA issuer (whole warp converged, one elected lane issues),
+// warps 2..5 epilogue (tcgen05.ld 32x32b -> bias / GELU-tanh / gate*y+residual -> 16-byte bf16 stores).
+// The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile i overlaps the main
+// loop of tile i+1. Tiles are walked N-fastest so A is read from HBM once and W stays L2-resident.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/arcflow_b200.h"
 
@@ -56,6 +66,60 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float inner = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.0f + tanh_approx(inner));
+}
+
+// One thread = one accumulator row: 256 fp32 columns from TMEM in 8 chunks of 32.
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_base, int n_tile, bool valid,
+                                              __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
+                                              const __nv_bfloat16* gate_b) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int n0 = n_tile * BN + c * 32;
+    if (n0 >= p.N) break;
+    uint32_t v[32];
+    tmem_ld_32x32(t_base + c * 32, v);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + g * 8;
+        if (n < p.N) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+          if (p.bias) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] += bf16_lo(bw[i]);
+              f[2 * i + 1] += bf16_hi(bw[i]);
+            }
+          }
+          if (p.epi == AFB_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_fast(f[i]);
+          } else if (p.epi == AFB_EPI_BIAS_GATE_RES) {
+            const uint4 gv = *reinterpret_cast<const uint4*>(gate_b + n);
+            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] = bf16_lo(rw[i]) + bf16_lo(gw[i]) * f[2 * i];
+              f[2 * i + 1] = bf16_hi(rw[i]) + bf16_hi(gw[i]) * f[2 * i + 1];
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(out_row + n) = o;
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -191,54 +255,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_tile * BN + c * 32;
-        if (n0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld_32x32(t_base + c * 32, v);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + g * 8;
-            if (n < p.N) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-              if (p.bias) {
-                const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n);
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  f[2 * i] += bf16_lo(bw[i]);
-                  f[2 * i + 1] += bf16_hi(bw[i]);
-                }
-              }
-              if (p.epi == AFB_EPI_BIAS_GELU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_fast(f[i]);
-              } else if (p.epi == AFB_EPI_BIAS_GATE_RES) {
-                const uint4 gv = *reinterpret_cast<const uint4*>(gate_b + n);
-                const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
-                const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  f[2 * i] = bf16_lo(rw[i]) + bf16_lo(gw[i]) * f[2 * i];
-                  f[2 * i + 1] = bf16_hi(rw[i]) + bf16_hi(gw[i]) * f[2 * i + 1];
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(out_row + n) = o;
-            }
-          }
-        }
-      }
+      epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -252,6 +269,234 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ================================================================================================
+// CTA-pair kernel (cta_group::2)
+// ================================================================================================
+constexpr int STAGES2 = 6;
+constexpr int HALF_N = BN / 2;                    // W rows staged per CTA
+constexpr int B2_STAGE_BYTES = HALF_N * BK * 2;   // 16 KiB
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
+constexpr size_t GEMM2_SMEM_BYTES = 1024 + size_t(STAGES2) * STAGE2_BYTES + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// shared::cluster address of `p` (a local shared pointer) in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                 int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the issuing thread's prior MMAs retire) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_2cta_mcast(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                      const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES2 * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES2 * B2_STAGE_BYTES);
+  uint64_t* full_bar = bars;                  // [STAGES2]  both CTAs' TMA -> leader's MMA (leader copy is used)
+  uint64_t* empty_bar = bars + STAGES2;       // [STAGES2]  leader's MMA -> each CTA's producer (multicast)
+  uint64_t* acc_full = bars + 2 * STAGES2;    // [2]        leader's MMA -> each CTA's epilogue (multicast)
+  uint64_t* acc_empty = acc_full + 2;         // [2]        both CTAs' epilogues -> leader's MMA (leader copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmA2);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx; bytes from both CTAs
+      mbar_init(&empty_bar[s], 1);  // one multicast commit per phase
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // peer barriers initialised + both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // 256 x 256 tiles
+  const int nk = p.nk_end[2];
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int b = m_tile / p.tiles_per_batch;
+        const int r0 = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM;
+        const int n0 = n_tile * BN + int(rank) * HALF_N;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          const CUtensorMap* am;
+          int kk;
+          if (kb < p.nk_end[0]) {
+            am = &tmA0;
+            kk = kb;
+          } else if (kb < p.nk_end[1]) {
+            am = &tmA1;
+            kk = kb - p.nk_end[0];
+          } else {
+            am = &tmA2;
+            kk = kb - p.nk_end[1];
+          }
+          tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
+          tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (leader CTA only) ---------------------------
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, false, false);
+      const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = make_sw128_desc(smem_u32(sB), 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = a_desc0 + uint64_t((stage * A_STAGE_BYTES) >> 4);
+          const uint64_t bdesc = b_desc0 + uint64_t((stage * B2_STAGE_BYTES) >> 4);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss_2cta(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+            tc_commit_2cta_mcast(&empty_bar[stage]);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (elect_one_sync()) tc_commit_2cta_mcast(&acc_full[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps (both CTAs) -----------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int b = m_tile / p.tiles_per_batch;
+      const int r = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM + row;
+      const bool valid = r < p.rows_per_batch;
+      __nv_bfloat16* out_row = p.out + (long long)b * p.out_batch_stride + (long long)r * p.out_ld;
+      const __nv_bfloat16* res_row =
+          p.res ? p.res + (long long)b * p.res_batch_stride + (long long)r * p.res_ld : nullptr;
+      const __nv_bfloat16* gate_b = p.gate ? p.gate + (long long)b * p.gate_batch_stride : nullptr;
+
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the leader's MMAs read the peer's smem; nobody leaves before everybody is done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
   }
 }
 
@@ -269,6 +514,14 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     AFB_REQUIRE(d->gate && d->res, "gemm: gate/residual epilogue needs gate and res pointers");
   AFB_REQUIRE(d->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
               "gemm: out must be 16-byte aligned with ld %% 8 == 0");
+
+  static int force_1cta = -1;
+  if (force_1cta < 0) {
+    const char* e = getenv("AFB_GEMM_1CTA");
+    force_1cta = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  const bool two_cta = !force_1cta;
+  const int tile_m = two_cta ? 2 * BM : BM;
 
   GemmParams p{};
   CUtensorMap tmA[3];
@@ -300,7 +553,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   {
     const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->n)};
     const uint64_t strides[1] = {uint64_t(d->w_ld) * 2};
-    const uint32_t box[2] = {BK, BN};
+    const uint32_t box[2] = {BK, uint32_t(two_cta ? HALF_N : BN)};
     AFB_REQUIRE(d->w_ld >= ktot, "gemm: w_ld=%lld < total K=%d", (long long)d->w_ld, ktot);
     int rc = make_tmap_bf16(&tmB, d->w, 2, dims, strides, box);
     if (rc != AFB_OK) return rc;
@@ -308,7 +561,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
 
   p.batches = d->batches;
   p.rows_per_batch = d->rows_per_batch;
-  p.tiles_per_batch = (d->rows_per_batch + BM - 1) / BM;
+  p.tiles_per_batch = (d->rows_per_batch + tile_m - 1) / tile_m;
   p.N = d->n;
   p.num_m_tiles = p.tiles_per_batch * d->batches;
   p.num_n_tiles = (d->n + BN - 1) / BN;
@@ -327,12 +580,21 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   if (!attr_set) {
     AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(GEMM_SMEM_BYTES)));
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(GEMM2_SMEM_BYTES)));
     attr_set = true;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = device_sm_count();
-  const int grid = num_tiles < sms ? num_tiles : sms;
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
+  if (two_cta) {
+    const int max_clusters = sms / 2;
+    const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+    gemm_bf16_2cta_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2],
+                                                                                  tmB, p);
+  } else {
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
+  }
   AFB_CHECK_CUDA(cudaGetLastError());
   return AFB_OK;
 }
