@@ -153,27 +153,20 @@ class PackedFluxWeights:
         return sum(t.numel() * t.element_size() for t in self.keep)
 
 
-class ArcFluxEngineModel:
-    """The ArcFlow-FLUX student transformer + 2-NFE sampler on the native engine (inference)."""
+class EngineModelBase:
+    """Shared plumbing of the engine-backed transformers: handle lifetime, workspace, RoPE cache, profiling."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ArcFluxConfig, device="cuda",
-                 consume_state_dict: bool = False):
+    def __init__(self, cfg, weights, model_desc: "_lib.ModelDesc", device="cuda"):
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
-            raise AfbError("ArcFluxEngineModel needs a CUDA device (there is no CPU path)")
+            raise AfbError("the engine needs a CUDA device (there is no CPU path)")
         self.num_gaussians = cfg.num_gaussians
         self.dtype = BF16
-        self.weights = PackedFluxWeights(state_dict, cfg, self.device, consume=consume_state_dict)
-        md = _lib.ModelDesc(
-            arch=_lib.AFB_ARCH_FLUX, num_double=cfg.num_layers, num_single=cfg.num_single_layers,
-            dim=cfg.inner_dim, heads=cfg.num_attention_heads, mlp_dim=cfg.mlp_dim,
-            in_channels=cfg.in_channels, txt_dim=cfg.joint_attention_dim, pooled_dim=cfg.pooled_projection_dim,
-            guidance=int(cfg.guidance_embeds), num_gaussians=cfg.num_gaussians, lora_rank=cfg.lora_rank,
-            head_mode=0)
+        self.weights = weights
         h = C.c_void_p()
-        _lib.check(self.lib.afb_engine_create(C.byref(md), C.byref(h)), "afb_engine_create")
+        _lib.check(self.lib.afb_engine_create(C.byref(model_desc), C.byref(h)), "afb_engine_create")
         self.handle = h
         _lib.check(self.lib.afb_engine_bind(self.handle, C.byref(self.weights.struct)), "afb_engine_bind")
         self._rope_cache = {}
@@ -191,13 +184,11 @@ class ArcFluxEngineModel:
     # -- attributes the pipelines read off `pipe.transformer` -----------------------
     @property
     def config(self):
-        return SimpleNamespace(in_channels=self.cfg.in_channels, guidance_embeds=self.cfg.guidance_embeds,
-                               **{k: v for k, v in self.cfg.to_dict().items() if k not in ("in_channels", "guidance_embeds")})
+        return SimpleNamespace(**self.cfg.to_dict())
 
     def cache_context(self, name: str):
         return contextlib.nullcontext()
 
-    # ------------------------------------------------------------------------------------------
     def _reserve(self, batch: int, txt_len: int, img_len: int):
         rb, rt, ri = self._reserved
         if batch > rb or txt_len > rt or img_len > ri:
@@ -216,14 +207,7 @@ class ArcFluxEngineModel:
     def workspace_bytes(self, batch: int, txt_len: int, img_len: int) -> int:
         return int(self.lib.afb_engine_workspace_bytes(self.handle, batch, txt_len, img_len))
 
-    def rope(self, txt_len: int, grid_h: int, grid_w: int):
-        key = (txt_len, grid_h, grid_w)
-        if key not in self._rope_cache:
-            self._rope_cache[key] = flux_rope_tables(txt_len, grid_h, grid_w, self.cfg.axes_dims_rope,
-                                                     round_bf16=True, device=self.device)
-        return self._rope_cache[key]
-
-    def _fwd_args(self, txt, pooled, timestep, guidance, cos, sin, batch, img_len) -> _lib.ForwardArgs:
+    def _fwd_args(self, txt, pooled, timestep, guidance, cos, sin, batch, img_len) -> "_lib.ForwardArgs":
         a = _lib.ForwardArgs()
         a.batch, a.txt_len, a.img_len = batch, txt.shape[1], img_len
         a.txt = txt.data_ptr()
@@ -232,6 +216,39 @@ class ArcFluxEngineModel:
         a.guidance = guidance.data_ptr() if guidance is not None else None
         a.rope_cos, a.rope_sin = cos.data_ptr(), sin.data_ptr()
         return a
+
+    def split_heads(self, head: torch.Tensor):
+        """Raw head tensor -> the reference's ArcFlowModelOutput fields in token layout
+        (means [B,S,K,64], logweights [B,S,K,4] log-softmaxed over K in bf16, loggammas [B,S,K-1,4])."""
+        cfg = self.cfg
+        nm, nw, ng = cfg.head_dims
+        B, S, _ = head.shape
+        means = head[..., :nm].reshape(B, S, cfg.num_gaussians, cfg.out_channels)
+        logw = head[..., nm:nm + nw].reshape(B, S, cfg.num_gaussians, cfg.logweights_channels).log_softmax(dim=-2)
+        gam = head[..., nm + nw:nm + nw + ng].reshape(B, S, cfg.num_gaussians - 1, cfg.logweights_channels)
+        return dict(means=means, logweights=logw, loggammas=gam)
+
+
+class ArcFluxEngineModel(EngineModelBase):
+    """The ArcFlow-FLUX student transformer + N-NFE sampler on the native engine (inference)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ArcFluxConfig, device="cuda",
+                 consume_state_dict: bool = False):
+        weights = PackedFluxWeights(state_dict, cfg, torch.device(device), consume=consume_state_dict)
+        md = _lib.ModelDesc(
+            arch=_lib.AFB_ARCH_FLUX, num_double=cfg.num_layers, num_single=cfg.num_single_layers,
+            dim=cfg.inner_dim, heads=cfg.num_attention_heads, mlp_dim=cfg.mlp_dim,
+            in_channels=cfg.in_channels, txt_dim=cfg.joint_attention_dim, pooled_dim=cfg.pooled_projection_dim,
+            guidance=int(cfg.guidance_embeds), num_gaussians=cfg.num_gaussians, lora_rank=cfg.lora_rank,
+            head_mode=0)
+        super().__init__(cfg, weights, md, device)
+
+    def rope(self, txt_len: int, grid_h: int, grid_w: int):
+        key = (txt_len, grid_h, grid_w)
+        if key not in self._rope_cache:
+            self._rope_cache[key] = flux_rope_tables(txt_len, grid_h, grid_w, self.cfg.axes_dims_rope,
+                                                     round_bf16=True, device=self.device)
+        return self._rope_cache[key]
 
     def _check_inputs(self, latents, txt, pooled, grid_hw):
         cfg = self.cfg
@@ -268,17 +285,6 @@ class ArcFluxEngineModel:
         _lib.check(self.lib.afb_engine_forward(self.handle, C.byref(a), torch.cuda.current_stream().cuda_stream),
                    "afb_engine_forward")
         return out
-
-    def split_heads(self, head: torch.Tensor):
-        """Raw head tensor -> the reference's ArcFlowModelOutput fields in token layout
-        (means [B,S,K,64], logweights [B,S,K,4] log-softmaxed over K in bf16, loggammas [B,S,K-1,4])."""
-        cfg = self.cfg
-        nm, nw, ng = cfg.head_dims
-        B, S, _ = head.shape
-        means = head[..., :nm].reshape(B, S, cfg.num_gaussians, cfg.out_channels)
-        logw = head[..., nm:nm + nw].reshape(B, S, cfg.num_gaussians, cfg.logweights_channels).log_softmax(dim=-2)
-        gam = head[..., nm + nw:nm + nw + ng].reshape(B, S, cfg.num_gaussians - 1, cfg.logweights_channels)
-        return dict(means=means, logweights=logw, loggammas=gam)
 
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int],

@@ -20,9 +20,11 @@ import torch
 
 from arcflow_b200.config import ArcFluxConfig
 from arcflow_b200.model import ArcFluxEngineModel
+from arcflow_b200.qwen import ArcQwenConfig, ArcQwenEngineModel
 
-LOCAL_CLASS_MAPPING = {"ArcFluxTransformer2DModel": ArcFluxEngineModel}
-_CONFIG_FIELDS = set(ArcFluxConfig.__dataclass_fields__)
+# same keys as the reference's LOCAL_CLASS_MAPPING (arcflow_loader.py:30-33)
+LOCAL_CLASS_MAPPING = {"ArcFluxTransformer2DModel": (ArcFluxEngineModel, ArcFluxConfig),
+                       "ArcQwenImageTransformer2DModel": (ArcQwenEngineModel, ArcQwenConfig)}
 
 
 def read_adapter_folder(path: Union[str, os.PathLike], subfolder: Optional[str] = None):
@@ -39,11 +41,12 @@ def read_adapter_folder(path: Union[str, os.PathLike], subfolder: Optional[str] 
     return config, load_file(w_file)
 
 
-def write_adapter_folder(path: Union[str, os.PathLike], cfg: ArcFluxConfig, adapter_sd: Dict[str, torch.Tensor]):
+def write_adapter_folder(path: Union[str, os.PathLike], cfg, adapter_sd: Dict[str, torch.Tensor]):
     """Writes the on-disk format export_arcflow_to_diffusers.py:104-127 produces (used by tests/tools)."""
     from safetensors.torch import save_file
     os.makedirs(path, exist_ok=True)
-    config = dict(cfg.to_dict(), _class_name="ArcFluxTransformer2DModel")
+    cls_name = "ArcQwenImageTransformer2DModel" if isinstance(cfg, ArcQwenConfig) else "ArcFluxTransformer2DModel"
+    config = dict(cfg.to_dict(), _class_name=cls_name)
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(config, f, indent=2)
     save_file({k: v.contiguous() for k, v in adapter_sd.items()},
@@ -84,11 +87,12 @@ class ArcFlowLoaderMixin:
         # accept both the exported (`lora_A.weight`) and the peft-internal (`lora_A.default.weight`) names
         for k, v in lora.items():
             base_sd[k.replace(".default.weight", ".weight")] = v
-        cfg = ArcFluxConfig(**{k: (tuple(v) if k == "axes_dims_rope" else v)
-                               for k, v in config.items() if k in _CONFIG_FIELDS})
+        model_cls, cfg_cls = LOCAL_CLASS_MAPPING[cls_name]
+        fields = set(cfg_cls.__dataclass_fields__)
+        cfg = cfg_cls(**{k: (tuple(v) if k == "axes_dims_rope" else v) for k, v in config.items() if k in fields})
         rank = next(iter(v.shape[0] for k, v in lora.items() if "lora_A" in k))
         cfg.lora_rank = int(rank)
         device = getattr(base, "device", torch.device("cuda"))
-        module = LOCAL_CLASS_MAPPING[cls_name](base_sd, cfg, device=device, consume_state_dict=True)
+        module = model_cls(base_sd, cfg, device=device, consume_state_dict=True)
         setattr(self, target_module_name, module)
         return adapter_name or f"{target_module_name}_arcflow"

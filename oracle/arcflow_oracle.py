@@ -325,3 +325,129 @@ def flux_denoise(sd, cfg, latents: Tensor, prompt_embeds: Tensor, pooled: Tensor
             trace.append(dict(sigma_src=float(sigma_src), sigma_end=float(t_end / 1000.0), out=out,
                               latents=latents.clone()))
     return (latents, trace) if return_trace else latents
+
+
+# =================================================================================================
+# Qwen-Image transformer — arcqwen.py:106-174 over diffusers blocks  [PARITY UNPINNED]
+# =================================================================================================
+class QwenEmbedRope:
+    """diffusers QwenEmbedRope(theta=10000, axes_dim, scale_rope=True) (constructed at arcqwen.py:46)."""
+
+    def __init__(self, theta: int = 10000, axes_dim=(16, 56, 56), scale_rope: bool = True):
+        self.theta, self.axes_dim, self.scale_rope = theta, list(axes_dim), scale_rope
+        pos_index = torch.arange(4096)
+        neg_index = torch.arange(4096).flip(0) * -1 - 1
+        self.pos_freqs = torch.cat([self.rope_params(pos_index, d, theta) for d in self.axes_dim], dim=1)
+        self.neg_freqs = torch.cat([self.rope_params(neg_index, d, theta) for d in self.axes_dim], dim=1)
+
+    @staticmethod
+    def rope_params(index, dim, theta=10000):
+        freqs = torch.outer(index, 1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float32).div(dim)))
+        return torch.polar(torch.ones_like(freqs), freqs)
+
+    def __call__(self, frame: int, height: int, width: int, max_txt_len: int):
+        split = [x // 2 for x in self.axes_dim]
+        fp, fn = self.pos_freqs.split(split, dim=1), self.neg_freqs.split(split, dim=1)
+        f_frame = fp[0][0:frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
+        if self.scale_rope:
+            f_h = torch.cat([fn[1][-(height - height // 2):], fp[1][: height // 2]], dim=0)
+            f_w = torch.cat([fn[2][-(width - width // 2):], fp[2][: width // 2]], dim=0)
+            max_vid_index = max(height // 2, width // 2)
+        else:
+            f_h, f_w = fp[1][:height], fp[2][:width]
+            max_vid_index = max(height, width)
+        f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
+        f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
+        vid = torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1)
+        txt = self.pos_freqs[max_vid_index: max_vid_index + max_txt_len]
+        return vid, txt
+
+
+def apply_rope_qwen(x: Tensor, freqs_cis: Tensor) -> Tensor:
+    """diffusers apply_rotary_emb_qwen(use_real=False): complex multiply on adjacent pairs, x [B, S, H, 128]."""
+    xc = torch.view_as_complex(x.float().reshape(*x.shape[:-1], -1, 2))
+    out = torch.view_as_real(xc * freqs_cis.unsqueeze(1)).flatten(3)
+    return out.type_as(x)
+
+
+def qwen_block(sd, p: str, x: Tensor, c: Tensor, temb: Tensor, rope, heads: int, dtype, ls: float):
+    """diffusers QwenImageTransformerBlock.forward + QwenDoubleStreamAttnProcessor2_0 (Appendix A.4),
+    called at arcqwen.py:147-155. The text mask is not used inside attention (0.35.1)."""
+    img_freqs, txt_freqs = rope
+    img_mod = _lin(sd, p + "img_mod.1", F.silu(temb), dtype)
+    txt_mod = _lin(sd, p + "txt_mod.1", F.silu(temb), dtype)
+    (i_sh1, i_sc1, i_g1), (i_sh2, i_sc2, i_g2) = [m.chunk(3, dim=-1) for m in img_mod.chunk(2, dim=-1)]
+    (t_sh1, t_sc1, t_g1), (t_sh2, t_sc2, t_g2) = [m.chunk(3, dim=-1) for m in txt_mod.chunk(2, dim=-1)]
+    xm = _ln(x) * (1 + i_sc1[:, None]) + i_sh1[:, None]
+    cm = _ln(c) * (1 + t_sc1[:, None]) + t_sh1[:, None]
+    a = p + "attn."
+    iq = rms_norm(_lin(sd, a + "to_q", xm, dtype).unflatten(-1, (heads, -1)), sd[a + "norm_q.weight"].to(dtype))
+    ik = rms_norm(_lin(sd, a + "to_k", xm, dtype).unflatten(-1, (heads, -1)), sd[a + "norm_k.weight"].to(dtype))
+    iv = _lin(sd, a + "to_v", xm, dtype).unflatten(-1, (heads, -1))
+    tq = rms_norm(_lin(sd, a + "add_q_proj", cm, dtype).unflatten(-1, (heads, -1)), sd[a + "norm_added_q.weight"].to(dtype))
+    tk = rms_norm(_lin(sd, a + "add_k_proj", cm, dtype).unflatten(-1, (heads, -1)), sd[a + "norm_added_k.weight"].to(dtype))
+    tv = _lin(sd, a + "add_v_proj", cm, dtype).unflatten(-1, (heads, -1))
+    iq, ik = apply_rope_qwen(iq, img_freqs), apply_rope_qwen(ik, img_freqs)
+    tq, tk = apply_rope_qwen(tq, txt_freqs), apply_rope_qwen(tk, txt_freqs)
+    o = _attention(torch.cat([tq, iq], 1), torch.cat([tk, ik], 1), torch.cat([tv, iv], 1)).to(iq.dtype)
+    St = c.shape[1]
+    x = x + i_g1[:, None] * _lin(sd, a + "to_out.0", o[:, St:], dtype)
+    c = c + t_g1[:, None] * _lin(sd, a + "to_add_out", o[:, :St], dtype)
+    xm2 = _ln(x) * (1 + i_sc2[:, None]) + i_sh2[:, None]
+    x = x + i_g2[:, None] * _lin(sd, p + "img_mlp.net.2",
+                                 F.gelu(_lin(sd, p + "img_mlp.net.0.proj", xm2, dtype, ls), approximate="tanh"), dtype, ls)
+    cm2 = _ln(c) * (1 + t_sc2[:, None]) + t_sh2[:, None]
+    c = c + t_g2[:, None] * _lin(sd, p + "txt_mlp.net.2",
+                                 F.gelu(_lin(sd, p + "txt_mlp.net.0.proj", cm2, dtype, ls), approximate="tanh"), dtype, ls)
+    return c, x
+
+
+def qwen_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
+                 timestep: Tensor, grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0,
+                 bf16_quirks: bool = True) -> Dict[str, Tensor]:
+    """_ArcQwenImageTransformer2DModel.forward (arcqwen.py:106-174). `timestep` is sigma in [0, 1]
+    (arcqwen_pipeline.py:412); it is cast to the hidden dtype (:128, bf16 in deployment) and scaled by 1000
+    inside Timesteps(scale=1000) in fp32 (QwenTimestepProjEmbeddings)."""
+    heads = cfg.num_attention_heads
+    x = _lin(sd, "img_in", hidden_states.to(dtype), dtype)
+    t = timestep.to(torch.bfloat16 if bf16_quirks else dtype)
+    c = rms_norm(encoder_hidden_states.to(dtype), sd["txt_norm.weight"].to(dtype))
+    c = _lin(sd, "txt_in", c, dtype)
+    te = "time_text_embed.timestep_embedder"
+    tproj = timestep_proj(t, scale=1000.0).to(dtype)
+    temb = _lin(sd, te + ".linear_2", F.silu(_lin(sd, te + ".linear_1", tproj, dtype, lora_scale)), dtype, lora_scale)
+    rope = QwenEmbedRope(10000, cfg.axes_dims_rope, True)(1, grid_hw[0], grid_hw[1], c.shape[1])
+    for i in range(cfg.num_layers):
+        c, x = qwen_block(sd, f"transformer_blocks.{i}.", x, c, temb, rope, heads, dtype, lora_scale)
+    emb = _lin(sd, "norm_out.linear", F.silu(temb).to(x.dtype), dtype)
+    scale, shift = emb.chunk(2, dim=1)
+    x = _ln(x) * (1 + scale)[:, None, :] + shift[:, None, :]
+    bs, seq, _ = x.shape
+    K, C, L = cfg.num_gaussians, cfg.out_channels, cfg.logweights_channels
+    return dict(means=_lin(sd, "proj_out_means", x, dtype).reshape(bs, seq, K, C),
+                logweights=_lin(sd, "proj_out_logweights", x, dtype).reshape(bs, seq, K, L).log_softmax(dim=-2),
+                loggammas=_lin(sd, "proj_out_loggamma", x, dtype).reshape(bs, seq, K - 1, L))
+
+
+def qwen_denoise(sd, cfg, latents: Tensor, prompt_embeds: Tensor, grid_hw: Sequence[int], num_inference_steps: int = 2,
+                 total_substeps: int = 128, timestep_ratio: float = 1.0, shift: float = 3.2, dtype=torch.float32,
+                 eps: float = 1e-4, net_dtype=torch.bfloat16):
+    """ArcQwenImagePipeline.__call__ denoising loop (arcqwen_pipeline.py:395-463); same structure as FLUX."""
+    gh, gw = grid_hw
+    raw, substeps, total = retrieve_raw_timesteps(num_inference_steps, total_substeps, timestep_ratio)
+    timesteps = scheduler_timesteps(raw, shift)
+    B = latents.shape[0]
+    tid = 0
+    latents = latents.to(torch.float32)
+    for i in range(num_inference_steps):
+        t_src = timesteps[tid]
+        sigma_src = t_src / 1000.0
+        out = qwen_forward(sd, cfg, latents.to(net_dtype), prompt_embeds, t_src.expand(B) / 1000, grid_hw, dtype=dtype)
+        out = {k: v.to(net_dtype).to(torch.float32) for k, v in out.items()}
+        mp = unpack_mp(out, gh, gw, cfg.num_gaussians)
+        tid += substeps[i]
+        t_end = timesteps[tid] if tid < len(timesteps) else torch.tensor(0.0)
+        x_img = momentum_integration(mp, unpack_latents(latents, gh, gw), float(sigma_src), float(sigma_src),
+                                     float(t_end / 1000.0), eps)
+        latents = pack_latents(x_img)
+    return latents

@@ -155,3 +155,31 @@ def test_oracle_forward_shapes_and_bf16_agreement():
     assert torch.allclose(a["logweights"].exp().sum(-2), torch.ones(1, 4, 4), atol=1e-5)
     err = ((a["means"] - b["means"].float()).norm() / a["means"].norm()).item()
     assert err < 5e-2
+
+
+@pytest.mark.parametrize("txt,gh,gw", [(512, 64, 64), (33, 3, 5), (7, 8, 2)])
+def test_qwen_rope_tables_match_oracle(txt, gh, gw):
+    from arcflow_b200.qwen import qwen_rope_tables
+    cos, sin = qwen_rope_tables(txt, gh, gw)
+    vid, tx = O.QwenEmbedRope()(1, gh, gw, txt)
+    fc = torch.cat([tx, vid], 0)            # text first in the joint sequence
+    assert cos.shape == (txt + gh * gw, 128)
+    for tab, ref in ((cos, fc.real), (sin, fc.imag)):
+        assert torch.allclose(tab[:, 0::2], ref, atol=2e-7) and torch.equal(tab[:, 0::2], tab[:, 1::2])
+
+
+def test_qwen_packing_and_lora_targets():
+    from arcflow_b200.qwen import PackedQwenWeights, make_qwen_state_dict, qwen_lora_targets, qwen_tiny, qwen_time_input
+    cfg = qwen_tiny(3, 2)
+    sd = make_qwen_state_dict(cfg, seed=9)
+    # configs/qwen/arcqwen_2nfe_k16.py:53-55: txt_mlp of the last block carries no LoRA
+    assert "transformer_blocks.2.txt_mlp.net.2.lora_A.weight" not in sd
+    assert "transformer_blocks.1.txt_mlp.net.2.lora_A.weight" in sd
+    assert len(qwen_lora_targets(cfg)) == 2 + 3 * 2 + 2 * 2
+    pk = PackedQwenWeights(dict(sd), cfg, device="cpu")
+    by_ptr = {t.data_ptr(): t for t in pk.keep}
+    D, M, r = cfg.inner_dim, cfg.mlp_dim, cfg.lora_rank
+    assert by_ptr[pk.dbl[0].txt_up_w].shape == (M, D + r)
+    assert by_ptr[pk.dbl[2].txt_up_w].shape == (M, D) and not pk.dbl[2].txt_up_la
+    assert pk.struct.mod_total == 3 * 12 * D + 2 * D
+    assert qwen_time_input(0.7619047761) == pytest.approx(761.71875)      # bf16(sigma) * 1000, SURVEY App. D

@@ -102,3 +102,30 @@ def test_generator_latents_and_errors(setup):
         pipe(**{**kw, "output_type": "pil"})
     with pytest.raises(ValueError, match="divisible by 16"):
         pipe(**{**kw, "height": 72})
+
+
+def test_qwen_pipeline_adapter_roundtrip(lib, tmp_path):
+    """ArcQwenImagePipeline + load_arcflow_adapter on the Qwen class name; mask trimming; parity vs oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from arcflow_b200.qwen import make_qwen_inputs, make_qwen_state_dict, qwen_tiny
+    from lakonlab.pipelines.arcflow_loader import write_adapter_folder
+    from lakonlab.pipelines.arcflux_pipeline import FluxBaseTransformer
+    from lakonlab.pipelines.arcqwen_pipeline import ArcQwenImagePipeline
+    cfg = qwen_tiny(2, 2)
+    sd = make_qwen_state_dict(cfg, seed=21)
+    adapter = {k: v for k, v in sd.items() if "lora" in k or k.startswith(("proj_out_", "norm_out."))}
+    base = {k: v for k, v in sd.items() if k not in adapter}
+    base["norm_out.linear.weight"] = torch.zeros_like(sd["norm_out.linear.weight"])
+    base["norm_out.linear.bias"] = torch.zeros_like(sd["norm_out.linear.bias"])
+    write_adapter_folder(tmp_path / "arcflow-qwen-2steps", cfg, adapter)
+    pipe = ArcQwenImagePipeline(transformer=FluxBaseTransformer(base, device="cuda"))
+    assert pipe.load_arcflow_adapter(str(tmp_path), subfolder="arcflow-qwen-2steps") == "transformer_arcflow"
+    x, txt = make_qwen_inputs(cfg, 2, 64, 64, txt_len=48, seed=3)
+    mask = torch.zeros(2, 48, dtype=torch.long)
+    mask[0, :30] = 1
+    mask[1, :24] = 1            # longest prompt: 30 tokens -> trimmed to 30
+    out = pipe(prompt_embeds=txt, prompt_embeds_mask=mask, latents=x, height=64, width=64, num_inference_steps=2,
+               timestep_ratio=1.0, output_type="latent").images
+    ref = O.qwen_denoise(sd, cfg, x, txt[:, :30], (4, 4), num_inference_steps=2)
+    assert rel(out, ref) < 2e-2
