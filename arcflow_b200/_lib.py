@@ -59,7 +59,7 @@ class AttnDesc(C.Structure):
 class ModelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "arch", "num_double", "num_single", "dim", "heads", "mlp_dim", "in_channels", "txt_dim",
-        "pooled_dim", "guidance", "num_gaussians", "lora_rank", "head_mode")]
+        "pooled_dim", "guidance", "num_gaussians", "lora_rank", "head_mode", "ignore_lora")]
 
 
 _P = C.c_void_p
@@ -87,7 +87,7 @@ class Weights(C.Structure):
         "g1_w", "g1_b", "g2_w", "g2_b", "p1_w", "p1_b", "p2_w", "p2_b",
         "mod_w", "mod_b")] + [
         ("mod_total", C.c_int64), ("norm_out_mod_off", C.c_int64),
-        ("head_w", _P), ("head_b", _P), ("head_n", C.c_int32),
+        ("head_w", _P), ("head_b", _P), ("alt_norm_out_w", _P), ("alt_norm_out_b", _P), ("head_n", C.c_int32),
         ("dbl", C.POINTER(DoubleBlock)), ("sgl", C.POINTER(SingleBlock))]
 
 
@@ -109,6 +109,17 @@ class DenoiseArgs(C.Structure):
         ("x", _P),
         ("eps", C.c_float),
     ]
+
+
+class PolicyArgs(C.Structure):
+    _fields_ = [("head", _P), ("head_ld", C.c_int64), ("batch", C.c_int32), ("tokens", C.c_int32),
+                ("num_gaussians", C.c_int32), ("mode", C.c_int32),
+                ("sigma_src", C.POINTER(C.c_float)), ("sigma_start", C.POINTER(C.c_float)),
+                ("sigma_end", C.POINTER(C.c_float)), ("drop_mask", C.POINTER(C.c_uint8)),
+                ("small", C.POINTER(C.c_uint8)), ("x_in", _P), ("out", _P), ("out_bf16", _P), ("eps", C.c_float)]
+
+
+AFB_POLICY_INTEGRATE, AFB_POLICY_VELOCITY, AFB_POLICY_AVERAGE_U = 0, 1, 2
 
 
 class Profile(C.Structure):
@@ -135,6 +146,9 @@ SIGNATURES = {
     "afb_sampler_step": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int32, C.c_float,
                                    C.c_float, C.c_float, C.c_float, _P]),
     "afb_cast_f32_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "afb_policy_eval": (C.c_int, [C.POINTER(PolicyArgs), _P]),
+    "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, _P]),
+    "afb_mse_rows": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P]),
     "afb_engine_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_P)]),
     "afb_engine_destroy": (None, [_P]),
     "afb_engine_bind": (C.c_int, [_P, C.POINTER(Weights)]),

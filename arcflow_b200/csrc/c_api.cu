@@ -23,6 +23,11 @@ int sampler_step_launch(const void* head, int64_t head_ld, const float* x_in, fl
                         void* x_out_bf16, int64_t tokens, int num_gaussians, float sigma_src,
                         float sigma_start, float sigma_end, float eps, cudaStream_t stream);
 int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t stream);
+int policy_eval_launch(const afb_policy_args* a, cudaStream_t stream);
+int axpy_rows_launch(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int batch,
+                     int64_t per_sample, cudaStream_t stream);
+int mse_rows_launch(const float* pred, const void* tgt_bf16, float* out, int batch, int64_t per_sample,
+                    cudaStream_t stream);
 }  // namespace afb
 
 extern "C" {
@@ -71,6 +76,16 @@ int afb_sampler_step(const void* head, int64_t head_ld, const float* x_in, float
   return afb::sampler_step_launch(head, head_ld, x_in, x_out, x_out_bf16, tokens, num_gaussians,
                                   sigma_src, sigma_start, sigma_end, eps,
                                   static_cast<cudaStream_t>(stream));
+}
+int afb_policy_eval(const afb_policy_args* args, void* stream) {
+  return afb::policy_eval_launch(args, static_cast<cudaStream_t>(stream));
+}
+int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int32_t batch,
+                  int64_t per_sample, void* stream) {
+  return afb::axpy_rows_launch(x, u_bf16, coef, out, out_bf16, batch, per_sample, static_cast<cudaStream_t>(stream));
+}
+int afb_mse_rows(const float* pred, const void* tgt_bf16, float* out, int32_t batch, int64_t per_sample, void* stream) {
+  return afb::mse_rows_launch(pred, tgt_bf16, out, batch, per_sample, static_cast<cudaStream_t>(stream));
 }
 int afb_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
   return afb::cast_f32_bf16_launch(in, out, n, static_cast<cudaStream_t>(stream));

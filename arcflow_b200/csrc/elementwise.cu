@@ -341,6 +341,137 @@ rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Training-side policy evaluation with PER-SAMPLE times and an optional mixture-component dropout mask.
+// One kernel, three modes, all in packed-token layout, all from the raw head tensor of one student call:
+//   INTEGRATE  x_end = x_start - sum_k w_k mu_k e^{lam_k (s_src - s_start)} dt phi(lam_k dt)
+//              (ArcFlowImitationBase.momentum_integration, lakonlab/models/diffusions/arcflow.py:28-79)
+//   VELOCITY   u = sum_k w_k mu_k e^{lam_k (s_src - s_t)}      (ArcFlowPolicy.velocity, policies/arcflow.py:52-76)
+//   AVERAGE_U  (x_start - x_end) / max(s_start - s_end, eps), or the local velocity where `small` is set
+//              (policy_average_u_momentum, arcflow.py:81-110)
+// drop[b][k] != 0 masks component k of sample b (ArcFlowPolicy.dropout_, policies/arcflow.py:96-106:
+// logweights.masked_fill(mask, -inf) before the softmax).
+// ------------------------------------------------------------------------------------------------
+constexpr int POLICY_MAX_BATCH = 64;
+struct PolicyParams {
+  float dt_past[POLICY_MAX_BATCH];   // s_src - s_start
+  float dt_step[POLICY_MAX_BATCH];   // s_start - s_end
+  uint32_t drop[POLICY_MAX_BATCH];   // bit k: component k dropped
+  uint8_t small[POLICY_MAX_BATCH];
+};
+
+__global__ void __launch_bounds__(256)
+policy_eval_k16_kernel(const __nv_bfloat16* __restrict__ head, long long head_ld, const float* __restrict__ x_in,
+                       float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16, int tokens_per_sample,
+                       long long tokens, int mode, float eps, const __grid_constant__ PolicyParams pp) {
+  constexpr int K = 16;
+  __shared__ float sF[8][K * 4];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long tok = (long long)blockIdx.x * 8 + wib;
+  if (tok >= tokens) return;
+  const int b = int(tok / tokens_per_sample);
+  const float dt_past = pp.dt_past[b], dt_step = pp.dt_step[b];
+  const uint32_t drop = pp.drop[b];
+  const bool local_u = mode == AFB_POLICY_VELOCITY || (mode == AFB_POLICY_AVERAGE_U && pp.small[b]);
+  const __nv_bfloat16* hrow = head + tok * head_ld;
+  const __nv_bfloat16* logit = hrow + K * 64;
+  const __nv_bfloat16* lgam = logit + K * 4;
+
+  const int k0 = lane >> 2, k1 = 8 + (lane >> 2);
+  const float a0 = __bfloat162float(logit[lane]);
+  const float a1 = __bfloat162float(logit[lane + 32]);
+  const float mx = group_max(fmaxf(a0, a1));
+  const float se = group_sum(expf(a0 - mx) + expf(a1 - mx));
+  const float lse = mx + logf(se);
+  float b0 = round_bf16(a0 - lse);
+  float b1 = round_bf16(a1 - lse);
+  if ((drop >> k0) & 1u) b0 = -INFINITY;
+  if ((drop >> k1) & 1u) b1 = -INFINITY;
+  const float mx2 = group_max(fmaxf(b0, b1));
+  const float e0 = expf(b0 - mx2), e1 = expf(b1 - mx2);
+  const float inv = 1.0f / group_sum(e0 + e1);
+  const float w0 = e0 * inv, w1 = e1 * inv;
+  const float lam0 = lane >= 4 ? __bfloat162float(lgam[lane - 4]) : 0.f;
+  const float lam1 = __bfloat162float(lgam[lane + 28]);
+  float f0, f1;
+  if (local_u) {
+    f0 = lane >= 4 ? w0 * expf(lam0 * dt_past) : w0;
+    f1 = w1 * expf(lam1 * dt_past);
+  } else {
+    // AVERAGE_U divides the displacement by max(dt, eps): fold it into the factors
+    const float scale = mode == AFB_POLICY_AVERAGE_U ? dt_step / fmaxf(dt_step, eps) : dt_step;
+    f0 = w0 * scale;
+    if (lane >= 4) f0 *= expf(lam0 * dt_past) * phi_expm1(lam0 * dt_step, eps);
+    f1 = w1 * scale * expf(lam1 * dt_past) * phi_expm1(lam1 * dt_step, eps);
+  }
+  sF[wib][lane] = f0;
+  sF[wib][lane + 32] = f1;
+  __syncwarp();
+  const int j0 = (2 * lane) & 3;
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t mv = *reinterpret_cast<const uint32_t*>(hrow + k * 64 + 2 * lane);
+    acc0 = fmaf(bf16_lo(mv), sF[wib][k * 4 + j0], acc0);
+    acc1 = fmaf(bf16_hi(mv), sF[wib][k * 4 + j0 + 1], acc1);
+  }
+  float2 o;
+  if (mode == AFB_POLICY_INTEGRATE) {
+    const float2 xi = *reinterpret_cast<const float2*>(x_in + tok * 64 + 2 * lane);
+    o = make_float2(xi.x - acc0, xi.y - acc1);
+  } else {
+    o = make_float2(acc0, acc1);
+  }
+  *reinterpret_cast<float2*>(out + tok * 64 + 2 * lane) = o;
+  if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + tok * 64 + 2 * lane) = pack_bf16x2(o.x, o.y);
+}
+
+// out[b, :] = x[b, :] + coef[b] * u[b, :]   (teacher Euler step, arcflow.py:190); u is bf16 (network output)
+struct RowCoef {
+  float c[POLICY_MAX_BATCH];
+};
+__global__ void axpy_rows_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ u,
+                                 float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16, long long per_sample,
+                                 long long total, const __grid_constant__ RowCoef rc) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= total) return;
+  const float c = rc.c[int(i / per_sample)];
+  const float2 xv = *reinterpret_cast<const float2*>(x + i);
+  const uint32_t uv = *reinterpret_cast<const uint32_t*>(u + i);
+  const float2 o = make_float2(fmaf(c, bf16_lo(uv), xv.x), fmaf(c, bf16_hi(uv), xv.y));
+  *reinterpret_cast<float2*>(out + i) = o;
+  if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + i) = pack_bf16x2(o.x, o.y);
+}
+
+// per-sample mean over all elements of (pred - tgt)^2: mmgen mse_loss(reduction='flatmean')
+__global__ void __launch_bounds__(256)
+mse_rows_kernel(const float* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt, float* __restrict__ out,
+                long long per_sample) {
+  __shared__ float red[8];
+  const int b = blockIdx.y;
+  const float* p = pred + (long long)b * per_sample;
+  const __nv_bfloat16* t = tgt + (long long)b * per_sample;
+  float acc = 0.f;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x * 2) {
+    const float2 pv = *reinterpret_cast<const float2*>(p + i);
+    const uint32_t tv = *reinterpret_cast<const uint32_t*>(t + i);
+    const float d0 = pv.x - bf16_lo(tv), d1 = pv.y - bf16_hi(tv);
+    acc = fmaf(d0, d0, fmaf(d1, d1, acc));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = red[threadIdx.x];
+    v += __shfl_xor_sync(0xffu, v, 4);
+    v += __shfl_xor_sync(0xffu, v, 2);
+    v += __shfl_xor_sync(0xffu, v, 1);
+    if (threadIdx.x == 0) atomicAdd(out + b, v / float(per_sample));
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                      long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -491,6 +622,66 @@ int rmsnorm_rows_launch(const void* x, void* y, const void* w, int64_t rows, int
   rmsnorm_rows_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
       static_cast<const __nv_bfloat16*>(w), rows, dim, eps);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int policy_eval_launch(const afb_policy_args* a, cudaStream_t stream) {
+  AFB_REQUIRE(a && a->head && a->out && a->sigma_src && a->sigma_start, "policy_eval: null argument");
+  AFB_REQUIRE(a->mode >= AFB_POLICY_INTEGRATE && a->mode <= AFB_POLICY_AVERAGE_U, "policy_eval: unknown mode %d", a->mode);
+  AFB_REQUIRE(a->mode == AFB_POLICY_VELOCITY || a->sigma_end, "policy_eval: sigma_end missing");
+  AFB_REQUIRE(a->mode != AFB_POLICY_INTEGRATE || a->x_in, "policy_eval: x_in missing");
+  AFB_REQUIRE(a->batch >= 1 && a->batch <= POLICY_MAX_BATCH, "policy_eval: batch=%d must be in [1, %d]", a->batch,
+              POLICY_MAX_BATCH);
+  AFB_REQUIRE(a->tokens >= 1, "policy_eval: no tokens");
+  if (a->num_gaussians != 16) {
+    set_last_error("policy_eval: only K=16 mixture components are built (got %d)", a->num_gaussians);
+    return AFB_ERR_UNSUPPORTED;
+  }
+  AFB_REQUIRE(a->head_ld >= 16 * 64 + 16 * 4 + 15 * 4 && a->head_ld % 2 == 0, "policy_eval: head_ld too small");
+  PolicyParams pp{};
+  for (int b = 0; b < a->batch; ++b) {
+    pp.dt_past[b] = a->sigma_src[b] - a->sigma_start[b];
+    pp.dt_step[b] = a->mode == AFB_POLICY_VELOCITY ? 0.f : a->sigma_start[b] - a->sigma_end[b];
+    uint32_t m = 0;
+    if (a->drop_mask)
+      for (int k = 0; k < 16; ++k) m |= (a->drop_mask[b * 16 + k] ? 1u : 0u) << k;
+    AFB_REQUIRE(m != 0xFFFFu, "policy_eval: sample %d drops every mixture component", b);
+    pp.drop[b] = m;
+    pp.small[b] = a->small ? a->small[b] : 0;
+  }
+  const long long tokens = (long long)a->batch * a->tokens;
+  policy_eval_k16_kernel<<<unsigned((tokens + 7) / 8), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(a->head), a->head_ld, a->x_in, a->out,
+      static_cast<__nv_bfloat16*>(a->out_bf16), a->tokens, tokens, a->mode, a->eps > 0.f ? a->eps : 1e-4f, pp);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int axpy_rows_launch(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int batch,
+                     int64_t per_sample, cudaStream_t stream) {
+  AFB_REQUIRE(x && u_bf16 && coef && out, "axpy_rows: null argument");
+  AFB_REQUIRE(batch >= 1 && batch <= POLICY_MAX_BATCH && per_sample >= 2 && per_sample % 2 == 0,
+              "axpy_rows: bad shape (batch=%d per_sample=%lld)", batch, (long long)per_sample);
+  RowCoef rc{};
+  for (int b = 0; b < batch; ++b) rc.c[b] = coef[b];
+  const long long total = (long long)batch * per_sample;
+  axpy_rows_kernel<<<unsigned((total / 2 + 255) / 256), 256, 0, stream>>>(
+      x, static_cast<const __nv_bfloat16*>(u_bf16), out, static_cast<__nv_bfloat16*>(out_bf16), per_sample, total, rc);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int mse_rows_launch(const float* pred, const void* tgt_bf16, float* out, int batch, int64_t per_sample,
+                    cudaStream_t stream) {
+  AFB_REQUIRE(pred && tgt_bf16 && out, "mse_rows: null argument");
+  AFB_REQUIRE(batch >= 1 && per_sample >= 2 && per_sample % 2 == 0, "mse_rows: bad shape");
+  AFB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * batch, stream));
+  dim3 grid(64, batch);
+  mse_rows_kernel<<<grid, 256, 0, stream>>>(pred, static_cast<const __nv_bfloat16*>(tgt_bf16), out, per_sample);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

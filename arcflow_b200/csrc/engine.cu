@@ -62,7 +62,7 @@ struct afb_engine {
   // carved pointers
   bf16 *h = nullptr, *y = nullptr, *qkv = nullptr, *attn = nullptr, *mlp = nullptr, *lt0 = nullptr,
        *lt1 = nullptr, *mod = nullptr, *temb = nullptr, *tmp = nullptr, *tproj = nullptr,
-       *ltv = nullptr, *head = nullptr, *x_bf16 = nullptr, *txtn = nullptr;
+       *ltv = nullptr, *head = nullptr, *x_bf16 = nullptr, *txtn = nullptr, *alt_nm = nullptr;
   float *t_dev = nullptr, *g_dev = nullptr;
   // optional per-launch CUDA-event profiling of the two tensor-core kernels
   bool profiling = false;
@@ -108,6 +108,7 @@ size_t carve(afb_engine* e, uint8_t* base, int B, int St, int Si) {
   e->head = c.take<bf16>(size_t(B) * Si * size_t(e->w.head_n > 0 ? e->w.head_n : 8));
   e->x_bf16 = c.take<bf16>(size_t(B) * Si * d.in_channels);
   e->txtn = c.take<bf16>(d.arch == AFB_ARCH_QWEN ? size_t(B) * St * d.txt_dim : 8);
+  e->alt_nm = c.take<bf16>(size_t(B) * 2 * D);
   e->t_dev = c.take<float>(B);
   e->g_dev = c.take<float>(B);
   return c.off;
@@ -244,20 +245,24 @@ int embed_mlp(afb_engine* e, const bf16* in, int in_dim, const void* w1, const v
 int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v, int rows, int B,
                const void* up_w, const void* up_b, const void* up_la, const void* down_w,
                const void* down_b, const void* down_la, const bf16* gate, cudaStream_t s) {
+  // `*_la != NULL` means the packed weight is [W | lora_B] (leading dim in + rank). A teacher engine
+  // (ignore_lora) shares those buffers with the student and simply never reads the extra K columns.
   const int D = e->desc.dim, M = e->desc.mlp_dim, r = e->desc.lora_rank;
+  const bool lora = !e->desc.ignore_lora;
   const int64_t mod_bs = e->w.mod_total;
-  if (up_la) {
+  const int64_t up_ld = D + (up_la ? r : 0), down_ld = M + (down_la ? r : 0);
+  if (up_la && lora) {
     AFB_TRY(Gemm(B, rows).a(yv, D).w(up_la, D, r, nullptr).out(lt0v, AFB_EPI_BIAS).run(e, s));
-    AFB_TRY(Gemm(B, rows).a(yv, D).a(lt0v, r).w(up_w, D + r, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(yv, D).a(lt0v, r).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
   } else {
-    AFB_TRY(Gemm(B, rows).a(yv, D).w(up_w, D, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(yv, D).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
   }
-  if (down_la) {
+  if (down_la && lora) {
     AFB_TRY(Gemm(B, rows).a(mlpv, M).w(down_la, M, r, nullptr).out(lt1v, AFB_EPI_BIAS).run(e, s));
-    AFB_TRY(Gemm(B, rows).a(mlpv, M).a(lt1v, r).w(down_w, M + r, D, down_b)
+    AFB_TRY(Gemm(B, rows).a(mlpv, M).a(lt1v, r).w(down_w, down_ld, D, down_b)
                 .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
   } else {
-    AFB_TRY(Gemm(B, rows).a(mlpv, M).w(down_w, M, D, down_b)
+    AFB_TRY(Gemm(B, rows).a(mlpv, M).w(down_w, down_ld, D, down_b)
                 .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
   }
   return AFB_OK;
@@ -268,7 +273,9 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   const afb_model_desc& d = e->desc;
   const afb_weights& w = e->w;
   const int B = a->batch, St = a->txt_len, Si = a->img_len, S = St + Si;
-  const int D = d.dim, M = d.mlp_dim, r = d.lora_rank, H = d.heads;
+  const int D = d.dim, M = d.mlp_dim, H = d.heads;
+  const int rpad = d.lora_rank;                    // K columns appended to LoRA-carrying packed weights
+  const int r = d.ignore_lora ? 0 : d.lora_rank;   // rank actually computed (0: frozen trunk / teacher)
   const int64_t mod_bs = w.mod_total;
   const bool flux = d.arch == AFB_ARCH_FLUX;
 
@@ -358,14 +365,14 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     AFB_TRY(afb::ln_modulate_launch(h_img.p, h_img.bs, const_cast<bf16*>(y_img.p), y_img.bs, im + 4 * D,
                                     im + 3 * D, mod_bs, B, Si, D, LN_EPS, s));
     AFB_TRY(mlp_branch(e, y_img, h_img, mlp_img, l0_img, l1_img, Si, B, k.img_up_w, k.img_up_b,
-                       r > 0 ? k.img_up_la : nullptr, k.img_down_w, k.img_down_b,
-                       r > 0 ? k.img_down_la : nullptr, im + 5 * D, s));
+                       k.img_up_la, k.img_down_w, k.img_down_b,
+                       k.img_down_la, im + 5 * D, s));
     if (!last_qwen_txt) {
       AFB_TRY(afb::ln_modulate_launch(h_txt.p, h_txt.bs, const_cast<bf16*>(y_txt.p), y_txt.bs, tm + 4 * D,
                                       tm + 3 * D, mod_bs, B, St, D, LN_EPS, s));
       AFB_TRY(mlp_branch(e, y_txt, h_txt, mlp_txt, l0_txt, l1_txt, St, B, k.txt_up_w, k.txt_up_b,
-                         r > 0 ? k.txt_up_la : nullptr, k.txt_down_w, k.txt_down_b,
-                         r > 0 ? k.txt_down_la : nullptr, tm + 5 * D, s));
+                         k.txt_up_la, k.txt_down_w, k.txt_down_b,
+                         k.txt_down_la, tm + 5 * D, s));
     }
   }
 
@@ -386,25 +393,33 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, 0, nullptr, nullptr,
                                      k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     AFB_TRY(run_attention(e, &at, s));
+    const int64_t mlp_ld = D + (k.mlp_la ? rpad : 0), out_ld = D + M + (k.out_la ? rpad : 0);
     if (r > 0 && k.mlp_la) {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
-      AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, D + r, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
+      AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
     } else {
-      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, D, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
     }
     if (r > 0 && k.out_la) {
       AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
-      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, D + M + r, D, k.out_b)
+      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, out_ld, D, k.out_b)
                   .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
     } else {
-      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_w, D + M, D, k.out_b)
+      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_w, out_ld, D, k.out_b)
                   .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
     }
   }
 
   // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + heads ------------------------
   const bf16* nm = e->mod + w.norm_out_mod_off;
-  AFB_TRY(afb::ln_modulate_launch(h_img.p, h_img.bs, const_cast<bf16*>(y_img.p), y_img.bs, nm, nm + D, mod_bs,
+  int64_t nm_bs = mod_bs;
+  if (w.alt_norm_out_w) {  // tied teacher: shares the trunk but has its own (frozen) norm_out Linear
+    AFB_TRY(small_linear_rows(e->temb, D, w.alt_norm_out_w, D, w.alt_norm_out_b, e->alt_nm, 2 * D, B, 2 * D, D,
+                              AFB_SL_SILU_IN, s));
+    nm = e->alt_nm;
+    nm_bs = 2 * D;
+  }
+  AFB_TRY(afb::ln_modulate_launch(h_img.p, h_img.bs, const_cast<bf16*>(y_img.p), y_img.bs, nm, nm + D, nm_bs,
                                   B, Si, D, LN_EPS, s));
   AFB_TRY(Gemm(B, Si).a(y_img, D).w(w.head_w, D, w.head_n, w.head_b)
               .out(View{head_out, w.head_n, int64_t(Si) * w.head_n}, AFB_EPI_BIAS).run(e, s));

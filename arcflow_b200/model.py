@@ -266,17 +266,22 @@ class ArcFluxEngineModel(EngineModelBase):
 
     @torch.no_grad()
     def forward_heads(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor,
-                      sigma: float, guidance_scale: float, grid_hw: Sequence[int]) -> torch.Tensor:
-        """One network call. Returns the raw head tensor bf16 [batch, tokens, head_n]
-        (means K*64 | logits K*4 | loggamma (K-1)*4 | pad) — logits are NOT yet log-softmaxed."""
+                      sigma, guidance_scale: float, grid_hw: Sequence[int]) -> torch.Tensor:
+        """One network call. `sigma`: a scalar or per-sample values. Returns the raw head tensor bf16
+        [batch, tokens, head_n] (means K*64 | logits K*4 | loggamma (K-1)*4 | pad) — logits NOT yet log-softmaxed
+        (for a teacher engine: the velocity [batch, tokens, 64])."""
         self._check_inputs(latents, txt, pooled, grid_hw)
         B, Si, _ = latents.shape
         lat = latents.to(BF16).contiguous()
         txt = txt.to(BF16).contiguous()
         pooled = pooled.to(BF16).contiguous()
         self._reserve(B, txt.shape[1], Si)
-        t_in, g_in = flux_time_inputs(sigma, guidance_scale)
-        tdev = torch.full((B,), t_in, dtype=torch.float32, device=self.device)
+        sig = [float(v) for v in (sigma.tolist() if isinstance(sigma, torch.Tensor) else
+                                  (sigma if isinstance(sigma, (list, tuple)) else [sigma] * B))]
+        if len(sig) != B:
+            raise AfbError(f"sigma: expected a scalar or {B} per-sample values")
+        tdev = torch.tensor([flux_time_inputs(v, guidance_scale)[0] for v in sig], dtype=torch.float32).to(self.device)
+        g_in = flux_time_inputs(sig[0], guidance_scale)[1]
         gdev = torch.full((B,), g_in, dtype=torch.float32, device=self.device) if self.cfg.guidance_embeds else None
         cos, sin = self.rope(txt.shape[1], grid_hw[0], grid_hw[1])
         out = torch.empty(B, Si, self.weights.head_n, dtype=BF16, device=self.device)
@@ -316,3 +321,46 @@ class ArcFluxEngineModel(EngineModelBase):
         _lib.check(self.lib.afb_engine_denoise(self.handle, C.byref(d), torch.cuda.current_stream().cuda_stream),
                    "afb_engine_denoise")
         return x
+
+
+class FluxTeacherEngine(ArcFluxEngineModel):
+    """Stock FLUX velocity network TIED to a student's frozen trunk (lakonlab/models/base_diffusion.py:93-94,
+    lakonlab/utils/misc.py:116-132: the teacher shares storage with the student's LoRA base layers): it borrows the
+    student's packed weights ([W | lora_B] buffers included — the extra K columns are never read) and adds only its own
+    `norm_out.linear` and `proj_out`. Forward = lakonlab/models/architecture/diffusers/flux.py:122-156."""
+
+    def __init__(self, student: ArcFluxEngineModel, teacher_sd: Dict[str, torch.Tensor]):
+        cfg = student.cfg
+        dev = student.device
+        self.student = student   # keeps the shared packed tensors alive
+        keep = []
+
+        def hold(name):
+            if name not in teacher_sd:
+                raise AfbError(f"teacher state dict is missing '{name}'")
+            t = teacher_sd[name].to(device=dev, dtype=BF16).contiguous()
+            keep.append(t)
+            return t
+
+        w = _lib.Weights()
+        C.memmove(C.byref(w), C.byref(student.weights.struct), C.sizeof(w))
+        pw, pb = hold("proj_out.weight"), hold("proj_out.bias")
+        nw, nb = hold("norm_out.linear.weight"), hold("norm_out.linear.bias")
+        if pw.shape != (cfg.out_channels, cfg.inner_dim) or nw.shape != (2 * cfg.inner_dim, cfg.inner_dim):
+            raise AfbError("teacher proj_out / norm_out.linear have unexpected shapes")
+        w.head_w, w.head_b, w.head_n = pw.data_ptr(), pb.data_ptr(), cfg.out_channels
+        w.alt_norm_out_w, w.alt_norm_out_b = nw.data_ptr(), nb.data_ptr()
+        weights = SimpleNamespace(struct=w, keep=keep, head_n=cfg.out_channels)
+        md = _lib.ModelDesc(
+            arch=_lib.AFB_ARCH_FLUX, num_double=cfg.num_layers, num_single=cfg.num_single_layers,
+            dim=cfg.inner_dim, heads=cfg.num_attention_heads, mlp_dim=cfg.mlp_dim, in_channels=cfg.in_channels,
+            txt_dim=cfg.joint_attention_dim, pooled_dim=cfg.pooled_projection_dim, guidance=int(cfg.guidance_embeds),
+            num_gaussians=cfg.num_gaussians, lora_rank=cfg.lora_rank, head_mode=1, ignore_lora=1)
+        EngineModelBase.__init__(self, cfg, weights, md, dev)
+
+    def velocity(self, latents, txt, pooled, sigma, guidance_scale, grid_hw) -> torch.Tensor:
+        """u(x_t, t) as bf16 [batch, tokens, 64] (packed-token layout)."""
+        return self.forward_heads(latents, txt, pooled, sigma, guidance_scale, grid_hw)
+
+    def denoise(self, *a, **k):
+        raise AfbError("the teacher has no ArcFlow heads; denoise() is a student method")

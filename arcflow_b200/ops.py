@@ -224,3 +224,92 @@ def sampler_step(head: torch.Tensor, x: torch.Tensor, sigma_src: float, sigma_st
                "afb_sampler_step")
     out = out.reshape(x.shape)
     return (out, out_bf.reshape(x.shape)) if want_bf16 else out
+
+
+# ------------------------------------------------------------------------------------------------
+# training-side (trajectory distillation roll-out) operators
+# ------------------------------------------------------------------------------------------------
+def _host_floats(v, n: int, name: str):
+    vals = [float(x) for x in (v.tolist() if isinstance(v, torch.Tensor) else v)]
+    if len(vals) == 1 and n > 1:
+        vals = vals * n
+    if len(vals) != n:
+        raise AfbError(f"{name}: expected {n} per-sample values, got {len(vals)}")
+    return (C.c_float * n)(*vals)
+
+
+def policy_eval(head: torch.Tensor, mode: int, sigma_src, sigma_start, sigma_end=None, x: Optional[torch.Tensor] = None,
+                batch: Optional[int] = None, drop_mask=None, small=None, num_gaussians: int = 16, eps: float = 1e-4,
+                want_bf16: bool = False):
+    """Per-sample-time policy evaluation on the raw head tensor [batch*tokens, head_ld] (see arcflow_b200.h:
+    AFB_POLICY_INTEGRATE / VELOCITY / AVERAGE_U). sigma_* are host sequences/tensors of length batch."""
+    lib = _lib.load()
+    _chk(head, BF16, "policy_eval head")
+    if head.dim() != 2 or head.stride(1) != 1:
+        raise AfbError("policy_eval: head must be [batch*tokens, head_ld]")
+    if batch is None:
+        batch = len(sigma_src)
+    if head.shape[0] % batch:
+        raise AfbError("policy_eval: rows of head not divisible by batch")
+    tokens = head.shape[0] // batch
+    a = _lib.PolicyArgs()
+    a.head, a.head_ld, a.batch, a.tokens = head.data_ptr(), head.stride(0), batch, tokens
+    a.num_gaussians, a.mode, a.eps = num_gaussians, mode, eps
+    keep = [_host_floats(sigma_src, batch, "sigma_src"), _host_floats(sigma_start, batch, "sigma_start")]
+    a.sigma_src, a.sigma_start = keep[0], keep[1]
+    if sigma_end is not None:
+        keep.append(_host_floats(sigma_end, batch, "sigma_end"))
+        a.sigma_end = keep[-1]
+    if drop_mask is not None:
+        dm = torch.as_tensor(drop_mask).to(torch.uint8).reshape(batch, num_gaussians).contiguous().cpu()
+        keep.append((C.c_uint8 * dm.numel())(*dm.flatten().tolist()))
+        a.drop_mask = keep[-1]
+    if small is not None:
+        sm = [int(bool(v)) for v in (small.tolist() if isinstance(small, torch.Tensor) else small)]
+        keep.append((C.c_uint8 * batch)(*sm))
+        a.small = keep[-1]
+    if mode == _lib.AFB_POLICY_INTEGRATE:
+        if x is None:
+            raise AfbError("policy_eval: INTEGRATE needs x")
+        _chk(x, torch.float32, "policy_eval x")
+        x2 = x.reshape(-1, 64)
+        if not x2.is_contiguous() or x2.shape[0] != head.shape[0]:
+            raise AfbError("policy_eval: x must be contiguous [batch*tokens, 64]")
+        a.x_in = x2.data_ptr()
+    out = torch.empty((head.shape[0], 64), dtype=torch.float32, device=head.device)
+    out_bf = torch.empty((head.shape[0], 64), dtype=BF16, device=head.device) if want_bf16 else None
+    a.out = out.data_ptr()
+    a.out_bf16 = out_bf.data_ptr() if want_bf16 else None
+    _lib.check(lib.afb_policy_eval(C.byref(a), _stream()), "afb_policy_eval")
+    shape = (batch, tokens, 64)
+    return (out.reshape(shape), out_bf.reshape(shape)) if want_bf16 else out.reshape(shape)
+
+
+def axpy_rows(x: torch.Tensor, u: torch.Tensor, coef, want_bf16: bool = False):
+    """out[b] = x[b] + coef[b] * u[b]; x fp32, u bf16 (a network output), coef host per-sample values."""
+    lib = _lib.load()
+    _chk(x, torch.float32, "axpy_rows x")
+    _chk(u, BF16, "axpy_rows u")
+    if x.shape != u.shape or not x.is_contiguous() or not u.is_contiguous():
+        raise AfbError("axpy_rows: x and u must be contiguous with the same shape")
+    batch = x.shape[0]
+    per = x.numel() // batch
+    out = torch.empty_like(x)
+    out_bf = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
+    _lib.check(lib.afb_axpy_rows(x.data_ptr(), u.data_ptr(), _host_floats(coef, batch, "coef"), out.data_ptr(),
+                                 out_bf.data_ptr() if want_bf16 else None, batch, per, _stream()), "afb_axpy_rows")
+    return (out, out_bf) if want_bf16 else out
+
+
+def mse_rows(pred: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:
+    """Per-sample mean squared error over all trailing dims; pred fp32, tgt bf16 -> fp32 [batch] (device)."""
+    lib = _lib.load()
+    _chk(pred, torch.float32, "mse_rows pred")
+    _chk(tgt, BF16, "mse_rows tgt")
+    if pred.shape != tgt.shape or not pred.is_contiguous() or not tgt.is_contiguous():
+        raise AfbError("mse_rows: pred and tgt must be contiguous with the same shape")
+    batch = pred.shape[0]
+    out = torch.empty(batch, dtype=torch.float32, device=pred.device)
+    _lib.check(lib.afb_mse_rows(pred.data_ptr(), tgt.data_ptr(), out.data_ptr(), batch, pred.numel() // batch,
+                                _stream()), "afb_mse_rows")
+    return out

@@ -110,3 +110,16 @@ def make_flux_inputs(cfg: ArcFluxConfig, batch: int, height: int, width: int, tx
            ).to(torch.bfloat16)
     pooled = torch.empty(batch, cfg.pooled_projection_dim, device=device).normal_(generator=g).to(torch.bfloat16)
     return x, txt, pooled
+
+
+def make_flux_teacher_extras(cfg: ArcFluxConfig, seed: int = 4321, device="cpu", dtype=torch.bfloat16):
+    """The teacher-only tensors of the stock FLUX transformer (its `norm_out.linear` and `proj_out`); the trunk is
+    tied to the student's frozen base layers (lakonlab/models/base_diffusion.py:93-94)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    D = cfg.inner_dim
+
+    def normal(shape, std):
+        return torch.empty(shape, device=device, dtype=torch.float32).normal_(0.0, std, generator=g).to(dtype)
+
+    return {"norm_out.linear.weight": normal((2 * D, D), 0.02), "norm_out.linear.bias": normal((2 * D,), 0.02),
+            "proj_out.weight": normal((cfg.out_channels, D), 0.02), "proj_out.bias": normal((cfg.out_channels,), 0.02)}

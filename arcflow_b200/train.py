@@ -1,0 +1,132 @@
+"""Data-free trajectory-distillation train step on the native kernels — FORWARD + LOSS (round 1).
+
+Restates, in packed-token layout and with every random draw injected,
+  ArcFlowImitationDataFree.forward_initialize / forward_train  lakonlab/models/diffusions/arcflow.py:343-420
+  ArcFlowImitationBase.piid_segment_momentum                   lakonlab/models/diffusions/arcflow.py:120-209
+  train_fwd_bwd (sum of per-step losses)                       lakonlab/models/base_diffusion.py:14-62
+  DiffusionMSELoss, constant rescale 30                        lakonlab/models/losses/diffusion_loss.py:45-83
+Per student step: 1 student forward (afb_engine_forward), 4 x {afb_policy_eval INTEGRATE with the detached, dropped
+policy -> teacher velocity (afb_engine_forward on the tied teacher) -> afb_policy_eval AVERAGE_U -> afb_mse_rows ->
+afb_axpy_rows (teacher Euler step)}, then one INTEGRATE to the segment end. Host code only does the O(batch)
+schedule arithmetic the reference also does on tiny tensors.
+
+NOT built yet (next round): the adapter-only backward (LoRA / heads / norm_out gradients through the
+frozen trunk), LoRA dropout (p = 0.05; this path is the p = 0 forward), optimizer / EMA / DDP all-reduce.
+`backward()` raises instead of silently doing nothing.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from ._lib import AfbError
+
+DEFAULT_TRAIN_CFG = dict(  # configs/flux/arcflux_2nfe_k16.py:89-99
+    num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4,
+    distilled_guidance_scale=3.5, teacher_distilled_guidance_scale=3.5, nfe=2, timestep_ratio=1.0,
+    total_substeps=128, eps=1e-4)
+
+
+def warp_t(t: torch.Tensor, shift: float) -> torch.Tensor:
+    """ContinuousTimeStepSampler.warp_t with a fixed shift (lakonlab/models/diffusions/sampler.py:46-48)."""
+    return shift * t / (1 + (shift - 1) * t)
+
+
+def draw_rollout_randoms(batch: int, num_states: int, num_gaussians: int, generator: Optional[torch.Generator] = None):
+    """The three uniform draws of one student step, in the reference's order (policies/arcflow.py:100-101,
+    arcflow.py:148-155)."""
+    r = lambda *s: torch.rand(s, generator=generator)
+    return dict(drop_u=r(batch, num_gaussians), student_u=r(batch, num_states), teacher_u=r(batch, num_states - 1))
+
+
+class ArcFlowDistillStep:
+    def __init__(self, student, teacher, train_cfg: Optional[Dict] = None, shift: float = 3.2, loss_scale: float = 30.0):
+        self.student, self.teacher = student, teacher
+        self.cfg = dict(DEFAULT_TRAIN_CFG)
+        if train_cfg:
+            self.cfg.update(train_cfg)
+        self.shift, self.loss_scale = shift, loss_scale
+
+    def teacher_ratio(self, iteration: int) -> float:
+        n = self.cfg.get("num_decay_iters", 0)
+        return 1 - min(iteration, n) / n if n > 0 else 0.0
+
+    @torch.no_grad()
+    def forward(self, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int], noise: torch.Tensor,
+                rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0):
+        """One train iteration, forward only. noise: fp32 packed tokens [B, S_i, 64] (the data-free x_t_src);
+        rands: one dict of uniforms per student step (see draw_rollout_randoms). Returns (loss, log_vars, extras)."""
+        cfg, st, te = self.cfg, self.student, self.teacher
+        if noise.dtype != torch.float32 or not noise.is_cuda:
+            raise AfbError("noise must be an fp32 CUDA tensor [batch, tokens, 64]")
+        B = noise.shape[0]
+        nfe, eps = cfg["nfe"], cfg.get("eps", 1e-4)
+        if len(rands) != nfe:
+            raise AfbError(f"need {nfe} sets of roll-out uniforms, got {len(rands)}")
+        ratio_t = max(cfg.get("timestep_ratio", 1.0), eps)
+        base_seg = 1.0 / (nfe - 1 + ratio_t)
+        n_states, total_sub = cfg["num_intermediate_states"], cfg["total_substeps"]
+        K = st.num_gaussians
+        g_student, g_teacher = cfg["distilled_guidance_scale"], cfg["teacher_distilled_guidance_scale"]
+        teacher_ratio = self.teacher_ratio(iteration)
+        log_vars = dict(teacher_ratio=teacher_ratio) if cfg.get("num_decay_iters", 0) > 0 else {}
+
+        x_src = noise.contiguous()
+        raw_t_src = torch.ones(B, dtype=torch.float32)
+        loss_total = 0.0
+        extras = dict(steps=[])
+        for step_id in range(nfe):
+            seg_f = base_seg * ratio_t if step_id == nfe - 1 else base_seg
+            seg = torch.tensor([seg_f], dtype=torch.float32)
+            num_sub = (seg * total_sub).round().to(torch.long).clamp(min=1)
+            window = torch.minimum(cfg["window_substeps"] * (seg / num_sub), seg)
+            raw_t_dst = raw_t_src - seg
+            sigma_src = warp_t(raw_t_src, self.shift)
+
+            head = st.forward_heads(x_src, txt, pooled, sigma_src, g_student, grid_hw)
+            head2 = head.reshape(-1, head.shape[-1])
+
+            rd = rands[step_id]
+            p = cfg.get("gm_dropout", 0.0)
+            drop = None
+            if 0 < p < 1:
+                m = rd["drop_u"].cpu() < p
+                drop = m & ~m.all(dim=1, keepdim=True)
+            s_iv = rd["student_u"].cpu() * ((1 - teacher_ratio) * (seg - window).unsqueeze(-1))
+            s_iv = torch.diff(torch.sort(s_iv, dim=-1)[0], dim=-1, prepend=torch.zeros((B, 1)))
+            t_iv = torch.diff(torch.sort(rd["teacher_u"].cpu(), dim=-1)[0], dim=-1, prepend=torch.zeros((B, 1)),
+                              append=torch.ones((B, 1))) * (teacher_ratio * (seg - window).unsqueeze(-1))
+
+            x_t, raw_t, sigma_t = x_src, raw_t_src, sigma_src
+            mse_sum = torch.zeros(B, dtype=torch.float32, device=noise.device)
+            for k in range(n_states):
+                raw_t_a = (raw_t - s_iv[:, k]).clamp(min=0)
+                raw_t_b = (raw_t_a - t_iv[:, k]).clamp(min=0)
+                sigma_a, sigma_b = warp_t(raw_t_a, self.shift), warp_t(raw_t_b, self.shift)
+                x_a, x_a_bf = ops.policy_eval(head2, _lib.AFB_POLICY_INTEGRATE, sigma_src, sigma_t, sigma_a, x=x_t,
+                                              batch=B, drop_mask=drop, num_gaussians=K, eps=eps, want_bf16=True)
+                tgt_u = te.velocity(x_a_bf, txt, pooled, sigma_a, g_teacher, grid_hw)
+                raw_end = raw_t_b - window
+                small = torch.round((raw_t_a - raw_end) * total_sub) < 2
+                pred_u = ops.policy_eval(head2, _lib.AFB_POLICY_AVERAGE_U, sigma_src, sigma_a, warp_t(raw_end, self.shift),
+                                         batch=B, small=small, num_gaussians=K, eps=eps)
+                mse_sum += ops.mse_rows(pred_u, tgt_u)
+                x_t = ops.axpy_rows(x_a, tgt_u, sigma_b - sigma_a)
+                raw_t, sigma_t = raw_t_b, sigma_b
+            # DiffusionMSELoss: 0.5 * flatmean -> x loss_scale -> mean over the 4B stacked samples
+            step_loss = float(mse_sum.sum().item()) * 0.5 * self.loss_scale / (n_states * B)
+            x_dst = ops.policy_eval(head2, _lib.AFB_POLICY_INTEGRATE, sigma_src, sigma_t, warp_t(raw_t_dst, self.shift),
+                                    x=x_t, batch=B, drop_mask=drop, num_gaussians=K, eps=eps)
+            loss_total += step_loss * seg_f
+            log_vars[f"loss_diffusion_step{step_id}"] = step_loss
+            log_vars["loss_diffusion"] = log_vars.get("loss_diffusion", 0.0) + step_loss * seg_f
+            extras["steps"].append(dict(x_t_dst=x_dst, head=head))
+            x_src, raw_t_src = x_dst, raw_t_dst
+        return loss_total, log_vars, extras
+
+    def backward(self, *a, **k):
+        raise NotImplementedError(
+            "adapter-only backward (LoRA / heads / norm_out grads through the frozen trunk) is not built yet; "
+            "this round ships the train-step forward + loss (see DESIGN.md §1, rows a15-a18)")

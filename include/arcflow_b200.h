@@ -154,6 +154,41 @@ int afb_sampler_step(const void* head, int64_t head_ld, const float* x_in, float
                      void* x_out_bf16, int64_t tokens, int32_t num_gaussians, float sigma_src,
                      float sigma_start, float sigma_end, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training-side policy evaluation (trajectory distillation roll-out) with PER-SAMPLE times, from the raw
+ * head tensor of one student call, in packed-token layout. Replaces, per call, the reference's
+ *   INTEGRATE  ArcFlowImitationBase.momentum_integration   lakonlab/models/diffusions/arcflow.py:28-79
+ *   VELOCITY   ArcFlowPolicy.velocity                       lakonlab/models/diffusions/policies/arcflow.py:52-76
+ *   AVERAGE_U  policy_average_u_momentum                    lakonlab/models/diffusions/arcflow.py:81-110
+ * plus ArcFlowPolicy.dropout_ (policies/arcflow.py:96-106) through drop_mask. sigma_* / drop_mask / small are
+ * HOST arrays (batch <= 64), passed to the kernel by value.
+ * ---------------------------------------------------------------------------------------------- */
+enum { AFB_POLICY_INTEGRATE = 0, AFB_POLICY_VELOCITY = 1, AFB_POLICY_AVERAGE_U = 2 };
+
+typedef struct afb_policy_args {
+  const void* head;         /* bf16 [batch*tokens, head_ld] raw heads (means | logits | loggamma) */
+  int64_t head_ld;
+  int32_t batch, tokens;    /* tokens per sample */
+  int32_t num_gaussians;    /* 16 */
+  int32_t mode;
+  const float* sigma_src;   /* host [batch] */
+  const float* sigma_start; /* host [batch] (VELOCITY: the evaluation time) */
+  const float* sigma_end;   /* host [batch] (unused for VELOCITY) */
+  const uint8_t* drop_mask; /* host [batch, 16] or NULL: 1 = component dropped */
+  const uint8_t* small;     /* host [batch] or NULL: AVERAGE_U falls back to the local velocity where set */
+  const float* x_in;        /* fp32 [batch*tokens, 64] (INTEGRATE) */
+  float* out;               /* fp32 [batch*tokens, 64]: x_end (INTEGRATE) or u */
+  void* out_bf16;           /* optional bf16 copy of out */
+  float eps;                /* 1e-4 */
+} afb_policy_args;
+int afb_policy_eval(const afb_policy_args* args, void* stream);
+
+/* out[b, :] = x[b, :] + coef[b] * u[b, :]  (teacher Euler step, arcflow.py:190). x/out fp32, u bf16, coef host. */
+int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16,
+                  int32_t batch, int64_t per_sample, void* stream);
+/* out[b] = mean_i (pred[b, i] - tgt[b, i])^2 — mmgen mse_loss(reduction='flatmean'); pred fp32, tgt bf16, out device fp32 [batch]. */
+int afb_mse_rows(const float* pred, const void* tgt_bf16, float* out, int32_t batch, int64_t per_sample, void* stream);
+
 /* fp32 -> bf16 cast of a contiguous buffer. */
 int afb_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
 
@@ -177,6 +212,7 @@ typedef struct afb_model_desc {
   int32_t num_gaussians; /* 16 */
   int32_t lora_rank;    /* 256; 0 = no adapter branches (teacher trunk) */
   int32_t head_mode;    /* 0 = ArcFlow 3 heads (means|logits|loggamma), 1 = stock proj_out (teacher) */
+  int32_t ignore_lora;  /* 1: frozen-trunk forward (teacher tied to the student's packed weights): LoRA A/B never read */
 } afb_model_desc;
 
 /* Packed per-block weights. All bf16. W*: [out, in(+rank)] K-major with the LoRA B matrix appended
@@ -220,6 +256,7 @@ typedef struct afb_weights {
   int64_t mod_total;
   int64_t norm_out_mod_off;               /* 2*D chunk (scale, shift) */
   const void *head_w, *head_b;            /* [head_n, D], [head_n]; head_n padded to a multiple of 8 */
+  const void *alt_norm_out_w, *alt_norm_out_b; /* optional [2D, D], [2D]: norm_out Linear used instead of the mod_w chunk */
   int32_t head_n;
   const afb_double_block* dbl;
   const afb_single_block* sgl;

@@ -237,18 +237,10 @@ def flux_single_block(sd, p: str, x: Tensor, c: Tensor, temb: Tensor, rope, head
     return h[:, :St], h[:, St:]
 
 
-def flux_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
-                 pooled_projections: Tensor, timestep: Tensor, guidance: Optional[Tensor],
-                 grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0,
-                 bf16_quirks: bool = True) -> Dict[str, Tensor]:
-    """_ArcFluxTransformer2DModel.forward (arcflux.py:134-257).
-
-    `timestep` is sigma in [0, 1] as the pipeline passes it (arcflux_pipeline.py:472), `guidance` the
-    guidance scale. `dtype` is the compute dtype (float32/float64 = oracle; bfloat16 = the reference's
-    own numerics on CPU). bf16_quirks reproduces the two input roundings that exist regardless of
-    compute dtype in the reference's bf16 deployment: `timestep.to(bf16) * 1000` (:160-162) and the
-    RoPE tables cast to the hidden dtype (:173) — SURVEY.md Appendix A.8.
-    """
+def flux_trunk(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
+               pooled_projections: Tensor, timestep: Tensor, guidance: Optional[Tensor],
+               grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0, bf16_quirks: bool = True):
+    """Embedders + 19 double + 38 single blocks (arcflux.py:158-230). Returns (image hidden states, temb)."""
     heads = cfg.num_attention_heads
     x = _lin(sd, "x_embedder", hidden_states.to(dtype), dtype)
     qd = torch.bfloat16 if bf16_quirks else dtype
@@ -276,7 +268,23 @@ def flux_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidd
         c, x = flux_double_block(sd, f"transformer_blocks.{i}.", x, c, temb, rope, heads, dtype, lora_scale)
     for i in range(cfg.num_single_layers):
         c, x = flux_single_block(sd, f"single_transformer_blocks.{i}.", x, c, temb, rope, heads, dtype, lora_scale)
+    return x, temb
 
+
+def flux_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
+                 pooled_projections: Tensor, timestep: Tensor, guidance: Optional[Tensor],
+                 grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0,
+                 bf16_quirks: bool = True) -> Dict[str, Tensor]:
+    """_ArcFluxTransformer2DModel.forward (arcflux.py:134-257).
+
+    `timestep` is sigma in [0, 1] as the pipeline passes it (arcflux_pipeline.py:472), `guidance` the
+    guidance scale. `dtype` is the compute dtype (float32/float64 = oracle; bfloat16 = the reference's
+    own numerics on CPU). bf16_quirks reproduces the two input roundings that exist regardless of
+    compute dtype in the reference's bf16 deployment: `timestep.to(bf16) * 1000` (:160-162) and the
+    RoPE tables cast to the hidden dtype (:173) — SURVEY.md Appendix A.8.
+    """
+    x, temb = flux_trunk(sd, cfg, hidden_states, encoder_hidden_states, pooled_projections, timestep, guidance,
+                         grid_hw, dtype=dtype, lora_scale=lora_scale, bf16_quirks=bf16_quirks)
     # AdaLayerNormContinuous: scale first, then shift (Appendix A.5)
     emb = _lin(sd, "norm_out.linear", F.silu(temb).to(x.dtype), dtype)
     scale, shift = emb.chunk(2, dim=1)

@@ -1,0 +1,133 @@
+"""GPU: the trajectory-distillation train step (forward + loss) through the C ABI vs the training oracle.
+Tolerances: policy kernels (fp32 math on bf16 inputs) max-abs 3e-5 vs reference-generated goldens; teacher velocity and
+loss follow the transformer rule (rel 2e-2 / 1.5x the reference's own bf16 numerics)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import arcflow_oracle as O  # noqa: E402
+from oracle import arcflow_train_oracle as T  # noqa: E402
+
+ROOT = Path(__file__).resolve().parent.parent
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+@pytest.fixture(scope="module")
+def ops(lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from arcflow_b200 import ops as _ops
+    return _ops
+
+
+def _head_from_image_major(means, logits, gam):
+    """[B,K,C,H,W] image-major policy tensors -> raw head rows [B*S, 1152] in packed-token layout (inverse of _unpack_mp)."""
+    B, K, C, H, W = means.shape
+    h, w = H // 2, W // 2
+    m = means.reshape(B, K, C, h, 2, w, 2).permute(0, 3, 5, 1, 2, 4, 6).reshape(B * h * w, K * C * 4)
+    lw = logits.reshape(B, K, 1, h, 2, w, 2).permute(0, 3, 5, 1, 2, 4, 6).reshape(B * h * w, K * 4)
+    gm = gam.reshape(B, K - 1, 1, h, 2, w, 2).permute(0, 3, 5, 1, 2, 4, 6).reshape(B * h * w, (K - 1) * 4)
+    head = torch.zeros(B * h * w, 1152)
+    head[:, :1024], head[:, 1024:1088], head[:, 1088:1148] = m, lw, gm
+    return head
+
+
+def test_policy_eval_modes_match_train_oracle(ops):
+    """INTEGRATE / VELOCITY / AVERAGE_U with per-sample times, dropout and the small-length select."""
+    from arcflow_b200 import _lib
+    g = np.load(ROOT / "tests" / "golden" / "reference_train_rollout.npz")
+    means, logw, gam, x = [torch.from_numpy(g[k]) for k in ("in_means", "in_logw", "in_gam", "in_x")]
+    B = x.shape[0]
+    # the golden log-weights are already bf16 log-softmaxed: feeding them as logits is idempotent up to rounding,
+    # so compare against the oracle evaluated on exactly what the kernel reconstructs
+    head = _head_from_image_major(means, logw, gam).bfloat16()
+    lw_k = logw.bfloat16().float().log_softmax(1).bfloat16().float()
+    drop = torch.zeros(B, 16, dtype=torch.bool)
+    drop[0, 3] = drop[0, 7] = drop[2, 0] = True
+    mp = dict(means=means, logweights=lw_k.masked_fill(drop.reshape(B, 16, 1, 1, 1), float("-inf")), loggammas=gam)
+    s_src = torch.tensor([1.0, 0.9, 0.7619]); s_start = torch.tensor([0.95, 0.9, 0.5]); s_end = torch.tensor([0.8, 0.55, 0.4999])
+    r4 = lambda t: t.reshape(B, 1, 1, 1)
+    x_tok = O.pack_latents(x).contiguous()
+    got = ops.policy_eval(head.to(DEV), _lib.AFB_POLICY_INTEGRATE, s_src, s_start, s_end, x=x_tok.to(DEV), batch=B, drop_mask=drop)
+    ref = O.pack_latents(T.momentum_integration(mp, x, r4(s_src), r4(s_start), r4(s_end)))
+    assert (got.cpu() - ref).abs().max() < 3e-5
+    mp_nodrop = dict(mp, logweights=lw_k)
+    got = ops.policy_eval(head.to(DEV), _lib.AFB_POLICY_VELOCITY, s_src, s_start, batch=B)
+    assert (got.cpu() - O.pack_latents(T.policy_velocity(mp_nodrop, r4(s_src), r4(s_start)))).abs().max() < 3e-5
+    small = torch.tensor([False, True, False])
+    got = ops.policy_eval(head.to(DEV), _lib.AFB_POLICY_AVERAGE_U, s_src, s_start, s_end, batch=B, small=small)
+    mean_u = (x - T.momentum_integration(mp_nodrop, x, r4(s_src), r4(s_start), r4(s_end))) / r4(s_start - s_end).clamp(min=1e-4)
+    ref = torch.where(r4(small), T.policy_velocity(mp_nodrop, r4(s_src), r4(s_start)), mean_u)
+    assert (got.cpu() - O.pack_latents(ref)).abs().max() < 1e-3 * ref.abs().max()
+
+
+def test_axpy_and_mse_rows(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 10, 64, generator=g)
+    u = torch.randn(3, 10, 64, generator=g).bfloat16()
+    coef = [0.25, -1.5, 0.0]
+    out, out_bf = ops.axpy_rows(x.to(DEV), u.to(DEV), coef, want_bf16=True)
+    ref = x + torch.tensor(coef).reshape(3, 1, 1) * u.float()
+    assert torch.allclose(out.cpu(), ref, atol=1e-6) and torch.equal(out_bf.cpu(), out.cpu().bfloat16())
+    m = ops.mse_rows(x.to(DEV), u.to(DEV))
+    assert torch.allclose(m.cpu(), ((x - u.float()) ** 2).flatten(1).mean(1), rtol=1e-5)
+
+
+def _setup(num_layers=1, num_single=2, heads=2, batch=2, px=64, txt_len=32):
+    from arcflow_b200.config import flux_tiny
+    from arcflow_b200.model import ArcFluxEngineModel, FluxTeacherEngine
+    from arcflow_b200.synthetic import make_flux_inputs, make_flux_state_dict, make_flux_teacher_extras
+    cfg = flux_tiny(num_layers, num_single, heads)
+    sd = make_flux_state_dict(cfg, seed=1234)
+    extra = make_flux_teacher_extras(cfg, seed=99)
+    x, txt, pooled = make_flux_inputs(cfg, batch, px, px, txt_len=txt_len, seed=8)
+    student = ArcFluxEngineModel(sd, cfg, device=DEV)
+    teacher = FluxTeacherEngine(student, extra)
+    return cfg, sd, extra, x, txt, pooled, (px // 16, px // 16), student, teacher
+
+
+def test_tied_teacher_velocity_parity(lib):
+    cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup()
+    sig = [0.83, 0.41]
+    u = teacher.velocity(x.to(DEV), txt.to(DEV), pooled.to(DEV), sig, 3.5, grid)
+    tsd = T.teacher_state_dict(sd, extra)
+    args = (x.bfloat16(), txt, pooled, torch.tensor(sig), torch.full([2], 3.5), grid)
+    ref = T.flux_teacher_velocity(tsd, cfg, *args, dtype=torch.float32)
+    ref_bf16 = T.flux_teacher_velocity(tsd, cfg, *args, dtype=torch.bfloat16)
+    assert u.shape == (2, 16, 64)
+    assert rel(u, ref) < max(2e-2, 1.5 * rel(ref_bf16, ref))
+    # the student still runs with its LoRA branches on the shared buffers
+    head = student.forward_heads(x.to(DEV), txt.to(DEV), pooled.to(DEV), sig, 3.5, grid)
+    ref_s = O.flux_forward(sd, cfg, *args, dtype=torch.float32)
+    assert rel(student.split_heads(head)["means"], ref_s["means"]) < 2e-2
+
+
+@pytest.mark.parametrize("iteration,p_drop", [(0, 0.1), (700, 0.1), (5000, 0.0)])
+def test_train_step_forward_loss_parity(lib, iteration, p_drop):
+    from arcflow_b200.train import ArcFlowDistillStep, draw_rollout_randoms
+    cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup()
+    tc = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=p_drop, num_intermediate_states=4, nfe=2,
+              timestep_ratio=1.0, total_substeps=128, eps=1e-4)
+    g = torch.Generator().manual_seed(5 + iteration)
+    rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
+    step = ArcFlowDistillStep(student, teacher, tc)
+    loss, log_vars, extras = step.forward(txt.to(DEV), pooled.to(DEV), grid, x.to(DEV), rands, iteration=iteration)
+    ref, ref_lv, ref_ex = T.flux_train_forward(sd, extra, cfg, txt, pooled, grid, x, rands, iteration, tc, dtype=torch.float32)
+    ref_b, _, _ = T.flux_train_forward(sd, extra, cfg, txt, pooled, grid, x, rands, iteration, tc, dtype=torch.bfloat16)
+    tol = max(2e-2, 1.5 * abs(float(ref_b) - float(ref)) / abs(float(ref)))
+    assert abs(loss - float(ref)) / abs(float(ref)) < tol, (loss, float(ref), float(ref_b))
+    assert log_vars["teacher_ratio"] == ref_lv["teacher_ratio"]
+    x_dst = extras["steps"][-1]["x_t_dst"].cpu()
+    ref_dst = O.pack_latents(ref_ex["trace"][-1]["x_t_dst"])
+    assert rel(x_dst, ref_dst) < 2e-2
+    with pytest.raises(NotImplementedError):
+        step.backward()
