@@ -99,42 +99,66 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, long long bs,
                     const __nv_bfloat16* __restrict__ wq_txt, const __nv_bfloat16* __restrict__ wk_txt,
                     const __nv_bfloat16* __restrict__ wq_img, const __nv_bfloat16* __restrict__ wk_img,
                     const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, float eps) {
+  // One warp per token row; a half-warp (16 lanes x 8 elements = 16 B per lane) owns one head at a time, so the
+  // warp streams two heads per step with 16-byte accesses; cos/sin/weights of this lane's 8 head-columns are
+  // loaded once and reused for all heads of the row.
   const int lane = threadIdx.x & 31;
+  const int hl = lane & 15;    // position inside the head: elements [8 hl, 8 hl + 8)
+  const int half = lane >> 4;  // which of the two heads of this step
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)batches * seq) return;
   const int b = int(row / seq);
   const int s = int(row - (long long)b * seq);
   __nv_bfloat16* base = qkv + (long long)b * bs + (long long)s * ld;
   const bool is_txt = s < txt_rows;
-  const float4 cs = *reinterpret_cast<const float4*>(cos_tab + (long long)s * 128 + lane * 4);
-  const float4 sn = *reinterpret_cast<const float4*>(sin_tab + (long long)s * 128 + lane * 4);
-  float wq[4], wk[4];
+  float cs[8], sn[8], wq[8], wk[8];
   {
-    const uint2 a = *reinterpret_cast<const uint2*>((is_txt ? wq_txt : wq_img) + lane * 4);
-    const uint2 c = *reinterpret_cast<const uint2*>((is_txt ? wk_txt : wk_img) + lane * 4);
-    wq[0] = bf16_lo(a.x); wq[1] = bf16_hi(a.x); wq[2] = bf16_lo(a.y); wq[3] = bf16_hi(a.y);
-    wk[0] = bf16_lo(c.x); wk[1] = bf16_hi(c.x); wk[2] = bf16_lo(c.y); wk[3] = bf16_hi(c.y);
+    const float4 c0 = *reinterpret_cast<const float4*>(cos_tab + (long long)s * 128 + hl * 8);
+    const float4 c1 = *reinterpret_cast<const float4*>(cos_tab + (long long)s * 128 + hl * 8 + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(sin_tab + (long long)s * 128 + hl * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(sin_tab + (long long)s * 128 + hl * 8 + 4);
+    cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+    sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+    unpack8(*reinterpret_cast<const uint4*>((is_txt ? wq_txt : wq_img) + hl * 8), wq);
+    unpack8(*reinterpret_cast<const uint4*>((is_txt ? wk_txt : wk_img) + hl * 8), wk);
   }
-  for (int slot = 0; slot < 2 * heads; ++slot) {
-    const bool is_k = slot >= heads;
-    const int h = is_k ? slot - heads : slot;
-    __nv_bfloat16* ptr = base + (is_k ? k_off : q_off) + h * 128 + lane * 4;
-    const uint2 u = *reinterpret_cast<const uint2*>(ptr);
-    float x[4] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)};
-    const float ss = warp_sum(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-    const float rs = rsqrtf(ss * (1.0f / 128.0f) + eps);
-    const float* w = is_k ? wk : wq;
+  const int slots = 2 * heads;  // q heads then k heads
+  constexpr int UNROLL = 4;     // 4 x 16-byte loads in flight per lane
+  for (int s0 = 0; s0 < slots; s0 += 2 * UNROLL) {
+    uint4 u[UNROLL];
+    __nv_bfloat16* ptr[UNROLL];
+    bool act[UNROLL], is_k[UNROLL];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = round_bf16(round_bf16(x[i] * rs) * w[i]);
-    float o[4];
-    o[0] = x[0] * cs.x - x[1] * sn.x;
-    o[1] = x[1] * cs.y + x[0] * sn.y;
-    o[2] = x[2] * cs.z - x[3] * sn.z;
-    o[3] = x[3] * cs.w + x[2] * sn.w;
-    uint2 w2;
-    w2.x = pack_bf16x2(o[0], o[1]);
-    w2.y = pack_bf16x2(o[2], o[3]);
-    *reinterpret_cast<uint2*>(ptr) = w2;
+    for (int i = 0; i < UNROLL; ++i) {
+      const int slot = s0 + 2 * i + half;
+      act[i] = slot < slots;
+      is_k[i] = slot >= heads;
+      const int h = is_k[i] ? slot - heads : slot;
+      ptr[i] = base + (is_k[i] ? k_off : q_off) + h * 128 + hl * 8;
+      u[i] = act[i] ? *reinterpret_cast<const uint4*>(ptr[i]) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < UNROLL; ++i) {
+      float x[8];
+      unpack8(u[i], x);
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      const float rs = rsqrtf(ss * (1.0f / 128.0f) + eps);
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = round_bf16(round_bf16(x[e] * rs) * (is_k[i] ? wk[e] : wq[e]));
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        o[e] = x[e] * cs[e] - x[e + 1] * sn[e];
+        o[e + 1] = x[e + 1] * cs[e + 1] + x[e] * sn[e + 1];
+      }
+      if (act[i]) *reinterpret_cast<uint4*>(ptr[i]) = pack8(o);
+    }
   }
 }
 
@@ -532,7 +556,8 @@ int rmsnorm_rope_launch(void* qkv, int64_t ld, int64_t bs, int q_off, int k_off,
                         const float* sin_tab, float eps, cudaStream_t stream) {
   AFB_REQUIRE(qkv && wq_img && wk_img && cos_tab && sin_tab, "rmsnorm_rope: null pointer");
   AFB_REQUIRE(txt_rows == 0 || (wq_txt && wk_txt), "rmsnorm_rope: text norm weights missing");
-  AFB_REQUIRE(ld % 4 == 0 && q_off % 4 == 0 && k_off % 4 == 0, "rmsnorm_rope: misaligned layout");
+  AFB_REQUIRE(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0,
+              "rmsnorm_rope: q/k columns must be 16-byte aligned");
   AFB_REQUIRE(batches >= 1 && seq >= 1 && heads >= 1, "rmsnorm_rope: empty input");
   const long long rows = (long long)batches * seq;
   const int wpb = 8;
