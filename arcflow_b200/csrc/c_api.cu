@@ -24,6 +24,15 @@ int sampler_step_launch(const void* head, int64_t head_ld, const float* x_in, fl
                         float sigma_start, float sigma_end, float eps, cudaStream_t stream);
 int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t stream);
 int policy_eval_launch(const afb_policy_args* a, cudaStream_t stream);
+int policy_backward_launch(const afb_policy_args* a, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
+                           int accumulate, cudaStream_t stream);
+int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
+int gemm_tn_launch(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
+                   int m, int n, cudaStream_t stream);
+int ln_mod_param_grad_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws, float* dscale,
+                             float* dshift, int batches, int rows_per_batch, int dim, float eps, cudaStream_t stream);
+int rowlinear_param_grad_launch(const float* de, int64_t de_ld, const void* t, int64_t t_ld, float* dw, int64_t dw_ld,
+                                float* dbias, int m, int n_out, int k_in, int silu_in, cudaStream_t stream);
 int axpy_rows_launch(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int batch,
                      int64_t per_sample, cudaStream_t stream);
 int mse_rows_launch(const float* pred, const void* tgt_bf16, float* out, int batch, int64_t per_sample,
@@ -79,6 +88,27 @@ int afb_sampler_step(const void* head, int64_t head_ld, const float* x_in, float
 }
 int afb_policy_eval(const afb_policy_args* args, void* stream) {
   return afb::policy_eval_launch(args, static_cast<cudaStream_t>(stream));
+}
+int afb_policy_backward(const afb_policy_args* args, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
+                        int32_t accumulate, void* stream) {
+  return afb::policy_backward_launch(args, tgt_bf16, dhead, dh_ld, coef, accumulate, static_cast<cudaStream_t>(stream));
+}
+int afb_colsum_f32(const float* x, int64_t ld, float* out, int64_t rows, int32_t n, void* stream) {
+  return afb::colsum_f32_launch(x, ld, out, rows, n, static_cast<cudaStream_t>(stream));
+}
+int afb_gemm_tn(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
+                int32_t m, int32_t n, void* stream) {
+  return afb::gemm_tn_launch(a, a_ld, b, b_ld, out, out_ld, tokens, m, n, static_cast<cudaStream_t>(stream));
+}
+int afb_ln_mod_param_grad(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws, float* dscale,
+                          float* dshift, int32_t batches, int32_t rows_per_batch, int32_t dim, float eps, void* stream) {
+  return afb::ln_mod_param_grad_launch(x, x_bs, dy, dy_bs, stats_ws, dscale, dshift, batches, rows_per_batch, dim, eps,
+                                       static_cast<cudaStream_t>(stream));
+}
+int afb_rowlinear_param_grad(const float* de, int64_t de_ld, const void* t, int64_t t_ld, float* dw, int64_t dw_ld,
+                             float* dbias, int32_t m, int32_t n_out, int32_t k_in, int32_t silu_in, void* stream) {
+  return afb::rowlinear_param_grad_launch(de, de_ld, t, t_ld, dw, dw_ld, dbias, m, n_out, k_in, silu_in,
+                                          static_cast<cudaStream_t>(stream));
 }
 int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int32_t batch,
                   int64_t per_sample, void* stream) {

@@ -496,6 +496,227 @@ mse_rows_kernel(const float* __restrict__ pred, const __nv_bfloat16* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the velocity-matching loss through AVERAGE_U (the only policy path that carries grad in
+// piid_segment_momentum, lakonlab/models/diffusions/arcflow.py:183-188):
+//   L += coef/2 * sum_o (pred_o - tgt_o)^2,   pred = policy_average_u(head)   ->   dhead (+)= dL/dhead
+// dhead rows mirror the head rows: d means | d logits (through softmax o bf16-round o log_softmax, rounding
+// straight-through) | d loggamma. One warp per token, same work split as the forward kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dphi_expm1(float z) {  // d/dz [expm1(z)/z]
+  if (fabsf(z) < 1e-2f) return 0.5f + z * (1.0f / 3.0f) + z * z * 0.125f;
+  return (expm1f(z) * (z - 1.0f) + z) / (z * z);
+}
+
+__global__ void __launch_bounds__(256)
+policy_avg_u_bwd_k16_kernel(const __nv_bfloat16* __restrict__ head, long long head_ld,
+                            const __nv_bfloat16* __restrict__ tgt, float* __restrict__ dhead, long long dh_ld,
+                            int tokens_per_sample, long long tokens, float coef, float eps, int accumulate,
+                            const __grid_constant__ PolicyParams pp) {
+  constexpr int K = 16;
+  __shared__ float sWF[8][K * 4], sA[8][K * 4];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long tok = (long long)blockIdx.x * 8 + wib;
+  if (tok >= tokens) return;
+  const int b = int(tok / tokens_per_sample);
+  const float dt_past = pp.dt_past[b], dt_step = pp.dt_step[b];
+  const bool local_u = pp.small[b] != 0;
+  const __nv_bfloat16* hrow = head + tok * head_ld;
+  const __nv_bfloat16* logit = hrow + K * 64;
+  const __nv_bfloat16* lgam = logit + K * 4;
+  float* drow = dhead + tok * dh_ld;
+
+  const float a0 = __bfloat162float(logit[lane]);
+  const float a1 = __bfloat162float(logit[lane + 32]);
+  const float mx = group_max(fmaxf(a0, a1));
+  const float lse = mx + logf(group_sum(expf(a0 - mx) + expf(a1 - mx)));
+  const float b0 = round_bf16(a0 - lse), b1 = round_bf16(a1 - lse);
+  const float mx2 = group_max(fmaxf(b0, b1));
+  const float e0 = expf(b0 - mx2), e1 = expf(b1 - mx2);
+  const float inv = 1.0f / group_sum(e0 + e1);
+  const float w0 = e0 * inv, w1 = e1 * inv;
+  const bool has0 = lane >= 4;  // component 0 has no rate
+  const float lam0 = has0 ? __bfloat162float(lgam[lane - 4]) : 0.f;
+  const float lam1 = __bfloat162float(lgam[lane + 28]);
+  float f0, f1, df0, df1;  // F and dF/dlambda
+  if (local_u) {
+    f0 = has0 ? expf(lam0 * dt_past) : 1.0f;
+    f1 = expf(lam1 * dt_past);
+    df0 = has0 ? dt_past * f0 : 0.f;
+    df1 = dt_past * f1;
+  } else {
+    const float scale = dt_step / fmaxf(dt_step, eps);
+    auto eval = [&](float lam, float& f, float& df) {
+      const float z = lam * dt_step;
+      const float sgn = z < 0.f ? -1.f : 1.f;
+      const float zs = sgn * fmaxf(fabsf(z), eps);
+      const float decay = expf(lam * dt_past);
+      f = decay * scale * (expm1f(zs) / zs);
+      df = dt_past * f + (fabsf(z) >= eps ? decay * scale * dphi_expm1(zs) * dt_step : 0.f);
+    };
+    eval(lam1, f1, df1);
+    if (has0) {
+      eval(lam0, f0, df0);
+    } else {
+      f0 = scale;
+      df0 = 0.f;
+    }
+  }
+  sWF[wib][lane] = w0 * f0;
+  sWF[wib][lane + 32] = w1 * f1;
+  __syncwarp();
+
+  const int j0 = (2 * lane) & 3;
+  float mu0[K], mu1[K];
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t mv = *reinterpret_cast<const uint32_t*>(hrow + k * 64 + 2 * lane);
+    mu0[k] = bf16_lo(mv);
+    mu1[k] = bf16_hi(mv);
+    acc0 = fmaf(mu0[k], sWF[wib][k * 4 + j0], acc0);
+    acc1 = fmaf(mu1[k], sWF[wib][k * 4 + j0 + 1], acc1);
+  }
+  const uint32_t tv = *reinterpret_cast<const uint32_t*>(tgt + tok * 64 + 2 * lane);
+  const float g0 = coef * (acc0 - bf16_lo(tv)), g1 = coef * (acc1 - bf16_hi(tv));
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float2 dm = make_float2(sWF[wib][k * 4 + j0] * g0, sWF[wib][k * 4 + j0 + 1] * g1);
+    float2* dst = reinterpret_cast<float2*>(drow + k * 64 + 2 * lane);
+    if (accumulate) {
+      const float2 old = *dst;
+      dm.x += old.x;
+      dm.y += old.y;
+    }
+    *dst = dm;
+    // A[k][j] = sum over the 16 channels of mu * g; lanes of equal parity share (j0, j0 + 1)
+    float p0 = mu0[k] * g0, p1 = mu1[k] * g1;
+#pragma unroll
+    for (int o = 2; o < 32; o <<= 1) {
+      p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+      p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+    }
+    if (lane < 2) {
+      sA[wib][k * 4 + j0] = p0;
+      sA[wib][k * 4 + j0 + 1] = p1;
+    }
+  }
+  __syncwarp();
+  const float A0 = sA[wib][lane], A1 = sA[wib][lane + 32];
+  const float dw0 = f0 * A0, dw1 = f1 * A1;
+  const float sdot = group_sum(w0 * dw0 + w1 * dw1);
+  float dl0 = w0 * (dw0 - sdot), dl1 = w1 * (dw1 - sdot);
+  float dg0 = w0 * A0 * df0, dg1 = w1 * A1 * df1;
+  float* dlog = drow + K * 64;
+  float* dgam = dlog + K * 4;
+  if (accumulate) {
+    dl0 += dlog[lane];
+    dl1 += dlog[lane + 32];
+    if (has0) dg0 += dgam[lane - 4];
+    dg1 += dgam[lane + 28];
+  }
+  dlog[lane] = dl0;
+  dlog[lane + 32] = dl1;
+  if (has0) dgam[lane - 4] = dg0;
+  dgam[lane + 28] = dg1;
+}
+
+// out[n] (+)= sum_t x[t, n]   (bias gradients); x fp32 [rows, ld], out fp32 [n]
+__global__ void __launch_bounds__(256)
+colsum_f32_kernel(const float* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int n,
+                  int rows_per_block) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += x[r * ld + col];
+  atomicAdd(out + col, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameter gradients of y = LN(x) * (1 + scale[b]) + shift[b]  (AdaLayerNormContinuous / Zero):
+//   dscale[b, d] += sum_rows dy * xhat,   dshift[b, d] += sum_rows dy,   xhat = (x - mean) * rstd
+// Step 1: per-row (mean, rstd); step 2: column reduction over row chunks with fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_row_stats_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, float2* __restrict__ stats, int batches,
+                    int rows_per_batch, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)batches * rows_per_batch) return;
+  const int b = int(row / rows_per_batch);
+  const __nv_bfloat16* xr = x + (long long)b * x_bs + (row - (long long)b * rows_per_batch) * dim;
+  float sum = 0.f;
+  for (int c = lane * 8; c < dim; c += 256) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += f[i];
+  }
+  const float mean = warp_sum(sum) / float(dim);
+  float sq = 0.f;
+  for (int c = lane * 8; c < dim; c += 256) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sq += (f[i] - mean) * (f[i] - mean);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / float(dim) + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+__global__ void __launch_bounds__(256)
+ln_mod_param_grad_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, const __nv_bfloat16* __restrict__ dy,
+                         long long dy_bs, const float2* __restrict__ stats, float* __restrict__ dscale,
+                         float* __restrict__ dshift, int rows_per_batch, int dim, int chunks_per_batch,
+                         int rows_per_chunk) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (col >= dim) return;
+  const int b = blockIdx.y / chunks_per_batch;
+  const int r0 = (blockIdx.y - b * chunks_per_batch) * rows_per_chunk;
+  const int r1 = min(rows_per_batch, r0 + rows_per_chunk);
+  const __nv_bfloat16* xb = x + (long long)b * x_bs;
+  const __nv_bfloat16* db = dy + (long long)b * dy_bs;
+  float s0 = 0.f, s1 = 0.f, h0 = 0.f, h1 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float2 st = stats[(long long)b * rows_per_batch + r];
+    const uint32_t xv = *reinterpret_cast<const uint32_t*>(xb + (long long)r * dim + col);
+    const uint32_t dv = *reinterpret_cast<const uint32_t*>(db + (long long)r * dim + col);
+    const float d0 = bf16_lo(dv), d1 = bf16_hi(dv);
+    s0 = fmaf(d0, (bf16_lo(xv) - st.x) * st.y, s0);
+    s1 = fmaf(d1, (bf16_hi(xv) - st.x) * st.y, s1);
+    h0 += d0;
+    h1 += d1;
+  }
+  atomicAdd(dscale + (long long)b * dim + col, s0);
+  atomicAdd(dscale + (long long)b * dim + col + 1, s1);
+  atomicAdd(dshift + (long long)b * dim + col, h0);
+  atomicAdd(dshift + (long long)b * dim + col + 1, h1);
+}
+
+// Gradients of a batch-row Linear  e[b, j] = sum_d W[j, d] * act(t[b, d]) + bias[j]  (the AdaLN modulation Linears):
+//   dW[j, d] += sum_b de[b, j] * act(t[b, d]),   dbias[j] += sum_b de[b, j];   act = SiLU when silu != 0
+__global__ void __launch_bounds__(256)
+rowlinear_param_grad_kernel(const float* __restrict__ de, long long de_ld, const __nv_bfloat16* __restrict__ t,
+                            long long t_ld, float* __restrict__ dw, long long dw_ld, float* __restrict__ dbias, int m,
+                            int n_out, int k_in, int silu_in) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (d >= k_in) return;
+  float acc = 0.f, bsum = 0.f;
+  for (int b = 0; b < m; ++b) {
+    float a = __bfloat162float(t[(long long)b * t_ld + d]);
+    if (silu_in) a = round_bf16(silu(a));
+    const float g = de[(long long)b * de_ld + j];
+    acc = fmaf(g, a, acc);
+    bsum += g;
+  }
+  dw[(long long)j * dw_ld + d] += acc;
+  if (d == 0 && dbias) dbias[j] += bsum;
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                      long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -707,6 +928,73 @@ int mse_rows_launch(const float* pred, const void* tgt_bf16, float* out, int bat
   AFB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * batch, stream));
   dim3 grid(64, batch);
   mse_rows_kernel<<<grid, 256, 0, stream>>>(pred, static_cast<const __nv_bfloat16*>(tgt_bf16), out, per_sample);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int policy_backward_launch(const afb_policy_args* a, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
+                           int accumulate, cudaStream_t stream) {
+  AFB_REQUIRE(a && a->head && tgt_bf16 && dhead && a->sigma_src && a->sigma_start && a->sigma_end,
+              "policy_backward: null argument");
+  AFB_REQUIRE(a->batch >= 1 && a->batch <= POLICY_MAX_BATCH && a->tokens >= 1, "policy_backward: bad batch/tokens");
+  if (a->num_gaussians != 16) {
+    set_last_error("policy_backward: only K=16 mixture components are built (got %d)", a->num_gaussians);
+    return AFB_ERR_UNSUPPORTED;
+  }
+  AFB_REQUIRE(a->head_ld >= 1148 && dh_ld >= 1148 && dh_ld % 2 == 0, "policy_backward: leading dims too small");
+  PolicyParams pp{};
+  for (int b = 0; b < a->batch; ++b) {
+    pp.dt_past[b] = a->sigma_src[b] - a->sigma_start[b];
+    pp.dt_step[b] = a->sigma_start[b] - a->sigma_end[b];
+    pp.small[b] = a->small ? a->small[b] : 0;
+  }
+  const long long tokens = (long long)a->batch * a->tokens;
+  policy_avg_u_bwd_k16_kernel<<<unsigned((tokens + 7) / 8), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(a->head), a->head_ld, static_cast<const __nv_bfloat16*>(tgt_bf16), dhead, dh_ld,
+      a->tokens, tokens, coef, a->eps > 0.f ? a->eps : 1e-4f, accumulate, pp);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream) {
+  AFB_REQUIRE(x && out && rows >= 1 && n >= 1, "colsum: bad arguments");
+  const int rpb = 256;
+  dim3 grid((n + 255) / 256, unsigned((rows + rpb - 1) / rpb));
+  colsum_f32_kernel<<<grid, 256, 0, stream>>>(x, ld, out, rows, n, rpb);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int ln_mod_param_grad_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws, float* dscale,
+                             float* dshift, int batches, int rows_per_batch, int dim, float eps, cudaStream_t stream) {
+  AFB_REQUIRE(x && dy && stats_ws && dscale && dshift, "ln_mod_param_grad: null pointer");
+  AFB_REQUIRE(batches >= 1 && rows_per_batch >= 1 && dim % 256 == 0, "ln_mod_param_grad: bad shape");
+  const long long rows = (long long)batches * rows_per_batch;
+  ln_row_stats_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_bs,
+                                                                   reinterpret_cast<float2*>(stats_ws), batches,
+                                                                   rows_per_batch, dim, eps);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  const int rpc = 64;
+  const int cpb = (rows_per_batch + rpc - 1) / rpc;
+  dim3 grid((dim / 2 + 255) / 256, unsigned(batches * cpb));
+  ln_mod_param_grad_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_bs,
+                                                     static_cast<const __nv_bfloat16*>(dy), dy_bs,
+                                                     reinterpret_cast<const float2*>(stats_ws), dscale, dshift,
+                                                     rows_per_batch, dim, cpb, rpc);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return AFB_OK;
+}
+
+int rowlinear_param_grad_launch(const float* de, int64_t de_ld, const void* t, int64_t t_ld, float* dw, int64_t dw_ld,
+                                float* dbias, int m, int n_out, int k_in, int silu_in, cudaStream_t stream) {
+  AFB_REQUIRE(de && t && dw && m >= 1 && n_out >= 1 && k_in >= 1, "rowlinear_param_grad: bad arguments");
+  dim3 grid((k_in + 255) / 256, n_out);
+  rowlinear_param_grad_kernel<<<grid, 256, 0, stream>>>(de, de_ld, static_cast<const __nv_bfloat16*>(t), t_ld, dw, dw_ld,
+                                                        dbias, m, n_out, k_in, silu_in);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

@@ -520,6 +520,23 @@ int afb_engine_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t im
   return AFB_OK;
 }
 
+int afb_engine_export(afb_engine* e, int32_t which, void* dst, int32_t batch, int32_t txt_len, int32_t img_len,
+                      void* stream) {
+  AFB_TRY(check_shapes(e, batch, txt_len, img_len));
+  AFB_REQUIRE(dst != nullptr && which >= 0 && which <= 2, "engine_export: bad arguments");
+  carve(e, static_cast<uint8_t*>(e->ws), batch, txt_len, img_len);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t D = e->desc.dim, S = size_t(txt_len) + img_len;
+  if (which == 2) {
+    AFB_CHECK_CUDA(cudaMemcpyAsync(dst, e->temb, size_t(batch) * D * 2, cudaMemcpyDeviceToDevice, s));
+    return AFB_OK;
+  }
+  const bf16* src = (which == 0 ? e->h : e->y) + size_t(txt_len) * D;  // image rows of the joint buffer
+  AFB_CHECK_CUDA(cudaMemcpy2DAsync(dst, size_t(img_len) * D * 2, src, S * D * 2, size_t(img_len) * D * 2, batch,
+                                   cudaMemcpyDeviceToDevice, s));
+  return AFB_OK;
+}
+
 int afb_engine_set_profiling(afb_engine* e, int32_t on) {
   AFB_REQUIRE(e != nullptr, "engine: null handle");
   e->profiling = on != 0;

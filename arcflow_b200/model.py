@@ -204,6 +204,17 @@ class EngineModelBase:
         _lib.check(self.lib.afb_engine_read_profile(self.handle, C.byref(p)), "afb_engine_read_profile")
         return {n: getattr(p, n) for n, _ in p._fields_}
 
+    def export_activation(self, which: str, batch: int, txt_len: int, img_len: int) -> torch.Tensor:
+        """Copy of an internal activation of the last forward: 'hidden' (final image hidden states), 'head_in'
+        (norm_out output = A operand of the head GEMM), 'temb'. Training keeps them for the backward."""
+        idx = {"hidden": 0, "head_in": 1, "temb": 2}[which]
+        D = self.cfg.inner_dim
+        shape = (batch, D) if idx == 2 else (batch, img_len, D)
+        out = torch.empty(shape, dtype=BF16, device=self.device)
+        _lib.check(self.lib.afb_engine_export(self.handle, idx, out.data_ptr(), batch, txt_len, img_len,
+                                              torch.cuda.current_stream().cuda_stream), "afb_engine_export")
+        return out
+
     def workspace_bytes(self, batch: int, txt_len: int, img_len: int) -> int:
         return int(self.lib.afb_engine_workspace_bytes(self.handle, batch, txt_len, img_len))
 

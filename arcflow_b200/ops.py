@@ -285,6 +285,107 @@ def policy_eval(head: torch.Tensor, mode: int, sigma_src, sigma_start, sigma_end
     return (out.reshape(shape), out_bf.reshape(shape)) if want_bf16 else out.reshape(shape)
 
 
+def policy_backward(head: torch.Tensor, tgt_u: torch.Tensor, sigma_src, sigma_start, sigma_end, coef: float,
+                    dhead: Optional[torch.Tensor] = None, small=None, num_gaussians: int = 16, eps: float = 1e-4):
+    """dL/dhead for L = coef/2 * sum (policy_average_u(head) - tgt_u)^2, accumulated into `dhead`
+    (fp32 [batch*tokens, head_ld]) when given, else written to a new tensor."""
+    lib = _lib.load()
+    _chk(head, BF16, "policy_backward head")
+    _chk(tgt_u, BF16, "policy_backward tgt_u")
+    batch = len(sigma_src)
+    tokens = head.shape[0] // batch
+    tg = tgt_u.reshape(-1, 64)
+    if head.dim() != 2 or head.stride(1) != 1 or not tg.is_contiguous() or tg.shape[0] != head.shape[0]:
+        raise AfbError("policy_backward: head must be [batch*tokens, head_ld], tgt_u contiguous [batch*tokens, 64]")
+    accumulate = dhead is not None
+    if dhead is None:
+        dhead = torch.zeros((head.shape[0], head.shape[1]), dtype=torch.float32, device=head.device)
+    _chk(dhead, torch.float32, "policy_backward dhead")
+    if dhead.shape != head.shape or dhead.stride(1) != 1:
+        raise AfbError("policy_backward: dhead must match head's shape")
+    a = _lib.PolicyArgs()
+    a.head, a.head_ld, a.batch, a.tokens = head.data_ptr(), head.stride(0), batch, tokens
+    a.num_gaussians, a.mode, a.eps = num_gaussians, _lib.AFB_POLICY_AVERAGE_U, eps
+    keep = [_host_floats(sigma_src, batch, "sigma_src"), _host_floats(sigma_start, batch, "sigma_start"),
+            _host_floats(sigma_end, batch, "sigma_end")]
+    a.sigma_src, a.sigma_start, a.sigma_end = keep
+    if small is not None:
+        sm = [int(bool(v)) for v in (small.tolist() if isinstance(small, torch.Tensor) else small)]
+        keep.append((C.c_uint8 * batch)(*sm))
+        a.small = keep[-1]
+    _lib.check(lib.afb_policy_backward(C.byref(a), tg.data_ptr(), dhead.data_ptr(), dhead.stride(0), float(coef),
+                                       int(accumulate), _stream()), "afb_policy_backward")
+    return dhead
+
+
+def colsum_f32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[n] += sum over rows of x[:, n] (fp32)."""
+    lib = _lib.load()
+    _chk(x, torch.float32, "colsum x")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise AfbError("colsum: x must be [rows, n] with contiguous columns")
+    if out is None:
+        out = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    _chk(out, torch.float32, "colsum out")
+    _lib.check(lib.afb_colsum_f32(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], _stream()),
+               "afb_colsum_f32")
+    return out
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[m, n] += sum_t a[t, m] * b[t, n] (weight gradients); a, b bf16 [tokens, *], out fp32 [m, n]."""
+    lib = _lib.load()
+    _chk(a, BF16, "gemm_tn a")
+    _chk(b, BF16, "gemm_tn b")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[0] != b.shape[0] or a.stride(1) != 1 or b.stride(1) != 1:
+        raise AfbError("gemm_tn: a [tokens, m] and b [tokens, n] with contiguous rows")
+    if out is None:
+        out = torch.zeros((a.shape[1], b.shape[1]), dtype=torch.float32, device=a.device)
+    _chk(out, torch.float32, "gemm_tn out")
+    if tuple(out.shape) != (a.shape[1], b.shape[1]) or out.stride(1) != 1:
+        raise AfbError("gemm_tn: out must be [m, n] fp32")
+    _lib.check(lib.afb_gemm_tn(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                               a.shape[0], a.shape[1], b.shape[1], _stream()), "afb_gemm_tn")
+    return out
+
+
+def ln_mod_param_grad(x: torch.Tensor, dy: torch.Tensor, dscale: Optional[torch.Tensor] = None,
+                      dshift: Optional[torch.Tensor] = None, eps: float = 1e-6):
+    """dscale[b, d] += sum_rows dy * LN(x), dshift[b, d] += sum_rows dy; x, dy bf16 [batches, rows, dim]."""
+    lib = _lib.load()
+    _chk(x, BF16, "ln_mod_param_grad x")
+    _chk(dy, BF16, "ln_mod_param_grad dy")
+    xptr, xld, xbs, nb, nr, dim = _rows3(x, "ln_mod_param_grad x")
+    dptr, dld, dbs, db_, dr, dd = _rows3(dy, "ln_mod_param_grad dy")
+    if (nb, nr, dim) != (db_, dr, dd) or xld != dim or dld != dim:
+        raise AfbError("ln_mod_param_grad: x and dy must share [batches, rows, dim] with contiguous rows")
+    if dscale is None:
+        dscale = torch.zeros((nb, dim), dtype=torch.float32, device=x.device)
+    if dshift is None:
+        dshift = torch.zeros((nb, dim), dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * nb * nr, dtype=torch.float32, device=x.device)
+    _lib.check(lib.afb_ln_mod_param_grad(xptr, xbs, dptr, dbs, ws.data_ptr(), dscale.data_ptr(), dshift.data_ptr(),
+                                         nb, nr, dim, eps, _stream()), "afb_ln_mod_param_grad")
+    return dscale, dshift
+
+
+def rowlinear_param_grad(de: torch.Tensor, t: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor] = None,
+                         silu_in: bool = True):
+    """dw[j, d] += sum_b de[b, j] * act(t[b, d]); dbias[j] += sum_b de[b, j] (fp32 grads of a batch-row Linear)."""
+    lib = _lib.load()
+    _chk(de, torch.float32, "rowlinear_param_grad de")
+    _chk(t, BF16, "rowlinear_param_grad t")
+    _chk(dw, torch.float32, "rowlinear_param_grad dw")
+    m, n_out = de.shape
+    k_in = t.shape[1]
+    if t.shape[0] != m or tuple(dw.shape) != (n_out, k_in) or de.stride(1) != 1 or t.stride(1) != 1 or dw.stride(1) != 1:
+        raise AfbError("rowlinear_param_grad: shape mismatch")
+    _lib.check(lib.afb_rowlinear_param_grad(de.data_ptr(), de.stride(0), t.data_ptr(), t.stride(0), dw.data_ptr(),
+                                            dw.stride(0), dbias.data_ptr() if dbias is not None else None, m, n_out,
+                                            k_in, int(silu_in), _stream()), "afb_rowlinear_param_grad")
+    return dw, dbias
+
+
 def axpy_rows(x: torch.Tensor, u: torch.Tensor, coef, want_bf16: bool = False):
     """out[b] = x[b] + coef[b] * u[b]; x fp32, u bf16 (a network output), coef host per-sample values."""
     lib = _lib.load()

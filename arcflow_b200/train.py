@@ -10,9 +10,13 @@ policy -> teacher velocity (afb_engine_forward on the tied teacher) -> afb_polic
 afb_axpy_rows (teacher Euler step)}, then one INTEGRATE to the segment end. Host code only does the O(batch)
 schedule arithmetic the reference also does on tiny tensors.
 
-NOT built yet (next round): the adapter-only backward (LoRA / heads / norm_out gradients through the
-frozen trunk), LoRA dropout (p = 0.05; this path is the p = 0 forward), optimizer / EMA / DDP all-reduce.
-`backward()` raises instead of silently doing nothing.
+Backward, round-1 state: `backward_heads()` returns the EXACT gradients of the adapter tensors that sit after the
+trunk — proj_out_means / proj_out_logweights / proj_out_loggamma (weight, bias) and norm_out.linear (weight, bias) —
+through afb_policy_backward (loss + average-velocity + softmax/log-softmax + integral term), afb_gemm_tn (dW = dY^T X on
+tcgen05), afb_gemm (dX through the head weights), afb_ln_mod_param_grad and afb_rowlinear_param_grad.
+NOT built yet (next round): the LoRA gradients, which need the backward through the frozen trunk
+(attention backward, dX GEMMs with transposed weights, LN/GELU/RMSNorm/RoPE backward, per-block recompute), LoRA dropout
+(p = 0.05; this path is the p = 0 forward), optimizer / EMA / DDP all-reduce. `backward()` raises for those.
 """
 from __future__ import annotations
 
@@ -55,7 +59,7 @@ class ArcFlowDistillStep:
 
     @torch.no_grad()
     def forward(self, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int], noise: torch.Tensor,
-                rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0):
+                rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0, save_for_backward: bool = False):
         """One train iteration, forward only. noise: fp32 packed tokens [B, S_i, 64] (the data-free x_t_src);
         rands: one dict of uniforms per student step (see draw_rollout_randoms). Returns (loss, log_vars, extras)."""
         cfg, st, te = self.cfg, self.student, self.teacher
@@ -87,6 +91,13 @@ class ArcFlowDistillStep:
 
             head = st.forward_heads(x_src, txt, pooled, sigma_src, g_student, grid_hw)
             head2 = head.reshape(-1, head.shape[-1])
+            saved = None
+            if save_for_backward:
+                St, Si = txt.shape[1], x_src.shape[1]
+                saved = dict(head=head2, seg=seg_f, sigma_src=sigma_src.clone(), states=[],
+                             hidden=st.export_activation("hidden", B, St, Si),
+                             head_in=st.export_activation("head_in", B, St, Si),
+                             temb=st.export_activation("temb", B, St, Si))
 
             rd = rands[step_id]
             p = cfg.get("gm_dropout", 0.0)
@@ -113,6 +124,9 @@ class ArcFlowDistillStep:
                 pred_u = ops.policy_eval(head2, _lib.AFB_POLICY_AVERAGE_U, sigma_src, sigma_a, warp_t(raw_end, self.shift),
                                          batch=B, small=small, num_gaussians=K, eps=eps)
                 mse_sum += ops.mse_rows(pred_u, tgt_u)
+                if saved is not None:
+                    saved["states"].append(dict(tgt_u=tgt_u, sigma_a=sigma_a.clone(), sigma_end=warp_t(raw_end, self.shift),
+                                                small=small.clone()))
                 x_t = ops.axpy_rows(x_a, tgt_u, sigma_b - sigma_a)
                 raw_t, sigma_t = raw_t_b, sigma_b
             # DiffusionMSELoss: 0.5 * flatmean -> x loss_scale -> mean over the 4B stacked samples
@@ -122,11 +136,55 @@ class ArcFlowDistillStep:
             loss_total += step_loss * seg_f
             log_vars[f"loss_diffusion_step{step_id}"] = step_loss
             log_vars["loss_diffusion"] = log_vars.get("loss_diffusion", 0.0) + step_loss * seg_f
-            extras["steps"].append(dict(x_t_dst=x_dst, head=head))
+            extras["steps"].append(dict(x_t_dst=x_dst, head=head, saved=saved))
             x_src, raw_t_src = x_dst, raw_t_dst
         return loss_total, log_vars, extras
 
+    @torch.no_grad()
+    def backward_heads(self, extras, head_weight_t: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Exact fp32 gradients of the summed train loss w.r.t. the post-trunk adapter tensors, from a forward run with
+        save_for_backward=True. head_weight_t: bf16 [D, head_n] = transpose of the fused head weight (dX operand)."""
+        cfg, st = self.cfg, self.student
+        n_states, eps = cfg["num_intermediate_states"], cfg.get("eps", 1e-4)
+        mcfg = st.cfg
+        D = mcfg.inner_dim
+        nm, nw, ng = mcfg.head_dims
+        head_n = st.weights.head_n
+        dev = st.device
+        g_w = torch.zeros(head_n, D, dtype=torch.float32, device=dev)
+        g_b = torch.zeros(head_n, dtype=torch.float32, device=dev)
+        g_nw = torch.zeros(2 * D, D, dtype=torch.float32, device=dev)
+        g_nb = torch.zeros(2 * D, dtype=torch.float32, device=dev)
+        for step in extras["steps"]:
+            sv = step["saved"]
+            if sv is None:
+                raise AfbError("backward_heads: run forward(save_for_backward=True) first")
+            head2 = sv["head"]
+            B = sv["temb"].shape[0]
+            tokens = head2.shape[0] // B
+            # d(loss)/d pred = seg * loss_scale * 0.5 * 2 (pred - tgt) / (elements per sample * n_states * B)
+            coef = sv["seg"] * self.loss_scale / (tokens * 64 * n_states * B)
+            dhead = None
+            for s in sv["states"]:
+                dhead = ops.policy_backward(head2, s["tgt_u"], sv["sigma_src"], s["sigma_a"], s["sigma_end"], coef,
+                                            dhead=dhead, small=s["small"], num_gaussians=st.num_gaussians, eps=eps)
+            ops.colsum_f32(dhead, g_b)
+            dhead_bf = dhead.to(torch.bfloat16)      # plumbing cast; the GEMM operands are bf16
+            x_in = sv["head_in"].reshape(-1, D)
+            ops.gemm_tn(dhead_bf, x_in, g_w)                                   # dW_heads += dHead^T y
+            dy = torch.empty(B, tokens, D, dtype=torch.bfloat16, device=dev)
+            ops.gemm(dhead_bf.reshape(B, tokens, head_n), head_weight_t, dy)   # dy = dHead W_heads
+            dscale, dshift = ops.ln_mod_param_grad(sv["hidden"], dy)
+            demb = torch.cat([dscale, dshift], dim=1).contiguous()             # AdaLayerNormContinuous: (scale, shift)
+            ops.rowlinear_param_grad(demb, sv["temb"], g_nw, g_nb, silu_in=True)
+        return {
+            "proj_out_means.weight": g_w[:nm], "proj_out_means.bias": g_b[:nm],
+            "proj_out_logweights.weight": g_w[nm:nm + nw], "proj_out_logweights.bias": g_b[nm:nm + nw],
+            "proj_out_loggamma.weight": g_w[nm + nw:nm + nw + ng], "proj_out_loggamma.bias": g_b[nm + nw:nm + nw + ng],
+            "norm_out.linear.weight": g_nw, "norm_out.linear.bias": g_nb,
+        }
+
     def backward(self, *a, **k):
         raise NotImplementedError(
-            "adapter-only backward (LoRA / heads / norm_out grads through the frozen trunk) is not built yet; "
-            "this round ships the train-step forward + loss (see DESIGN.md §1, rows a15-a18)")
+            "full adapter backward (LoRA grads through the frozen trunk) is not built yet; backward_heads() gives the "
+            "exact gradients of the heads and norm_out (see DESIGN.md §1, rows a15-a18)")

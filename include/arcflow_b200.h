@@ -33,6 +33,8 @@
 extern "C" {
 #endif
 
+typedef struct afb_engine afb_engine;
+
 #define AFB_OK 0
 #define AFB_ERR_INVALID (-1)
 #define AFB_ERR_CUDA (-2)
@@ -183,6 +185,33 @@ typedef struct afb_policy_args {
 } afb_policy_args;
 int afb_policy_eval(const afb_policy_args* args, void* stream);
 
+/* Backward of the velocity-matching loss through AVERAGE_U (args as afb_policy_eval with mode AVERAGE_U; drop_mask is
+ * ignored — the grad-carrying policy is never dropped, arcflow.py:183-188):
+ *   L = coef/2 * sum (policy_average_u(head) - tgt)^2   ->   dhead[tokens, dh_ld] (fp32, same column layout as head)
+ * gets dL/d(means | logits | loggamma); accumulate != 0 adds to the existing contents (the 4 roll-out states of one
+ * student step share one head tensor). The rounding of the bf16 log-softmax is treated as straight-through. */
+int afb_policy_backward(const afb_policy_args* args, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
+                        int32_t accumulate, void* stream);
+/* out[n] += sum_t x[t, n]; x fp32 [rows, ld] (bias gradients). out must be initialised by the caller. */
+int afb_colsum_f32(const float* x, int64_t ld, float* out, int64_t rows, int32_t n, void* stream);
+
+/* Weight-gradient ("TN") GEMM: out[m, n] += sum_t a[t, m] * b[t, n]; a bf16 [tokens, m] (ld a_ld), b bf16 [tokens, n],
+ * out fp32 [m, n] (must be initialised; results are ADDED). dW = dY^T X for the heads / LoRA pairs. */
+int afb_gemm_tn(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
+                int32_t m, int32_t n, void* stream);
+/* Parameter gradients of y = LN(x) * (1 + scale[b]) + shift[b]: dscale/dshift fp32 [batches, dim] are ADDED to.
+ * stats_ws: fp32 scratch of 2 * batches * rows_per_batch floats. x, dy: bf16 [batches, rows, dim] with batch strides. */
+int afb_ln_mod_param_grad(const void* x, int64_t x_batch_stride, const void* dy, int64_t dy_batch_stride, float* stats_ws,
+                          float* dscale, float* dshift, int32_t batches, int32_t rows_per_batch, int32_t dim, float eps,
+                          void* stream);
+/* Gradients of a batch-row Linear e = W act(t) + bias (AdaLN modulation Linears): dw[j, d] += sum_b de[b, j] act(t[b, d]),
+ * dbias[j] += sum_b de[b, j]. de fp32 [m, n_out], t bf16 [m, k_in], silu_in: act = SiLU (rounded to bf16 as in the forward). */
+int afb_rowlinear_param_grad(const float* de, int64_t de_ld, const void* t, int64_t t_ld, float* dw, int64_t dw_ld,
+                             float* dbias, int32_t m, int32_t n_out, int32_t k_in, int32_t silu_in, void* stream);
+/* Copies an internal activation of the LAST afb_engine_forward to caller memory (training saves them for the backward):
+ * which = 0 final image hidden states [batch, img_len, dim], 1 head input (norm_out output) [batch, img_len, dim], 2 temb [batch, dim]. */
+int afb_engine_export(afb_engine* e, int32_t which, void* dst, int32_t batch, int32_t txt_len, int32_t img_len, void* stream);
+
 /* out[b, :] = x[b, :] + coef[b] * u[b, :]  (teacher Euler step, arcflow.py:190). x/out fp32, u bf16, coef host. */
 int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16,
                   int32_t batch, int64_t per_sample, void* stream);
@@ -262,7 +291,6 @@ typedef struct afb_weights {
   const afb_single_block* sgl;
 } afb_weights;
 
-typedef struct afb_engine afb_engine;
 
 int afb_engine_create(const afb_model_desc* desc, afb_engine** out);
 void afb_engine_destroy(afb_engine* e);

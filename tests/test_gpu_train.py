@@ -70,6 +70,47 @@ def test_policy_eval_modes_match_train_oracle(ops):
     assert (got.cpu() - O.pack_latents(ref)).abs().max() < 1e-3 * ref.abs().max()
 
 
+@pytest.mark.parametrize("small", [[False, False, False], [False, True, False]])
+def test_policy_backward_matches_autograd(ops, small):
+    """dL/d(means, logits, loggamma) of L = coef/2 * sum (average_u - tgt)^2 vs torch autograd on the training oracle
+    (whose roll-out gradients are themselves pinned on the reference's, tests/test_oracle_train_golden.py)."""
+    g = np.load(ROOT / "tests" / "golden" / "reference_train_rollout.npz")
+    means, logw, gam, x = [torch.from_numpy(g[k]) for k in ("in_means", "in_logw", "in_gam", "in_x")]
+    gam = gam.clone()
+    gam[0, 0] = 0.0            # exercises the |z| < eps clamp (zero gradient through phi) and sign(0) := +1
+    B, K = x.shape[0], 16
+    head = _head_from_image_major(means, logw, gam).bfloat16()
+    tgt = torch.randn(B, 16, 64, generator=torch.Generator().manual_seed(3)).bfloat16()
+    s_src = torch.tensor([1.0, 0.9, 0.7619]); s_start = torch.tensor([0.95, 0.9, 0.5]); s_end = torch.tensor([0.8, 0.55, 0.4999])
+    coef = 0.37
+    dhead = ops.policy_backward(head.to(DEV), tgt.to(DEV), s_src, s_start, s_end, coef, small=small).cpu()
+    # oracle: leaves are the bf16 values the kernel sees; logits -> log_softmax -> bf16 round (straight-through) -> policy
+    m = means.clone().requires_grad_(True)
+    lg = logw.bfloat16().float().clone().requires_grad_(True)
+    gm = gam.bfloat16().float().clone().requires_grad_(True)
+    ls = lg.log_softmax(1)
+    ls = ls + (ls.bfloat16().float() - ls).detach()
+    mp = dict(means=m, logweights=ls, loggammas=gm)
+    r4 = lambda t: t.reshape(B, 1, 1, 1)
+    mean_u = (x - T.momentum_integration(mp, x, r4(s_src), r4(s_start), r4(s_end))) / r4(s_start - s_end).clamp(min=1e-4)
+    pred = torch.where(r4(torch.tensor(small)), T.policy_velocity(mp, r4(s_src), r4(s_start)), mean_u)
+    loss = 0.5 * coef * ((O.pack_latents(pred) - tgt.float()) ** 2).sum()
+    loss.backward()
+    ref = _head_from_image_major(m.grad, lg.grad, gm.grad)
+    for name, sl in (("means", slice(0, 1024)), ("logits", slice(1024, 1088)), ("loggamma", slice(1088, 1148))):
+        a, b = dhead[:, sl], ref[:, sl]
+        assert (a - b).abs().max() < 1e-3 * b.abs().max() + 1e-7, (name, (a - b).abs().max(), b.abs().max())
+    # accumulate flag adds on top
+    again = ops.policy_backward(head.to(DEV), tgt.to(DEV), s_src, s_start, s_end, coef, small=small, dhead=dhead.to(DEV))
+    assert torch.allclose(again.cpu()[:, :1148], 2 * dhead[:, :1148], rtol=1e-5, atol=1e-8)
+
+
+def test_colsum(ops):
+    x = torch.randn(1000, 1152, generator=torch.Generator().manual_seed(1))
+    out = ops.colsum_f32(x.to(DEV))
+    assert torch.allclose(out.cpu(), x.sum(0), rtol=1e-4, atol=1e-4)
+
+
 def test_axpy_and_mse_rows(ops):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(3, 10, 64, generator=g)
@@ -131,3 +172,55 @@ def test_train_step_forward_loss_parity(lib, iteration, p_drop):
     assert rel(x_dst, ref_dst) < 2e-2
     with pytest.raises(NotImplementedError):
         step.backward()
+
+
+def test_gemm_tn_parity(ops):
+    g = torch.Generator().manual_seed(2)
+    for T_, M, N in [(64, 128, 256), (1000, 1152, 512), (333, 256, 3072), (4608, 264, 72)]:
+        a = torch.randn(T_, M, generator=g).mul(0.5).bfloat16()
+        b = torch.randn(T_, N, generator=g).mul(0.5).bfloat16()
+        out = ops.gemm_tn(a.to(DEV), b.to(DEV))
+        ref = a.float().t() @ b.float()
+        assert rel(out, ref) < 1e-5, (T_, M, N, rel(out, ref))
+        again = ops.gemm_tn(a.to(DEV), b.to(DEV), out)       # accumulates
+        assert rel(again, 2 * ref) < 1e-5
+
+
+def test_ln_and_rowlinear_param_grads(ops):
+    g = torch.Generator().manual_seed(4)
+    B, R, D = 2, 70, 512
+    x = torch.randn(B, R, D, generator=g).mul(2).add(0.3).bfloat16()
+    dy = torch.randn(B, R, D, generator=g).bfloat16()
+    dscale, dshift = ops.ln_mod_param_grad(x.to(DEV), dy.to(DEV))
+    xh = O._ln(x.float())
+    assert rel(dscale, (dy.float() * xh).sum(1)) < 1e-4 and rel(dshift, dy.float().sum(1)) < 1e-5
+    de = torch.randn(B, 96, generator=g)
+    t = torch.randn(B, D, generator=g).bfloat16()
+    dw, db = torch.zeros(96, D), torch.zeros(96)
+    dw, db = ops.rowlinear_param_grad(de.to(DEV), t.to(DEV), dw.to(DEV), db.to(DEV), silu_in=True)
+    act = torch.nn.functional.silu(t.float()).bfloat16().float()
+    assert rel(dw, de.t() @ act) < 1e-5 and rel(db, de.sum(0)) < 1e-5
+
+
+def test_head_and_norm_out_gradients_match_autograd(lib):
+    """backward_heads(): exact grads of the post-trunk adapter tensors vs torch autograd through the training oracle."""
+    from arcflow_b200.train import ArcFlowDistillStep, draw_rollout_randoms
+    cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup()
+    tc = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, nfe=2,
+              timestep_ratio=1.0, total_substeps=128, eps=1e-4)
+    g = torch.Generator().manual_seed(77)
+    rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
+    step = ArcFlowDistillStep(student, teacher, tc)
+    loss, _, extras = step.forward(txt.to(DEV), pooled.to(DEV), grid, x.to(DEV), rands, iteration=700, save_for_backward=True)
+    names = ["proj_out_means.weight", "proj_out_means.bias", "proj_out_logweights.weight", "proj_out_logweights.bias",
+             "proj_out_loggamma.weight", "proj_out_loggamma.bias", "norm_out.linear.weight", "norm_out.linear.bias"]
+    head_w = torch.cat([sd["proj_out_means.weight"], sd["proj_out_logweights.weight"], sd["proj_out_loggamma.weight"],
+                        torch.zeros(4, cfg.inner_dim, dtype=torch.bfloat16)], 0)
+    grads = step.backward_heads(extras, head_w.t().contiguous().to(DEV))
+    ref_loss, _, ex = T.flux_train_forward(sd, extra, cfg, txt, pooled, grid, x, rands, 700, tc, dtype=torch.float32,
+                                           require_grad=names)
+    ref_loss.backward()
+    for n in names:
+        ref = ex["leaves"][n].grad
+        e = rel(grads[n], ref)
+        assert e < 3e-2, f"{n}: rel-L2 {e:.3e} (|ref| {ref.norm():.3e})"
