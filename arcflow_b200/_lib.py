@@ -122,6 +122,14 @@ class PolicyArgs(C.Structure):
 AFB_POLICY_INTEGRATE, AFB_POLICY_VELOCITY, AFB_POLICY_AVERAGE_U = 0, 1, 2
 
 
+class AdamwArgs(C.Structure):
+    _fields_ = [("params", _P), ("grads", _P), ("exp_avg", _P), ("exp_avg_sq", _P), ("ema", _P), ("bf16_shadow", _P),
+                ("n", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step", C.c_int32), ("max_norm", C.c_float), ("grad_norm_sq", _P),
+                ("skipped", _P), ("ema_momentum", C.c_float), ("ema_copy", C.c_int32),
+                ("lr_mult_begin", C.c_int64), ("lr_mult_end", C.c_int64), ("lr_mult", C.c_float)]
+
+
 class Profile(C.Structure):
     _fields_ = [("gemm_ms", C.c_double), ("attn_ms", C.c_double), ("gemm_flops", C.c_double),
                 ("attn_flops", C.c_double), ("gemm_launches", C.c_int64), ("attn_launches", C.c_int64)]
@@ -155,6 +163,8 @@ SIGNATURES = {
     "afb_rowlinear_param_grad": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, _P]),
     "afb_engine_export": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "afb_grad_norm_sq": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "afb_adamw_ema_step": (C.c_int, [C.POINTER(AdamwArgs), _P]),
     "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, _P]),
     "afb_mse_rows": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P]),
     "afb_engine_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_P)]),

@@ -27,6 +27,8 @@ int policy_eval_launch(const afb_policy_args* a, cudaStream_t stream);
 int policy_backward_launch(const afb_policy_args* a, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
                            int accumulate, cudaStream_t stream);
 int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
+int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream);
+int adamw_ema_launch(const afb_adamw_args* a, cudaStream_t stream);
 int gemm_tn_launch(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
                    int m, int n, cudaStream_t stream);
 int ln_mod_param_grad_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws, float* dscale,
@@ -109,6 +111,12 @@ int afb_rowlinear_param_grad(const float* de, int64_t de_ld, const void* t, int6
                              float* dbias, int32_t m, int32_t n_out, int32_t k_in, int32_t silu_in, void* stream) {
   return afb::rowlinear_param_grad_launch(de, de_ld, t, t_ld, dw, dw_ld, dbias, m, n_out, k_in, silu_in,
                                           static_cast<cudaStream_t>(stream));
+}
+int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream) {
+  return afb::grad_norm_sq_launch(grads, n, out, static_cast<cudaStream_t>(stream));
+}
+int afb_adamw_ema_step(const afb_adamw_args* args, void* stream) {
+  return afb::adamw_ema_launch(args, static_cast<cudaStream_t>(stream));
 }
 int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int32_t batch,
                   int64_t per_sample, void* stream) {

@@ -1,0 +1,128 @@
+// arcflow_b200 — the step glue after the backward as three HBM-bound passes over ONE flat fp32 parameter arena
+// (all trainable adapter tensors live back to back: params | grads | exp_avg | exp_avg_sq | ema):
+//   grad-norm^2 -> [clip, skip on NaN/Inf] + AdamW + Karras EMA lerp + bf16 shadow for the engine, fused.
+// Reference: BaseModel.step_optimizer (lakonlab/models/base.py:76-103: clip_grad_norm_(50) from iteration 100, skip the
+// step on a non-finite norm), optimizer AdamW8bit lr 1e-4 betas (0.9, 0.95) wd 0 with `proj_out_loggamma` lr x 0.1
+// (configs/flux/_ddp_train.py:13-26), ExponentialMovingAverageHookMod (lakonlab/runner/hooks/ema_hook.py:86-121:
+// ema = m * ema + (1 - m) * net, m = min((1 - 1/t)^(gamma+1), 1); straight copy before start_iter).
+// The 8-bit optimizer state of bitsandbytes is NOT reproduced (unpinned): state is fp32, torch.optim.AdamW math.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace afb {
+namespace {
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(g + i);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (long long e = i; e < n; ++e) acc += g[e] * g[e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(out, s);
+  }
+}
+
+struct AdamParams {
+  float lr, beta1, beta2, eps, weight_decay, bias1, bias2;  // bias_k = 1 - beta_k^step
+  float max_norm;      // <= 0: no clipping
+  float ema_momentum;  // < 0: EMA not touched; ema = m * ema + (1 - m) * p
+  int ema_copy;        // before start_iter: ema = p
+  long long lo_begin, lo_end;  // element range that uses lr * lo_mult (proj_out_loggamma)
+  float lo_mult;
+};
+
+__global__ void __launch_bounds__(256)
+adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 float* __restrict__ ema, __nv_bfloat16* __restrict__ shadow, long long n,
+                 const float* __restrict__ gnorm_sq, int* __restrict__ skipped, const AdamParams a) {
+  float clip = 1.0f;
+  if (a.max_norm > 0.f) {
+    const float norm = sqrtf(*gnorm_sq);
+    if (!isfinite(norm)) {  // reference: zero_grad + skip the optimizer step; EMA still runs afterwards
+      if (blockIdx.x == 0 && threadIdx.x == 0) *skipped = 1;
+      clip = -1.0f;
+    } else {
+      clip = fminf(1.0f, a.max_norm / (norm + 1e-6f));  // torch.nn.utils.clip_grad_norm_
+    }
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    if (clip >= 0.f) {
+      const float gi = g[i] * clip;
+      const float lr = (i >= a.lo_begin && i < a.lo_end) ? a.lr * a.lo_mult : a.lr;
+      w *= 1.0f - lr * a.weight_decay;
+      const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * gi;
+      const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      w -= lr * (mi / a.bias1) / (sqrtf(vi / a.bias2) + a.eps);
+      p[i] = w;
+    }
+    if (ema) {
+      if (a.ema_copy) ema[i] = w;
+      else if (a.ema_momentum >= 0.f) ema[i] = w + (ema[i] - w) * a.ema_momentum;
+    }
+    if (shadow) shadow[i] = __float2bfloat16_rn(w);
+  }
+}
+
+}  // namespace
+
+int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream) {
+  AFB_REQUIRE(g && out && n >= 1, "grad_norm_sq: bad arguments");
+  AFB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  int blocks = int((n / 4 + 255) / 256);
+  const int cap = device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<blocks, 256, 0, stream>>>(g, n, out);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int adamw_ema_launch(const afb_adamw_args* a, cudaStream_t stream) {
+  AFB_REQUIRE(a && a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->n >= 1, "adamw: bad arguments");
+  AFB_REQUIRE(a->step >= 1, "adamw: step counts from 1");
+  AFB_REQUIRE(a->max_norm <= 0.f || (a->grad_norm_sq && a->skipped), "adamw: clipping needs grad_norm_sq and skipped");
+  AdamParams k{};
+  k.lr = a->lr;
+  k.beta1 = a->beta1;
+  k.beta2 = a->beta2;
+  k.eps = a->eps;
+  k.weight_decay = a->weight_decay;
+  k.bias1 = 1.0f - powf(a->beta1, float(a->step));
+  k.bias2 = 1.0f - powf(a->beta2, float(a->step));
+  k.max_norm = a->max_norm;
+  k.ema_momentum = a->ema_momentum;
+  k.ema_copy = a->ema_copy;
+  k.lo_begin = a->lr_mult_begin;
+  k.lo_end = a->lr_mult_end;
+  k.lo_mult = a->lr_mult;
+  if (a->skipped) AFB_CHECK_CUDA(cudaMemsetAsync(a->skipped, 0, sizeof(int), stream));
+  int blocks = int((a->n + 255) / 256);
+  const int cap = device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adamw_ema_kernel<<<blocks, 256, 0, stream>>>(a->params, a->grads, a->exp_avg, a->exp_avg_sq, a->ema,
+                                               static_cast<__nv_bfloat16*>(a->bf16_shadow), a->n, a->grad_norm_sq,
+                                               a->skipped, k);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+}  // namespace afb

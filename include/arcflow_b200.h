@@ -218,6 +218,33 @@ int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* 
 /* out[b] = mean_i (pred[b, i] - tgt[b, i])^2 — mmgen mse_loss(reduction='flatmean'); pred fp32, tgt bf16, out device fp32 [batch]. */
 int afb_mse_rows(const float* pred, const void* tgt_bf16, float* out, int32_t batch, int64_t per_sample, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Step glue over ONE flat fp32 arena of all trainable adapter tensors (reference
+ * lakonlab/models/base.py:76-103 + configs/flux/_ddp_train.py:13-26 + lakonlab/runner/hooks/ema_hook.py:86-121).
+ * ---------------------------------------------------------------------------------------------- */
+/* out[0] = sum g^2 (device scalar, fp32). */
+int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream);
+
+typedef struct afb_adamw_args {
+  float* params;          /* fp32 [n], updated in place */
+  const float* grads;     /* fp32 [n] (already all-reduced / averaged) */
+  float* exp_avg;         /* fp32 [n] */
+  float* exp_avg_sq;      /* fp32 [n] */
+  float* ema;             /* fp32 [n] or NULL */
+  void* bf16_shadow;      /* bf16 [n] or NULL: rounded copy of the new params for the engine's packed weights */
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;           /* 1-based optimizer step (bias correction) */
+  float max_norm;         /* > 0: clip_grad_norm_ with *grad_norm_sq; a non-finite norm skips the update */
+  const float* grad_norm_sq; /* device scalar from afb_grad_norm_sq */
+  int32_t* skipped;       /* device flag, set to 1 when the update was skipped */
+  float ema_momentum;     /* ema = m * ema + (1 - m) * p; < 0 leaves ema untouched */
+  int32_t ema_copy;       /* 1: ema = p (before the EMA start iteration) */
+  int64_t lr_mult_begin, lr_mult_end; /* element range using lr * lr_mult (proj_out_loggamma: 0.1) */
+  float lr_mult;
+} afb_adamw_args;
+int afb_adamw_ema_step(const afb_adamw_args* args, void* stream);
+
 /* fp32 -> bf16 cast of a contiguous buffer. */
 int afb_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
 

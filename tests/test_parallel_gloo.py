@@ -61,3 +61,32 @@ def test_single_process_is_identity():
     x = torch.randn(3, 4, 64)
     assert shard_batch(x, 0, 1) is not None and torch.equal(shard_batch(x, 0, 1), x)
     assert torch.equal(gather_latents(x, 3), x)
+
+
+def _opt_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from arcflow_b200.optim import FlatAdamW
+        o = FlatAdamW.__new__(FlatAdamW)          # host-side logic only: the arena all-reduce (no CUDA on this box)
+        o.grads = torch.full((10,), float(rank + 1))
+        o.all_reduce_grads()
+        q.put((rank, o.grads.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_arena_all_reduce_is_a_mean_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_opt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, g in res:
+        assert g == [1.5] * 10
