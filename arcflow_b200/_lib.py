@@ -52,8 +52,16 @@ class AttnDesc(C.Structure):
         ("q_batch_stride", C.c_int64), ("k_batch_stride", C.c_int64),
         ("v_batch_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
-        ("scale", C.c_float),
+        ("scale", C.c_float), ("lse", C.c_void_p),
     ]
+
+
+class AttnBwdDesc(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("qkv_ld", C.c_int64), ("qkv_batch_stride", C.c_int64),
+                ("o", C.c_void_p), ("d_o", C.c_void_p), ("o_ld", C.c_int64), ("o_batch_stride", C.c_int64),
+                ("lse", C.c_void_p), ("delta_ws", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+                ("dqkv_ld", C.c_int64), ("dqkv_batch_stride", C.c_int64),
+                ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32), ("scale", C.c_float)]
 
 
 class ModelDesc(C.Structure):
@@ -142,6 +150,7 @@ SIGNATURES = {
     "afb_launch_count": (C.c_uint64, []),
     "afb_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "afb_attention": (C.c_int, [C.POINTER(AttnDesc), _P]),
+    "afb_attention_backward": (C.c_int, [C.POINTER(AttnBwdDesc), _P]),
     "afb_debug_attention_trace": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
     "afb_ln_modulate": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_float, _P]),

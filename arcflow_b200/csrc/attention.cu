@@ -53,6 +53,7 @@ struct AttnParams {
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* o;
   long long o_ld, o_batch_stride;
+  float* lse;  // optional [batch, heads, seq]: log2-domain logsumexp of the scaled scores (for the backward)
   int debug_mode;  // 0 = normal. Developer timing probes (results invalid): 1 = no exp, 2 = barriers only
 };
 
@@ -365,6 +366,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float inv_l = 1.0f / l;
     const int qrow = q0 + t * QT + row;
     const bool valid_row = qrow < p.seq;
+    if (p.lse && valid_row) p.lse[((long long)b * p.heads + h) * p.seq + qrow] = m * c + log2f(l);
     __nv_bfloat16* orow =
         p.o + (long long)b * p.o_batch_stride + (long long)qrow * p.o_ld + h * HD;
 #pragma unroll 1
@@ -430,6 +432,7 @@ int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
   p.o = static_cast<__nv_bfloat16*>(d->o);
   p.o_ld = d->o_ld;
   p.o_batch_stride = d->o_batch_stride;
+  p.lse = d->lse;
   {
     static int dbg = -1;
     if (dbg < 0) {

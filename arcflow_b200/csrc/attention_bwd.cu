@@ -1,0 +1,336 @@
+// arcflow_b200 — attention backward on tcgen05 (adapter-only backward needs the full activation-gradient chain
+// through the frozen attention; the reference gets it from torch autograd through F.scaled_dot_product_attention,
+// reached at lakonlab/models/architecture/arcflow/arcflux.py:180-230 under gradient checkpointing :181-189).
+//
+// Two kernels, no atomics and no cross-CTA reduction (7 MMAs per tile pair instead of FlashAttention-2's 5; simple first):
+//   dq kernel    CTA = 128 query rows of one (batch, head), loops over KV tiles:
+//                  S = Q K^T, dP = dO V^T (SS) -> P = exp2(c S - lse), dS = scale P (dP - delta)  -> dQ += dS K   (TS)
+//   dkdv kernel  CTA = 128 KV rows of one (batch, head), loops over Q tiles (everything transposed so the accumulators
+//                stay CTA-local): S^T = K Q^T, dP^T = V dO^T (SS) -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q       (TS)
+// P / dS are written back as packed bf16 into the TMEM columns of S / dP and consumed as the A operand; the B operands
+// of the TS products are the resident [rows, 128] tiles read MN-major (as V in the forward).
+// lse is the forward's log2-domain logsumexp, delta[b,h,s] = sum_d dO O (attn_delta_kernel).
+#include <math.h>
+
+#include "common.cuh"
+#include "../../include/arcflow_b200.h"
+
+namespace afb {
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int T = 128;  // tile rows (both q and kv)
+constexpr int HALF_BYTES = 128 * 64 * 2;
+constexpr int TILE_BYTES = 2 * HALF_BYTES;
+constexpr int BWD_THREADS = 256;  // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-7 math (one row per thread)
+constexpr size_t BWD_SMEM_BYTES = 1024 + 6 * size_t(TILE_BYTES) + 1024 + 256;
+
+struct BwdParams {
+  int seq, heads, batch;
+  float scale, scale_log2;
+  const float* lse;    // [batch, heads, seq]
+  const float* delta;  // [batch, heads, seq]
+  __nv_bfloat16* out0;  // dq kernel: dQ;  dkdv kernel: dK
+  __nv_bfloat16* out1;  // dkdv kernel: dV
+  long long out_ld, out_bs;
+};
+
+__device__ __forceinline__ void math_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Loads one [128 rows x 128 cols] bf16 tile (two SW128 halves) at rows r0.. of (b, h)
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int h, int r0, int b) {
+  for (int hf = 0; hf < 2; ++hf) tma_load_3d(dst + hf * HALF_BYTES, tm, bar, h * HD + hf * 64, r0, b);
+}
+
+// D[tmem] = A[smem, K-major over d] * B[smem, K-major over d]^T : 128 x 128 x 128
+__device__ __forceinline__ void mma_ss_128(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc) {
+  constexpr uint32_t idesc = make_idesc_bf16(T, T, false, false);
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk) {
+    const uint32_t off = ((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4;
+    umma_ss(d_tmem, a_desc + off, b_desc + off, idesc, kk > 0);
+  }
+}
+// D[tmem] (+)= A[tmem bf16, 128 x 128] * B[smem rows = K, 128 cols MN-major]
+__device__ __forceinline__ void mma_ts_128(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc_mn, bool acc) {
+  constexpr uint32_t idesc = make_idesc_bf16(T, HD, false, true);
+#pragma unroll
+  for (int kk = 0; kk < T / 16; ++kk)
+    umma_ts(d_tmem, a_tmem + kk * 8, b_desc_mn + uint64_t((kk * 2048) >> 4), idesc, (acc || kk > 0) ? 1u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MODE 0: dQ kernel (outer = q tile, inner = kv tiles).  MODE 1: dK/dV kernel (outer = kv tile, inner = q tiles).
+// smem: R0, R1 resident tiles (Q,dO | K,V), ring of 2 x (X, Y) inner tiles (K,V | Q,dO).
+// TMEM: [0,128) S or S^T, [128,256) dP or dP^T, [256,384) dQ | dV, [384,512) dK.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR0 = smem;                    // Q (dq) | K (dkdv)
+  uint8_t* sR1 = smem + TILE_BYTES;       // dO (dq) | V (dkdv)
+  uint8_t* sX = smem + 2 * TILE_BYTES;    // ring[2]: K (dq) | Q (dkdv)
+  uint8_t* sY = smem + 4 * TILE_BYTES;    // ring[2]: V (dq) | dO (dkdv)
+  float* sLse = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);  // [128] per-inner-tile lse (dkdv)
+  float* sDelta = sLse + 128;                                     // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES + 1024);
+  uint64_t* r_full = bars;          // resident tiles landed
+  uint64_t* x_full = bars + 1;      // [2]
+  uint64_t* x_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;      // S and dP ready (one commit after both MMAs)
+  uint64_t* p_full = bars + 6;      // dkdv: P^T written; dq: unused
+  uint64_t* ds_full = bars + 7;     // dS written
+  uint64_t* acc_done = bars + 8;    // last accumulating MMAs retired
+  uint64_t* iter_done = bars + 9;   // TS MMAs of this inner tile retired (S / dP columns reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * T;  // outer tile rows
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_inner = (p.seq + T - 1) / T;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmdO);
+    mbar_init(r_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(ds_full, 4);
+    mbar_init(acc_done, 1);
+    mbar_init(iter_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(r_full, 2 * TILE_BYTES);
+      load_tile(sR0, MODE == 0 ? &tmQ : &tmK, r_full, h, r0, b);
+      load_tile(sR1, MODE == 0 ? &tmdO : &tmV, r_full, h, r0, b);
+      for (int j = 0; j < n_inner; ++j) {
+        const int st = j & 1;
+        mbar_wait(&x_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&x_full[st], 2 * TILE_BYTES);
+        load_tile(sX + st * TILE_BYTES, MODE == 0 ? &tmK : &tmQ, &x_full[st], h, j * T, b);
+        load_tile(sY + st * TILE_BYTES, MODE == 0 ? &tmV : &tmdO, &x_full[st], h, j * T, b);
+      }
+    }
+  } else if (warp == 1) {
+    const uint64_t r0_k = make_sw128_desc(smem_u32(sR0), 16, 1024);   // K-major views (contraction over d)
+    const uint64_t r1_k = make_sw128_desc(smem_u32(sR1), 16, 1024);
+    const uint64_t x_k = make_sw128_desc(smem_u32(sX), 16, 1024);
+    const uint64_t y_k = make_sw128_desc(smem_u32(sY), 16, 1024);
+    const uint64_t x_mn = make_sw128_desc(smem_u32(sX), HALF_BYTES, 1024);  // MN-major views (contraction over rows)
+    const uint64_t y_mn = make_sw128_desc(smem_u32(sY), HALF_BYTES, 1024);
+    const uint32_t tS = tmem_base, tdP = tmem_base + 128, tA0 = tmem_base + 256, tA1 = tmem_base + 384;
+    mbar_wait(r_full, 0);
+    for (int j = 0; j < n_inner; ++j) {
+      const int st = j & 1;
+      const uint64_t so = uint64_t((st * TILE_BYTES) >> 4);
+      mbar_wait(&x_full[st], (j >> 1) & 1);
+      if (j > 0) mbar_wait(iter_done, (j - 1) & 1);  // previous dS / P consumed before S / dP are overwritten
+      tc_fence_after();
+      if (elect_one_sync()) {
+        if (MODE == 0) {
+          mma_ss_128(tS, r0_k, x_k + so);    // S    = Q  K_j^T
+          mma_ss_128(tdP, r1_k, y_k + so);   // dP   = dO V_j^T
+        } else {
+          mma_ss_128(tS, r0_k, x_k + so);    // S^T  = K  Q_i^T
+          mma_ss_128(tdP, r1_k, y_k + so);   // dP^T = V  dO_i^T
+        }
+        tc_commit(s_full);
+      }
+      __syncwarp();
+      if (MODE == 1) {
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        if (elect_one_sync()) mma_ts_128(tA0, tS, y_mn + so, j > 0);   // dV += P^T dO_i
+        __syncwarp();
+      }
+      mbar_wait(ds_full, j & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        if (MODE == 0) mma_ts_128(tA0, tS, x_mn + so, j > 0);          // dQ += dS K_j      (dS sits in the S columns)
+        else mma_ts_128(tA1, tdP, x_mn + so, j > 0);                   // dK += dS^T Q_i    (dS^T sits in the dP columns)
+        tc_commit(&x_empty[st]);
+        tc_commit(iter_done);
+        if (j == n_inner - 1) tc_commit(acc_done);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base, tdP = tS + 128;
+    const int grow = r0 + row;  // global row of this thread in the OUTER tile
+    const long long bh = ((long long)b * p.heads + h) * p.seq;
+    float my_lse = 0.f, my_delta = 0.f;
+    if (MODE == 0 && grow < p.seq) {
+      my_lse = p.lse[bh + grow];
+      my_delta = p.delta[bh + grow];
+    }
+    for (int j = 0; j < n_inner; ++j) {
+      if (MODE == 1) {  // per-column (query) statistics of this inner tile
+        const int q = j * T + row;
+        math_bar_sync();  // previous iteration's readers are done with sLse / sDelta
+        sLse[row] = q < p.seq ? p.lse[bh + q] : 0.f;
+        sDelta[row] = q < p.seq ? p.delta[bh + q] : 0.f;
+        math_bar_sync();
+      }
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t s[T];
+#pragma unroll
+      for (int i = 0; i < T / 32; ++i) tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
+      tmem_ld_wait();
+      const int valid = p.seq - j * T;  // inner columns beyond the sequence contribute nothing
+      uint32_t pk[T / 2];
+#pragma unroll
+      for (int i = 0; i < T; i += 2) {
+        const float l0 = MODE == 0 ? my_lse : sLse[i], l1 = MODE == 0 ? my_lse : sLse[i + 1];
+        float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -l0));
+        float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -l1));
+        if (i >= valid) p0 = 0.f;
+        if (i + 1 >= valid) p1 = 0.f;
+        if (grow >= p.seq) p0 = p1 = 0.f;  // padded outer rows (zero-filled by TMA) must not pollute dK/dV
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      if (MODE == 1) {  // P^T is an MMA operand here: publish it first (dV can start while dS^T is computed)
+#pragma unroll
+        for (int i = 0; i < T / 32; ++i) tmem_st_32x16(tS + i * 16, reinterpret_cast<const uint32_t(&)[16]>(pk[i * 16]));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // dS = scale * P * (dP - delta), 32 columns at a time
+#pragma unroll
+      for (int cidx = 0; cidx < T / 32; ++cidx) {
+        uint32_t d[32];
+        tmem_ld_32x32(tdP + cidx * 32, d);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int col = cidx * 32 + i;
+          const float d0 = MODE == 0 ? my_delta : sDelta[col], d1 = MODE == 0 ? my_delta : sDelta[col + 1];
+          const uint32_t pv = pk[col >> 1];
+          o[i >> 1] = pack_bf16x2(p.scale * bf16_lo(pv) * (__uint_as_float(d[i]) - d0),
+                                  p.scale * bf16_hi(pv) * (__uint_as_float(d[i + 1]) - d1));
+        }
+        tmem_st_32x16((MODE == 0 ? tS : tdP) + cidx * 16, o);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    // epilogue: accumulators -> bf16 -> global
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const bool valid_row = grow < p.seq;
+    for (int a = 0; a < (MODE == 0 ? 1 : 2); ++a) {
+      __nv_bfloat16* dst = (a == 0 ? (MODE == 0 ? p.out0 : p.out1) : p.out0);  // dkdv: accumulator 0 = dV, 1 = dK
+      __nv_bfloat16* orow = dst + (long long)b * p.out_bs + (long long)grow * p.out_ld + h * HD;
+      const uint32_t tA = tmem_base + lane_base + 256 + a * 128;
+#pragma unroll 1
+      for (int i = 0; i < HD / 32; ++i) {
+        uint32_t o[32];
+        tmem_ld_32x32(tA + i * 32, o);
+        tmem_ld_wait();
+        if (valid_row) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+            w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+            w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+            w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(orow + i * 32 + g * 8) = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int make_view_map(CUtensorMap* tm, const void* ptr, int64_t ld, int64_t bs, int batch, int seq, int heads) {
+  const uint64_t dims[3] = {uint64_t(heads) * HD, uint64_t(seq), uint64_t(batch)};
+  const uint64_t bstride = batch > 1 ? uint64_t(bs) : uint64_t(seq) * uint64_t(ld);
+  const uint64_t strides[2] = {uint64_t(ld) * 2, bstride * 2};
+  const uint32_t box[3] = {64, 128, 1};
+  return make_tmap_bf16(tm, ptr, 3, dims, strides, box);
+}
+
+}  // namespace
+
+int attn_delta_launch(const void* o, int64_t o_ld, int64_t o_bs, const void* d_o, int64_t do_ld, int64_t do_bs, float* delta,
+                      int batch, int seq, int heads, cudaStream_t stream);
+
+int attention_backward_launch(const afb_attn_bwd_desc* d, cudaStream_t stream) {
+  AFB_REQUIRE(d != nullptr, "attention_backward: null descriptor");
+  AFB_REQUIRE(d->q && d->k && d->v && d->o && d->d_o && d->lse && d->delta_ws && d->dq && d->dk && d->dv,
+              "attention_backward: null pointer");
+  AFB_REQUIRE(d->batch >= 1 && d->seq >= 1 && d->heads >= 1, "attention_backward: empty problem");
+  AFB_REQUIRE(d->dqkv_ld % 8 == 0, "attention_backward: gradient leading dim must be a multiple of 8");
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = make_view_map(&tq, d->q, d->qkv_ld, d->qkv_batch_stride, d->batch, d->seq, d->heads)) != AFB_OK) return rc;
+  if ((rc = make_view_map(&tk, d->k, d->qkv_ld, d->qkv_batch_stride, d->batch, d->seq, d->heads)) != AFB_OK) return rc;
+  if ((rc = make_view_map(&tv, d->v, d->qkv_ld, d->qkv_batch_stride, d->batch, d->seq, d->heads)) != AFB_OK) return rc;
+  if ((rc = make_view_map(&tdo, d->d_o, d->o_ld, d->o_batch_stride, d->batch, d->seq, d->heads)) != AFB_OK) return rc;
+  if ((rc = attn_delta_launch(d->o, d->o_ld, d->o_batch_stride, d->d_o, d->o_ld, d->o_batch_stride, d->delta_ws, d->batch,
+                              d->seq, d->heads, stream)) != AFB_OK)
+    return rc;
+  BwdParams p{};
+  p.seq = d->seq;
+  p.heads = d->heads;
+  p.batch = d->batch;
+  p.scale = d->scale > 0.f ? d->scale : 1.0f / sqrtf(float(HD));
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.lse = d->lse;
+  p.delta = d->delta_ws;
+  p.out_ld = d->dqkv_ld;
+  p.out_bs = d->dqkv_batch_stride;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BWD_SMEM_BYTES)));
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BWD_SMEM_BYTES)));
+    attr_set = true;
+  }
+  dim3 grid((d->seq + T - 1) / T, d->heads, d->batch);
+  p.out0 = static_cast<__nv_bfloat16*>(d->dq);
+  p.out1 = nullptr;
+  attention_bwd_kernel<0><<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  p.out0 = static_cast<__nv_bfloat16*>(d->dk);
+  p.out1 = static_cast<__nv_bfloat16*>(d->dv);
+  attention_bwd_kernel<1><<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return AFB_OK;
+}
+
+}  // namespace afb

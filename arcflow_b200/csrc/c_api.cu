@@ -9,6 +9,7 @@ void count_launch(int n);
 int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream);
 int attention_launch(const afb_attn_desc* d, cudaStream_t stream);
 int attention_read_trace(long long* out, int n);
+int attention_backward_launch(const afb_attn_bwd_desc* d, cudaStream_t stream);
 int ln_modulate_launch(const void* x, int64_t x_bs, void* y, int64_t y_bs, const void* scale,
                        const void* shift, int64_t mod_bs, int batches, int rows_per_batch, int dim,
                        float eps, cudaStream_t stream);
@@ -51,6 +52,9 @@ int afb_gemm(const afb_gemm_desc* desc, void* stream) {
   int rc = afb::gemm_launch(desc, static_cast<cudaStream_t>(stream));
   if (rc == AFB_OK) afb::count_launch(1);
   return rc;
+}
+int afb_attention_backward(const afb_attn_bwd_desc* desc, void* stream) {
+  return afb::attention_backward_launch(desc, static_cast<cudaStream_t>(stream));
 }
 int afb_debug_attention_trace(int64_t* out, int32_t n) {
   return afb::attention_read_trace(reinterpret_cast<long long*>(out), n);

@@ -717,6 +717,201 @@ rowlinear_param_grad_kernel(const float* __restrict__ de, long long de_ld, const
   if (d == 0 && dbias) dbias[j] += bsum;
 }
 
+// ================================================================================================
+// Backward of the streaming ops (adapter-only backward through the FROZEN trunk: only activation
+// gradients are needed here; the modulation vectors are treated as constants — see DESIGN.md).
+// ================================================================================================
+// dh[b, r, :] += LNmod_bwd(dy):  g = dy * (1 + scale[b]);  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
+template <int NCH>
+__global__ void __launch_bounds__(256)
+ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, const __nv_bfloat16* __restrict__ dy,
+                       long long dy_bs, __nv_bfloat16* __restrict__ dh, long long dh_bs,
+                       const __nv_bfloat16* __restrict__ scale, long long mod_bs, int batches, int rows_per_batch,
+                       float eps, int accumulate) {
+  constexpr int DIM = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)batches * rows_per_batch) return;
+  const int b = int(row / rows_per_batch);
+  const long long r = row - (long long)b * rows_per_batch;
+  const __nv_bfloat16* xr = x + (long long)b * x_bs + r * DIM;
+  const __nv_bfloat16* dr = dy + (long long)b * dy_bs + r * DIM;
+  __nv_bfloat16* hr = dh + (long long)b * dh_bs + r * DIM;
+  const __nv_bfloat16* sc = scale + (long long)b * mod_bs;
+  float v[NCH][8], g[NCH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8), v[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += v[c][i];
+  }
+  const float mean = warp_sum(sum) * (1.0f / DIM);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[c][i] -= mean;
+      sq += v[c][i] * v[c][i];
+    }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / DIM) + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float s8[8];
+    unpack8(*reinterpret_cast<const uint4*>(dr + c * 256 + lane * 8), g[c]);
+    unpack8(*reinterpret_cast<const uint4*>(sc + c * 256 + lane * 8), s8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[c][i] *= rstd;  // xhat
+      g[c][i] *= 1.0f + s8[i];
+      sg += g[c][i];
+      sgx = fmaf(g[c][i], v[c][i], sgx);
+    }
+  }
+  const float mg = warp_sum(sg) * (1.0f / DIM), mgx = warp_sum(sgx) * (1.0f / DIM);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - mg - v[c][i] * mgx);
+    if (accumulate) {
+      float old[8];
+      unpack8(*reinterpret_cast<const uint4*>(hr + c * 256 + lane * 8), old);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += old[i];
+    }
+    *reinterpret_cast<uint4*>(hr + c * 256 + lane * 8) = pack8(o);
+  }
+}
+
+// out[b, r, :] = vec[b, :] * x[b, r, :]   (du = gate (.) dh'), generic leading dims
+__global__ void __launch_bounds__(256)
+rowscale_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, long long x_bs, const __nv_bfloat16* __restrict__ vec,
+                long long vec_bs, __nv_bfloat16* __restrict__ out, long long out_ld, long long out_bs, int rows_per_batch,
+                int cols, long long total_chunks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int cpr = cols / 8;
+  const long long row = i / cpr;
+  const int c = int(i - row * cpr) * 8;
+  const int b = int(row / rows_per_batch);
+  const long long r = row - (long long)b * rows_per_batch;
+  float xv[8], gv[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(x + (long long)b * x_bs + r * x_ld + c), xv);
+  unpack8(*reinterpret_cast<const uint4*>(vec + (long long)b * vec_bs + c), gv);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = xv[k] * gv[k];
+  *reinterpret_cast<uint4*>(out + (long long)b * out_bs + r * out_ld + c) = pack8(o);
+}
+
+// dpre = dm * gelu_tanh'(pre)  (in place on dm), generic leading dims, rows x cols
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(__nv_bfloat16* __restrict__ dm, long long dm_ld, const __nv_bfloat16* __restrict__ pre, long long pre_ld,
+                int cols, long long total_chunks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int cpr = cols / 8;
+  const long long row = i / cpr;
+  const int c = int(i - row * cpr) * 8;
+  float d[8], x[8];
+  unpack8(*reinterpret_cast<const uint4*>(dm + row * dm_ld + c), d);
+  unpack8(*reinterpret_cast<const uint4*>(pre + row * pre_ld + c), x);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float t = tanhf(k0 * (x[k] + k1 * x[k] * x[k] * x[k]));
+    d[k] *= 0.5f * (1.0f + t) + 0.5f * x[k] * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x[k] * x[k]);
+  }
+  *reinterpret_cast<uint4*>(dm + row * dm_ld + c) = pack8(d);
+}
+
+// In place on the q|k columns of dqkv: d(out) -> d(raw) through RoPE^T and the per-head RMSNorm (weights frozen).
+// raw: the projection output BEFORE norm/rope (saved by the recompute). Same work split as rmsnorm_rope_kernel.
+__global__ void __launch_bounds__(256)
+rmsnorm_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restrict__ raw, long long ld, long long bs,
+                        int q_off, int k_off, int batches, int seq, int heads, int txt_rows,
+                        const __nv_bfloat16* __restrict__ wq_txt, const __nv_bfloat16* __restrict__ wk_txt,
+                        const __nv_bfloat16* __restrict__ wq_img, const __nv_bfloat16* __restrict__ wk_img,
+                        const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int hl = lane & 15, half = lane >> 4;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)batches * seq) return;
+  const int b = int(row / seq);
+  const int s = int(row - (long long)b * seq);
+  const long long base = (long long)b * bs + (long long)s * ld;
+  const bool is_txt = s < txt_rows;
+  float cs[8], sn[8], wq[8], wk[8];
+  {
+    const float4 c0 = *reinterpret_cast<const float4*>(cos_tab + (long long)s * 128 + hl * 8);
+    const float4 c1 = *reinterpret_cast<const float4*>(cos_tab + (long long)s * 128 + hl * 8 + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(sin_tab + (long long)s * 128 + hl * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(sin_tab + (long long)s * 128 + hl * 8 + 4);
+    cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+    sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+    unpack8(*reinterpret_cast<const uint4*>((is_txt ? wq_txt : wq_img) + hl * 8), wq);
+    unpack8(*reinterpret_cast<const uint4*>((is_txt ? wk_txt : wk_img) + hl * 8), wk);
+  }
+  const int slots = 2 * heads;
+  for (int s0 = 0; s0 < slots; s0 += 2) {
+    const int slot = s0 + half;
+    const bool act = slot < slots, is_k = slot >= heads;
+    const int h = is_k ? slot - heads : slot;
+    const long long off = base + (is_k ? k_off : q_off) + h * 128 + hl * 8;
+    float d[8], x[8];
+    unpack8(act ? *reinterpret_cast<const uint4*>(dqkv + off) : make_uint4(0, 0, 0, 0), d);
+    unpack8(act ? *reinterpret_cast<const uint4*>(raw + off) : make_uint4(0, 0, 0, 0), x);
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    const float rs = rsqrtf(ss * (1.0f / 128.0f) + eps);
+    float dyv[8], dot = 0.f;  // dy = d(x * rs) = RoPE^T(d) * w
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      const float da = d[e] * cs[e] + d[e + 1] * sn[e + 1];
+      const float db = -d[e] * sn[e] + d[e + 1] * cs[e + 1];
+      dyv[e] = da * (is_k ? wk[e] : wq[e]);
+      dyv[e + 1] = db * (is_k ? wk[e + 1] : wq[e + 1]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dot = fmaf(dyv[e], x[e] * rs, dot);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 8);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot *= (1.0f / 128.0f);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = rs * (dyv[e] - x[e] * rs * dot);
+    if (act) *reinterpret_cast<uint4*>(dqkv + off) = pack8(o);
+  }
+}
+
+// delta[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d]   (attention backward pre-pass); one warp per (row, head)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long o_ld, long long o_bs, const __nv_bfloat16* __restrict__ d_o,
+                  long long do_ld, long long do_bs, float* __restrict__ delta, int batch, int seq, int heads) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)batch * seq * heads) return;
+  const int h = int(w % heads);
+  const long long row = w / heads;
+  const int b = int(row / seq);
+  const int s = int(row - (long long)b * seq);
+  const uint2 ov = *reinterpret_cast<const uint2*>(o + (long long)b * o_bs + (long long)s * o_ld + h * 128 + lane * 4);
+  const uint2 dv = *reinterpret_cast<const uint2*>(d_o + (long long)b * do_bs + (long long)s * do_ld + h * 128 + lane * 4);
+  float acc = bf16_lo(ov.x) * bf16_lo(dv.x) + bf16_hi(ov.x) * bf16_hi(dv.x) + bf16_lo(ov.y) * bf16_lo(dv.y) +
+              bf16_hi(ov.y) * bf16_hi(dv.y);
+  acc = warp_sum(acc);
+  if (lane == 0) delta[((long long)b * heads + h) * seq + s] = acc;
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                      long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -995,6 +1190,88 @@ int rowlinear_param_grad_launch(const float* de, int64_t de_ld, const void* t, i
   dim3 grid((k_in + 255) / 256, n_out);
   rowlinear_param_grad_kernel<<<grid, 256, 0, stream>>>(de, de_ld, static_cast<const __nv_bfloat16*>(t), t_ld, dw, dw_ld,
                                                         dbias, m, n_out, k_in, silu_in);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int ln_modulate_bwd_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs,
+                           const void* scale, int64_t mod_bs, int batches, int rows_per_batch, int dim, float eps,
+                           int accumulate, cudaStream_t stream) {
+  AFB_REQUIRE(x && dy && dh && scale, "ln_modulate_bwd: null pointer");
+  AFB_REQUIRE(batches >= 1 && rows_per_batch >= 1 && dim % 256 == 0, "ln_modulate_bwd: bad shape");
+  const long long rows = (long long)batches * rows_per_batch;
+  const unsigned grid = unsigned((rows + 7) / 8);
+#define AFB_LNB_CASE(NCH)                                                                                       \
+  case NCH:                                                                                                     \
+    ln_modulate_bwd_kernel<NCH><<<grid, 256, 0, stream>>>(                                                      \
+        static_cast<const __nv_bfloat16*>(x), x_bs, static_cast<const __nv_bfloat16*>(dy), dy_bs,               \
+        static_cast<__nv_bfloat16*>(dh), dh_bs, static_cast<const __nv_bfloat16*>(scale), mod_bs, batches,      \
+        rows_per_batch, eps, accumulate);                                                                       \
+    break;
+  switch (dim / 256) {
+    AFB_LNB_CASE(1)
+    AFB_LNB_CASE(2)
+    AFB_LNB_CASE(4)
+    AFB_LNB_CASE(8)
+    AFB_LNB_CASE(12)
+    default:
+      set_last_error("ln_modulate_bwd: unsupported dim %d", dim);
+      return AFB_ERR_UNSUPPORTED;
+  }
+#undef AFB_LNB_CASE
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int rowscale_launch(const void* x, int64_t x_ld, int64_t x_bs, const void* vec, int64_t vec_bs, void* out, int64_t out_ld,
+                    int64_t out_bs, int batches, int rows_per_batch, int cols, cudaStream_t stream) {
+  AFB_REQUIRE(x && vec && out && batches >= 1 && rows_per_batch >= 1 && cols % 8 == 0, "rowscale: bad arguments");
+  const long long chunks = (long long)batches * rows_per_batch * (cols / 8);
+  rowscale_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), x_ld, x_bs, static_cast<const __nv_bfloat16*>(vec), vec_bs,
+      static_cast<__nv_bfloat16*>(out), out_ld, out_bs, rows_per_batch, cols, chunks);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int gelu_bwd_launch(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, int64_t rows, int cols, cudaStream_t stream) {
+  AFB_REQUIRE(dm && pre && rows >= 1 && cols % 8 == 0, "gelu_bwd: bad arguments");
+  const long long chunks = rows * (cols / 8);
+  gelu_bwd_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dm), dm_ld,
+                                                                     static_cast<const __nv_bfloat16*>(pre), pre_ld, cols,
+                                                                     chunks);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int rmsnorm_rope_bwd_launch(void* dqkv, const void* raw, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
+                            int heads, int txt_rows, const void* wq_txt, const void* wk_txt, const void* wq_img,
+                            const void* wk_img, const float* cos_tab, const float* sin_tab, float eps, cudaStream_t stream) {
+  AFB_REQUIRE(dqkv && raw && wq_img && wk_img && cos_tab && sin_tab, "rmsnorm_rope_bwd: null pointer");
+  AFB_REQUIRE(txt_rows == 0 || (wq_txt && wk_txt), "rmsnorm_rope_bwd: text norm weights missing");
+  AFB_REQUIRE(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "rmsnorm_rope_bwd: misaligned layout");
+  const long long rows = (long long)batches * seq;
+  rmsnorm_rope_bwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(
+      static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(raw), ld, bs, q_off, k_off, batches, seq, heads,
+      txt_rows, static_cast<const __nv_bfloat16*>(wq_txt ? wq_txt : wq_img),
+      static_cast<const __nv_bfloat16*>(wk_txt ? wk_txt : wk_img), static_cast<const __nv_bfloat16*>(wq_img),
+      static_cast<const __nv_bfloat16*>(wk_img), cos_tab, sin_tab, eps);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int attn_delta_launch(const void* o, int64_t o_ld, int64_t o_bs, const void* d_o, int64_t do_ld, int64_t do_bs, float* delta,
+                      int batch, int seq, int heads, cudaStream_t stream) {
+  AFB_REQUIRE(o && d_o && delta && batch >= 1 && seq >= 1 && heads >= 1, "attn_delta: bad arguments");
+  const long long warps = (long long)batch * seq * heads;
+  attn_delta_kernel<<<unsigned((warps + 7) / 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(o), o_ld, o_bs,
+                                                                  static_cast<const __nv_bfloat16*>(d_o), do_ld, do_bs, delta,
+                                                                  batch, seq, heads);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

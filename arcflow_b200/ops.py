@@ -92,8 +92,9 @@ def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.T
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None,
-              scale: float = 0.0) -> torch.Tensor:
-    """Joint non-causal attention. q/k/v: [batch, seq, heads*128] views (last dim contiguous)."""
+              scale: float = 0.0, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Joint non-causal attention. q/k/v: [batch, seq, heads*128] views (last dim contiguous).
+    lse (optional, fp32 [batch, heads, seq]) receives the log2-domain logsumexp needed by attention_backward."""
     lib = _lib.load()
     d = AttnDesc()
     shp = None
@@ -119,8 +120,44 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[t
     d.o, d.o_ld, d.o_batch_stride = optr, old, obs
     d.batch, d.seq, d.heads = nb, ns, nc // 128
     d.scale = scale
+    if lse is not None:
+        _chk(lse, torch.float32, "attention lse")
+        if tuple(lse.shape) != (nb, nc // 128, ns) or not lse.is_contiguous():
+            raise AfbError("attention: lse must be contiguous fp32 [batch, heads, seq]")
+        d.lse = lse.data_ptr()
     _lib.check(lib.afb_attention(C.byref(d), _stream()), "afb_attention")
     return out
+
+
+def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor,
+                       lse: torch.Tensor, scale: float = 0.0):
+    """dq, dk, dv (views of one fused [batch, seq, 3*heads*128] gradient buffer) for afb_attention.
+    q/k/v must share leading dim and batch stride (views of one fused buffer); o and d_o likewise."""
+    lib = _lib.load()
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o), ("d_o", d_o)):
+        _chk(t, BF16, f"attention_backward {name}")
+    qp, qld, qbs, nb, ns, nc = _rows3(q, "attention_backward q")
+    for t in (k, v):
+        _, ld, bs, b2, s2, c2 = _rows3(t, "attention_backward k/v")
+        if (ld, bs, b2, s2, c2) != (qld, qbs, nb, ns, nc):
+            raise AfbError("attention_backward: q/k/v must be views of one fused buffer")
+    op, old, obs, ob, os_, oc = _rows3(o, "attention_backward o")
+    dp, dld, dbs, db_, ds_, dc = _rows3(d_o, "attention_backward d_o")
+    if (old, obs) != (dld, dbs) or (ob, os_, oc) != (nb, ns, nc) or (db_, ds_, dc) != (nb, ns, nc):
+        raise AfbError("attention_backward: o and d_o must share shape and strides")
+    _chk(lse, torch.float32, "attention_backward lse")
+    heads = nc // 128
+    dqkv = torch.empty((nb, ns, 3 * nc), dtype=BF16, device=q.device)
+    delta = torch.empty((nb, heads, ns), dtype=torch.float32, device=q.device)
+    d = _lib.AttnBwdDesc()
+    d.q, d.k, d.v, d.qkv_ld, d.qkv_batch_stride = qp, k.data_ptr(), v.data_ptr(), qld, qbs
+    d.o, d.d_o, d.o_ld, d.o_batch_stride = op, dp, old, obs
+    d.lse, d.delta_ws = lse.data_ptr(), delta.data_ptr()
+    d.dq, d.dk, d.dv = dqkv.data_ptr(), dqkv[..., nc:].data_ptr(), dqkv[..., 2 * nc:].data_ptr()
+    d.dqkv_ld, d.dqkv_batch_stride = 3 * nc, ns * 3 * nc
+    d.batch, d.seq, d.heads, d.scale = nb, ns, heads, scale
+    _lib.check(lib.afb_attention_backward(C.byref(d), _stream()), "afb_attention_backward")
+    return dqkv[..., :nc], dqkv[..., nc:2 * nc], dqkv[..., 2 * nc:]
 
 
 def ln_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,

@@ -101,9 +101,28 @@ typedef struct afb_attn_desc {
   int64_t q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride;
   int32_t batch, seq, heads;
   float scale; /* 0 -> 1/sqrt(128) */
+  float* lse;  /* optional fp32 [batch, heads, seq]: log2-domain logsumexp of the scaled scores, saved for afb_attention_backward */
 } afb_attn_desc;
 
 int afb_attention(const afb_attn_desc* desc, void* stream);
+
+/* Backward of afb_attention: dq/dk/dv from d_o, given q, k, v, o and the forward's lse (fp32 [batch, heads, seq]).
+ * q/k/v share one leading dim / batch stride (views of a fused QKV buffer), o and d_o another; dq/dk/dv are written with
+ * dqkv_ld / dqkv_batch_stride (they may be the three thirds of one fused gradient buffer). delta_ws: fp32 scratch
+ * [batch, heads, seq]. Replaces torch autograd through F.scaled_dot_product_attention (arcflux.py:180-230). */
+typedef struct afb_attn_bwd_desc {
+  const void *q, *k, *v;
+  int64_t qkv_ld, qkv_batch_stride;
+  const void *o, *d_o;
+  int64_t o_ld, o_batch_stride;
+  const float* lse;
+  float* delta_ws;
+  void *dq, *dk, *dv;
+  int64_t dqkv_ld, dqkv_batch_stride;
+  int32_t batch, seq, heads;
+  float scale; /* 0 -> 1/sqrt(128) */
+} afb_attn_bwd_desc;
+int afb_attention_backward(const afb_attn_bwd_desc* desc, void* stream);
 /* Developer instrumentation: with env AFB_ATTN_DEBUG_MODE=7 the kernel records SM-clock stamps of the softmax
  * hand-shake of CTA 0 ([warpgroup 2][iteration 64][stamp 8] int64); this copies them out. Not a product path. */
 int afb_debug_attention_trace(int64_t* out, int32_t n);
