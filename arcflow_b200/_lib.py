@@ -11,7 +11,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libarcflow_b200.so"
 
 AFB_OK = 0
-AFB_EPI_BIAS, AFB_EPI_BIAS_GELU, AFB_EPI_BIAS_GATE_RES = 0, 1, 2
+AFB_EPI_BIAS, AFB_EPI_BIAS_GELU, AFB_EPI_BIAS_GATE_RES, AFB_EPI_BIAS_RES = 0, 1, 2, 3
 AFB_SL_SILU_IN, AFB_SL_ACCUMULATE = 1, 2
 AFB_ARCH_FLUX, AFB_ARCH_QWEN = 0, 1
 AFB_ABI_VERSION = 1
@@ -42,6 +42,10 @@ class GemmDesc(C.Structure):
         ("res", C.c_void_p),
         ("res_ld", C.c_int64),
         ("res_batch_stride", C.c_int64),
+        ("w_transposed", C.c_int32),
+        ("w_k", C.c_int32),
+        ("w2", C.c_void_p),
+        ("w2_ld", C.c_int64),
     ]
 
 
@@ -172,6 +176,13 @@ SIGNATURES = {
     "afb_rowlinear_param_grad": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, _P]),
     "afb_engine_export": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "afb_ln_modulate_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_float, C.c_int32, _P]),
+    "afb_rowscale": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                               C.c_int32, _P]),
+    "afb_gelu_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, _P]),
+    "afb_rmsnorm_rope_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, _P]),
     "afb_grad_norm_sq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "afb_adamw_ema_step": (C.c_int, [C.POINTER(AdamwArgs), _P]),
     "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, _P]),

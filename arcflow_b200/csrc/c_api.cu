@@ -29,6 +29,15 @@ int policy_backward_launch(const afb_policy_args* a, const void* tgt_bf16, float
                            int accumulate, cudaStream_t stream);
 int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream);
+int ln_modulate_bwd_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs,
+                           const void* scale, int64_t mod_bs, int batches, int rows_per_batch, int dim, float eps,
+                           int accumulate, cudaStream_t stream);
+int rowscale_launch(const void* x, int64_t x_ld, int64_t x_bs, const void* vec, int64_t vec_bs, void* out, int64_t out_ld,
+                    int64_t out_bs, int batches, int rows_per_batch, int cols, cudaStream_t stream);
+int gelu_bwd_launch(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, int64_t rows, int cols, cudaStream_t stream);
+int rmsnorm_rope_bwd_launch(void* dqkv, const void* raw, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
+                            int heads, int txt_rows, const void* wq_txt, const void* wk_txt, const void* wq_img,
+                            const void* wk_img, const float* cos_tab, const float* sin_tab, float eps, cudaStream_t stream);
 int adamw_ema_launch(const afb_adamw_args* a, cudaStream_t stream);
 int gemm_tn_launch(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
                    int m, int n, cudaStream_t stream);
@@ -115,6 +124,27 @@ int afb_rowlinear_param_grad(const float* de, int64_t de_ld, const void* t, int6
                              float* dbias, int32_t m, int32_t n_out, int32_t k_in, int32_t silu_in, void* stream) {
   return afb::rowlinear_param_grad_launch(de, de_ld, t, t_ld, dw, dw_ld, dbias, m, n_out, k_in, silu_in,
                                           static_cast<cudaStream_t>(stream));
+}
+int afb_ln_modulate_bwd(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs, const void* scale,
+                        int64_t mod_bs, int32_t batches, int32_t rows_per_batch, int32_t dim, float eps, int32_t accumulate,
+                        void* stream) {
+  return afb::ln_modulate_bwd_launch(x, x_bs, dy, dy_bs, dh, dh_bs, scale, mod_bs, batches, rows_per_batch, dim, eps,
+                                     accumulate, static_cast<cudaStream_t>(stream));
+}
+int afb_rowscale(const void* x, int64_t x_ld, int64_t x_bs, const void* vec, int64_t vec_bs, void* out, int64_t out_ld,
+                 int64_t out_bs, int32_t batches, int32_t rows_per_batch, int32_t cols, void* stream) {
+  return afb::rowscale_launch(x, x_ld, x_bs, vec, vec_bs, out, out_ld, out_bs, batches, rows_per_batch, cols,
+                              static_cast<cudaStream_t>(stream));
+}
+int afb_gelu_bwd(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, int64_t rows, int32_t cols, void* stream) {
+  return afb::gelu_bwd_launch(dm, dm_ld, pre, pre_ld, rows, cols, static_cast<cudaStream_t>(stream));
+}
+int afb_rmsnorm_rope_bwd(void* dqkv, const void* raw, int64_t ld, int64_t bs, int32_t q_off, int32_t k_off, int32_t batches,
+                         int32_t seq, int32_t heads, int32_t txt_rows, const void* wq_txt, const void* wk_txt,
+                         const void* wq_img, const void* wk_img, const float* cos_tab, const float* sin_tab, float eps,
+                         void* stream) {
+  return afb::rmsnorm_rope_bwd_launch(dqkv, raw, ld, bs, q_off, k_off, batches, seq, heads, txt_rows, wq_txt, wk_txt, wq_img,
+                                      wk_img, cos_tab, sin_tab, eps, static_cast<cudaStream_t>(stream));
 }
 int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream) {
   return afb::grad_norm_sq_launch(grads, n, out, static_cast<cudaStream_t>(stream));

@@ -48,6 +48,8 @@ struct GemmParams {
   int nk_end[3];  // cumulative K-block (64) boundaries of the A segments
   int num_m_tiles, num_n_tiles;
   int epi;
+  int w_trans;   // W given as [K, N] row-major (dX = dY W): MN-major B operand (2-CTA kernel only)
+  int nkb_w0;    // K blocks served by the first W buffer (the rest come from the second one; transposed mode)
   __nv_bfloat16* out;
   long long out_ld, out_batch_stride;
   const __nv_bfloat16* bias;
@@ -99,6 +101,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
           if (p.epi == AFB_EPI_BIAS_GELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_fast(f[i]);
+          } else if (p.epi == AFB_EPI_BIAS_RES) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] += bf16_lo(rw[i]);
+              f[2 * i + 1] += bf16_hi(rw[i]);
+            }
           } else if (p.epi == AFB_EPI_BIAS_GATE_RES) {
             const uint4 gv = *reinterpret_cast<const uint4*>(gate_b + n);
             const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
@@ -339,7 +349,7 @@ __device__ __forceinline__ void tc_commit_2cta_mcast(uint64_t* bar) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-                      const GemmParams p) {
+                      const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -362,6 +372,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     prefetch_tmap(&tmA1);
     prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmB1);
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx; bytes from both CTAs
       mbar_init(&empty_bar[s], 1);  // one multicast commit per phase
@@ -416,7 +427,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             kk = kb - p.nk_end[1];
           }
           tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
-          tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+          if (!p.w_trans) {
+            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+          } else {  // W is [K, N] row-major: two [64 k x 64 n] boxes, N contiguous (MN-major operand)
+            const CUtensorMap* bm = kb < p.nkb_w0 ? &tmB : &tmB1;
+            const int kr = (kb < p.nkb_w0 ? kb : kb - p.nkb_w0) * BK;
+            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, bm, leader_full, n0, kr);
+            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES + HALF_N * BK, bm, leader_full, n0 + 64, kr);
+          }
           if (++stage == STAGES2) {
             stage = 0;
             phase ^= 1;
@@ -427,9 +445,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (leader CTA only) ---------------------------
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, false, false);
+      const uint32_t idesc = p.w_trans ? make_idesc_bf16(2 * BM, BN, false, true) : make_idesc_bf16(2 * BM, BN, false, false);
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 16, 1024);
-      const uint64_t b_desc0 = make_sw128_desc(smem_u32(sB), 16, 1024);
+      // K-major W: 16-element k step = 32 bytes; MN-major W: 64-n chunks 8 KiB apart, k step = 16 rows of 128 bytes
+      const uint64_t b_desc0 = p.w_trans ? make_sw128_desc(smem_u32(sB), HALF_N * BK, 1024) : make_sw128_desc(smem_u32(sB), 16, 1024);
+      const uint64_t b_kstep = p.w_trans ? uint64_t(2048 >> 4) : uint64_t(2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -446,7 +466,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_ss_2cta(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
+              umma_ss_2cta(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k) * b_kstep, idesc,
                            (kb | k) != 0 ? 1u : 0u);
             tc_commit_2cta_mcast(&empty_bar[stage]);
           }
@@ -508,10 +528,11 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   AFB_REQUIRE(d->batches >= 1 && d->rows_per_batch >= 1, "gemm: empty M (batches=%d rows=%d)",
               d->batches, d->rows_per_batch);
   AFB_REQUIRE(d->n >= 8 && d->n % 8 == 0, "gemm: N=%d must be a positive multiple of 8", d->n);
-  AFB_REQUIRE(d->epilogue >= AFB_EPI_BIAS && d->epilogue <= AFB_EPI_BIAS_GATE_RES,
+  AFB_REQUIRE(d->epilogue >= AFB_EPI_BIAS && d->epilogue <= AFB_EPI_BIAS_RES,
               "gemm: unknown epilogue %d", d->epilogue);
   if (d->epilogue == AFB_EPI_BIAS_GATE_RES)
     AFB_REQUIRE(d->gate && d->res, "gemm: gate/residual epilogue needs gate and res pointers");
+  if (d->epilogue == AFB_EPI_BIAS_RES) AFB_REQUIRE(d->res, "gemm: residual epilogue needs the res pointer");
   AFB_REQUIRE(d->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
               "gemm: out must be 16-byte aligned with ld %% 8 == 0");
 
@@ -520,7 +541,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     const char* e = getenv("AFB_GEMM_1CTA");
     force_1cta = (e && atoi(e) != 0) ? 1 : 0;
   }
-  const bool two_cta = !force_1cta;
+  const bool two_cta = !force_1cta || d->w_transposed;
   const int tile_m = two_cta ? 2 * BM : BM;
 
   GemmParams p{};
@@ -549,14 +570,39 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     p.nk_end[s] = ktot / BK;
     ++nseg;
   }
-  CUtensorMap tmB;
-  {
+  CUtensorMap tmB, tmB1;
+  p.nkb_w0 = ktot / BK;
+  if (d->w_transposed) {
+    // W: [K rows, N cols] row-major, optionally continued by a second buffer w2 after w_k rows
+    const int k0 = d->w2 ? d->w_k : ktot;
+    AFB_REQUIRE(k0 > 0 && k0 % BK == 0 && k0 <= ktot, "gemm: transposed W: bad w_k=%d (K=%d)", k0, ktot);
+    AFB_REQUIRE(d->w_ld >= d->n && d->w_ld % 8 == 0, "gemm: transposed W: w_ld=%lld < N=%d", (long long)d->w_ld, d->n);
+    const uint32_t box[2] = {64, BK};
+    {
+      const uint64_t dims[2] = {uint64_t(d->n), uint64_t(k0)};
+      const uint64_t strides[1] = {uint64_t(d->w_ld) * 2};
+      int rc = make_tmap_bf16(&tmB, d->w, 2, dims, strides, box);
+      if (rc != AFB_OK) return rc;
+    }
+    tmB1 = tmB;
+    if (d->w2) {
+      AFB_REQUIRE(k0 < ktot && d->w2_ld >= d->n && d->w2_ld % 8 == 0, "gemm: transposed W: bad second W buffer");
+      const uint64_t dims[2] = {uint64_t(d->n), uint64_t(ktot - k0)};
+      const uint64_t strides[1] = {uint64_t(d->w2_ld) * 2};
+      int rc = make_tmap_bf16(&tmB1, d->w2, 2, dims, strides, box);
+      if (rc != AFB_OK) return rc;
+    }
+    p.w_trans = 1;
+    p.nkb_w0 = k0 / BK;
+  } else {
+    AFB_REQUIRE(d->w2 == nullptr, "gemm: a second W buffer needs w_transposed");
     const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->n)};
     const uint64_t strides[1] = {uint64_t(d->w_ld) * 2};
     const uint32_t box[2] = {BK, uint32_t(two_cta ? HALF_N : BN)};
     AFB_REQUIRE(d->w_ld >= ktot, "gemm: w_ld=%lld < total K=%d", (long long)d->w_ld, ktot);
     int rc = make_tmap_bf16(&tmB, d->w, 2, dims, strides, box);
     if (rc != AFB_OK) return rc;
+    tmB1 = tmB;
   }
 
   p.batches = d->batches;
@@ -590,7 +636,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     const int max_clusters = sms / 2;
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
     gemm_bf16_2cta_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2],
-                                                                                  tmB, p);
+                                                                                  tmB, tmB1, p);
   } else {
     const int grid = num_tiles < sms ? num_tiles : sms;
     gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);

@@ -40,11 +40,13 @@ def _rows3(t: torch.Tensor, name: str):
 
 def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.Tensor,
          bias: Optional[torch.Tensor] = None, epilogue: int = _lib.AFB_EPI_BIAS,
-         gate: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
+         gate: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, transposed: bool = False,
+         w2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b, r, :] = epi(sum_s a_s[b, r, :] @ w[:, koff_s : koff_s + K_s].T).
 
     `a` is one tensor or up to three K-segments sharing [batches, rows]; `w` is [N, sum K_s] (torch
     Linear layout); `gate` is [batches, N]; `res` has the shape of `out` and may alias it.
+    transposed=True: `w` is [K, N] (dX = dY W with the forward's [out, in] weight); `w2` [K2, N] continues the K rows.
     """
     lib = _lib.load()
     segs = [a] if isinstance(a, torch.Tensor) else list(a)
@@ -63,14 +65,25 @@ def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.T
     _chk(w, BF16, "gemm w")
     _chk(out, BF16, "gemm out")
     if w.dim() != 2 or w.stride(1) != 1:
-        raise AfbError("gemm: w must be [N, K] with contiguous K")
+        raise AfbError("gemm: w must be 2-D with a contiguous last dim")
     optr, old, obs, ob, orows, on = _rows3(out, "gemm out")
-    if (ob, orows) != (batches, rows) or on != w.shape[0]:
-        raise AfbError(f"gemm: out shape {tuple(out.shape)} does not match [{batches}, {rows}, {w.shape[0]}]")
-    if w.shape[1] != sum(s.shape[-1] for s in segs):
+    n_w = w.shape[1] if transposed else w.shape[0]
+    k_w = (w.shape[0] + (w2.shape[0] if w2 is not None else 0)) if transposed else w.shape[1]
+    if (ob, orows) != (batches, rows) or on != n_w:
+        raise AfbError(f"gemm: out shape {tuple(out.shape)} does not match [{batches}, {rows}, {n_w}]")
+    if k_w != sum(s.shape[-1] for s in segs):
         raise AfbError("gemm: w K does not match the A segments")
     d.batches, d.rows_per_batch = batches, rows
-    d.w, d.w_ld, d.n = w.data_ptr(), w.stride(0), w.shape[0]
+    d.w, d.w_ld, d.n = w.data_ptr(), w.stride(0), n_w
+    if transposed:
+        d.w_transposed, d.w_k = 1, w.shape[0]
+        if w2 is not None:
+            _chk(w2, BF16, "gemm w2")
+            if w2.dim() != 2 or w2.stride(1) != 1 or w2.shape[1] != n_w:
+                raise AfbError("gemm: w2 must be [K2, N]")
+            d.w2, d.w2_ld = w2.data_ptr(), w2.stride(0)
+    elif w2 is not None:
+        raise AfbError("gemm: w2 needs transposed=True")
     d.epilogue = epilogue
     d.out, d.out_ld, d.out_batch_stride = optr, old, obs
     if bias is not None:
@@ -451,3 +464,63 @@ def mse_rows(pred: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:
     _lib.check(lib.afb_mse_rows(pred.data_ptr(), tgt.data_ptr(), out.data_ptr(), batch, pred.numel() // batch,
                                 _stream()), "afb_mse_rows")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# activation-gradient kernels of the streaming ops
+# ------------------------------------------------------------------------------------------------
+def ln_modulate_bwd(x: torch.Tensor, dy: torch.Tensor, scale: torch.Tensor, dh: Optional[torch.Tensor] = None,
+                    eps: float = 1e-6) -> torch.Tensor:
+    """dh (+)= LNmod_bwd(dy); x, dy, dh: bf16 [batches, rows, dim]; scale: [batches, dim] view. dh given -> accumulate."""
+    lib = _lib.load()
+    xp, xld, xbs, nb, nr, dim = _rows3(x, "ln_modulate_bwd x")
+    dp, dld, dbs, *_ = _rows3(dy, "ln_modulate_bwd dy")
+    acc = dh is not None
+    if dh is None:
+        dh = torch.empty((nb, nr, dim), dtype=BF16, device=x.device)
+    hp, hld, hbs, *_ = _rows3(dh, "ln_modulate_bwd dh")
+    for t in (x, dy, dh, scale):
+        _chk(t, BF16, "ln_modulate_bwd")
+    if xld != dim or dld != dim or hld != dim:
+        raise AfbError("ln_modulate_bwd: rows must be contiguous")
+    _lib.check(lib.afb_ln_modulate_bwd(xp, xbs, dp, dbs, hp, hbs, scale.data_ptr(), scale.stride(0), nb, nr, dim, eps,
+                                       int(acc), _stream()), "afb_ln_modulate_bwd")
+    return dh
+
+
+def rowscale(x: torch.Tensor, vec: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    xp, xld, xbs, nb, nr, cols = _rows3(x, "rowscale x")
+    if out is None:
+        out = torch.empty((nb, nr, cols), dtype=BF16, device=x.device)
+    op, old, obs, *_ = _rows3(out, "rowscale out")
+    _chk(x, BF16, "rowscale x"); _chk(vec, BF16, "rowscale vec"); _chk(out, BF16, "rowscale out")
+    _lib.check(lib.afb_rowscale(xp, xld, xbs, vec.data_ptr(), vec.stride(0), op, old, obs, nb, nr, cols, _stream()),
+               "afb_rowscale")
+    return out
+
+
+def gelu_bwd(dm: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    """In place: dm *= gelu_tanh'(pre); 2-D views [rows, cols] (any leading dim)."""
+    lib = _lib.load()
+    _chk(dm, BF16, "gelu_bwd dm"); _chk(pre, BF16, "gelu_bwd pre")
+    if dm.dim() != 2 or pre.shape != dm.shape or dm.stride(1) != 1 or pre.stride(1) != 1:
+        raise AfbError("gelu_bwd: need 2-D [rows, cols] views with contiguous columns")
+    _lib.check(lib.afb_gelu_bwd(dm.data_ptr(), dm.stride(0), pre.data_ptr(), pre.stride(0), dm.shape[0], dm.shape[1],
+                                _stream()), "afb_gelu_bwd")
+    return dm
+
+
+def rmsnorm_rope_bwd(dqkv: torch.Tensor, raw: torch.Tensor, q_off: int, k_off: int, heads: int, txt_rows: int,
+                     wq_img, wk_img, cos, sin, wq_txt=None, wk_txt=None, eps: float = 1e-6) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(dqkv, BF16, "rmsnorm_rope_bwd dqkv"); _chk(raw, BF16, "rmsnorm_rope_bwd raw")
+    ptr, ld, bs, nb, ns, _ = _rows3(dqkv, "rmsnorm_rope_bwd dqkv")
+    rp, rld, rbs, *_ = _rows3(raw, "rmsnorm_rope_bwd raw")
+    if (rld, rbs) != (ld, bs):
+        raise AfbError("rmsnorm_rope_bwd: dqkv and raw must share strides")
+    _lib.check(lib.afb_rmsnorm_rope_bwd(
+        ptr, rp, ld, bs, q_off, k_off, nb, ns, heads, txt_rows,
+        wq_txt.data_ptr() if wq_txt is not None else None, wk_txt.data_ptr() if wk_txt is not None else None,
+        wq_img.data_ptr(), wk_img.data_ptr(), cos.data_ptr(), sin.data_ptr(), eps, _stream()), "afb_rmsnorm_rope_bwd")
+    return dqkv

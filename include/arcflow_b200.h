@@ -54,7 +54,8 @@ uint64_t afb_launch_count(void);
 enum {
   AFB_EPI_BIAS = 0,          /* y + bias                                   (bias may be NULL)        */
   AFB_EPI_BIAS_GELU = 1,     /* gelu_tanh(y + bias)                                                   */
-  AFB_EPI_BIAS_GATE_RES = 2  /* res + gate[b, n] * (y + bias)              (AdaLN-Zero gate+residual) */
+  AFB_EPI_BIAS_GATE_RES = 2, /* res + gate[b, n] * (y + bias)              (AdaLN-Zero gate+residual) */
+  AFB_EPI_BIAS_RES = 3       /* res + y + bias                             (gradient accumulation)   */
 };
 
 typedef struct afb_gemm_desc {
@@ -82,6 +83,13 @@ typedef struct afb_gemm_desc {
   const void* res; /* bf16, same shape as out; may alias out */
   int64_t res_ld;
   int64_t res_batch_stride;
+  /* Activation-gradient form (dX = dY W): w_transposed != 0 reads W as bf16 [K, n] row-major (leading dim w_ld >= n),
+   * i.e. the forward's [out, in] Linear weight used without a transposed copy. The K rows may continue in a second
+   * buffer w2 (leading dim w2_ld) after the first w_k rows (dX = dY W + dT A_lora in one accumulation). */
+  int32_t w_transposed;
+  int32_t w_k;
+  const void* w2;
+  int64_t w2_ld;
 } afb_gemm_desc;
 
 int afb_gemm(const afb_gemm_desc* desc, void* stream);
@@ -213,6 +221,22 @@ int afb_policy_backward(const afb_policy_args* args, const void* tgt_bf16, float
                         int32_t accumulate, void* stream);
 /* out[n] += sum_t x[t, n]; x fp32 [rows, ld] (bias gradients). out must be initialised by the caller. */
 int afb_colsum_f32(const float* x, int64_t ld, float* out, int64_t rows, int32_t n, void* stream);
+
+/* Activation-gradient kernels of the streaming ops (the trunk is frozen: modulation vectors are constants here).
+ *  afb_ln_modulate_bwd   dh[b,r,:] (+)= d/dx [LN(x) * (1 + scale[b]) + shift[b]] applied to dy
+ *  afb_rowscale          out[b,r,:] = vec[b,:] * x[b,r,:]                         (du = gate (.) dh')
+ *  afb_gelu_bwd          dm[r,:] *= gelu_tanh'(pre[r,:])                          (in place)
+ *  afb_rmsnorm_rope_bwd  in place on the q|k columns of dqkv: gradient w.r.t. the projection output `raw` */
+int afb_ln_modulate_bwd(const void* x, int64_t x_batch_stride, const void* dy, int64_t dy_batch_stride, void* dh,
+                        int64_t dh_batch_stride, const void* scale, int64_t mod_batch_stride, int32_t batches,
+                        int32_t rows_per_batch, int32_t dim, float eps, int32_t accumulate, void* stream);
+int afb_rowscale(const void* x, int64_t x_ld, int64_t x_batch_stride, const void* vec, int64_t vec_batch_stride, void* out,
+                 int64_t out_ld, int64_t out_batch_stride, int32_t batches, int32_t rows_per_batch, int32_t cols, void* stream);
+int afb_gelu_bwd(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, int64_t rows, int32_t cols, void* stream);
+int afb_rmsnorm_rope_bwd(void* dqkv, const void* raw, int64_t ld, int64_t batch_stride, int32_t q_off, int32_t k_off,
+                         int32_t batches, int32_t seq, int32_t heads, int32_t txt_rows, const void* wq_txt,
+                         const void* wk_txt, const void* wq_img, const void* wk_img, const float* cos_tab,
+                         const float* sin_tab, float eps, void* stream);
 
 /* Weight-gradient ("TN") GEMM: out[m, n] += sum_t a[t, m] * b[t, n]; a bf16 [tokens, m] (ld a_ld), b bf16 [tokens, n],
  * out fp32 [m, n] (must be initialised; results are ADDED). dW = dY^T X for the heads / LoRA pairs. */
