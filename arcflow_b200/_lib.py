@@ -142,6 +142,20 @@ class AdamwArgs(C.Structure):
                 ("lr_mult_begin", C.c_int64), ("lr_mult_end", C.c_int64), ("lr_mult", C.c_float)]
 
 
+class DoubleBlockGrads(C.Structure):
+    _fields_ = [(n, _P) for n in ("img_up_la", "img_up_lb", "img_down_la", "img_down_lb",
+                                  "txt_up_la", "txt_up_lb", "txt_down_la", "txt_down_lb")]
+
+
+class SingleBlockGrads(C.Structure):
+    _fields_ = [(n, _P) for n in ("mlp_la", "mlp_lb", "out_la", "out_lb")]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [("fwd", ForwardArgs), ("d_head_in", _P), ("dbl", C.POINTER(DoubleBlockGrads)),
+                ("sgl", C.POINTER(SingleBlockGrads)), ("d_mod", _P)]
+
+
 class Profile(C.Structure):
     _fields_ = [("gemm_ms", C.c_double), ("attn_ms", C.c_double), ("gemm_flops", C.c_double),
                 ("attn_flops", C.c_double), ("gemm_launches", C.c_int64), ("attn_launches", C.c_int64)]
@@ -183,6 +197,9 @@ SIGNATURES = {
     "afb_gelu_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, _P]),
     "afb_rmsnorm_rope_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, _P]),
+    "afb_engine_train_reserve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "afb_engine_forward_train": (C.c_int, [_P, C.POINTER(ForwardArgs), _P]),
+    "afb_engine_backward": (C.c_int, [_P, C.POINTER(BackwardArgs), _P]),
     "afb_grad_norm_sq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "afb_adamw_ema_step": (C.c_int, [C.POINTER(AdamwArgs), _P]),
     "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, _P]),

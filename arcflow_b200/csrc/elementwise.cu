@@ -827,6 +827,27 @@ gelu_bwd_kernel(__nv_bfloat16* __restrict__ dm, long long dm_ld, const __nv_bflo
   *reinterpret_cast<uint4*>(dm + row * dm_ld + c) = pack8(d);
 }
 
+// out = gelu_tanh(pre) (the recompute's copy of the GEMM's fused GELU epilogue; tanh.approx like gemm.cu)
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, long long pre_ld, __nv_bfloat16* __restrict__ out, long long out_ld,
+                int cols, long long total_chunks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int cpr = cols / 8;
+  const long long row = i / cpr;
+  const int c = int(i - row * cpr) * 8;
+  float x[8];
+  unpack8(*reinterpret_cast<const uint4*>(pre + row * pre_ld + c), x);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k0 * (x[k] + k1 * x[k] * x[k] * x[k])));
+    x[k] = 0.5f * x[k] * (1.0f + t);
+  }
+  *reinterpret_cast<uint4*>(out + row * out_ld + c) = pack8(x);
+}
+
 // In place on the q|k columns of dqkv: d(out) -> d(raw) through RoPE^T and the per-head RMSNorm (weights frozen).
 // raw: the projection output BEFORE norm/rope (saved by the recompute). Same work split as rmsnorm_rope_kernel.
 __global__ void __launch_bounds__(256)
@@ -1243,6 +1264,16 @@ int gelu_bwd_launch(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, in
   gelu_bwd_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dm), dm_ld,
                                                                      static_cast<const __nv_bfloat16*>(pre), pre_ld, cols,
                                                                      chunks);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int gelu_fwd_launch(const void* pre, int64_t pre_ld, void* out, int64_t out_ld, int64_t rows, int cols, cudaStream_t stream) {
+  AFB_REQUIRE(pre && out && rows >= 1 && cols % 8 == 0, "gelu_fwd: bad arguments");
+  const long long chunks = rows * (cols / 8);
+  gelu_fwd_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(pre), pre_ld,
+                                                                     static_cast<__nv_bfloat16*>(out), out_ld, cols, chunks);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

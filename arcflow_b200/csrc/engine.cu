@@ -44,6 +44,20 @@ int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t str
 int fill_f32_launch(float* p, float v, int n, cudaStream_t stream);
 int rmsnorm_rows_launch(const void* x, void* y, const void* w, int64_t rows, int dim, float eps,
                         cudaStream_t stream);
+// training path
+int attention_backward_launch(const afb_attn_bwd_desc* d, cudaStream_t stream);
+int gemm_tn_launch(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
+                   int m, int n, cudaStream_t stream);
+int ln_modulate_bwd_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs,
+                           const void* scale, int64_t mod_bs, int batches, int rows_per_batch, int dim, float eps,
+                           int accumulate, cudaStream_t stream);
+int rowscale_launch(const void* x, int64_t x_ld, int64_t x_bs, const void* vec, int64_t vec_bs, void* out, int64_t out_ld,
+                    int64_t out_bs, int batches, int rows_per_batch, int cols, cudaStream_t stream);
+int gelu_bwd_launch(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, int64_t rows, int cols, cudaStream_t stream);
+int gelu_fwd_launch(const void* pre, int64_t pre_ld, void* out, int64_t out_ld, int64_t rows, int cols, cudaStream_t stream);
+int rmsnorm_rope_bwd_launch(void* dqkv, const void* raw, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
+                            int heads, int txt_rows, const void* wq_txt, const void* wk_txt, const void* wq_img,
+                            const void* wk_img, const float* cos_tab, const float* sin_tab, float eps, cudaStream_t stream);
 }  // namespace afb
 
 using bf16 = __nv_bfloat16;
@@ -64,6 +78,14 @@ struct afb_engine {
        *lt1 = nullptr, *mod = nullptr, *temb = nullptr, *tmp = nullptr, *tproj = nullptr,
        *ltv = nullptr, *head = nullptr, *x_bf16 = nullptr, *txtn = nullptr, *alt_nm = nullptr;
   float *t_dev = nullptr, *g_dev = nullptr;
+  // training workspace (afb_engine_train_reserve): checkpoints + recompute / gradient buffers
+  void* tws = nullptr;
+  size_t tws_bytes = 0;
+  int tcap_batch = 0, tcap_txt = 0, tcap_img = 0;
+  int saved_batch = 0, saved_txt = 0, saved_img = 0;  // shape of the checkpoints currently held
+  bf16 *ckpt = nullptr, *dh = nullptr, *qkv_raw = nullptr, *dqkv = nullptr, *mlp_pre = nullptr, *dmlp = nullptr,
+       *dattn = nullptr, *du = nullptr, *dy = nullptr, *dl = nullptr, *h_mid = nullptr;
+  float *lse = nullptr, *delta = nullptr;
   // optional per-launch CUDA-event profiling of the two tensor-core kernels
   bool profiling = false;
   struct ProfRec { int cls; double flops; cudaEvent_t e0, e1; };
@@ -111,6 +133,27 @@ size_t carve(afb_engine* e, uint8_t* base, int B, int St, int Si) {
   e->alt_nm = c.take<bf16>(size_t(B) * 2 * D);
   e->t_dev = c.take<float>(B);
   e->g_dev = c.take<float>(B);
+  return c.off;
+}
+
+size_t carve_train(afb_engine* e, uint8_t* base, int B, int St, int Si) {
+  const afb_model_desc& d = e->desc;
+  const size_t S = size_t(St) + Si, D = d.dim, M = d.mlp_dim, r = d.lora_rank > 0 ? d.lora_rank : 8;
+  const size_t blocks = size_t(d.num_double) + d.num_single;
+  Carver c{base};
+  e->ckpt = c.take<bf16>((blocks + 1) * B * S * D);
+  e->dh = c.take<bf16>(B * S * D);
+  e->qkv_raw = c.take<bf16>(B * S * 3 * D);
+  e->dqkv = c.take<bf16>(B * S * 3 * D);
+  e->mlp_pre = c.take<bf16>(B * S * M);
+  e->dmlp = c.take<bf16>(B * S * M);
+  e->dattn = c.take<bf16>(B * S * D);
+  e->du = c.take<bf16>(B * S * D);
+  e->dy = c.take<bf16>(B * S * D);
+  e->dl = c.take<bf16>(B * S * r);
+  e->h_mid = c.take<bf16>(B * S * D);
+  e->lse = c.take<float>(size_t(B) * d.heads * S);
+  e->delta = c.take<float>(size_t(B) * d.heads * S);
   return c.off;
 }
 
@@ -172,6 +215,23 @@ struct Gemm {
     d.w_ld = ld;
     d.n = n;
     d.bias = bias;
+    return *this;
+  }
+  // W read as [K, n] row-major (dX = dY W); the K rows past k0 come from `second` (leading dim ld2) when given
+  Gemm& wt(const void* wp, int64_t ld, int n, int k0, const void* second = nullptr, int64_t ld2 = 0) {
+    d.w = wp;
+    d.w_ld = ld;
+    d.n = n;
+    d.w_transposed = 1;
+    d.w_k = k0;
+    d.w2 = second;
+    d.w2_ld = ld2;
+    return *this;
+  }
+  Gemm& res(View v) {
+    d.res = v.p;
+    d.res_ld = v.ld;
+    d.res_batch_stride = v.bs;
     return *this;
   }
   Gemm& out(View v, int epi) {
@@ -269,7 +329,7 @@ int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v,
 }
 
 int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, bf16* head_out,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool save_ckpt = false) {
   const afb_model_desc& d = e->desc;
   const afb_weights& w = e->w;
   const int B = a->batch, St = a->txt_len, Si = a->img_len, S = St + Si;
@@ -341,9 +401,18 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   at.heads = H;
   at.scale = 0.f;
 
+  const size_t ckpt_elems = size_t(B) * S * D;
+  auto save = [&](int idx) -> int {
+    if (!save_ckpt) return AFB_OK;
+    AFB_CHECK_CUDA(cudaMemcpyAsync(e->ckpt + size_t(idx) * ckpt_elems, e->h, ckpt_elems * sizeof(bf16),
+                                   cudaMemcpyDeviceToDevice, s));
+    return AFB_OK;
+  };
+
   // ---- double-stream blocks --------------------------------------------------------------------
   for (int i = 0; i < d.num_double; ++i) {
     const afb_double_block& k = e->dbl[i];
+    AFB_TRY(save(i));
     // chunk(6): shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
     const bf16* im = e->mod + k.img_mod_off;
     const bf16* tm = e->mod + k.txt_mod_off;
@@ -387,6 +456,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   for (int i = 0; i < d.num_single; ++i) {
     const afb_single_block& k = e->sgl[i];
     const bf16* m = e->mod + k.mod_off;  // chunk(3): shift, scale, gate
+    AFB_TRY(save(d.num_double + i));
     AFB_TRY(afb::ln_modulate_launch(e->h, int64_t(S) * D, e->y, int64_t(S) * D, m + D, m, mod_bs, B, S, D,
                                     LN_EPS, s));
     AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(qkv_all, AFB_EPI_BIAS).run(e, s));
@@ -410,6 +480,8 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     }
   }
 
+  AFB_TRY(save(d.num_double + d.num_single));
+
   // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + heads ------------------------
   const bf16* nm = e->mod + w.norm_out_mod_off;
   int64_t nm_bs = mod_bs;
@@ -423,6 +495,278 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
                                   B, Si, D, LN_EPS, s));
   AFB_TRY(Gemm(B, Si).a(y_img, D).w(w.head_w, D, w.head_n, w.head_b)
               .out(View{head_out, w.head_n, int64_t(Si) * w.head_n}, AFB_EPI_BIAS).run(e, s));
+  return AFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Adapter-only backward. Per block (reverse order): recompute the block's activations from its checkpoint, then push
+// dh (gradient w.r.t. the residual stream, bf16 [B, S, D]) back through it. The trunk weights are frozen: every big
+// GEMM is a dX product that reads the forward weight transposed in place; the LoRA pairs get dB = dY^T T, dA = dT^T X
+// from the token-contraction GEMM. Modulation vectors are constants here.
+// ------------------------------------------------------------------------------------------------------------------
+int tn_rows(View a, int m, View b, int n, float* out, int64_t out_ld, int B, int rows, cudaStream_t s) {
+  if (!out) return AFB_OK;
+  for (int bi = 0; bi < B; ++bi)
+    AFB_TRY(afb::gemm_tn_launch(a.p + int64_t(bi) * a.bs, a.ld, b.p + int64_t(bi) * b.bs, b.ld, out, out_ld, rows, m, n, s));
+  return AFB_OK;
+}
+
+// Backward of one LoRA-extended Linear  out = [x | t] [W | Bl]^T,  t = x A^T  (packed weight `w`, leading dim w_ld =
+// in + rank when `la` is set). dout -> dx (= dout W + dt A), dBl += dout^T t, dA += dt^T x. x may be two column
+// segments (FLUX single block: [attn | mlp]); dx is produced per segment.
+struct LoraBwd {
+  afb_engine* e;
+  int B, rows;
+  cudaStream_t s;
+  // dt = dout Bl   (rank columns after the `in` columns of the packed weight), and the two LoRA gradients
+  int lora_grads(View dout, int out_n, const bf16* w, int64_t w_ld, int in, View t, View dt, View x0, int k0, View x1, int k1,
+                 float* g_la, float* g_lb) {
+    const int r = e->desc.lora_rank;
+    AFB_TRY(tn_rows(dout, out_n, t, r, g_lb, r, B, rows, s));
+    AFB_TRY(Gemm(B, rows).a(dout, out_n).wt(w + in, w_ld, r, out_n).out(dt, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(tn_rows(dt, r, x0, k0, g_la, in, B, rows, s));
+    if (k1 > 0) AFB_TRY(tn_rows(dt, r, x1, k1, g_la ? g_la + k0 : nullptr, in, B, rows, s));
+    return AFB_OK;
+  }
+  // dx[:, col0 : col0 + n] = dout W[:, col0:...] (+ dt A[:, col0:...]) (+ res)
+  int dx(View dout, int out_n, const bf16* w, int64_t w_ld, const bf16* la, int64_t la_ld, View dt, int col0, int n, View out,
+         bool add_res) {
+    Gemm g(B, rows);
+    g.a(dout, out_n);
+    if (la) {
+      g.a(dt, e->desc.lora_rank);
+      g.wt(w + col0, w_ld, n, out_n, la + col0, la_ld);
+    } else {
+      g.wt(w + col0, w_ld, n, out_n);
+    }
+    g.out(out, add_res ? AFB_EPI_BIAS_RES : AFB_EPI_BIAS);
+    if (add_res) g.res(out);
+    return g.run(e, s);
+  }
+};
+
+int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
+  const afb_model_desc& d = e->desc;
+  const afb_weights& w = e->w;
+  const afb_forward_args* a = &ba->fwd;
+  const int B = a->batch, St = a->txt_len, Si = a->img_len, S = St + Si;
+  const int D = d.dim, M = d.mlp_dim, H = d.heads;
+  const int rpad = d.lora_rank;
+  const int r = d.ignore_lora ? 0 : d.lora_rank;
+  const int rr = r > 0 ? r : 8;
+  const int64_t mod_bs = w.mod_total;
+  const size_t ckpt_elems = size_t(B) * S * D;
+  const int64_t bsD = int64_t(S) * D, bs3 = int64_t(S) * 3 * D, bsM = int64_t(S) * M, bsR = int64_t(S) * rr;
+
+  auto img = [&](bf16* p, int64_t ld) { return View{p + int64_t(St) * ld, ld, int64_t(S) * ld}; };
+  auto txt = [&](bf16* p, int64_t ld) { return View{p, ld, int64_t(S) * ld}; };
+
+  afb_attn_desc at{};
+  at.q = e->qkv;
+  at.k = e->qkv + D;
+  at.v = e->qkv + 2 * D;
+  at.o = e->attn;
+  at.q_ld = at.k_ld = at.v_ld = 3 * D;
+  at.o_ld = D;
+  at.q_batch_stride = at.k_batch_stride = at.v_batch_stride = bs3;
+  at.o_batch_stride = bsD;
+  at.batch = B;
+  at.seq = S;
+  at.heads = H;
+  at.scale = 0.f;
+  at.lse = e->lse;
+  afb_attn_bwd_desc ab{};
+  ab.q = e->qkv;
+  ab.k = e->qkv + D;
+  ab.v = e->qkv + 2 * D;
+  ab.qkv_ld = 3 * D;
+  ab.qkv_batch_stride = bs3;
+  ab.o = e->attn;
+  ab.d_o = e->dattn;
+  ab.o_ld = D;
+  ab.o_batch_stride = bsD;
+  ab.lse = e->lse;
+  ab.delta_ws = e->delta;
+  ab.dq = e->dqkv;
+  ab.dk = e->dqkv + D;
+  ab.dv = e->dqkv + 2 * D;
+  ab.dqkv_ld = 3 * D;
+  ab.dqkv_batch_stride = bs3;
+  ab.batch = B;
+  ab.seq = S;
+  ab.heads = H;
+  ab.scale = 0.f;
+  auto attention_bwd = [&]() -> int {
+    ProfScope ps(e, s, 1, 10.0 * B * H * double(S) * S * 128.0);
+    return afb::attention_backward_launch(&ab, s);
+  };
+
+  // ---- dh <- gradient through norm_out's LayerNorm into the image rows; text rows start at zero -----------------
+  AFB_CHECK_CUDA(cudaMemsetAsync(e->dh, 0, ckpt_elems * sizeof(bf16), s));
+  {
+    const bf16* h_fin = e->ckpt + size_t(d.num_double + d.num_single) * ckpt_elems;
+    const bf16* nm = e->mod + w.norm_out_mod_off;  // (scale, shift)
+    AFB_TRY(afb::ln_modulate_bwd_launch(h_fin + int64_t(St) * D, bsD, ba->d_head_in, int64_t(Si) * D, e->dh + int64_t(St) * D,
+                                        bsD, nm, mod_bs, B, Si, D, LN_EPS, 0, s));
+  }
+
+  const View y_all{e->y, D, bsD}, at_all{e->attn, D, bsD}, mlp_all{e->mlp, M, bsM}, pre_all{e->mlp_pre, M, bsM};
+  const View raw_all{e->qkv_raw, 3 * D, bs3}, l0_all{e->lt0, rr, bsR}, l1_all{e->lt1, rr, bsR}, dl_all{e->dl, rr, bsR};
+  const View dh_all{e->dh, D, bsD}, du_all{e->du, D, bsD}, dy_all{e->dy, D, bsD}, dat_all{e->dattn, D, bsD};
+  const View dmlp_all{e->dmlp, M, bsM}, dqkv_all{e->dqkv, 3 * D, bs3};
+  LoraBwd lb{e, B, S, s};
+
+  // ---- single-stream blocks, last to first ----------------------------------------------------------------------
+  for (int i = d.num_single - 1; i >= 0; --i) {
+    const afb_single_block& k = e->sgl[i];
+    const afb_single_block_grads* g = ba->sgl ? &ba->sgl[i] : nullptr;
+    const bf16* m = e->mod + k.mod_off;  // shift, scale, gate
+    const bf16* h_in = e->ckpt + size_t(d.num_double + i) * ckpt_elems;
+    const bool lm = r > 0 && k.mlp_la, lo = r > 0 && k.out_la;
+    const int64_t mlp_ld = D + (k.mlp_la ? rpad : 0), out_ld = D + M + (k.out_la ? rpad : 0);
+    const bf16* mlp_w = static_cast<const bf16*>(k.mlp_w);
+    const bf16* out_w = static_cast<const bf16*>(k.out_w);
+    // -- recompute
+    AFB_TRY(afb::ln_modulate_launch(h_in, bsD, e->y, bsD, m + D, m, mod_bs, B, S, D, LN_EPS, s));
+    AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(raw_all, AFB_EPI_BIAS).run(e, s));
+    AFB_CHECK_CUDA(cudaMemcpyAsync(e->qkv, e->qkv_raw, size_t(B) * S * 3 * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+    AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, bs3, 0, D, B, S, H, 0, nullptr, nullptr, k.nq, k.nk, a->rope_cos,
+                                     a->rope_sin, LN_EPS, s));
+    AFB_TRY(run_attention(e, &at, s));
+    if (lm) {
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
+    } else {
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
+    }
+    AFB_TRY(afb::gelu_fwd_launch(e->mlp_pre, M, e->mlp, M, int64_t(B) * S, M, s));
+    if (lo) AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+    // -- backward
+    AFB_TRY(afb::rowscale_launch(e->dh, D, bsD, m + 2 * D, mod_bs, e->du, D, bsD, B, S, D, s));
+    if (lo)
+      AFB_TRY(lb.lora_grads(du_all, D, out_w, out_ld, D + M, l1_all, dl_all, at_all, D, mlp_all, M, g ? g->out_la : nullptr,
+                            g ? g->out_lb : nullptr));
+    const bf16* ola = lo ? static_cast<const bf16*>(k.out_la) : nullptr;
+    AFB_TRY(lb.dx(du_all, D, out_w, out_ld, ola, D + M, dl_all, 0, D, dat_all, false));
+    AFB_TRY(lb.dx(du_all, D, out_w, out_ld, ola, D + M, dl_all, D, M, dmlp_all, false));
+    AFB_TRY(afb::gelu_bwd_launch(e->dmlp, M, e->mlp_pre, M, int64_t(B) * S, M, s));
+    if (lm)
+      AFB_TRY(lb.lora_grads(dmlp_all, M, mlp_w, mlp_ld, D, l0_all, dl_all, y_all, D, View{}, 0, g ? g->mlp_la : nullptr,
+                            g ? g->mlp_lb : nullptr));
+    AFB_TRY(lb.dx(dmlp_all, M, mlp_w, mlp_ld, lm ? static_cast<const bf16*>(k.mlp_la) : nullptr, D, dl_all, 0, D, dy_all, false));
+    AFB_TRY(attention_bwd());
+    AFB_TRY(afb::rmsnorm_rope_bwd_launch(e->dqkv, e->qkv_raw, 3 * D, bs3, 0, D, B, S, H, 0, nullptr, nullptr, k.nq, k.nk,
+                                         a->rope_cos, a->rope_sin, LN_EPS, s));
+    AFB_TRY(Gemm(B, S).a(dqkv_all, 3 * D).wt(k.qkv_w, D, D, 3 * D).out(dy_all, AFB_EPI_BIAS_RES).res(dy_all).run(e, s));
+    AFB_TRY(afb::ln_modulate_bwd_launch(h_in, bsD, e->dy, bsD, e->dh, bsD, m + D, mod_bs, B, S, D, LN_EPS, 1, s));
+  }
+
+  // ---- double-stream blocks, last to first ----------------------------------------------------------------------
+  for (int i = d.num_double - 1; i >= 0; --i) {
+    const afb_double_block& k = e->dbl[i];
+    const afb_double_block_grads* g = ba->dbl ? &ba->dbl[i] : nullptr;
+    const bf16* im = e->mod + k.img_mod_off;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+    const bf16* tm = e->mod + k.txt_mod_off;
+    bf16* h_in = e->ckpt + size_t(i) * ckpt_elems;
+    struct Stream {
+      int rows;
+      const bf16* mod;
+      View h_in, h_mid, y, qkv_raw, attn, mlp, pre, l0, l1, dl, dh, du, dy, dattn, dmlp, dqkv;
+      const void *qkv_w, *qkv_b, *out_w, *out_b, *up_w, *up_b, *up_la, *down_w, *down_b, *down_la;
+      float *g_up_la, *g_up_lb, *g_down_la, *g_down_lb;
+    };
+    auto mk = [&](bool is_img) {
+      auto v = [&](bf16* p, int64_t ld) { return is_img ? img(p, ld) : txt(p, ld); };
+      Stream t{};
+      t.rows = is_img ? Si : St;
+      t.mod = is_img ? im : tm;
+      t.h_in = v(h_in, D);
+      t.h_mid = v(e->h_mid, D);
+      t.y = v(e->y, D);
+      t.qkv_raw = v(e->qkv_raw, 3 * D);
+      t.attn = v(e->attn, D);
+      t.mlp = v(e->mlp, M);
+      t.pre = v(e->mlp_pre, M);
+      t.l0 = v(e->lt0, rr);
+      t.l1 = v(e->lt1, rr);
+      t.dl = v(e->dl, rr);
+      t.dh = v(e->dh, D);
+      t.du = v(e->du, D);
+      t.dy = v(e->dy, D);
+      t.dattn = v(e->dattn, D);
+      t.dmlp = v(e->dmlp, M);
+      t.dqkv = v(e->dqkv, 3 * D);
+      if (is_img) {
+        t.qkv_w = k.img_qkv_w, t.qkv_b = k.img_qkv_b, t.out_w = k.img_out_w, t.out_b = k.img_out_b;
+        t.up_w = k.img_up_w, t.up_b = k.img_up_b, t.up_la = k.img_up_la;
+        t.down_w = k.img_down_w, t.down_b = k.img_down_b, t.down_la = k.img_down_la;
+        if (g) t.g_up_la = g->img_up_la, t.g_up_lb = g->img_up_lb, t.g_down_la = g->img_down_la, t.g_down_lb = g->img_down_lb;
+      } else {
+        t.qkv_w = k.txt_qkv_w, t.qkv_b = k.txt_qkv_b, t.out_w = k.txt_out_w, t.out_b = k.txt_out_b;
+        t.up_w = k.txt_up_w, t.up_b = k.txt_up_b, t.up_la = k.txt_up_la;
+        t.down_w = k.txt_down_w, t.down_b = k.txt_down_b, t.down_la = k.txt_down_la;
+        if (g) t.g_up_la = g->txt_up_la, t.g_up_lb = g->txt_up_lb, t.g_down_la = g->txt_down_la, t.g_down_lb = g->txt_down_lb;
+      }
+      return t;
+    };
+    Stream st2[2] = {mk(true), mk(false)};
+    // -- recompute: attention half
+    for (Stream& t : st2) {
+      AFB_TRY(afb::ln_modulate_launch(t.h_in.p, t.h_in.bs, const_cast<bf16*>(t.y.p), t.y.bs, t.mod + D, t.mod, mod_bs, B,
+                                      t.rows, D, LN_EPS, s));
+      AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.qkv_w, D, 3 * D, t.qkv_b).out(t.qkv_raw, AFB_EPI_BIAS).run(e, s));
+    }
+    AFB_CHECK_CUDA(cudaMemcpyAsync(e->qkv, e->qkv_raw, size_t(B) * S * 3 * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+    AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, bs3, 0, D, B, S, H, St, k.txt_nq, k.txt_nk, k.img_nq, k.img_nk,
+                                     a->rope_cos, a->rope_sin, LN_EPS, s));
+    AFB_TRY(run_attention(e, &at, s));
+    // -- recompute: h_mid and the MLP half; then the MLP half's backward (per stream)
+    for (Stream& t : st2) {
+      LoraBwd sb{e, B, t.rows, s};
+      const bool lu = r > 0 && t.up_la, ld_ = r > 0 && t.down_la;
+      const int64_t up_ld = D + (t.up_la ? rpad : 0), down_ld = M + (t.down_la ? rpad : 0);
+      const bf16* up_w = static_cast<const bf16*>(t.up_w);
+      const bf16* down_w = static_cast<const bf16*>(t.down_w);
+      AFB_TRY(Gemm(B, t.rows).a(t.attn, D).w(t.out_w, D, D, t.out_b).out(t.h_mid, AFB_EPI_BIAS_GATE_RES)
+                  .gate_res(t.mod + 2 * D, mod_bs, t.h_in).run(e, s));
+      AFB_TRY(afb::ln_modulate_launch(t.h_mid.p, t.h_mid.bs, const_cast<bf16*>(t.y.p), t.y.bs, t.mod + 4 * D, t.mod + 3 * D,
+                                      mod_bs, B, t.rows, D, LN_EPS, s));
+      if (lu) {
+        AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.up_la, D, r, nullptr).out(t.l0, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(Gemm(B, t.rows).a(t.y, D).a(t.l0, r).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
+      } else {
+        AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
+      }
+      for (int bi = 0; bi < B; ++bi)
+        AFB_TRY(afb::gelu_fwd_launch(t.pre.p + int64_t(bi) * t.pre.bs, M, const_cast<bf16*>(t.mlp.p) + int64_t(bi) * t.mlp.bs, M,
+                                     t.rows, M, s));
+      if (ld_) AFB_TRY(Gemm(B, t.rows).a(t.mlp, M).w(t.down_la, M, r, nullptr).out(t.l1, AFB_EPI_BIAS).run(e, s));
+      // backward of  h_out = h_mid + gate_mlp * down(gelu(up(LNmod2(h_mid))))
+      AFB_TRY(afb::rowscale_launch(t.dh.p, D, t.dh.bs, t.mod + 5 * D, mod_bs, const_cast<bf16*>(t.du.p), D, t.du.bs, B, t.rows,
+                                   D, s));
+      if (ld_) AFB_TRY(sb.lora_grads(t.du, D, down_w, down_ld, M, t.l1, t.dl, t.mlp, M, View{}, 0, t.g_down_la, t.g_down_lb));
+      AFB_TRY(sb.dx(t.du, D, down_w, down_ld, ld_ ? static_cast<const bf16*>(t.down_la) : nullptr, M, t.dl, 0, M, t.dmlp, false));
+      for (int bi = 0; bi < B; ++bi)
+        AFB_TRY(afb::gelu_bwd_launch(const_cast<bf16*>(t.dmlp.p) + int64_t(bi) * t.dmlp.bs, M, t.pre.p + int64_t(bi) * t.pre.bs,
+                                     M, t.rows, M, s));
+      if (lu) AFB_TRY(sb.lora_grads(t.dmlp, M, up_w, up_ld, D, t.l0, t.dl, t.y, D, View{}, 0, t.g_up_la, t.g_up_lb));
+      AFB_TRY(sb.dx(t.dmlp, M, up_w, up_ld, lu ? static_cast<const bf16*>(t.up_la) : nullptr, D, t.dl, 0, D, t.dy, false));
+      AFB_TRY(afb::ln_modulate_bwd_launch(t.h_mid.p, t.h_mid.bs, t.dy.p, t.dy.bs, const_cast<bf16*>(t.dh.p), t.dh.bs,
+                                          t.mod + 4 * D, mod_bs, B, t.rows, D, LN_EPS, 1, s));
+      // attention half: dattn = (gate_msa * dh) W_out
+      AFB_TRY(afb::rowscale_launch(t.dh.p, D, t.dh.bs, t.mod + 2 * D, mod_bs, const_cast<bf16*>(t.du.p), D, t.du.bs, B, t.rows,
+                                   D, s));
+      AFB_TRY(Gemm(B, t.rows).a(t.du, D).wt(t.out_w, D, D, D).out(t.dattn, AFB_EPI_BIAS).run(e, s));
+    }
+    AFB_TRY(attention_bwd());
+    AFB_TRY(afb::rmsnorm_rope_bwd_launch(e->dqkv, e->qkv_raw, 3 * D, bs3, 0, D, B, S, H, St, k.txt_nq, k.txt_nk, k.img_nq,
+                                         k.img_nk, a->rope_cos, a->rope_sin, LN_EPS, s));
+    for (Stream& t : st2) {
+      AFB_TRY(Gemm(B, t.rows).a(t.dqkv, 3 * D).wt(t.qkv_w, D, D, 3 * D).out(t.dy, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(afb::ln_modulate_bwd_launch(t.h_in.p, t.h_in.bs, t.dy.p, t.dy.bs, const_cast<bf16*>(t.dh.p), t.dh.bs, t.mod + D,
+                                          mod_bs, B, t.rows, D, LN_EPS, 1, s));
+    }
+  }
   return AFB_OK;
 }
 
@@ -459,6 +803,7 @@ int afb_engine_create(const afb_model_desc* desc, afb_engine** out) {
 void afb_engine_destroy(afb_engine* e) {
   if (!e) return;
   if (e->ws) cudaFree(e->ws);
+  if (e->tws) cudaFree(e->tws);
   for (auto& r : e->prof) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -576,6 +921,60 @@ int afb_engine_forward(afb_engine* e, const afb_forward_args* a, void* stream) {
   carve(e, static_cast<uint8_t*>(e->ws), a->batch, a->txt_len, a->img_len);
   return forward_impl(e, a, static_cast<const bf16*>(a->latents), static_cast<bf16*>(a->head_out),
                       static_cast<cudaStream_t>(stream));
+}
+
+int afb_engine_train_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  AFB_REQUIRE(e->bound, "engine_train_reserve: bind weights first");
+  AFB_REQUIRE(batch >= 1 && txt_len >= 1 && img_len >= 1, "engine_train_reserve: empty problem");
+  AFB_TRY(afb_engine_reserve(e, batch, txt_len, img_len));
+  if (e->tws && batch <= e->tcap_batch && txt_len <= e->tcap_txt && img_len <= e->tcap_img) return AFB_OK;
+  if (e->tws) {
+    AFB_CHECK_CUDA(cudaDeviceSynchronize());
+    AFB_CHECK_CUDA(cudaFree(e->tws));
+    e->tws = nullptr;
+  }
+  const size_t bytes = carve_train(e, nullptr, batch, txt_len, img_len);
+  AFB_CHECK_CUDA(cudaMalloc(&e->tws, bytes));
+  e->tws_bytes = bytes;
+  e->tcap_batch = batch;
+  e->tcap_txt = txt_len;
+  e->tcap_img = img_len;
+  e->saved_batch = 0;
+  return AFB_OK;
+}
+
+int afb_engine_forward_train(afb_engine* e, const afb_forward_args* a, void* stream) {
+  AFB_REQUIRE(a != nullptr, "engine_forward_train: null args");
+  AFB_TRY(check_shapes(e, a->batch, a->txt_len, a->img_len));
+  AFB_REQUIRE(e->tws && a->batch <= e->tcap_batch && a->txt_len <= e->tcap_txt && a->img_len <= e->tcap_img,
+              "engine_forward_train: call afb_engine_train_reserve first");
+  AFB_REQUIRE(a->latents && a->txt && a->timestep && a->rope_cos && a->rope_sin && a->head_out,
+              "engine_forward_train: null tensor argument");
+  carve(e, static_cast<uint8_t*>(e->ws), a->batch, a->txt_len, a->img_len);
+  carve_train(e, static_cast<uint8_t*>(e->tws), a->batch, a->txt_len, a->img_len);
+  e->saved_batch = a->batch;
+  e->saved_txt = a->txt_len;
+  e->saved_img = a->img_len;
+  return forward_impl(e, a, static_cast<const bf16*>(a->latents), static_cast<bf16*>(a->head_out),
+                      static_cast<cudaStream_t>(stream), true);
+}
+
+int afb_engine_backward(afb_engine* e, const afb_backward_args* ba, void* stream) {
+  AFB_REQUIRE(ba != nullptr, "engine_backward: null args");
+  const afb_forward_args& a = ba->fwd;
+  AFB_TRY(check_shapes(e, a.batch, a.txt_len, a.img_len));
+  AFB_REQUIRE(e->desc.arch == AFB_ARCH_FLUX, "engine_backward: only the FLUX trunk has a backward so far");
+  AFB_REQUIRE(e->tws && e->saved_batch == a.batch && e->saved_txt == a.txt_len && e->saved_img == a.img_len,
+              "engine_backward: no checkpoints of this shape (run afb_engine_forward_train first)");
+  AFB_REQUIRE(ba->d_head_in && a.rope_cos && a.rope_sin, "engine_backward: null tensor argument");
+  if (ba->d_mod) {
+    afb::set_last_error("engine_backward: modulation-vector gradients (d_mod) are not built yet");
+    return AFB_ERR_UNSUPPORTED;
+  }
+  carve(e, static_cast<uint8_t*>(e->ws), a.batch, a.txt_len, a.img_len);
+  carve_train(e, static_cast<uint8_t*>(e->tws), a.batch, a.txt_len, a.img_len);
+  return backward_impl(e, ba, static_cast<cudaStream_t>(stream));
 }
 
 int afb_engine_denoise(afb_engine* e, const afb_denoise_args* a, void* stream) {

@@ -143,7 +143,8 @@ class PackedFluxWeights:
         if pad:
             heads_w.append(torch.zeros(pad, D, device=device, dtype=BF16))
             heads_b.append(torch.zeros(pad, device=device, dtype=BF16))
-        w.head_w, w.head_b, w.head_n = hold(torch.cat(heads_w, 0)), hold(torch.cat(heads_b, 0)), n + pad
+        self.head_w_tensor = torch.cat(heads_w, 0).contiguous()
+        w.head_w, w.head_b, w.head_n = hold(self.head_w_tensor), hold(torch.cat(heads_b, 0)), n + pad
         self.head_n = n + pad
         w.dbl = C.cast(self.dbl, C.POINTER(_lib.DoubleBlock))
         w.sgl = C.cast(self.sgl, C.POINTER(_lib.SingleBlock))
@@ -277,10 +278,11 @@ class ArcFluxEngineModel(EngineModelBase):
 
     @torch.no_grad()
     def forward_heads(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor,
-                      sigma, guidance_scale: float, grid_hw: Sequence[int]) -> torch.Tensor:
+                      sigma, guidance_scale: float, grid_hw: Sequence[int], train: bool = False) -> torch.Tensor:
         """One network call. `sigma`: a scalar or per-sample values. Returns the raw head tensor bf16
         [batch, tokens, head_n] (means K*64 | logits K*4 | loggamma (K-1)*4 | pad) — logits NOT yet log-softmaxed
-        (for a teacher engine: the velocity [batch, tokens, 64])."""
+        (for a teacher engine: the velocity [batch, tokens, 64]). train=True also stores the per-block residual-stream
+        checkpoints `backward_trunk` recomputes from."""
         self._check_inputs(latents, txt, pooled, grid_hw)
         B, Si, _ = latents.shape
         lat = latents.to(BF16).contiguous()
@@ -298,9 +300,83 @@ class ArcFluxEngineModel(EngineModelBase):
         out = torch.empty(B, Si, self.weights.head_n, dtype=BF16, device=self.device)
         a = self._fwd_args(txt, pooled, tdev, gdev, cos, sin, B, Si)
         a.latents, a.head_out = lat.data_ptr(), out.data_ptr()
-        _lib.check(self.lib.afb_engine_forward(self.handle, C.byref(a), torch.cuda.current_stream().cuda_stream),
-                   "afb_engine_forward")
+        stream = torch.cuda.current_stream().cuda_stream
+        if train:
+            _lib.check(self.lib.afb_engine_train_reserve(self.handle, *self._reserved), "afb_engine_train_reserve")
+            _lib.check(self.lib.afb_engine_forward_train(self.handle, C.byref(a), stream), "afb_engine_forward_train")
+            self._train_ctx = dict(args=a, keep=(lat, txt, pooled, tdev, gdev, cos, sin, out))   # alive until the backward
+        else:
+            _lib.check(self.lib.afb_engine_forward(self.handle, C.byref(a), stream), "afb_engine_forward")
         return out
+
+    # LoRA tensor of the engine's block structs -> state-dict prefix (export_arcflow_to_diffusers.py:104-127 names)
+    _DBL_LORA = (("img_up", "ff.net.0.proj"), ("img_down", "ff.net.2"), ("txt_up", "ff_context.net.0.proj"),
+                 ("txt_down", "ff_context.net.2"))
+    _SGL_LORA = (("mlp", "proj_mlp"), ("out", "proj_out"))
+
+    def head_weight(self) -> torch.Tensor:
+        """The fused [head_n, D] head weight (means | logits | loggamma | pad) the engine reads."""
+        return self.weights.head_w_tensor
+
+    def trunk_lora_shapes(self) -> Dict[str, tuple]:
+        D, M, r = self.cfg.inner_dim, self.cfg.mlp_dim, self.cfg.lora_rank
+        io = {"ff.net.0.proj": (M, D), "ff.net.2": (D, M), "ff_context.net.0.proj": (M, D), "ff_context.net.2": (D, M),
+              "proj_mlp": (M, D), "proj_out": (D, D + M)}
+        out = {}
+        for n in self.trunk_lora_names():
+            base, ab = n.rsplit(".lora_", 1)
+            o, i = io[base.split(".", 2)[2]]
+            out[n] = (r, i) if ab.startswith("A") else (o, r)
+        return out
+
+    def trunk_lora_names(self):
+        """State-dict names of the LoRA tensors the trunk backward produces gradients for."""
+        names = []
+        for i in range(self.cfg.num_layers):
+            names += [f"transformer_blocks.{i}.{n}.lora_{ab}.weight" for _, n in self._DBL_LORA for ab in "AB"]
+        for i in range(self.cfg.num_single_layers):
+            names += [f"single_transformer_blocks.{i}.{n}.lora_{ab}.weight" for _, n in self._SGL_LORA for ab in "AB"]
+        return names
+
+    @torch.no_grad()
+    def backward_trunk(self, d_head_in: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+        """Accumulate (+=) the LoRA gradients of the last `forward_heads(train=True)` into `grads` (fp32 tensors keyed by
+        state-dict name, shapes of the LoRA tensors; missing names are skipped). d_head_in: bf16 [batch, tokens, dim],
+        the gradient w.r.t. the norm_out output. Replaces torch autograd + checkpointing through the diffusers blocks
+        (lakonlab/models/base_diffusion.py:14-62)."""
+        ctx = getattr(self, "_train_ctx", None)
+        if ctx is None:
+            raise AfbError("backward_trunk: run forward_heads(train=True) first")
+        a = ctx["args"]
+        D = self.cfg.inner_dim
+        if d_head_in.dtype != BF16 or tuple(d_head_in.shape) != (a.batch, a.img_len, D) or not d_head_in.is_contiguous():
+            raise AfbError(f"d_head_in must be contiguous bf16 [{a.batch}, {a.img_len}, {D}]")
+
+        def ptr(name):
+            t = grads.get(name)
+            if t is None:
+                return None
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise AfbError(f"gradient buffer '{name}' must be a contiguous fp32 CUDA tensor")
+            return t.data_ptr()
+
+        dbl = (_lib.DoubleBlockGrads * max(self.cfg.num_layers, 1))()
+        for i in range(self.cfg.num_layers):
+            for field, n in self._DBL_LORA:
+                setattr(dbl[i], field + "_la", ptr(f"transformer_blocks.{i}.{n}.lora_A.weight"))
+                setattr(dbl[i], field + "_lb", ptr(f"transformer_blocks.{i}.{n}.lora_B.weight"))
+        sgl = (_lib.SingleBlockGrads * max(self.cfg.num_single_layers, 1))()
+        for i in range(self.cfg.num_single_layers):
+            for field, n in self._SGL_LORA:
+                setattr(sgl[i], field + "_la", ptr(f"single_transformer_blocks.{i}.{n}.lora_A.weight"))
+                setattr(sgl[i], field + "_lb", ptr(f"single_transformer_blocks.{i}.{n}.lora_B.weight"))
+        b = _lib.BackwardArgs()
+        b.fwd = a
+        b.d_head_in = d_head_in.data_ptr()
+        b.dbl = C.cast(dbl, C.POINTER(_lib.DoubleBlockGrads))
+        b.sgl = C.cast(sgl, C.POINTER(_lib.SingleBlockGrads))
+        _lib.check(self.lib.afb_engine_backward(self.handle, C.byref(b), torch.cuda.current_stream().cuda_stream),
+                   "afb_engine_backward")
 
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int],

@@ -59,9 +59,12 @@ class ArcFlowDistillStep:
 
     @torch.no_grad()
     def forward(self, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int], noise: torch.Tensor,
-                rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0, save_for_backward: bool = False):
+                rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0, save_for_backward: bool = False,
+                step_hook=None):
         """One train iteration, forward only. noise: fp32 packed tokens [B, S_i, 64] (the data-free x_t_src);
-        rands: one dict of uniforms per student step (see draw_rollout_randoms). Returns (loss, log_vars, extras)."""
+        rands: one dict of uniforms per student step (see draw_rollout_randoms). Returns (loss, log_vars, extras).
+        step_hook(saved): called after each student step's roll-out while that step's trunk checkpoints are still live
+        (forward_backward() uses it to run the step's backward before the next student forward overwrites them)."""
         cfg, st, te = self.cfg, self.student, self.teacher
         if noise.dtype != torch.float32 or not noise.is_cuda:
             raise AfbError("noise must be an fp32 CUDA tensor [batch, tokens, 64]")
@@ -89,7 +92,7 @@ class ArcFlowDistillStep:
             raw_t_dst = raw_t_src - seg
             sigma_src = warp_t(raw_t_src, self.shift)
 
-            head = st.forward_heads(x_src, txt, pooled, sigma_src, g_student, grid_hw)
+            head = st.forward_heads(x_src, txt, pooled, sigma_src, g_student, grid_hw, train=step_hook is not None)
             head2 = head.reshape(-1, head.shape[-1])
             saved = None
             if save_for_backward:
@@ -136,55 +139,99 @@ class ArcFlowDistillStep:
             loss_total += step_loss * seg_f
             log_vars[f"loss_diffusion_step{step_id}"] = step_loss
             log_vars["loss_diffusion"] = log_vars.get("loss_diffusion", 0.0) + step_loss * seg_f
+            if step_hook is not None:
+                step_hook(saved)
             extras["steps"].append(dict(x_t_dst=x_dst, head=head, saved=saved))
             x_src, raw_t_src = x_dst, raw_t_dst
         return loss_total, log_vars, extras
 
-    @torch.no_grad()
-    def backward_heads(self, extras, head_weight_t: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Exact fp32 gradients of the summed train loss w.r.t. the post-trunk adapter tensors, from a forward run with
-        save_for_backward=True. head_weight_t: bf16 [D, head_n] = transpose of the fused head weight (dX operand)."""
-        cfg, st = self.cfg, self.student
-        n_states, eps = cfg["num_intermediate_states"], cfg.get("eps", 1e-4)
-        mcfg = st.cfg
-        D = mcfg.inner_dim
-        nm, nw, ng = mcfg.head_dims
-        head_n = st.weights.head_n
-        dev = st.device
-        g_w = torch.zeros(head_n, D, dtype=torch.float32, device=dev)
-        g_b = torch.zeros(head_n, dtype=torch.float32, device=dev)
-        g_nw = torch.zeros(2 * D, D, dtype=torch.float32, device=dev)
-        g_nb = torch.zeros(2 * D, dtype=torch.float32, device=dev)
-        for step in extras["steps"]:
-            sv = step["saved"]
-            if sv is None:
-                raise AfbError("backward_heads: run forward(save_for_backward=True) first")
-            head2 = sv["head"]
-            B = sv["temb"].shape[0]
-            tokens = head2.shape[0] // B
-            # d(loss)/d pred = seg * loss_scale * 0.5 * 2 (pred - tgt) / (elements per sample * n_states * B)
-            coef = sv["seg"] * self.loss_scale / (tokens * 64 * n_states * B)
-            dhead = None
-            for s in sv["states"]:
-                dhead = ops.policy_backward(head2, s["tgt_u"], sv["sigma_src"], s["sigma_a"], s["sigma_end"], coef,
-                                            dhead=dhead, small=s["small"], num_gaussians=st.num_gaussians, eps=eps)
-            ops.colsum_f32(dhead, g_b)
-            dhead_bf = dhead.to(torch.bfloat16)      # plumbing cast; the GEMM operands are bf16
-            x_in = sv["head_in"].reshape(-1, D)
-            ops.gemm_tn(dhead_bf, x_in, g_w)                                   # dW_heads += dHead^T y
-            dy = torch.empty(B, tokens, D, dtype=torch.bfloat16, device=dev)
-            ops.gemm(dhead_bf.reshape(B, tokens, head_n), head_weight_t, dy)   # dy = dHead W_heads
-            dscale, dshift = ops.ln_mod_param_grad(sv["hidden"], dy)
-            demb = torch.cat([dscale, dshift], dim=1).contiguous()             # AdaLayerNormContinuous: (scale, shift)
-            ops.rowlinear_param_grad(demb, sv["temb"], g_nw, g_nb, silu_in=True)
+    def _head_grad_buffers(self):
+        st = self.student
+        D, head_n, dev = st.cfg.inner_dim, st.weights.head_n, st.device
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        return dict(g_w=z(head_n, D), g_b=z(head_n), g_nw=z(2 * D, D), g_nb=z(2 * D))
+
+    def _split_head_grads(self, acc) -> Dict[str, torch.Tensor]:
+        nm, nw, ng = self.student.cfg.head_dims
+        g_w, g_b = acc["g_w"], acc["g_b"]
         return {
             "proj_out_means.weight": g_w[:nm], "proj_out_means.bias": g_b[:nm],
             "proj_out_logweights.weight": g_w[nm:nm + nw], "proj_out_logweights.bias": g_b[nm:nm + nw],
             "proj_out_loggamma.weight": g_w[nm + nw:nm + nw + ng], "proj_out_loggamma.bias": g_b[nm + nw:nm + nw + ng],
-            "norm_out.linear.weight": g_nw, "norm_out.linear.bias": g_nb,
+            "norm_out.linear.weight": acc["g_nw"], "norm_out.linear.bias": acc["g_nb"],
         }
 
+    @torch.no_grad()
+    def _backward_step_heads(self, sv, acc) -> torch.Tensor:
+        """One student step: loss -> d(raw heads) -> head / norm_out gradients (accumulated into acc). Returns dy, the
+        gradient w.r.t. the norm_out output (bf16 [B, tokens, D]) that the trunk backward starts from."""
+        cfg, st = self.cfg, self.student
+        n_states, eps = cfg["num_intermediate_states"], cfg.get("eps", 1e-4)
+        D, head_n, dev = st.cfg.inner_dim, st.weights.head_n, st.device
+        head2 = sv["head"]
+        B = sv["temb"].shape[0]
+        tokens = head2.shape[0] // B
+        # d(loss)/d pred = seg * loss_scale * 0.5 * 2 (pred - tgt) / (elements per sample * n_states * B)
+        coef = sv["seg"] * self.loss_scale / (tokens * 64 * n_states * B)
+        dhead = None
+        for s in sv["states"]:
+            dhead = ops.policy_backward(head2, s["tgt_u"], sv["sigma_src"], s["sigma_a"], s["sigma_end"], coef,
+                                        dhead=dhead, small=s["small"], num_gaussians=st.num_gaussians, eps=eps)
+        ops.colsum_f32(dhead, acc["g_b"])
+        dhead_bf = dhead.to(torch.bfloat16)      # plumbing cast; the GEMM operands are bf16
+        x_in = sv["head_in"].reshape(-1, D)
+        ops.gemm_tn(dhead_bf, x_in, acc["g_w"])                                # dW_heads += dHead^T y
+        dy = torch.empty(B, tokens, D, dtype=torch.bfloat16, device=dev)
+        # dy = dHead W_heads: the fused [head_n, D] head weight read transposed in place
+        ops.gemm(dhead_bf.reshape(B, tokens, head_n), st.head_weight(), dy, transposed=True)
+        dscale, dshift = ops.ln_mod_param_grad(sv["hidden"], dy)
+        demb = torch.cat([dscale, dshift], dim=1).contiguous()             # AdaLayerNormContinuous: (scale, shift)
+        ops.rowlinear_param_grad(demb, sv["temb"], acc["g_nw"], acc["g_nb"], silu_in=True)
+        return dy
+
+    @torch.no_grad()
+    def backward_heads(self, extras, head_weight_t: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Exact fp32 gradients of the summed train loss w.r.t. the post-trunk adapter tensors (proj_out_* and
+        norm_out.linear), from a forward run with save_for_backward=True. (head_weight_t is no longer needed: the dX
+        GEMM reads the head weight transposed in place.)"""
+        acc = self._head_grad_buffers()
+        for step in extras["steps"]:
+            if step["saved"] is None:
+                raise AfbError("backward_heads: run forward(save_for_backward=True) first")
+            self._backward_step_heads(step["saved"], acc)
+        return self._split_head_grads(acc)
+
+    @torch.no_grad()
+    def forward_backward(self, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int], noise: torch.Tensor,
+                         rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0,
+                         grads: Optional[Dict[str, torch.Tensor]] = None):
+        """train_fwd_bwd (lakonlab/models/base_diffusion.py:14-62): forward + loss + the gradients of every adapter
+        tensor except the timestep-embedder LoRA (its only path is through the AdaLN modulation vectors).
+        grads: fp32 CUDA tensors keyed by state-dict name, accumulated into (+=); created zero-filled when None.
+        Each student step's backward runs right after its roll-out: heads / norm_out (backward_heads path), then the
+        frozen trunk in reverse with per-block recompute (afb_engine_backward)."""
+        st = self.student
+        if grads is None:
+            grads = {}
+        shapes = st.trunk_lora_shapes()
+        for n, shp in shapes.items():
+            if n not in grads:
+                grads[n] = torch.zeros(shp, dtype=torch.float32, device=st.device)
+        acc = self._head_grad_buffers()
+
+        def hook(saved):
+            dy = self._backward_step_heads(saved, acc)
+            st.backward_trunk(dy, grads)
+
+        loss, log_vars, extras = self.forward(txt, pooled, grid_hw, noise, rands, iteration, save_for_backward=True,
+                                              step_hook=hook)
+        for n, g in self._split_head_grads(acc).items():
+            if n in grads:
+                grads[n] += g
+            else:
+                grads[n] = g.clone()
+        return loss, log_vars, grads
+
     def backward(self, *a, **k):
-        raise NotImplementedError(
-            "full adapter backward (LoRA grads through the frozen trunk) is not built yet; backward_heads() gives the "
-            "exact gradients of the heads and norm_out (see DESIGN.md §1, rows a15-a18)")
+        raise NotImplementedError("use forward_backward(): each student step's backward must run before the next student "
+                                  "forward overwrites the trunk checkpoints")

@@ -398,6 +398,37 @@ typedef struct afb_denoise_args {
 
 int afb_engine_denoise(afb_engine* e, const afb_denoise_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Adapter-only backward through the frozen trunk (train_fwd_bwd, lakonlab/models/base_diffusion.py:14-62: the
+ * reference gets these from torch autograd + gradient checkpointing over the diffusers blocks).
+ *   afb_engine_train_reserve   training workspace: one residual-stream checkpoint per block (+ the final one) and the
+ *                              recompute / gradient buffers
+ *   afb_engine_forward_train   afb_engine_forward that also stores the checkpoints
+ *   afb_engine_backward        walks the blocks in reverse: recompute the block from its checkpoint, then
+ *                              dX GEMMs with the forward weights read transposed, tcgen05 attention backward,
+ *                              LN / GELU / RMSNorm+RoPE backward, and the LoRA gradients dB = dY^T T, dA = dT^T X
+ *                              accumulated (+=) in fp32 into the caller's buffers (NULL = skip that tensor).
+ * d_head_in: bf16 [batch, img_len, dim] = gradient w.r.t. the norm_out output (the heads' input). The modulation
+ * vectors are treated as constants (no gradient to the timestep-embedder LoRA through the AdaLN vectors) unless
+ * d_mod (fp32 [batch, mod_total], accumulated) is given.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct afb_double_block_grads {
+  float *img_up_la, *img_up_lb, *img_down_la, *img_down_lb, *txt_up_la, *txt_up_lb, *txt_down_la, *txt_down_lb;
+} afb_double_block_grads;
+typedef struct afb_single_block_grads {
+  float *mlp_la, *mlp_lb, *out_la, *out_lb;
+} afb_single_block_grads;
+typedef struct afb_backward_args {
+  afb_forward_args fwd;      /* the forward's arguments (latents / head_out unused) */
+  const void* d_head_in;     /* bf16 [batch, img_len, dim] */
+  const afb_double_block_grads* dbl; /* [num_double] */
+  const afb_single_block_grads* sgl; /* [num_single] */
+  float* d_mod;              /* optional fp32 [batch, mod_total] */
+} afb_backward_args;
+int afb_engine_train_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
+int afb_engine_forward_train(afb_engine* e, const afb_forward_args* args, void* stream);
+int afb_engine_backward(afb_engine* e, const afb_backward_args* args, void* stream);
+
 /* Optional instrumentation: when on, every tensor-core launch of forward/denoise is bracketed by CUDA
  * events on the caller's stream. afb_engine_read_profile synchronises the device, returns the totals
  * since the last read (algorithmic FLOPs: 2*M*N*K per GEMM incl. LoRA K-extension, 4*B*H*S^2*128 per
