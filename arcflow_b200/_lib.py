@@ -156,6 +156,10 @@ class BackwardArgs(C.Structure):
                 ("sgl", C.POINTER(SingleBlockGrads)), ("d_mod", _P)]
 
 
+class EmbedGrads(C.Structure):
+    _fields_ = [(n, _P) for n in ("t1_la", "t1_lb", "t2_la", "t2_lb")]
+
+
 class Profile(C.Structure):
     _fields_ = [("gemm_ms", C.c_double), ("attn_ms", C.c_double), ("gemm_flops", C.c_double),
                 ("attn_flops", C.c_double), ("gemm_launches", C.c_int64), ("attn_launches", C.c_int64)]
@@ -200,6 +204,7 @@ SIGNATURES = {
     "afb_engine_train_reserve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "afb_engine_forward_train": (C.c_int, [_P, C.POINTER(ForwardArgs), _P]),
     "afb_engine_backward": (C.c_int, [_P, C.POINTER(BackwardArgs), _P]),
+    "afb_engine_backward_embed": (C.c_int, [_P, C.POINTER(ForwardArgs), _P, C.POINTER(EmbedGrads), _P]),
     "afb_grad_norm_sq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "afb_adamw_ema_step": (C.c_int, [C.POINTER(AdamwArgs), _P]),
     "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, _P]),

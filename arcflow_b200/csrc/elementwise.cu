@@ -670,8 +670,8 @@ ln_row_stats_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, float2*
 __global__ void __launch_bounds__(256)
 ln_mod_param_grad_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, const __nv_bfloat16* __restrict__ dy,
                          long long dy_bs, const float2* __restrict__ stats, float* __restrict__ dscale,
-                         float* __restrict__ dshift, int rows_per_batch, int dim, int chunks_per_batch,
-                         int rows_per_chunk) {
+                         float* __restrict__ dshift, long long out_bs, int rows_per_batch, int dim,
+                         int chunks_per_batch, int rows_per_chunk) {
   const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (col >= dim) return;
   const int b = blockIdx.y / chunks_per_batch;
@@ -690,10 +690,10 @@ ln_mod_param_grad_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, co
     h0 += d0;
     h1 += d1;
   }
-  atomicAdd(dscale + (long long)b * dim + col, s0);
-  atomicAdd(dscale + (long long)b * dim + col + 1, s1);
-  atomicAdd(dshift + (long long)b * dim + col, h0);
-  atomicAdd(dshift + (long long)b * dim + col + 1, h1);
+  atomicAdd(dscale + (long long)b * out_bs + col, s0);
+  atomicAdd(dscale + (long long)b * out_bs + col + 1, s1);
+  atomicAdd(dshift + (long long)b * out_bs + col, h0);
+  atomicAdd(dshift + (long long)b * out_bs + col + 1, h1);
 }
 
 // Gradients of a batch-row Linear  e[b, j] = sum_d W[j, d] * act(t[b, d]) + bias[j]  (the AdaLN modulation Linears):
@@ -715,6 +715,107 @@ rowlinear_param_grad_kernel(const float* __restrict__ de, long long de_ld, const
   }
   dw[(long long)j * dw_ld + d] += acc;
   if (d == 0 && dbias) dbias[j] += bsum;
+}
+
+
+// ================================================================================================
+// Modulation-vector gradients (the only path to the timestep-embedder LoRA)
+// ================================================================================================
+// du = gate[b] (.) dh   and   dgate[b, :] += sum_rows dh (.) u      (u = the branch output the gate multiplied)
+__global__ void __launch_bounds__(128)
+gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, long long dh_bs, const __nv_bfloat16* __restrict__ u, long long u_bs,
+                const __nv_bfloat16* __restrict__ gate, long long gate_bs, __nv_bfloat16* __restrict__ du, long long du_bs,
+                float* __restrict__ dgate, long long dgate_bs, int rows_per_batch, int cols, int chunks_per_batch,
+                int rows_per_chunk) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= cols) return;
+  const int b = blockIdx.y / chunks_per_batch;
+  const int r0 = (blockIdx.y - b * chunks_per_batch) * rows_per_chunk;
+  const int r1 = min(rows_per_batch, r0 + rows_per_chunk);
+  float g[8], acc[8];
+  unpack8(*reinterpret_cast<const uint4*>(gate + (long long)b * gate_bs + c), g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    float d[8], uv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dh + (long long)b * dh_bs + (long long)r * cols + c), d);
+    unpack8(*reinterpret_cast<const uint4*>(u + (long long)b * u_bs + (long long)r * cols + c), uv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] = fmaf(d[i], uv[i], acc[i]);
+      o[i] = d[i] * g[i];
+    }
+    *reinterpret_cast<uint4*>(du + (long long)b * du_bs + (long long)r * cols + c) = pack8(o);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(dgate + (long long)b * dgate_bs + c + i, acc[i]);
+}
+
+// out = res + gate[b] (.) u   (the recompute's unfused form of the GEMM's gate+residual epilogue)
+__global__ void __launch_bounds__(256)
+gate_res_kernel(const __nv_bfloat16* __restrict__ res, long long res_bs, const __nv_bfloat16* __restrict__ u, long long u_bs,
+                const __nv_bfloat16* __restrict__ gate, long long gate_bs, __nv_bfloat16* __restrict__ out, long long out_bs,
+                int rows_per_batch, int cols, long long total_chunks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int cpr = cols / 8;
+  const long long row = i / cpr;
+  const int c = int(i - row * cpr) * 8;
+  const int b = int(row / rows_per_batch);
+  const long long r = row - (long long)b * rows_per_batch;
+  float rv[8], uv[8], gv[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(res + (long long)b * res_bs + r * cols + c), rv);
+  unpack8(*reinterpret_cast<const uint4*>(u + (long long)b * u_bs + r * cols + c), uv);
+  unpack8(*reinterpret_cast<const uint4*>(gate + (long long)b * gate_bs + c), gv);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = fmaf(gv[k], uv[k], rv[k]);
+  *reinterpret_cast<uint4*>(out + (long long)b * out_bs + r * cols + c) = pack8(o);
+}
+
+// out[b, n] += sum_j de[b, j] * W[j, n]   (dX of a batch-row Linear: W bf16 [J, N] row-major, streamed once; m <= 8)
+constexpr int RDX_JC = 64;
+__global__ void __launch_bounds__(128)
+rowlinear_dx_kernel(const float* __restrict__ de, long long de_ld, const __nv_bfloat16* __restrict__ w, long long w_ld,
+                    float* __restrict__ out, long long out_ld, int m, int J, int N) {
+  __shared__ float sde[8][RDX_JC];
+  const int j0 = blockIdx.y * RDX_JC;
+  const int jn = min(RDX_JC, J - j0);
+  for (int i = threadIdx.x; i < 8 * RDX_JC; i += blockDim.x) {
+    const int b = i / RDX_JC, j = i - b * RDX_JC;
+    sde[b][j] = (b < m && j < jn) ? de[(long long)b * de_ld + j0 + j] : 0.f;
+  }
+  __syncthreads();
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= N) return;
+  float acc[8][8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[b][i] = 0.f;
+  for (int j = 0; j < jn; ++j) {
+    float wv[8];
+    unpack8(*reinterpret_cast<const uint4*>(w + (long long)(j0 + j) * w_ld + c), wv);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const float g = sde[b][j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[b][i] = fmaf(g, wv[i], acc[b][i]);
+    }
+  }
+  for (int b = 0; b < m; ++b)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(out + (long long)b * out_ld + c + i, acc[b][i]);
+}
+
+// d[i] *= silu'(x[i])   (fp32 gradient, bf16 pre-activation)
+__global__ void __launch_bounds__(256)
+silu_bwd_kernel(float* __restrict__ d, long long d_ld, const __nv_bfloat16* __restrict__ x, long long x_ld, int rows, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= cols || r >= rows) return;
+  const float v = __bfloat162float(x[(long long)r * x_ld + c]);
+  const float sg = 1.0f / (1.0f + __expf(-v));
+  d[(long long)r * d_ld + c] *= sg * (1.0f + v * (1.0f - sg));
 }
 
 // ================================================================================================
@@ -1184,8 +1285,18 @@ int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int 
   return AFB_OK;
 }
 
+int ln_mod_param_grad_strided_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws,
+                                     float* dscale, float* dshift, int64_t out_bs, int batches, int rows_per_batch, int dim,
+                                     float eps, cudaStream_t stream);
 int ln_mod_param_grad_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws, float* dscale,
                              float* dshift, int batches, int rows_per_batch, int dim, float eps, cudaStream_t stream) {
+  return ln_mod_param_grad_strided_launch(x, x_bs, dy, dy_bs, stats_ws, dscale, dshift, dim, batches, rows_per_batch, dim, eps,
+                                          stream);
+}
+// dscale / dshift rows are out_bs floats apart (slots of one [batch, mod_total] modulation-gradient buffer)
+int ln_mod_param_grad_strided_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws,
+                                     float* dscale, float* dshift, int64_t out_bs, int batches, int rows_per_batch, int dim,
+                                     float eps, cudaStream_t stream) {
   AFB_REQUIRE(x && dy && stats_ws && dscale && dshift, "ln_mod_param_grad: null pointer");
   AFB_REQUIRE(batches >= 1 && rows_per_batch >= 1 && dim % 256 == 0, "ln_mod_param_grad: bad shape");
   const long long rows = (long long)batches * rows_per_batch;
@@ -1198,7 +1309,7 @@ int ln_mod_param_grad_launch(const void* x, int64_t x_bs, const void* dy, int64_
   dim3 grid((dim / 2 + 255) / 256, unsigned(batches * cpb));
   ln_mod_param_grad_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_bs,
                                                      static_cast<const __nv_bfloat16*>(dy), dy_bs,
-                                                     reinterpret_cast<const float2*>(stats_ws), dscale, dshift,
+                                                     reinterpret_cast<const float2*>(stats_ws), dscale, dshift, out_bs,
                                                      rows_per_batch, dim, cpb, rpc);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
@@ -1264,6 +1375,58 @@ int gelu_bwd_launch(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, in
   gelu_bwd_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dm), dm_ld,
                                                                      static_cast<const __nv_bfloat16*>(pre), pre_ld, cols,
                                                                      chunks);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int gate_bwd_launch(const void* dh, int64_t dh_bs, const void* u, int64_t u_bs, const void* gate, int64_t gate_bs, void* du,
+                    int64_t du_bs, float* dgate, int64_t dgate_bs, int batches, int rows_per_batch, int cols,
+                    cudaStream_t stream) {
+  AFB_REQUIRE(dh && u && gate && du && dgate, "gate_bwd: null pointer");
+  AFB_REQUIRE(batches >= 1 && rows_per_batch >= 1 && cols % 8 == 0, "gate_bwd: bad shape");
+  const int rpc = 32;
+  const int cpb = (rows_per_batch + rpc - 1) / rpc;
+  dim3 grid((cols / 8 + 127) / 128, unsigned(batches * cpb));
+  gate_bwd_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dh), dh_bs, static_cast<const __nv_bfloat16*>(u),
+                                            u_bs, static_cast<const __nv_bfloat16*>(gate), gate_bs,
+                                            static_cast<__nv_bfloat16*>(du), du_bs, dgate, dgate_bs, rows_per_batch, cols, cpb,
+                                            rpc);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int gate_res_launch(const void* res, int64_t res_bs, const void* u, int64_t u_bs, const void* gate, int64_t gate_bs, void* out,
+                    int64_t out_bs, int batches, int rows_per_batch, int cols, cudaStream_t stream) {
+  AFB_REQUIRE(res && u && gate && out && batches >= 1 && rows_per_batch >= 1 && cols % 8 == 0, "gate_res: bad arguments");
+  const long long chunks = (long long)batches * rows_per_batch * (cols / 8);
+  gate_res_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(res), res_bs, static_cast<const __nv_bfloat16*>(u), u_bs,
+      static_cast<const __nv_bfloat16*>(gate), gate_bs, static_cast<__nv_bfloat16*>(out), out_bs, rows_per_batch, cols, chunks);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int rowlinear_dx_launch(const float* de, int64_t de_ld, const void* w, int64_t w_ld, float* out, int64_t out_ld, int m, int J,
+                        int N, cudaStream_t stream) {
+  AFB_REQUIRE(de && w && out && m >= 1 && J >= 1 && N >= 8 && N % 8 == 0 && w_ld % 8 == 0, "rowlinear_dx: bad arguments");
+  dim3 grid((N / 8 + 127) / 128, unsigned((J + RDX_JC - 1) / RDX_JC));
+  for (int r0 = 0; r0 < m; r0 += 8) {
+    const int mm = m - r0 < 8 ? m - r0 : 8;
+    rowlinear_dx_kernel<<<grid, 128, 0, stream>>>(de + (int64_t)r0 * de_ld, de_ld, static_cast<const __nv_bfloat16*>(w), w_ld,
+                                                  out + (int64_t)r0 * out_ld, out_ld, mm, J, N);
+    AFB_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
+  return AFB_OK;
+}
+
+int silu_bwd_launch(float* d, int64_t d_ld, const void* x, int64_t x_ld, int rows, int cols, cudaStream_t stream) {
+  AFB_REQUIRE(d && x && rows >= 1 && cols >= 1, "silu_bwd: bad arguments");
+  dim3 grid((cols + 255) / 256, rows);
+  silu_bwd_kernel<<<grid, 256, 0, stream>>>(d, d_ld, static_cast<const __nv_bfloat16*>(x), x_ld, rows, cols);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

@@ -58,6 +58,19 @@ int gelu_fwd_launch(const void* pre, int64_t pre_ld, void* out, int64_t out_ld, 
 int rmsnorm_rope_bwd_launch(void* dqkv, const void* raw, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
                             int heads, int txt_rows, const void* wq_txt, const void* wk_txt, const void* wq_img,
                             const void* wk_img, const float* cos_tab, const float* sin_tab, float eps, cudaStream_t stream);
+int gate_bwd_launch(const void* dh, int64_t dh_bs, const void* u, int64_t u_bs, const void* gate, int64_t gate_bs, void* du,
+                    int64_t du_bs, float* dgate, int64_t dgate_bs, int batches, int rows_per_batch, int cols,
+                    cudaStream_t stream);
+int gate_res_launch(const void* res, int64_t res_bs, const void* u, int64_t u_bs, const void* gate, int64_t gate_bs, void* out,
+                    int64_t out_bs, int batches, int rows_per_batch, int cols, cudaStream_t stream);
+int rowlinear_dx_launch(const float* de, int64_t de_ld, const void* w, int64_t w_ld, float* out, int64_t out_ld, int m, int J,
+                        int N, cudaStream_t stream);
+int silu_bwd_launch(float* d, int64_t d_ld, const void* x, int64_t x_ld, int rows, int cols, cudaStream_t stream);
+int ln_mod_param_grad_strided_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws,
+                                     float* dscale, float* dshift, int64_t out_bs, int batches, int rows_per_batch, int dim,
+                                     float eps, cudaStream_t stream);
+int rowlinear_param_grad_launch(const float* de, int64_t de_ld, const void* t, int64_t t_ld, float* dw, int64_t dw_ld,
+                                float* dbias, int m, int n_out, int k_in, int silu_in, cudaStream_t stream);
 }  // namespace afb
 
 using bf16 = __nv_bfloat16;
@@ -84,8 +97,9 @@ struct afb_engine {
   int tcap_batch = 0, tcap_txt = 0, tcap_img = 0;
   int saved_batch = 0, saved_txt = 0, saved_img = 0;  // shape of the checkpoints currently held
   bf16 *ckpt = nullptr, *dh = nullptr, *qkv_raw = nullptr, *dqkv = nullptr, *mlp_pre = nullptr, *dmlp = nullptr,
-       *dattn = nullptr, *du = nullptr, *dy = nullptr, *dl = nullptr, *h_mid = nullptr;
-  float *lse = nullptr, *delta = nullptr;
+       *dattn = nullptr, *du = nullptr, *dy = nullptr, *dl = nullptr, *h_mid = nullptr, *u1 = nullptr, *u2 = nullptr,
+       *tproj_t = nullptr, *tmp_t = nullptr, *ltv1 = nullptr, *ltv2 = nullptr;
+  float *lse = nullptr, *delta = nullptr, *stats = nullptr, *dsilu = nullptr, *dtmp = nullptr, *dltv = nullptr;
   // optional per-launch CUDA-event profiling of the two tensor-core kernels
   bool profiling = false;
   struct ProfRec { int cls; double flops; cudaEvent_t e0, e1; };
@@ -154,6 +168,17 @@ size_t carve_train(afb_engine* e, uint8_t* base, int B, int St, int Si) {
   e->h_mid = c.take<bf16>(B * S * D);
   e->lse = c.take<float>(size_t(B) * d.heads * S);
   e->delta = c.take<float>(size_t(B) * d.heads * S);
+  // modulation-gradient path
+  e->u1 = c.take<bf16>(B * S * D);
+  e->u2 = c.take<bf16>(B * S * D);
+  e->stats = c.take<float>(size_t(2) * B * S);
+  e->tproj_t = c.take<bf16>(size_t(B) * 256);
+  e->tmp_t = c.take<bf16>(B * D);
+  e->ltv1 = c.take<bf16>(B * r);
+  e->ltv2 = c.take<bf16>(B * r);
+  e->dsilu = c.take<float>(B * D);
+  e->dtmp = c.take<float>(B * D);
+  e->dltv = c.take<float>(B * r);
   return c.off;
 }
 
@@ -613,8 +638,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
   const View y_all{e->y, D, bsD}, at_all{e->attn, D, bsD}, mlp_all{e->mlp, M, bsM}, pre_all{e->mlp_pre, M, bsM};
   const View raw_all{e->qkv_raw, 3 * D, bs3}, l0_all{e->lt0, rr, bsR}, l1_all{e->lt1, rr, bsR}, dl_all{e->dl, rr, bsR};
   const View dh_all{e->dh, D, bsD}, du_all{e->du, D, bsD}, dy_all{e->dy, D, bsD}, dat_all{e->dattn, D, bsD};
-  const View dmlp_all{e->dmlp, M, bsM}, dqkv_all{e->dqkv, 3 * D, bs3};
+  const View dmlp_all{e->dmlp, M, bsM}, dqkv_all{e->dqkv, 3 * D, bs3}, u1_all{e->u1, D, bsD};
   LoraBwd lb{e, B, S, s};
+  float* dmod = ba->d_mod;  // fp32 [B, mod_total] or NULL
 
   // ---- single-stream blocks, last to first ----------------------------------------------------------------------
   for (int i = d.num_single - 1; i >= 0; --i) {
@@ -642,7 +668,16 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_TRY(afb::gelu_fwd_launch(e->mlp_pre, M, e->mlp, M, int64_t(B) * S, M, s));
     if (lo) AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
     // -- backward
-    AFB_TRY(afb::rowscale_launch(e->dh, D, bsD, m + 2 * D, mod_bs, e->du, D, bsD, B, S, D, s));
+    if (dmod) {  // the gate's gradient needs the branch output u = proj_out([attn | mlp]) the forward never stores
+      if (lo)
+        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, out_ld, D, k.out_b).out(u1_all, AFB_EPI_BIAS).run(e, s));
+      else
+        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_w, out_ld, D, k.out_b).out(u1_all, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(afb::gate_bwd_launch(e->dh, bsD, e->u1, bsD, m + 2 * D, mod_bs, e->du, bsD, dmod + k.mod_off + 2 * D, mod_bs, B, S,
+                                   D, s));
+    } else {
+      AFB_TRY(afb::rowscale_launch(e->dh, D, bsD, m + 2 * D, mod_bs, e->du, D, bsD, B, S, D, s));
+    }
     if (lo)
       AFB_TRY(lb.lora_grads(du_all, D, out_w, out_ld, D + M, l1_all, dl_all, at_all, D, mlp_all, M, g ? g->out_la : nullptr,
                             g ? g->out_lb : nullptr));
@@ -658,6 +693,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_TRY(afb::rmsnorm_rope_bwd_launch(e->dqkv, e->qkv_raw, 3 * D, bs3, 0, D, B, S, H, 0, nullptr, nullptr, k.nq, k.nk,
                                          a->rope_cos, a->rope_sin, LN_EPS, s));
     AFB_TRY(Gemm(B, S).a(dqkv_all, 3 * D).wt(k.qkv_w, D, D, 3 * D).out(dy_all, AFB_EPI_BIAS_RES).res(dy_all).run(e, s));
+    if (dmod)
+      AFB_TRY(afb::ln_mod_param_grad_strided_launch(h_in, bsD, e->dy, bsD, e->stats, dmod + k.mod_off + D, dmod + k.mod_off,
+                                                    mod_bs, B, S, D, LN_EPS, s));
     AFB_TRY(afb::ln_modulate_bwd_launch(h_in, bsD, e->dy, bsD, e->dh, bsD, m + D, mod_bs, B, S, D, LN_EPS, 1, s));
   }
 
@@ -671,7 +709,8 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     struct Stream {
       int rows;
       const bf16* mod;
-      View h_in, h_mid, y, qkv_raw, attn, mlp, pre, l0, l1, dl, dh, du, dy, dattn, dmlp, dqkv;
+      View h_in, h_mid, y, qkv_raw, attn, mlp, pre, l0, l1, dl, dh, du, dy, dattn, dmlp, dqkv, u1, u2;
+      int64_t mod_off;
       const void *qkv_w, *qkv_b, *out_w, *out_b, *up_w, *up_b, *up_la, *down_w, *down_b, *down_la;
       float *g_up_la, *g_up_lb, *g_down_la, *g_down_lb;
     };
@@ -696,6 +735,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       t.dattn = v(e->dattn, D);
       t.dmlp = v(e->dmlp, M);
       t.dqkv = v(e->dqkv, 3 * D);
+      t.u1 = v(e->u1, D);
+      t.u2 = v(e->u2, D);
+      t.mod_off = is_img ? k.img_mod_off : k.txt_mod_off;
       if (is_img) {
         t.qkv_w = k.img_qkv_w, t.qkv_b = k.img_qkv_b, t.out_w = k.img_out_w, t.out_b = k.img_out_b;
         t.up_w = k.img_up_w, t.up_b = k.img_up_b, t.up_la = k.img_up_la;
@@ -727,8 +769,14 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       const int64_t up_ld = D + (t.up_la ? rpad : 0), down_ld = M + (t.down_la ? rpad : 0);
       const bf16* up_w = static_cast<const bf16*>(t.up_w);
       const bf16* down_w = static_cast<const bf16*>(t.down_w);
-      AFB_TRY(Gemm(B, t.rows).a(t.attn, D).w(t.out_w, D, D, t.out_b).out(t.h_mid, AFB_EPI_BIAS_GATE_RES)
-                  .gate_res(t.mod + 2 * D, mod_bs, t.h_in).run(e, s));
+      if (dmod) {  // keep the un-gated attention branch output for the gate's gradient
+        AFB_TRY(Gemm(B, t.rows).a(t.attn, D).w(t.out_w, D, D, t.out_b).out(t.u1, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(afb::gate_res_launch(t.h_in.p, t.h_in.bs, t.u1.p, t.u1.bs, t.mod + 2 * D, mod_bs, const_cast<bf16*>(t.h_mid.p),
+                                     t.h_mid.bs, B, t.rows, D, s));
+      } else {
+        AFB_TRY(Gemm(B, t.rows).a(t.attn, D).w(t.out_w, D, D, t.out_b).out(t.h_mid, AFB_EPI_BIAS_GATE_RES)
+                    .gate_res(t.mod + 2 * D, mod_bs, t.h_in).run(e, s));
+      }
       AFB_TRY(afb::ln_modulate_launch(t.h_mid.p, t.h_mid.bs, const_cast<bf16*>(t.y.p), t.y.bs, t.mod + 4 * D, t.mod + 3 * D,
                                       mod_bs, B, t.rows, D, LN_EPS, s));
       if (lu) {
@@ -742,8 +790,17 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
                                      t.rows, M, s));
       if (ld_) AFB_TRY(Gemm(B, t.rows).a(t.mlp, M).w(t.down_la, M, r, nullptr).out(t.l1, AFB_EPI_BIAS).run(e, s));
       // backward of  h_out = h_mid + gate_mlp * down(gelu(up(LNmod2(h_mid))))
-      AFB_TRY(afb::rowscale_launch(t.dh.p, D, t.dh.bs, t.mod + 5 * D, mod_bs, const_cast<bf16*>(t.du.p), D, t.du.bs, B, t.rows,
-                                   D, s));
+      if (dmod) {
+        if (ld_)
+          AFB_TRY(Gemm(B, t.rows).a(t.mlp, M).a(t.l1, r).w(t.down_w, down_ld, D, t.down_b).out(t.u2, AFB_EPI_BIAS).run(e, s));
+        else
+          AFB_TRY(Gemm(B, t.rows).a(t.mlp, M).w(t.down_w, down_ld, D, t.down_b).out(t.u2, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(afb::gate_bwd_launch(t.dh.p, t.dh.bs, t.u2.p, t.u2.bs, t.mod + 5 * D, mod_bs, const_cast<bf16*>(t.du.p), t.du.bs,
+                                     dmod + t.mod_off + 5 * D, mod_bs, B, t.rows, D, s));
+      } else {
+        AFB_TRY(afb::rowscale_launch(t.dh.p, D, t.dh.bs, t.mod + 5 * D, mod_bs, const_cast<bf16*>(t.du.p), D, t.du.bs, B,
+                                     t.rows, D, s));
+      }
       if (ld_) AFB_TRY(sb.lora_grads(t.du, D, down_w, down_ld, M, t.l1, t.dl, t.mlp, M, View{}, 0, t.g_down_la, t.g_down_lb));
       AFB_TRY(sb.dx(t.du, D, down_w, down_ld, ld_ ? static_cast<const bf16*>(t.down_la) : nullptr, M, t.dl, 0, M, t.dmlp, false));
       for (int bi = 0; bi < B; ++bi)
@@ -751,11 +808,19 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
                                      M, t.rows, M, s));
       if (lu) AFB_TRY(sb.lora_grads(t.dmlp, M, up_w, up_ld, D, t.l0, t.dl, t.y, D, View{}, 0, t.g_up_la, t.g_up_lb));
       AFB_TRY(sb.dx(t.dmlp, M, up_w, up_ld, lu ? static_cast<const bf16*>(t.up_la) : nullptr, D, t.dl, 0, D, t.dy, false));
+      if (dmod)
+        AFB_TRY(afb::ln_mod_param_grad_strided_launch(t.h_mid.p, t.h_mid.bs, t.dy.p, t.dy.bs, e->stats,
+                                                      dmod + t.mod_off + 4 * D, dmod + t.mod_off + 3 * D, mod_bs, B, t.rows, D,
+                                                      LN_EPS, s));
       AFB_TRY(afb::ln_modulate_bwd_launch(t.h_mid.p, t.h_mid.bs, t.dy.p, t.dy.bs, const_cast<bf16*>(t.dh.p), t.dh.bs,
                                           t.mod + 4 * D, mod_bs, B, t.rows, D, LN_EPS, 1, s));
       // attention half: dattn = (gate_msa * dh) W_out
-      AFB_TRY(afb::rowscale_launch(t.dh.p, D, t.dh.bs, t.mod + 2 * D, mod_bs, const_cast<bf16*>(t.du.p), D, t.du.bs, B, t.rows,
-                                   D, s));
+      if (dmod)
+        AFB_TRY(afb::gate_bwd_launch(t.dh.p, t.dh.bs, t.u1.p, t.u1.bs, t.mod + 2 * D, mod_bs, const_cast<bf16*>(t.du.p), t.du.bs,
+                                     dmod + t.mod_off + 2 * D, mod_bs, B, t.rows, D, s));
+      else
+        AFB_TRY(afb::rowscale_launch(t.dh.p, D, t.dh.bs, t.mod + 2 * D, mod_bs, const_cast<bf16*>(t.du.p), D, t.du.bs, B,
+                                     t.rows, D, s));
       AFB_TRY(Gemm(B, t.rows).a(t.du, D).wt(t.out_w, D, D, D).out(t.dattn, AFB_EPI_BIAS).run(e, s));
     }
     AFB_TRY(attention_bwd());
@@ -763,6 +828,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
                                          k.img_nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     for (Stream& t : st2) {
       AFB_TRY(Gemm(B, t.rows).a(t.dqkv, 3 * D).wt(t.qkv_w, D, D, 3 * D).out(t.dy, AFB_EPI_BIAS).run(e, s));
+      if (dmod)
+        AFB_TRY(afb::ln_mod_param_grad_strided_launch(t.h_in.p, t.h_in.bs, t.dy.p, t.dy.bs, e->stats, dmod + t.mod_off + D,
+                                                      dmod + t.mod_off, mod_bs, B, t.rows, D, LN_EPS, s));
       AFB_TRY(afb::ln_modulate_bwd_launch(t.h_in.p, t.h_in.bs, t.dy.p, t.dy.bs, const_cast<bf16*>(t.dh.p), t.dh.bs, t.mod + D,
                                           mod_bs, B, t.rows, D, LN_EPS, 1, s));
     }
@@ -968,13 +1036,51 @@ int afb_engine_backward(afb_engine* e, const afb_backward_args* ba, void* stream
   AFB_REQUIRE(e->tws && e->saved_batch == a.batch && e->saved_txt == a.txt_len && e->saved_img == a.img_len,
               "engine_backward: no checkpoints of this shape (run afb_engine_forward_train first)");
   AFB_REQUIRE(ba->d_head_in && a.rope_cos && a.rope_sin, "engine_backward: null tensor argument");
-  if (ba->d_mod) {
-    afb::set_last_error("engine_backward: modulation-vector gradients (d_mod) are not built yet");
-    return AFB_ERR_UNSUPPORTED;
-  }
   carve(e, static_cast<uint8_t*>(e->ws), a.batch, a.txt_len, a.img_len);
   carve_train(e, static_cast<uint8_t*>(e->tws), a.batch, a.txt_len, a.img_len);
   return backward_impl(e, ba, static_cast<cudaStream_t>(stream));
+}
+
+// d_mod (gradient of every AdaLN vector, fp32 [B, mod_total]) -> temb -> the timestep embedder's two LoRA pairs.
+// temb = t2(silu(t1(sinusoid(t)))) + guidance path + pooled-text path (both frozen), mod = mod_w silu(temb) + mod_b.
+int afb_engine_backward_embed(afb_engine* e, const afb_forward_args* a, const float* d_mod, const afb_embed_grads* g,
+                              void* stream) {
+  AFB_REQUIRE(a && d_mod && g, "engine_backward_embed: null argument");
+  AFB_TRY(check_shapes(e, a->batch, a->txt_len, a->img_len));
+  AFB_REQUIRE(e->tws && e->saved_batch == a->batch && e->saved_txt == a->txt_len && e->saved_img == a->img_len,
+              "engine_backward_embed: run afb_engine_forward_train first");
+  AFB_REQUIRE(a->timestep != nullptr, "engine_backward_embed: timestep missing");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  carve(e, static_cast<uint8_t*>(e->ws), a->batch, a->txt_len, a->img_len);
+  carve_train(e, static_cast<uint8_t*>(e->tws), a->batch, a->txt_len, a->img_len);
+  const afb_weights& w = e->w;
+  const int B = a->batch, D = e->desc.dim, r = e->desc.ignore_lora ? 0 : e->desc.lora_rank;
+  if (r == 0 || !w.t1_la || !w.t1_lb || !w.t2_la || !w.t2_lb) return AFB_OK;  // nothing trainable upstream of temb
+  // dtemb = (d_mod mod_w) * silu'(temb)
+  AFB_CHECK_CUDA(cudaMemsetAsync(e->dsilu, 0, size_t(B) * D * sizeof(float), s));
+  AFB_TRY(afb::rowlinear_dx_launch(d_mod, w.mod_total, w.mod_w, D, e->dsilu, D, B, int(w.mod_total), D, s));
+  AFB_TRY(afb::silu_bwd_launch(e->dsilu, D, e->temb, D, B, D, s));
+  // recompute the timestep path's intermediates
+  AFB_TRY(afb::timestep_embed_launch(a->timestep, e->tproj_t, B, s));
+  AFB_TRY(small_linear_rows(e->tproj_t, 256, w.t1_w, 256, w.t1_b, e->tmp_t, D, B, D, 256, 0, s));
+  AFB_TRY(small_linear_rows(e->tproj_t, 256, w.t1_la, 256, nullptr, e->ltv1, r, B, r, 256, 0, s));
+  AFB_TRY(small_linear_rows(e->ltv1, r, w.t1_lb, r, nullptr, e->tmp_t, D, B, D, r, AFB_SL_ACCUMULATE, s));
+  AFB_TRY(small_linear_rows(e->tmp_t, D, w.t2_la, D, nullptr, e->ltv2, r, B, r, D, AFB_SL_SILU_IN, s));
+  // linear_2: temb_t = W2 silu(tmp) + B2 (A2 silu(tmp))
+  if (g->t2_lb) AFB_TRY(afb::rowlinear_param_grad_launch(e->dsilu, D, e->ltv2, r, g->t2_lb, r, nullptr, B, D, r, 0, s));
+  AFB_CHECK_CUDA(cudaMemsetAsync(e->dltv, 0, size_t(B) * r * sizeof(float), s));
+  AFB_TRY(afb::rowlinear_dx_launch(e->dsilu, D, w.t2_lb, r, e->dltv, r, B, D, r, s));
+  if (g->t2_la) AFB_TRY(afb::rowlinear_param_grad_launch(e->dltv, r, e->tmp_t, D, g->t2_la, D, nullptr, B, r, D, 1, s));
+  AFB_CHECK_CUDA(cudaMemsetAsync(e->dtmp, 0, size_t(B) * D * sizeof(float), s));
+  AFB_TRY(afb::rowlinear_dx_launch(e->dsilu, D, w.t2_w, D, e->dtmp, D, B, D, D, s));
+  AFB_TRY(afb::rowlinear_dx_launch(e->dltv, r, w.t2_la, D, e->dtmp, D, B, r, D, s));
+  AFB_TRY(afb::silu_bwd_launch(e->dtmp, D, e->tmp_t, D, B, D, s));
+  // linear_1: tmp = W1 p + B1 (A1 p)
+  if (g->t1_lb) AFB_TRY(afb::rowlinear_param_grad_launch(e->dtmp, D, e->ltv1, r, g->t1_lb, r, nullptr, B, D, r, 0, s));
+  AFB_CHECK_CUDA(cudaMemsetAsync(e->dltv, 0, size_t(B) * r * sizeof(float), s));
+  AFB_TRY(afb::rowlinear_dx_launch(e->dtmp, D, w.t1_lb, r, e->dltv, r, B, D, r, s));
+  if (g->t1_la) AFB_TRY(afb::rowlinear_param_grad_launch(e->dltv, r, e->tproj_t, 256, g->t1_la, 256, nullptr, B, r, 256, 0, s));
+  return AFB_OK;
 }
 
 int afb_engine_denoise(afb_engine* e, const afb_denoise_args* a, void* stream) {

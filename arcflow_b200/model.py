@@ -338,8 +338,43 @@ class ArcFluxEngineModel(EngineModelBase):
             names += [f"single_transformer_blocks.{i}.{n}.lora_{ab}.weight" for _, n in self._SGL_LORA for ab in "AB"]
         return names
 
+    _TEMB_LORA = (("t1", "time_text_embed.timestep_embedder.linear_1"), ("t2", "time_text_embed.timestep_embedder.linear_2"))
+
+    def embed_lora_shapes(self) -> Dict[str, tuple]:
+        D, r = self.cfg.inner_dim, self.cfg.lora_rank
+        return {"time_text_embed.timestep_embedder.linear_1.lora_A.weight": (r, 256),
+                "time_text_embed.timestep_embedder.linear_1.lora_B.weight": (D, r),
+                "time_text_embed.timestep_embedder.linear_2.lora_A.weight": (r, D),
+                "time_text_embed.timestep_embedder.linear_2.lora_B.weight": (D, r)}
+
+    @property
+    def mod_total(self) -> int:
+        return int(self.weights.struct.mod_total)
+
+    @property
+    def norm_out_mod_off(self) -> int:
+        return int(self.weights.struct.norm_out_mod_off)
+
     @torch.no_grad()
-    def backward_trunk(self, d_head_in: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+    def backward_embed(self, d_mod: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+        """d_mod (fp32 [batch, mod_total], every AdaLN vector's gradient) -> timestep-embedder LoRA gradients (+=)."""
+        ctx = getattr(self, "_train_ctx", None)
+        if ctx is None:
+            raise AfbError("backward_embed: run forward_heads(train=True) first")
+        a = ctx["args"]
+        if d_mod.dtype != torch.float32 or tuple(d_mod.shape) != (a.batch, self.mod_total) or not d_mod.is_contiguous():
+            raise AfbError(f"d_mod must be contiguous fp32 [{a.batch}, {self.mod_total}]")
+        g = _lib.EmbedGrads()
+        for tag, name in self._TEMB_LORA:
+            for ab in "ab":
+                t = grads.get(f"{name}.lora_{ab.upper()}.weight")
+                setattr(g, f"{tag}_l{ab}", t.data_ptr() if t is not None else None)
+        _lib.check(self.lib.afb_engine_backward_embed(self.handle, C.byref(a), d_mod.data_ptr(), C.byref(g),
+                                                      torch.cuda.current_stream().cuda_stream), "afb_engine_backward_embed")
+
+    @torch.no_grad()
+    def backward_trunk(self, d_head_in: torch.Tensor, grads: Dict[str, torch.Tensor],
+                       d_mod: Optional[torch.Tensor] = None) -> None:
         """Accumulate (+=) the LoRA gradients of the last `forward_heads(train=True)` into `grads` (fp32 tensors keyed by
         state-dict name, shapes of the LoRA tensors; missing names are skipped). d_head_in: bf16 [batch, tokens, dim],
         the gradient w.r.t. the norm_out output. Replaces torch autograd + checkpointing through the diffusers blocks
@@ -375,6 +410,10 @@ class ArcFluxEngineModel(EngineModelBase):
         b.d_head_in = d_head_in.data_ptr()
         b.dbl = C.cast(dbl, C.POINTER(_lib.DoubleBlockGrads))
         b.sgl = C.cast(sgl, C.POINTER(_lib.SingleBlockGrads))
+        if d_mod is not None:
+            if d_mod.dtype != torch.float32 or tuple(d_mod.shape) != (a.batch, self.mod_total) or not d_mod.is_contiguous():
+                raise AfbError(f"d_mod must be contiguous fp32 [{a.batch}, {self.mod_total}]")
+            b.d_mod = d_mod.data_ptr()
         _lib.check(self.lib.afb_engine_backward(self.handle, C.byref(b), torch.cuda.current_stream().cuda_stream),
                    "afb_engine_backward")
 

@@ -162,9 +162,10 @@ class ArcFlowDistillStep:
         }
 
     @torch.no_grad()
-    def _backward_step_heads(self, sv, acc) -> torch.Tensor:
+    def _backward_step_heads(self, sv, acc, d_mod: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One student step: loss -> d(raw heads) -> head / norm_out gradients (accumulated into acc). Returns dy, the
-        gradient w.r.t. the norm_out output (bf16 [B, tokens, D]) that the trunk backward starts from."""
+        gradient w.r.t. the norm_out output (bf16 [B, tokens, D]) that the trunk backward starts from. d_mod (fp32
+        [B, mod_total]) receives norm_out's (scale, shift) gradient in its slot."""
         cfg, st = self.cfg, self.student
         n_states, eps = cfg["num_intermediate_states"], cfg.get("eps", 1e-4)
         D, head_n, dev = st.cfg.inner_dim, st.weights.head_n, st.device
@@ -187,6 +188,9 @@ class ArcFlowDistillStep:
         dscale, dshift = ops.ln_mod_param_grad(sv["hidden"], dy)
         demb = torch.cat([dscale, dshift], dim=1).contiguous()             # AdaLayerNormContinuous: (scale, shift)
         ops.rowlinear_param_grad(demb, sv["temb"], acc["g_nw"], acc["g_nb"], silu_in=True)
+        if d_mod is not None:
+            off = st.norm_out_mod_off
+            d_mod[:, off:off + 2 * D] += demb
         return dy
 
     @torch.no_grad()
@@ -206,22 +210,26 @@ class ArcFlowDistillStep:
                          rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0,
                          grads: Optional[Dict[str, torch.Tensor]] = None):
         """train_fwd_bwd (lakonlab/models/base_diffusion.py:14-62): forward + loss + the gradients of every adapter
-        tensor except the timestep-embedder LoRA (its only path is through the AdaLN modulation vectors).
+        tensor: heads, norm_out.linear, the trunk's LoRA pairs, and — through the gradients of every AdaLN shift / scale /
+        gate vector — the timestep embedder's LoRA pairs.
         grads: fp32 CUDA tensors keyed by state-dict name, accumulated into (+=); created zero-filled when None.
         Each student step's backward runs right after its roll-out: heads / norm_out (backward_heads path), then the
-        frozen trunk in reverse with per-block recompute (afb_engine_backward)."""
+        frozen trunk in reverse with per-block recompute (afb_engine_backward), then afb_engine_backward_embed."""
         st = self.student
         if grads is None:
             grads = {}
-        shapes = st.trunk_lora_shapes()
+        shapes = dict(st.trunk_lora_shapes())
+        shapes.update(st.embed_lora_shapes())
         for n, shp in shapes.items():
             if n not in grads:
                 grads[n] = torch.zeros(shp, dtype=torch.float32, device=st.device)
         acc = self._head_grad_buffers()
 
         def hook(saved):
-            dy = self._backward_step_heads(saved, acc)
-            st.backward_trunk(dy, grads)
+            d_mod = torch.zeros(noise.shape[0], st.mod_total, dtype=torch.float32, device=st.device)
+            dy = self._backward_step_heads(saved, acc, d_mod)
+            st.backward_trunk(dy, grads, d_mod)
+            st.backward_embed(d_mod, grads)
 
         loss, log_vars, extras = self.forward(txt, pooled, grid_hw, noise, rands, iteration, save_for_backward=True,
                                               step_hook=hook)

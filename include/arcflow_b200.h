@@ -408,9 +408,10 @@ int afb_engine_denoise(afb_engine* e, const afb_denoise_args* args, void* stream
  *                              dX GEMMs with the forward weights read transposed, tcgen05 attention backward,
  *                              LN / GELU / RMSNorm+RoPE backward, and the LoRA gradients dB = dY^T T, dA = dT^T X
  *                              accumulated (+=) in fp32 into the caller's buffers (NULL = skip that tensor).
- * d_head_in: bf16 [batch, img_len, dim] = gradient w.r.t. the norm_out output (the heads' input). The modulation
- * vectors are treated as constants (no gradient to the timestep-embedder LoRA through the AdaLN vectors) unless
- * d_mod (fp32 [batch, mod_total], accumulated) is given.
+ * d_head_in: bf16 [batch, img_len, dim] = gradient w.r.t. the norm_out output (the heads' input). With d_mod (fp32
+ * [batch, mod_total], accumulated into) the gradients of every AdaLN shift / scale / gate vector are produced too (one
+ * extra GEMM per gate: the un-gated branch output is recomputed); afb_engine_backward_embed turns them into the
+ * timestep-embedder LoRA gradients. Without d_mod the modulation vectors are treated as constants.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct afb_double_block_grads {
   float *img_up_la, *img_up_lb, *img_down_la, *img_down_lb, *txt_up_la, *txt_up_lb, *txt_down_la, *txt_down_lb;
@@ -428,6 +429,13 @@ typedef struct afb_backward_args {
 int afb_engine_train_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
 int afb_engine_forward_train(afb_engine* e, const afb_forward_args* args, void* stream);
 int afb_engine_backward(afb_engine* e, const afb_backward_args* args, void* stream);
+/* d_mod (fp32 [batch, mod_total]: afb_engine_backward's output plus the caller-written norm_out slot) -> temb ->
+ * gradients of the timestep embedder's LoRA pairs (time_text_embed.timestep_embedder.linear_1/2), accumulated (+=). */
+typedef struct afb_embed_grads {
+  float *t1_la, *t1_lb, *t2_la, *t2_lb;
+} afb_embed_grads;
+int afb_engine_backward_embed(afb_engine* e, const afb_forward_args* fwd, const float* d_mod, const afb_embed_grads* grads,
+                              void* stream);
 
 /* Optional instrumentation: when on, every tensor-core launch of forward/denoise is bracketed by CUDA
  * events on the caller's stream. afb_engine_read_profile synchronises the device, returns the totals

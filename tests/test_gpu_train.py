@@ -230,7 +230,7 @@ def test_trunk_lora_gradients_match_autograd(lib):
     """forward_backward(): LoRA gradients through the frozen trunk (per-block recompute, tcgen05 attention backward,
     transposed-weight dX GEMMs, token-contraction dW GEMMs) vs torch autograd through the fp32 training oracle.
     Tolerance: the native backward carries activations and activation gradients in bf16 (like the reference's bf16
-    autocast run) while the oracle differentiates in fp32 -> rel-L2 <= 5e-2 per tensor, cosine >= 0.998."""
+    autocast run) while the oracle differentiates in fp32 -> rel-L2 <= 2e-2 per tensor, cosine >= 0.9995 (measured worst: 7.4e-3, 0.99997)."""
     from arcflow_b200.train import ArcFlowDistillStep, draw_rollout_randoms
     cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup(num_layers=2, num_single=2)
     tc = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, nfe=2,
@@ -239,7 +239,7 @@ def test_trunk_lora_gradients_match_autograd(lib):
     rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
     step = ArcFlowDistillStep(student, teacher, tc)
     loss, _, grads = step.forward_backward(txt.to(DEV), pooled.to(DEV), grid, x.to(DEV), rands, iteration=700)
-    names = student.trunk_lora_names() + ["proj_out_means.weight", "norm_out.linear.weight"]
+    names = student.trunk_lora_names() + list(student.embed_lora_shapes()) + ["proj_out_means.weight", "norm_out.linear.weight"]
     ref_loss, _, ex = T.flux_train_forward(sd, extra, cfg, txt, pooled, grid, x, rands, 700, tc, dtype=torch.float32,
                                            require_grad=names)
     ref_loss.backward()
@@ -251,5 +251,5 @@ def test_trunk_lora_gradients_match_autograd(lib):
         e = rel(got, ref)
         cos = float((got * ref).sum() / (got.norm() * ref.norm() + 1e-30))
         worst.append((e, cos, n))
-        assert e < 5e-2 and cos > 0.998, f"{n}: rel-L2 {e:.3e} cos {cos:.5f} (|ref| {ref.norm():.3e})"
+        assert e < 2e-2 and cos > 0.9995, f"{n}: rel-L2 {e:.3e} cos {cos:.5f} (|ref| {ref.norm():.3e})"
     print("worst:", sorted(worst, reverse=True)[:3])
