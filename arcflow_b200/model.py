@@ -36,6 +36,10 @@ class PackedFluxWeights:
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: ArcFluxConfig, device, consume: bool = False):
         self.cfg = cfg
         self.keep: List[torch.Tensor] = []
+        # state-dict name of every trainable (adapter) tensor -> the bf16 view inside the packed buffers the engine reads
+        # (the optimizer's write-back target: lora_B lives in the K-extension columns of [W | B], the heads are row slices
+        # of the fused head weight, norm_out.linear is the last row block of the fused modulation weight)
+        self.adapter_views: Dict[str, torch.Tensor] = {}
         D = cfg.inner_dim
         r = cfg.lora_rank
 
@@ -47,11 +51,20 @@ class PackedFluxWeights:
                 return None
             return t.to(device=device, dtype=BF16)
 
-        def hold(t: Optional[torch.Tensor]):
+        def hold(t: Optional[torch.Tensor], view_name: Optional[str] = None):
             if t is None:
                 return None
             t = t.contiguous()
             self.keep.append(t)
+            if view_name is not None:
+                self.adapter_views[view_name] = t
+            return t.data_ptr()
+
+        def hold_packed(w_: torch.Tensor, lb_: Optional[torch.Tensor], prefix: str):
+            t = _cat_k(w_, lb_)
+            self.keep.append(t)
+            if lb_ is not None:
+                self.adapter_views[prefix + ".lora_B.weight"] = t[:, w_.shape[1]:]
             return t.data_ptr()
 
         def lora(prefix: str):
@@ -79,8 +92,8 @@ class PackedFluxWeights:
                 setattr(w, f"{tag}{li}_b", hold(get(pre + ".bias")))
                 if with_lora:
                     a, b = lora(pre)
-                    setattr(w, f"{tag}{li}_la", hold(a))
-                    setattr(w, f"{tag}{li}_lb", hold(b))
+                    setattr(w, f"{tag}{li}_la", hold(a, pre + ".lora_A.weight"))
+                    setattr(w, f"{tag}{li}_lb", hold(b, pre + ".lora_B.weight"))
 
         mod_w: List[torch.Tensor] = []
         mod_b: List[torch.Tensor] = []
@@ -108,13 +121,13 @@ class PackedFluxWeights:
                 setattr(k, f"{side}_out_w", hold(get(p + f"attn.{out_name}.weight")))
                 setattr(k, f"{side}_out_b", hold(get(p + f"attn.{out_name}.bias")))
                 la, lb = lora(p + f"{ff}.net.0.proj")
-                setattr(k, f"{side}_up_w", hold(_cat_k(get(p + f"{ff}.net.0.proj.weight"), lb)))
+                setattr(k, f"{side}_up_w", hold_packed(get(p + f"{ff}.net.0.proj.weight"), lb, p + f"{ff}.net.0.proj"))
                 setattr(k, f"{side}_up_b", hold(get(p + f"{ff}.net.0.proj.bias")))
-                setattr(k, f"{side}_up_la", hold(la))
+                setattr(k, f"{side}_up_la", hold(la, p + f"{ff}.net.0.proj.lora_A.weight"))
                 la, lb = lora(p + f"{ff}.net.2")
-                setattr(k, f"{side}_down_w", hold(_cat_k(get(p + f"{ff}.net.2.weight"), lb)))
+                setattr(k, f"{side}_down_w", hold_packed(get(p + f"{ff}.net.2.weight"), lb, p + f"{ff}.net.2"))
                 setattr(k, f"{side}_down_b", hold(get(p + f"{ff}.net.2.bias")))
-                setattr(k, f"{side}_down_la", hold(la))
+                setattr(k, f"{side}_down_la", hold(la, p + f"{ff}.net.2.lora_A.weight"))
             k.img_nq, k.img_nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
             k.txt_nq, k.txt_nk = hold(get(p + "attn.norm_added_q.weight")), hold(get(p + "attn.norm_added_k.weight"))
 
@@ -127,13 +140,18 @@ class PackedFluxWeights:
             k.qkv_b = hold(torch.cat([get(p + f"attn.{n}.bias") for n in ("to_q", "to_k", "to_v")], 0))
             k.nq, k.nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
             la, lb = lora(p + "proj_mlp")
-            k.mlp_w, k.mlp_b, k.mlp_la = hold(_cat_k(get(p + "proj_mlp.weight"), lb)), hold(get(p + "proj_mlp.bias")), hold(la)
+            k.mlp_w = hold_packed(get(p + "proj_mlp.weight"), lb, p + "proj_mlp")
+            k.mlp_b, k.mlp_la = hold(get(p + "proj_mlp.bias")), hold(la, p + "proj_mlp.lora_A.weight")
             la, lb = lora(p + "proj_out")
-            k.out_w, k.out_b, k.out_la = hold(_cat_k(get(p + "proj_out.weight"), lb)), hold(get(p + "proj_out.bias")), hold(la)
+            k.out_w = hold_packed(get(p + "proj_out.weight"), lb, p + "proj_out")
+            k.out_b, k.out_la = hold(get(p + "proj_out.bias")), hold(la, p + "proj_out.lora_A.weight")
 
         w.norm_out_mod_off = add_mod("norm_out.linear")
-        w.mod_w, w.mod_b = hold(torch.cat(mod_w, 0)), hold(torch.cat(mod_b, 0))
+        mod_w_t, mod_b_t = torch.cat(mod_w, 0), torch.cat(mod_b, 0)
+        w.mod_w, w.mod_b = hold(mod_w_t), hold(mod_b_t)
         w.mod_total = mod_off
+        self.adapter_views["norm_out.linear.weight"] = mod_w_t[w.norm_out_mod_off:]
+        self.adapter_views["norm_out.linear.bias"] = mod_b_t[w.norm_out_mod_off:]
         del mod_w, mod_b
 
         heads_w = [get("proj_out_means.weight"), get("proj_out_logweights.weight"), get("proj_out_loggamma.weight")]
@@ -144,7 +162,13 @@ class PackedFluxWeights:
             heads_w.append(torch.zeros(pad, D, device=device, dtype=BF16))
             heads_b.append(torch.zeros(pad, device=device, dtype=BF16))
         self.head_w_tensor = torch.cat(heads_w, 0).contiguous()
-        w.head_w, w.head_b, w.head_n = hold(self.head_w_tensor), hold(torch.cat(heads_b, 0)), n + pad
+        head_b_tensor = torch.cat(heads_b, 0).contiguous()
+        row = 0
+        for hn, hw in zip(("proj_out_means", "proj_out_logweights", "proj_out_loggamma"), heads_w):
+            self.adapter_views[hn + ".weight"] = self.head_w_tensor[row:row + hw.shape[0]]
+            self.adapter_views[hn + ".bias"] = head_b_tensor[row:row + hw.shape[0]]
+            row += hw.shape[0]
+        w.head_w, w.head_b, w.head_n = hold(self.head_w_tensor), hold(head_b_tensor), n + pad
         self.head_n = n + pad
         w.dbl = C.cast(self.dbl, C.POINTER(_lib.DoubleBlock))
         w.sgl = C.cast(self.sgl, C.POINTER(_lib.SingleBlock))

@@ -243,3 +243,47 @@ class ArcFlowDistillStep:
     def backward(self, *a, **k):
         raise NotImplementedError("use forward_backward(): each student step's backward must run before the next student "
                                   "forward overwrites the trunk checkpoints")
+
+
+class ArcFlowTrainer:
+    """One optimisation iteration of the data-free distillation: forward_backward -> (DDP all-reduce) -> grad clip ->
+    AdamW -> Karras EMA -> write the updated bf16 adapter back into the engine's packed weights.
+    Reference: the mmcv iter-based runner driving BaseModel.train_step (lakonlab/models/base.py:76-103,
+    lakonlab/models/base_diffusion.py:14-62) with configs/flux/_ddp_train.py's optimizer and the EMA hook
+    (lakonlab/runner/hooks/ema_hook.py:86-121). Every adapter tensor (LoRA pairs, proj_out_*, norm_out.linear) lives in ONE
+    flat fp32 arena (arcflow_b200/optim.py), its gradient view is what the native backward accumulates into."""
+
+    def __init__(self, student, teacher, train_cfg: Optional[Dict] = None, shift: float = 3.2, loss_scale: float = 30.0,
+                 **optim_kwargs):
+        from .optim import FlatAdamW
+        self.student = student
+        self.distill = ArcFlowDistillStep(student, teacher, train_cfg, shift, loss_scale)
+        views = student.weights.adapter_views
+        if not views:
+            raise AfbError("ArcFlowTrainer: the student carries no adapter tensors")
+        self.opt = FlatAdamW({n: tuple(v.shape) for n, v in views.items()}, student.device, **optim_kwargs)
+        self.opt.load_params(views)
+        self.grads = {n: self.opt.grad(n) for n in views}
+        self.iteration = 0
+
+    @torch.no_grad()
+    def write_back(self, use_ema: bool = False):
+        """bf16 shadow of the arena (or of the EMA weights, for evaluation / export) -> the engine's packed buffers."""
+        src = self.opt.ema.to(torch.bfloat16) if use_ema else self.opt.shadow
+        for n, dst in self.student.weights.adapter_views.items():
+            dst.copy_(self.opt.view(src, n))
+
+    def adapter_state_dict(self, use_ema: bool = True) -> Dict[str, torch.Tensor]:
+        """The adapter tensors under the reference's on-disk names (export_arcflow_to_diffusers.py:104-127)."""
+        buf = self.opt.ema if use_ema else self.opt.params
+        return {n: self.opt.view(buf, n).to(torch.bfloat16).clone() for n in self.student.weights.adapter_views}
+
+    @torch.no_grad()
+    def train_step(self, txt, pooled, grid_hw, noise, rands, iteration: Optional[int] = None):
+        it = self.iteration if iteration is None else iteration
+        self.opt.grads.zero_()
+        loss, log_vars, _ = self.distill.forward_backward(txt, pooled, grid_hw, noise, rands, it, grads=self.grads)
+        log_vars.update(self.opt.step(it))
+        self.write_back()
+        self.iteration = it + 1
+        return loss, log_vars

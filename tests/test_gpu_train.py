@@ -253,3 +253,32 @@ def test_trunk_lora_gradients_match_autograd(lib):
         worst.append((e, cos, n))
         assert e < 2e-2 and cos > 0.9995, f"{n}: rel-L2 {e:.3e} cos {cos:.5f} (|ref| {ref.norm():.3e})"
     print("worst:", sorted(worst, reverse=True)[:3])
+
+
+def test_trainer_step_updates_engine_weights(lib):
+    """ArcFlowTrainer.train_step: gradients land in the arena, AdamW moves every adapter tensor, and the write-back puts
+    the new bf16 values where the engine reads them (a fresh engine built from the exported state dict is bit-identical)."""
+    from arcflow_b200.model import ArcFluxEngineModel
+    from arcflow_b200.train import ArcFlowTrainer, draw_rollout_randoms
+    cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup(num_layers=1, num_single=1)
+    tc = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, nfe=2,
+              timestep_ratio=1.0, total_substeps=128, eps=1e-4)
+    trainer = ArcFlowTrainer(student, teacher, tc, lr=1e-3, warmup_iters=0)
+    g = torch.Generator().manual_seed(3)
+    before = {n: v.clone() for n, v in student.weights.adapter_views.items()}
+    losses = []
+    for it in range(2):
+        rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
+        loss, lv = trainer.train_step(txt.to(DEV), pooled.to(DEV), grid, x.to(DEV), rands)
+        assert loss == loss and lv["diffusion_grad_norm"] > 0 and not lv["skipped"]
+        losses.append(loss)
+    for n, v in student.weights.adapter_views.items():
+        # the fp32 master moves for every tensor (a 2e-4 step on an O(1) loggamma bias is below one bf16 ulp)
+        assert not torch.equal(trainer.opt.param(n), before[n].float()), f"{n} did not move"
+        assert torch.equal(v, trainer.opt.view(trainer.opt.shadow, n)), f"{n}: write-back mismatch"
+    sd2 = dict(sd)
+    sd2.update({n: t.cpu() for n, t in trainer.adapter_state_dict(use_ema=False).items()})
+    fresh = ArcFluxEngineModel(sd2, cfg, device=DEV)
+    a = student.forward_heads(x.to(DEV), txt.to(DEV), pooled.to(DEV), 0.7, 3.5, grid)
+    b = fresh.forward_heads(x.to(DEV), txt.to(DEV), pooled.to(DEV), 0.7, 3.5, grid)
+    assert torch.equal(a, b)
