@@ -186,7 +186,8 @@ SIGNATURES = {
                                    C.c_float, C.c_float, C.c_float, _P]),
     "afb_cast_f32_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
     "afb_policy_eval": (C.c_int, [C.POINTER(PolicyArgs), _P]),
-    "afb_policy_backward": (C.c_int, [C.POINTER(PolicyArgs), _P, _P, C.c_int64, C.c_float, C.c_int32, _P]),
+    "afb_policy_backward": (C.c_int, [C.POINTER(PolicyArgs), _P, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32, _P]),
+    "afb_cfg_combine": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P]),
     "afb_colsum_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P]),
     "afb_gemm_tn": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
     "afb_ln_mod_param_grad": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
@@ -207,8 +208,8 @@ SIGNATURES = {
     "afb_engine_backward_embed": (C.c_int, [_P, C.POINTER(ForwardArgs), _P, C.POINTER(EmbedGrads), _P]),
     "afb_grad_norm_sq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "afb_adamw_ema_step": (C.c_int, [C.POINTER(AdamwArgs), _P]),
-    "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, _P]),
-    "afb_mse_rows": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P]),
+    "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),
+    "afb_mse_rows": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),
     "afb_engine_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_P)]),
     "afb_engine_destroy": (None, [_P]),
     "afb_engine_bind": (C.c_int, [_P, C.POINTER(Weights)]),

@@ -25,8 +25,9 @@ int sampler_step_launch(const void* head, int64_t head_ld, const float* x_in, fl
                         float sigma_start, float sigma_end, float eps, cudaStream_t stream);
 int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t stream);
 int policy_eval_launch(const afb_policy_args* a, cudaStream_t stream);
-int policy_backward_launch(const afb_policy_args* a, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
-                           int accumulate, cudaStream_t stream);
+int policy_backward_launch(const afb_policy_args* a, const void* tgt, float* dhead, int64_t dh_ld, float coef,
+                           int accumulate, int tgt_f32, cudaStream_t stream);
+int cfg_combine_launch(const void* both_bf16, float* out, int64_t half, float guidance_scale, cudaStream_t stream);
 int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream);
 int ln_modulate_bwd_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs,
@@ -45,9 +46,9 @@ int ln_mod_param_grad_launch(const void* x, int64_t x_bs, const void* dy, int64_
                              float* dshift, int batches, int rows_per_batch, int dim, float eps, cudaStream_t stream);
 int rowlinear_param_grad_launch(const float* de, int64_t de_ld, const void* t, int64_t t_ld, float* dw, int64_t dw_ld,
                                 float* dbias, int m, int n_out, int k_in, int silu_in, cudaStream_t stream);
-int axpy_rows_launch(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int batch,
-                     int64_t per_sample, cudaStream_t stream);
-int mse_rows_launch(const float* pred, const void* tgt_bf16, float* out, int batch, int64_t per_sample,
+int axpy_rows_launch(const float* x, const void* u, const float* coef, float* out, void* out_bf16, int batch,
+                     int64_t per_sample, int u_f32, cudaStream_t stream);
+int mse_rows_launch(const float* pred, const void* tgt, float* out, int batch, int64_t per_sample, int tgt_f32,
                     cudaStream_t stream);
 }  // namespace afb
 
@@ -104,9 +105,12 @@ int afb_sampler_step(const void* head, int64_t head_ld, const float* x_in, float
 int afb_policy_eval(const afb_policy_args* args, void* stream) {
   return afb::policy_eval_launch(args, static_cast<cudaStream_t>(stream));
 }
-int afb_policy_backward(const afb_policy_args* args, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
-                        int32_t accumulate, void* stream) {
-  return afb::policy_backward_launch(args, tgt_bf16, dhead, dh_ld, coef, accumulate, static_cast<cudaStream_t>(stream));
+int afb_policy_backward(const afb_policy_args* args, const void* tgt, float* dhead, int64_t dh_ld, float coef,
+                        int32_t accumulate, int32_t tgt_is_f32, void* stream) {
+  return afb::policy_backward_launch(args, tgt, dhead, dh_ld, coef, accumulate, tgt_is_f32, static_cast<cudaStream_t>(stream));
+}
+int afb_cfg_combine(const void* both_bf16, float* out, int64_t half, float guidance_scale, void* stream) {
+  return afb::cfg_combine_launch(both_bf16, out, half, guidance_scale, static_cast<cudaStream_t>(stream));
 }
 int afb_colsum_f32(const float* x, int64_t ld, float* out, int64_t rows, int32_t n, void* stream) {
   return afb::colsum_f32_launch(x, ld, out, rows, n, static_cast<cudaStream_t>(stream));
@@ -152,12 +156,13 @@ int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream) {
 int afb_adamw_ema_step(const afb_adamw_args* args, void* stream) {
   return afb::adamw_ema_launch(args, static_cast<cudaStream_t>(stream));
 }
-int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int32_t batch,
-                  int64_t per_sample, void* stream) {
-  return afb::axpy_rows_launch(x, u_bf16, coef, out, out_bf16, batch, per_sample, static_cast<cudaStream_t>(stream));
+int afb_axpy_rows(const float* x, const void* u, const float* coef, float* out, void* out_bf16, int32_t batch,
+                  int64_t per_sample, int32_t u_is_f32, void* stream) {
+  return afb::axpy_rows_launch(x, u, coef, out, out_bf16, batch, per_sample, u_is_f32, static_cast<cudaStream_t>(stream));
 }
-int afb_mse_rows(const float* pred, const void* tgt_bf16, float* out, int32_t batch, int64_t per_sample, void* stream) {
-  return afb::mse_rows_launch(pred, tgt_bf16, out, batch, per_sample, static_cast<cudaStream_t>(stream));
+int afb_mse_rows(const float* pred, const void* tgt, float* out, int32_t batch, int64_t per_sample, int32_t tgt_is_f32,
+                 void* stream) {
+  return afb::mse_rows_launch(pred, tgt, out, batch, per_sample, tgt_is_f32, static_cast<cudaStream_t>(stream));
 }
 int afb_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
   return afb::cast_f32_bf16_launch(in, out, n, static_cast<cudaStream_t>(stream));

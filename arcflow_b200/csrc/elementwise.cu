@@ -451,37 +451,53 @@ policy_eval_k16_kernel(const __nv_bfloat16* __restrict__ head, long long head_ld
   if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + tok * 64 + 2 * lane) = pack_bf16x2(o.x, o.y);
 }
 
-// out[b, :] = x[b, :] + coef[b] * u[b, :]   (teacher Euler step, arcflow.py:190); u is bf16 (network output)
+// teacher targets are bf16 network outputs (FLUX) or their fp32 true-CFG combination (Qwen)
+__device__ __forceinline__ float2 load_pair(const void* p, long long i, int is_f32) {
+  if (is_f32) return *reinterpret_cast<const float2*>(static_cast<const float*>(p) + i);
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(p) + i);
+  return make_float2(bf16_lo(v), bf16_hi(v));
+}
+
+// out = pos + (pos - neg) * (g - 1) on the two halves [neg; pos] of a batch-doubled bf16 network output (fp32 result):
+// guidance_jit + forward_u (lakonlab/models/diffusions/gaussian_flow.py:18-26, 224-254)
+__global__ void cfg_combine_kernel(const __nv_bfloat16* __restrict__ both, float* __restrict__ out, long long half, float gm1) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= half) return;
+  const float2 n = load_pair(both, i, 0), q = load_pair(both, half + i, 0);
+  *reinterpret_cast<float2*>(out + i) = make_float2(q.x + (q.x - n.x) * gm1, q.y + (q.y - n.y) * gm1);
+}
+
+// out[b, :] = x[b, :] + coef[b] * u[b, :]   (teacher Euler step, arcflow.py:190)
 struct RowCoef {
   float c[POLICY_MAX_BATCH];
 };
-__global__ void axpy_rows_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ u,
+__global__ void axpy_rows_kernel(const float* __restrict__ x, const void* __restrict__ u, int u_f32,
                                  float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16, long long per_sample,
                                  long long total, const __grid_constant__ RowCoef rc) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (i >= total) return;
   const float c = rc.c[int(i / per_sample)];
   const float2 xv = *reinterpret_cast<const float2*>(x + i);
-  const uint32_t uv = *reinterpret_cast<const uint32_t*>(u + i);
-  const float2 o = make_float2(fmaf(c, bf16_lo(uv), xv.x), fmaf(c, bf16_hi(uv), xv.y));
+  const float2 uv = load_pair(u, i, u_f32);
+  const float2 o = make_float2(fmaf(c, uv.x, xv.x), fmaf(c, uv.y, xv.y));
   *reinterpret_cast<float2*>(out + i) = o;
   if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + i) = pack_bf16x2(o.x, o.y);
 }
 
 // per-sample mean over all elements of (pred - tgt)^2: mmgen mse_loss(reduction='flatmean')
 __global__ void __launch_bounds__(256)
-mse_rows_kernel(const float* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt, float* __restrict__ out,
+mse_rows_kernel(const float* __restrict__ pred, const void* __restrict__ tgt_all, int tgt_f32, float* __restrict__ out,
                 long long per_sample) {
   __shared__ float red[8];
   const int b = blockIdx.y;
   const float* p = pred + (long long)b * per_sample;
-  const __nv_bfloat16* t = tgt + (long long)b * per_sample;
+  const long long t0 = (long long)b * per_sample;
   float acc = 0.f;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < per_sample;
        i += (long long)gridDim.x * blockDim.x * 2) {
     const float2 pv = *reinterpret_cast<const float2*>(p + i);
-    const uint32_t tv = *reinterpret_cast<const uint32_t*>(t + i);
-    const float d0 = pv.x - bf16_lo(tv), d1 = pv.y - bf16_hi(tv);
+    const float2 tv = load_pair(tgt_all, t0 + i, tgt_f32);
+    const float d0 = pv.x - tv.x, d1 = pv.y - tv.y;
     acc = fmaf(d0, d0, fmaf(d1, d1, acc));
   }
   acc = warp_sum(acc);
@@ -510,7 +526,7 @@ __device__ __forceinline__ float dphi_expm1(float z) {  // d/dz [expm1(z)/z]
 
 __global__ void __launch_bounds__(256)
 policy_avg_u_bwd_k16_kernel(const __nv_bfloat16* __restrict__ head, long long head_ld,
-                            const __nv_bfloat16* __restrict__ tgt, float* __restrict__ dhead, long long dh_ld,
+                            const void* __restrict__ tgt, int tgt_f32, float* __restrict__ dhead, long long dh_ld,
                             int tokens_per_sample, long long tokens, float coef, float eps, int accumulate,
                             const __grid_constant__ PolicyParams pp) {
   constexpr int K = 16;
@@ -578,8 +594,8 @@ policy_avg_u_bwd_k16_kernel(const __nv_bfloat16* __restrict__ head, long long he
     acc0 = fmaf(mu0[k], sWF[wib][k * 4 + j0], acc0);
     acc1 = fmaf(mu1[k], sWF[wib][k * 4 + j0 + 1], acc1);
   }
-  const uint32_t tv = *reinterpret_cast<const uint32_t*>(tgt + tok * 64 + 2 * lane);
-  const float g0 = coef * (acc0 - bf16_lo(tv)), g1 = coef * (acc1 - bf16_hi(tv));
+  const float2 tv = load_pair(tgt, tok * 64 + 2 * lane, tgt_f32);
+  const float g0 = coef * (acc0 - tv.x), g1 = coef * (acc1 - tv.y);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     float2 dm = make_float2(sWF[wib][k * 4 + j0] * g0, sWF[wib][k * 4 + j0 + 1] * g1);
@@ -1223,36 +1239,45 @@ int policy_eval_launch(const afb_policy_args* a, cudaStream_t stream) {
   return AFB_OK;
 }
 
-int axpy_rows_launch(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16, int batch,
-                     int64_t per_sample, cudaStream_t stream) {
-  AFB_REQUIRE(x && u_bf16 && coef && out, "axpy_rows: null argument");
+int cfg_combine_launch(const void* both_bf16, float* out, int64_t half, float guidance_scale, cudaStream_t stream) {
+  AFB_REQUIRE(both_bf16 && out && half >= 2 && half % 2 == 0, "cfg_combine: bad arguments");
+  cfg_combine_kernel<<<unsigned((half / 2 + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(both_bf16), out,
+                                                                          half, guidance_scale - 1.0f);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int axpy_rows_launch(const float* x, const void* u, const float* coef, float* out, void* out_bf16, int batch,
+                     int64_t per_sample, int u_f32, cudaStream_t stream) {
+  AFB_REQUIRE(x && u && coef && out, "axpy_rows: null argument");
   AFB_REQUIRE(batch >= 1 && batch <= POLICY_MAX_BATCH && per_sample >= 2 && per_sample % 2 == 0,
               "axpy_rows: bad shape (batch=%d per_sample=%lld)", batch, (long long)per_sample);
   RowCoef rc{};
   for (int b = 0; b < batch; ++b) rc.c[b] = coef[b];
   const long long total = (long long)batch * per_sample;
   axpy_rows_kernel<<<unsigned((total / 2 + 255) / 256), 256, 0, stream>>>(
-      x, static_cast<const __nv_bfloat16*>(u_bf16), out, static_cast<__nv_bfloat16*>(out_bf16), per_sample, total, rc);
+      x, u, u_f32, out, static_cast<__nv_bfloat16*>(out_bf16), per_sample, total, rc);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
 }
 
-int mse_rows_launch(const float* pred, const void* tgt_bf16, float* out, int batch, int64_t per_sample,
+int mse_rows_launch(const float* pred, const void* tgt, float* out, int batch, int64_t per_sample, int tgt_f32,
                     cudaStream_t stream) {
-  AFB_REQUIRE(pred && tgt_bf16 && out, "mse_rows: null argument");
+  AFB_REQUIRE(pred && tgt && out, "mse_rows: null argument");
   AFB_REQUIRE(batch >= 1 && per_sample >= 2 && per_sample % 2 == 0, "mse_rows: bad shape");
   AFB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * batch, stream));
   dim3 grid(64, batch);
-  mse_rows_kernel<<<grid, 256, 0, stream>>>(pred, static_cast<const __nv_bfloat16*>(tgt_bf16), out, per_sample);
+  mse_rows_kernel<<<grid, 256, 0, stream>>>(pred, tgt, tgt_f32, out, per_sample);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
 }
 
-int policy_backward_launch(const afb_policy_args* a, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
-                           int accumulate, cudaStream_t stream) {
-  AFB_REQUIRE(a && a->head && tgt_bf16 && dhead && a->sigma_src && a->sigma_start && a->sigma_end,
+int policy_backward_launch(const afb_policy_args* a, const void* tgt, float* dhead, int64_t dh_ld, float coef,
+                           int accumulate, int tgt_f32, cudaStream_t stream) {
+  AFB_REQUIRE(a && a->head && tgt && dhead && a->sigma_src && a->sigma_start && a->sigma_end,
               "policy_backward: null argument");
   AFB_REQUIRE(a->batch >= 1 && a->batch <= POLICY_MAX_BATCH && a->tokens >= 1, "policy_backward: bad batch/tokens");
   if (a->num_gaussians != 16) {
@@ -1268,7 +1293,7 @@ int policy_backward_launch(const afb_policy_args* a, const void* tgt_bf16, float
   }
   const long long tokens = (long long)a->batch * a->tokens;
   policy_avg_u_bwd_k16_kernel<<<unsigned((tokens + 7) / 8), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(a->head), a->head_ld, static_cast<const __nv_bfloat16*>(tgt_bf16), dhead, dh_ld,
+      static_cast<const __nv_bfloat16*>(a->head), a->head_ld, tgt, tgt_f32, dhead, dh_ld,
       a->tokens, tokens, coef, a->eps > 0.f ? a->eps : 1e-4f, accumulate, pp);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

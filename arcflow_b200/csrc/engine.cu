@@ -46,8 +46,8 @@ int rmsnorm_rows_launch(const void* x, void* y, const void* w, int64_t rows, int
                         cudaStream_t stream);
 // training path
 int attention_backward_launch(const afb_attn_bwd_desc* d, cudaStream_t stream);
-int gemm_tn_launch(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
-                   int m, int n, cudaStream_t stream);
+int gemm_tn_batched_launch(const void* a, int64_t a_ld, int64_t a_bs, const void* b, int64_t b_ld, int64_t b_bs, float* out,
+                           int64_t out_ld, int batches, int64_t rows, int m, int n, cudaStream_t stream);
 int ln_modulate_bwd_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs,
                            const void* scale, int64_t mod_bs, int batches, int rows_per_batch, int dim, float eps,
                            int accumulate, cudaStream_t stream);
@@ -531,9 +531,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
 // ------------------------------------------------------------------------------------------------------------------
 int tn_rows(View a, int m, View b, int n, float* out, int64_t out_ld, int B, int rows, cudaStream_t s) {
   if (!out) return AFB_OK;
-  for (int bi = 0; bi < B; ++bi)
-    AFB_TRY(afb::gemm_tn_launch(a.p + int64_t(bi) * a.bs, a.ld, b.p + int64_t(bi) * b.bs, b.ld, out, out_ld, rows, m, n, s));
-  return AFB_OK;
+  return afb::gemm_tn_batched_launch(a.p, a.ld, a.bs, b.p, b.ld, b.bs, out, out_ld, B, rows, m, n, s);
 }
 
 // Backward of one LoRA-extended Linear  out = [x | t] [W | Bl]^T,  t = x A^T  (packed weight `w`, leading dim w_ld =
@@ -752,6 +750,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       return t;
     };
     Stream st2[2] = {mk(true), mk(false)};
+    // Qwen: the last block's text-stream output is never read (forward_impl skips its out-projection and MLP), so that
+    // stream only contributes through its K / V rows: its dattn is zero and its MLP half has no gradient.
+    const bool skip_txt_tail = d.arch != AFB_ARCH_FLUX && i == d.num_double - 1;
     // -- recompute: attention half
     for (Stream& t : st2) {
       AFB_TRY(afb::ln_modulate_launch(t.h_in.p, t.h_in.bs, const_cast<bf16*>(t.y.p), t.y.bs, t.mod + D, t.mod, mod_bs, B,
@@ -764,6 +765,11 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_TRY(run_attention(e, &at, s));
     // -- recompute: h_mid and the MLP half; then the MLP half's backward (per stream)
     for (Stream& t : st2) {
+      if (skip_txt_tail && &t == &st2[1]) {
+        AFB_CHECK_CUDA(cudaMemset2DAsync(const_cast<bf16*>(t.dattn.p), size_t(t.dattn.bs) * sizeof(bf16), 0,
+                                         size_t(t.rows) * D * sizeof(bf16), B, s));
+        continue;
+      }
       LoraBwd sb{e, B, t.rows, s};
       const bool lu = r > 0 && t.up_la, ld_ = r > 0 && t.down_la;
       const int64_t up_ld = D + (t.up_la ? rpad : 0), down_ld = M + (t.down_la ? rpad : 0);
@@ -1032,7 +1038,6 @@ int afb_engine_backward(afb_engine* e, const afb_backward_args* ba, void* stream
   AFB_REQUIRE(ba != nullptr, "engine_backward: null args");
   const afb_forward_args& a = ba->fwd;
   AFB_TRY(check_shapes(e, a.batch, a.txt_len, a.img_len));
-  AFB_REQUIRE(e->desc.arch == AFB_ARCH_FLUX, "engine_backward: only the FLUX trunk has a backward so far");
   AFB_REQUIRE(e->tws && e->saved_batch == a.batch && e->saved_txt == a.txt_len && e->saved_img == a.img_len,
               "engine_backward: no checkpoints of this shape (run afb_engine_forward_train first)");
   AFB_REQUIRE(ba->d_head_in && a.rope_cos && a.rope_sin, "engine_backward: null tensor argument");

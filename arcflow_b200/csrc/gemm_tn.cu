@@ -6,8 +6,10 @@
 // configs/flux/arcflux_2nfe_k16.py:20-25). Both operands are row-major [tokens, features], i.e. MN-major for UMMA:
 // TMA drops [64 tokens x 64 features] boxes (128-byte swizzle) and the MMA reads them through MN-major descriptors
 // (LBO = next 64-feature chunk, SBO = next 8 token rows) — no transpose pass over HBM.
-// One CTA per 128 x 256 output tile and token split; fp32 result added with red.global (the outputs are small:
-// [1152, 3072] heads, [12288, 256] / [256, 3072] LoRA), 4-stage ring, roles as in gemm.cu.
+// One CTA per 128 x 256 output tile and token split; fp32 result added with 16-byte red.global.add.v4.f32 (the outputs
+// are small: [1152, 3072] heads, [12288, 256] / [256, 3072] LoRA), 4-stage ring, roles as in gemm.cu. The operands are
+// [batches, rows, features] views (3-D tensor maps): one launch contracts over every batch, and rows past the end of a
+// batch are zero-filled by TMA instead of running into the next batch.
 #include "common.cuh"
 #include "../../include/arcflow_b200.h"
 
@@ -26,7 +28,7 @@ constexpr int TN_THREADS = 192;
 constexpr size_t TN_SMEM_BYTES = 1024 + size_t(TSTAGES) * (TA_STAGE_BYTES + TB_STAGE_BYTES) + 256;
 
 struct TnParams {
-  int M, N, kblocks, kb_per_split;
+  int M, N, kblocks, kb_per_split, kb_per_batch;
   float* out;
   long long out_ld;
 };
@@ -72,10 +74,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], TA_STAGE_BYTES + TB_STAGE_BYTES);
+        const int b = kb / p.kb_per_batch;
+        const int t0 = (kb - b * p.kb_per_batch) * TK;
         for (int c = 0; c < TM / 64; ++c)
-          tma_load_2d(sA + stage * TA_STAGE_BYTES + c * CHUNK_BYTES, &tmA, &full_bar[stage], m0 + c * 64, kb * TK);
+          tma_load_3d(sA + stage * TA_STAGE_BYTES + c * CHUNK_BYTES, &tmA, &full_bar[stage], m0 + c * 64, t0, b);
         for (int c = 0; c < TN / 64; ++c)
-          tma_load_2d(sB + stage * TB_STAGE_BYTES + c * CHUNK_BYTES, &tmB, &full_bar[stage], n0 + c * 64, kb * TK);
+          tma_load_3d(sB + stage * TB_STAGE_BYTES + c * CHUNK_BYTES, &tmB, &full_bar[stage], n0 + c * 64, t0, b);
         if (++stage == TSTAGES) {
           stage = 0;
           phase ^= 1;
@@ -124,8 +128,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         if (m < p.M) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) atomicAdd(orow + nb + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4) {
+            if (nb + i + 3 < p.N) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + nb + i), "f"(__uint_as_float(v[i])),
+                           "f"(__uint_as_float(v[i + 1])), "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                           : "memory");
+            } else {
+              for (int j = i; j < i + 4; ++j)
+                if (nb + j < p.N) atomicAdd(orow + nb + j, __uint_as_float(v[j]));
+            }
+          }
         }
       }
     }
@@ -140,34 +152,44 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 }  // namespace
 
+int gemm_tn_batched_launch(const void* a, int64_t a_ld, int64_t a_bs, const void* b, int64_t b_ld, int64_t b_bs, float* out,
+                           int64_t out_ld, int batches, int64_t rows, int m, int n, cudaStream_t stream);
 int gemm_tn_launch(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
                    int m, int n, cudaStream_t stream) {
+  return gemm_tn_batched_launch(a, a_ld, tokens * a_ld, b, b_ld, tokens * b_ld, out, out_ld, 1, tokens, m, n, stream);
+}
+
+int gemm_tn_batched_launch(const void* a, int64_t a_ld, int64_t a_bs, const void* b, int64_t b_ld, int64_t b_bs, float* out,
+                           int64_t out_ld, int batches, int64_t rows, int m, int n, cudaStream_t stream) {
   AFB_REQUIRE(a && b && out, "gemm_tn: null pointer");
-  AFB_REQUIRE(tokens >= 1 && m >= 1 && n >= 1, "gemm_tn: empty problem");
-  AFB_REQUIRE(m % 8 == 0 && n % 8 == 0 && a_ld % 8 == 0 && b_ld % 8 == 0, "gemm_tn: M, N and leading dims must be multiples of 8");
+  AFB_REQUIRE(batches >= 1 && rows >= 1 && m >= 1 && n >= 1, "gemm_tn: empty problem");
+  AFB_REQUIRE(m % 8 == 0 && n % 8 == 0 && a_ld % 8 == 0 && b_ld % 8 == 0 && a_bs % 8 == 0 && b_bs % 8 == 0,
+              "gemm_tn: M, N, leading dims and batch strides must be multiples of 8");
+  AFB_REQUIRE(out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm_tn: out must be 16-byte aligned, ld %% 4 == 0");
   CUtensorMap tmA, tmB;
   {
-    const uint64_t dims[2] = {uint64_t(m), uint64_t(tokens)};
-    const uint64_t strides[1] = {uint64_t(a_ld) * 2};
-    const uint32_t box[2] = {64, TK};
-    int rc = make_tmap_bf16(&tmA, a, 2, dims, strides, box);
+    const uint64_t dims[3] = {uint64_t(m), uint64_t(rows), uint64_t(batches)};
+    const uint64_t strides[2] = {uint64_t(a_ld) * 2, uint64_t(batches > 1 ? a_bs : rows * a_ld) * 2};
+    const uint32_t box[3] = {64, TK, 1};
+    int rc = make_tmap_bf16(&tmA, a, 3, dims, strides, box);
     if (rc != AFB_OK) return rc;
   }
   {
-    const uint64_t dims[2] = {uint64_t(n), uint64_t(tokens)};
-    const uint64_t strides[1] = {uint64_t(b_ld) * 2};
-    const uint32_t box[2] = {64, TK};
-    int rc = make_tmap_bf16(&tmB, b, 2, dims, strides, box);
+    const uint64_t dims[3] = {uint64_t(n), uint64_t(rows), uint64_t(batches)};
+    const uint64_t strides[2] = {uint64_t(b_ld) * 2, uint64_t(batches > 1 ? b_bs : rows * b_ld) * 2};
+    const uint32_t box[3] = {64, TK, 1};
+    int rc = make_tmap_bf16(&tmB, b, 3, dims, strides, box);
     if (rc != AFB_OK) return rc;
   }
   TnParams p{};
   p.M = m;
   p.N = n;
-  p.kblocks = int((tokens + TK - 1) / TK);
+  p.kb_per_batch = int((rows + TK - 1) / TK);
+  p.kblocks = p.kb_per_batch * batches;
   p.out = out;
   p.out_ld = out_ld;
   const int tiles = ((m + TM - 1) / TM) * ((n + TN - 1) / TN);
-  int splits = (2 * device_sm_count() + tiles - 1) / tiles;
+  int splits = (device_sm_count() + tiles - 1) / tiles;  // one wave; every extra split is another fp32 red pass
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kblocks + splits - 1) / splits;

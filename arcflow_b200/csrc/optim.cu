@@ -13,8 +13,11 @@
 namespace afb {
 namespace {
 
+// Deterministic: per-block partials in a fixed slot, the last block to finish adds them in a fixed order — every DDP rank
+// gets the bit-identical norm (and clip coefficient) from the all-reduced gradients, so the replicas cannot drift apart.
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out, float* __restrict__ partials,
+             unsigned int* __restrict__ ticket) {
   float acc = 0.f;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
     if (i + 3 < n) {
@@ -29,10 +32,29 @@ sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) 
   __shared__ float red[8];
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
+  __shared__ bool last;
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[i];
-    atomicAdd(out, s);
+    partials[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += partials[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    *out = s;
+    *ticket = 0;
   }
 }
 
@@ -84,12 +106,19 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream) {
   AFB_REQUIRE(g && out && n >= 1, "grad_norm_sq: bad arguments");
-  AFB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
   int blocks = int((n / 4 + 255) / 256);
   const int cap = device_sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<blocks, 256, 0, stream>>>(g, n, out);
+  int dev = 0;
+  AFB_CHECK_CUDA(cudaGetDevice(&dev));
+  static float* scratch[64] = {};  // per device: [cap] partials + 1 ticket, allocated once, never freed
+  AFB_REQUIRE(dev >= 0 && dev < 64, "grad_norm_sq: device ordinal out of range");
+  if (!scratch[dev]) {
+    AFB_CHECK_CUDA(cudaMalloc(&scratch[dev], (size_t(cap) + 1) * sizeof(float)));
+    AFB_CHECK_CUDA(cudaMemsetAsync(scratch[dev], 0, (size_t(cap) + 1) * sizeof(float), stream));
+  }
+  sumsq_kernel<<<blocks, 256, 0, stream>>>(g, n, out, scratch[dev], reinterpret_cast<unsigned int*>(scratch[dev] + cap));
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

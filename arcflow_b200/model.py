@@ -253,6 +253,117 @@ class EngineModelBase:
         a.rope_cos, a.rope_sin = cos.data_ptr(), sin.data_ptr()
         return a
 
+    # ---- training: checkpointed forward + adapter-only backward (shared by the FLUX and Qwen students) -------------
+    # LoRA tensor of the engine's block structs -> state-dict suffix (export_arcflow_to_diffusers.py:104-127 names);
+    # subclasses set these. Tensors the state dict does not carry (Qwen: txt_mlp of the last block) are skipped.
+    _DBL_LORA: tuple = ()
+    _SGL_LORA: tuple = ()
+
+    def _launch_forward(self, a: "_lib.ForwardArgs", keep: tuple, train: bool):
+        stream = torch.cuda.current_stream().cuda_stream
+        if train:
+            _lib.check(self.lib.afb_engine_train_reserve(self.handle, *self._reserved), "afb_engine_train_reserve")
+            _lib.check(self.lib.afb_engine_forward_train(self.handle, C.byref(a), stream), "afb_engine_forward_train")
+            self._train_ctx = dict(args=a, keep=keep)   # inputs stay alive until the backward has run
+        else:
+            _lib.check(self.lib.afb_engine_forward(self.handle, C.byref(a), stream), "afb_engine_forward")
+
+    def head_weight(self) -> torch.Tensor:
+        """The fused [head_n, D] head weight (means | logits | loggamma | pad) the engine reads."""
+        return self.weights.head_w_tensor
+
+    def trunk_lora_shapes(self) -> Dict[str, tuple]:
+        views = self.weights.adapter_views
+        return {n: tuple(views[n].shape) for n in self.trunk_lora_names()}
+
+    def trunk_lora_names(self):
+        """State-dict names of the LoRA tensors the trunk backward produces gradients for."""
+        names = []
+        for i in range(self.cfg.num_layers):
+            names += [f"transformer_blocks.{i}.{n}.lora_{ab}.weight" for _, n in self._DBL_LORA for ab in "AB"]
+        for i in range(getattr(self.cfg, "num_single_layers", 0)):
+            names += [f"single_transformer_blocks.{i}.{n}.lora_{ab}.weight" for _, n in self._SGL_LORA for ab in "AB"]
+        views = self.weights.adapter_views
+        return [n for n in names if n in views]
+
+    _TEMB_LORA = (("t1", "time_text_embed.timestep_embedder.linear_1"), ("t2", "time_text_embed.timestep_embedder.linear_2"))
+
+    def embed_lora_shapes(self) -> Dict[str, tuple]:
+        views = self.weights.adapter_views
+        names = [f"{name}.lora_{ab}.weight" for _, name in self._TEMB_LORA for ab in "AB"]
+        return {n: tuple(views[n].shape) for n in names if n in views}
+
+    @property
+    def mod_total(self) -> int:
+        return int(self.weights.struct.mod_total)
+
+    @property
+    def norm_out_mod_off(self) -> int:
+        return int(self.weights.struct.norm_out_mod_off)
+
+    @torch.no_grad()
+    def backward_embed(self, d_mod: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+        """d_mod (fp32 [batch, mod_total], every AdaLN vector's gradient) -> timestep-embedder LoRA gradients (+=)."""
+        ctx = getattr(self, "_train_ctx", None)
+        if ctx is None:
+            raise AfbError("backward_embed: run forward_heads(train=True) first")
+        a = ctx["args"]
+        if d_mod.dtype != torch.float32 or tuple(d_mod.shape) != (a.batch, self.mod_total) or not d_mod.is_contiguous():
+            raise AfbError(f"d_mod must be contiguous fp32 [{a.batch}, {self.mod_total}]")
+        g = _lib.EmbedGrads()
+        for tag, name in self._TEMB_LORA:
+            for ab in "ab":
+                t = grads.get(f"{name}.lora_{ab.upper()}.weight")
+                setattr(g, f"{tag}_l{ab}", t.data_ptr() if t is not None else None)
+        _lib.check(self.lib.afb_engine_backward_embed(self.handle, C.byref(a), d_mod.data_ptr(), C.byref(g),
+                                                      torch.cuda.current_stream().cuda_stream), "afb_engine_backward_embed")
+
+    @torch.no_grad()
+    def backward_trunk(self, d_head_in: torch.Tensor, grads: Dict[str, torch.Tensor],
+                       d_mod: Optional[torch.Tensor] = None) -> None:
+        """Accumulate (+=) the LoRA gradients of the last `forward_heads(train=True)` into `grads` (fp32 tensors keyed by
+        state-dict name, shapes of the LoRA tensors; missing names are skipped). d_head_in: bf16 [batch, tokens, dim],
+        the gradient w.r.t. the norm_out output. Replaces torch autograd + checkpointing through the diffusers blocks
+        (lakonlab/models/base_diffusion.py:14-62)."""
+        ctx = getattr(self, "_train_ctx", None)
+        if ctx is None:
+            raise AfbError("backward_trunk: run forward_heads(train=True) first")
+        a = ctx["args"]
+        D = self.cfg.inner_dim
+        if d_head_in.dtype != BF16 or tuple(d_head_in.shape) != (a.batch, a.img_len, D) or not d_head_in.is_contiguous():
+            raise AfbError(f"d_head_in must be contiguous bf16 [{a.batch}, {a.img_len}, {D}]")
+
+        def ptr(name):
+            t = grads.get(name)
+            if t is None:
+                return None
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise AfbError(f"gradient buffer '{name}' must be a contiguous fp32 CUDA tensor")
+            return t.data_ptr()
+
+        dbl = (_lib.DoubleBlockGrads * max(self.cfg.num_layers, 1))()
+        for i in range(self.cfg.num_layers):
+            for field, n in self._DBL_LORA:
+                setattr(dbl[i], field + "_la", ptr(f"transformer_blocks.{i}.{n}.lora_A.weight"))
+                setattr(dbl[i], field + "_lb", ptr(f"transformer_blocks.{i}.{n}.lora_B.weight"))
+        n_single = getattr(self.cfg, "num_single_layers", 0)
+        sgl = (_lib.SingleBlockGrads * max(n_single, 1))()
+        for i in range(n_single):
+            for field, n in self._SGL_LORA:
+                setattr(sgl[i], field + "_la", ptr(f"single_transformer_blocks.{i}.{n}.lora_A.weight"))
+                setattr(sgl[i], field + "_lb", ptr(f"single_transformer_blocks.{i}.{n}.lora_B.weight"))
+        b = _lib.BackwardArgs()
+        b.fwd = a
+        b.d_head_in = d_head_in.data_ptr()
+        b.dbl = C.cast(dbl, C.POINTER(_lib.DoubleBlockGrads))
+        b.sgl = C.cast(sgl, C.POINTER(_lib.SingleBlockGrads))
+        if d_mod is not None:
+            if d_mod.dtype != torch.float32 or tuple(d_mod.shape) != (a.batch, self.mod_total) or not d_mod.is_contiguous():
+                raise AfbError(f"d_mod must be contiguous fp32 [{a.batch}, {self.mod_total}]")
+            b.d_mod = d_mod.data_ptr()
+        _lib.check(self.lib.afb_engine_backward(self.handle, C.byref(b), torch.cuda.current_stream().cuda_stream),
+                   "afb_engine_backward")
+
     def split_heads(self, head: torch.Tensor):
         """Raw head tensor -> the reference's ArcFlowModelOutput fields in token layout
         (means [B,S,K,64], logweights [B,S,K,4] log-softmaxed over K in bf16, loggammas [B,S,K-1,4])."""
@@ -266,7 +377,11 @@ class EngineModelBase:
 
 
 class ArcFluxEngineModel(EngineModelBase):
-    """The ArcFlow-FLUX student transformer + N-NFE sampler on the native engine (inference)."""
+    """The ArcFlow-FLUX student transformer + N-NFE sampler on the native engine (inference and training)."""
+    arch = "flux"
+    _DBL_LORA = (("img_up", "ff.net.0.proj"), ("img_down", "ff.net.2"), ("txt_up", "ff_context.net.0.proj"),
+                 ("txt_down", "ff_context.net.2"))
+    _SGL_LORA = (("mlp", "proj_mlp"), ("out", "proj_out"))
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ArcFluxConfig, device="cuda",
                  consume_state_dict: bool = False):
@@ -324,122 +439,8 @@ class ArcFluxEngineModel(EngineModelBase):
         out = torch.empty(B, Si, self.weights.head_n, dtype=BF16, device=self.device)
         a = self._fwd_args(txt, pooled, tdev, gdev, cos, sin, B, Si)
         a.latents, a.head_out = lat.data_ptr(), out.data_ptr()
-        stream = torch.cuda.current_stream().cuda_stream
-        if train:
-            _lib.check(self.lib.afb_engine_train_reserve(self.handle, *self._reserved), "afb_engine_train_reserve")
-            _lib.check(self.lib.afb_engine_forward_train(self.handle, C.byref(a), stream), "afb_engine_forward_train")
-            self._train_ctx = dict(args=a, keep=(lat, txt, pooled, tdev, gdev, cos, sin, out))   # alive until the backward
-        else:
-            _lib.check(self.lib.afb_engine_forward(self.handle, C.byref(a), stream), "afb_engine_forward")
+        self._launch_forward(a, (lat, txt, pooled, tdev, gdev, cos, sin, out), train)
         return out
-
-    # LoRA tensor of the engine's block structs -> state-dict prefix (export_arcflow_to_diffusers.py:104-127 names)
-    _DBL_LORA = (("img_up", "ff.net.0.proj"), ("img_down", "ff.net.2"), ("txt_up", "ff_context.net.0.proj"),
-                 ("txt_down", "ff_context.net.2"))
-    _SGL_LORA = (("mlp", "proj_mlp"), ("out", "proj_out"))
-
-    def head_weight(self) -> torch.Tensor:
-        """The fused [head_n, D] head weight (means | logits | loggamma | pad) the engine reads."""
-        return self.weights.head_w_tensor
-
-    def trunk_lora_shapes(self) -> Dict[str, tuple]:
-        D, M, r = self.cfg.inner_dim, self.cfg.mlp_dim, self.cfg.lora_rank
-        io = {"ff.net.0.proj": (M, D), "ff.net.2": (D, M), "ff_context.net.0.proj": (M, D), "ff_context.net.2": (D, M),
-              "proj_mlp": (M, D), "proj_out": (D, D + M)}
-        out = {}
-        for n in self.trunk_lora_names():
-            base, ab = n.rsplit(".lora_", 1)
-            o, i = io[base.split(".", 2)[2]]
-            out[n] = (r, i) if ab.startswith("A") else (o, r)
-        return out
-
-    def trunk_lora_names(self):
-        """State-dict names of the LoRA tensors the trunk backward produces gradients for."""
-        names = []
-        for i in range(self.cfg.num_layers):
-            names += [f"transformer_blocks.{i}.{n}.lora_{ab}.weight" for _, n in self._DBL_LORA for ab in "AB"]
-        for i in range(self.cfg.num_single_layers):
-            names += [f"single_transformer_blocks.{i}.{n}.lora_{ab}.weight" for _, n in self._SGL_LORA for ab in "AB"]
-        return names
-
-    _TEMB_LORA = (("t1", "time_text_embed.timestep_embedder.linear_1"), ("t2", "time_text_embed.timestep_embedder.linear_2"))
-
-    def embed_lora_shapes(self) -> Dict[str, tuple]:
-        D, r = self.cfg.inner_dim, self.cfg.lora_rank
-        return {"time_text_embed.timestep_embedder.linear_1.lora_A.weight": (r, 256),
-                "time_text_embed.timestep_embedder.linear_1.lora_B.weight": (D, r),
-                "time_text_embed.timestep_embedder.linear_2.lora_A.weight": (r, D),
-                "time_text_embed.timestep_embedder.linear_2.lora_B.weight": (D, r)}
-
-    @property
-    def mod_total(self) -> int:
-        return int(self.weights.struct.mod_total)
-
-    @property
-    def norm_out_mod_off(self) -> int:
-        return int(self.weights.struct.norm_out_mod_off)
-
-    @torch.no_grad()
-    def backward_embed(self, d_mod: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
-        """d_mod (fp32 [batch, mod_total], every AdaLN vector's gradient) -> timestep-embedder LoRA gradients (+=)."""
-        ctx = getattr(self, "_train_ctx", None)
-        if ctx is None:
-            raise AfbError("backward_embed: run forward_heads(train=True) first")
-        a = ctx["args"]
-        if d_mod.dtype != torch.float32 or tuple(d_mod.shape) != (a.batch, self.mod_total) or not d_mod.is_contiguous():
-            raise AfbError(f"d_mod must be contiguous fp32 [{a.batch}, {self.mod_total}]")
-        g = _lib.EmbedGrads()
-        for tag, name in self._TEMB_LORA:
-            for ab in "ab":
-                t = grads.get(f"{name}.lora_{ab.upper()}.weight")
-                setattr(g, f"{tag}_l{ab}", t.data_ptr() if t is not None else None)
-        _lib.check(self.lib.afb_engine_backward_embed(self.handle, C.byref(a), d_mod.data_ptr(), C.byref(g),
-                                                      torch.cuda.current_stream().cuda_stream), "afb_engine_backward_embed")
-
-    @torch.no_grad()
-    def backward_trunk(self, d_head_in: torch.Tensor, grads: Dict[str, torch.Tensor],
-                       d_mod: Optional[torch.Tensor] = None) -> None:
-        """Accumulate (+=) the LoRA gradients of the last `forward_heads(train=True)` into `grads` (fp32 tensors keyed by
-        state-dict name, shapes of the LoRA tensors; missing names are skipped). d_head_in: bf16 [batch, tokens, dim],
-        the gradient w.r.t. the norm_out output. Replaces torch autograd + checkpointing through the diffusers blocks
-        (lakonlab/models/base_diffusion.py:14-62)."""
-        ctx = getattr(self, "_train_ctx", None)
-        if ctx is None:
-            raise AfbError("backward_trunk: run forward_heads(train=True) first")
-        a = ctx["args"]
-        D = self.cfg.inner_dim
-        if d_head_in.dtype != BF16 or tuple(d_head_in.shape) != (a.batch, a.img_len, D) or not d_head_in.is_contiguous():
-            raise AfbError(f"d_head_in must be contiguous bf16 [{a.batch}, {a.img_len}, {D}]")
-
-        def ptr(name):
-            t = grads.get(name)
-            if t is None:
-                return None
-            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
-                raise AfbError(f"gradient buffer '{name}' must be a contiguous fp32 CUDA tensor")
-            return t.data_ptr()
-
-        dbl = (_lib.DoubleBlockGrads * max(self.cfg.num_layers, 1))()
-        for i in range(self.cfg.num_layers):
-            for field, n in self._DBL_LORA:
-                setattr(dbl[i], field + "_la", ptr(f"transformer_blocks.{i}.{n}.lora_A.weight"))
-                setattr(dbl[i], field + "_lb", ptr(f"transformer_blocks.{i}.{n}.lora_B.weight"))
-        sgl = (_lib.SingleBlockGrads * max(self.cfg.num_single_layers, 1))()
-        for i in range(self.cfg.num_single_layers):
-            for field, n in self._SGL_LORA:
-                setattr(sgl[i], field + "_la", ptr(f"single_transformer_blocks.{i}.{n}.lora_A.weight"))
-                setattr(sgl[i], field + "_lb", ptr(f"single_transformer_blocks.{i}.{n}.lora_B.weight"))
-        b = _lib.BackwardArgs()
-        b.fwd = a
-        b.d_head_in = d_head_in.data_ptr()
-        b.dbl = C.cast(dbl, C.POINTER(_lib.DoubleBlockGrads))
-        b.sgl = C.cast(sgl, C.POINTER(_lib.SingleBlockGrads))
-        if d_mod is not None:
-            if d_mod.dtype != torch.float32 or tuple(d_mod.shape) != (a.batch, self.mod_total) or not d_mod.is_contiguous():
-                raise AfbError(f"d_mod must be contiguous fp32 [{a.batch}, {self.mod_total}]")
-            b.d_mod = d_mod.data_ptr()
-        _lib.check(self.lib.afb_engine_backward(self.handle, C.byref(b), torch.cuda.current_stream().cuda_stream),
-                   "afb_engine_backward")
 
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int],

@@ -341,7 +341,7 @@ def policy_backward(head: torch.Tensor, tgt_u: torch.Tensor, sigma_src, sigma_st
     (fp32 [batch*tokens, head_ld]) when given, else written to a new tensor."""
     lib = _lib.load()
     _chk(head, BF16, "policy_backward head")
-    _chk(tgt_u, BF16, "policy_backward tgt_u")
+    tgt_f32 = _target_is_f32(tgt_u, "policy_backward tgt_u")
     batch = len(sigma_src)
     tokens = head.shape[0] // batch
     tg = tgt_u.reshape(-1, 64)
@@ -364,7 +364,7 @@ def policy_backward(head: torch.Tensor, tgt_u: torch.Tensor, sigma_src, sigma_st
         keep.append((C.c_uint8 * batch)(*sm))
         a.small = keep[-1]
     _lib.check(lib.afb_policy_backward(C.byref(a), tg.data_ptr(), dhead.data_ptr(), dhead.stride(0), float(coef),
-                                       int(accumulate), _stream()), "afb_policy_backward")
+                                       int(accumulate), tgt_f32, _stream()), "afb_policy_backward")
     return dhead
 
 
@@ -436,11 +436,30 @@ def rowlinear_param_grad(de: torch.Tensor, t: torch.Tensor, dw: torch.Tensor, db
     return dw, dbias
 
 
+def _target_is_f32(t: torch.Tensor, what: str) -> int:
+    """Teacher targets are bf16 (a network output) or fp32 (the true-CFG combination of two)."""
+    if not t.is_cuda or t.dtype not in (BF16, torch.float32):
+        raise AfbError(f"{what}: expected a CUDA bf16 or fp32 tensor, got {t.dtype} on {t.device}")
+    return int(t.dtype == torch.float32)
+
+
+def cfg_combine(both: torch.Tensor, guidance_scale: float) -> torch.Tensor:
+    """[neg; pos] (bf16, batch-doubled network output) -> pos + (pos - neg) * (g - 1), fp32 [batch, ...]."""
+    lib = _lib.load()
+    _chk(both, BF16, "cfg_combine both")
+    if both.shape[0] % 2 or not both.is_contiguous():
+        raise AfbError("cfg_combine: need a contiguous tensor with an even batch ([neg; pos])")
+    out = torch.empty((both.shape[0] // 2,) + tuple(both.shape[1:]), dtype=torch.float32, device=both.device)
+    _lib.check(lib.afb_cfg_combine(both.data_ptr(), out.data_ptr(), out.numel(), float(guidance_scale), _stream()),
+               "afb_cfg_combine")
+    return out
+
+
 def axpy_rows(x: torch.Tensor, u: torch.Tensor, coef, want_bf16: bool = False):
-    """out[b] = x[b] + coef[b] * u[b]; x fp32, u bf16 (a network output), coef host per-sample values."""
+    """out[b] = x[b] + coef[b] * u[b]; x fp32, u bf16 or fp32 (teacher velocity), coef host per-sample values."""
     lib = _lib.load()
     _chk(x, torch.float32, "axpy_rows x")
-    _chk(u, BF16, "axpy_rows u")
+    u_f32 = _target_is_f32(u, "axpy_rows u")
     if x.shape != u.shape or not x.is_contiguous() or not u.is_contiguous():
         raise AfbError("axpy_rows: x and u must be contiguous with the same shape")
     batch = x.shape[0]
@@ -448,21 +467,21 @@ def axpy_rows(x: torch.Tensor, u: torch.Tensor, coef, want_bf16: bool = False):
     out = torch.empty_like(x)
     out_bf = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
     _lib.check(lib.afb_axpy_rows(x.data_ptr(), u.data_ptr(), _host_floats(coef, batch, "coef"), out.data_ptr(),
-                                 out_bf.data_ptr() if want_bf16 else None, batch, per, _stream()), "afb_axpy_rows")
+                                 out_bf.data_ptr() if want_bf16 else None, batch, per, u_f32, _stream()), "afb_axpy_rows")
     return (out, out_bf) if want_bf16 else out
 
 
 def mse_rows(pred: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:
-    """Per-sample mean squared error over all trailing dims; pred fp32, tgt bf16 -> fp32 [batch] (device)."""
+    """Per-sample mean squared error over all trailing dims; pred fp32, tgt bf16 or fp32 -> fp32 [batch] (device)."""
     lib = _lib.load()
     _chk(pred, torch.float32, "mse_rows pred")
-    _chk(tgt, BF16, "mse_rows tgt")
+    tgt_f32 = _target_is_f32(tgt, "mse_rows tgt")
     if pred.shape != tgt.shape or not pred.is_contiguous() or not tgt.is_contiguous():
         raise AfbError("mse_rows: pred and tgt must be contiguous with the same shape")
     batch = pred.shape[0]
     out = torch.empty(batch, dtype=torch.float32, device=pred.device)
     _lib.check(lib.afb_mse_rows(pred.data_ptr(), tgt.data_ptr(), out.data_ptr(), batch, pred.numel() // batch,
-                                _stream()), "afb_mse_rows")
+                                tgt_f32, _stream()), "afb_mse_rows")
     return out
 
 

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 from ._lib import AfbError
 from .model import BF16, _cat_k, EngineModelBase
 from .schedule import denoise_sigmas
@@ -158,6 +158,7 @@ class PackedQwenWeights:
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: ArcQwenConfig, device, consume: bool = False):
         self.cfg = cfg
         self.keep: List[torch.Tensor] = []
+        self.adapter_views: Dict[str, torch.Tensor] = {}   # see PackedFluxWeights.adapter_views
         D, r = cfg.inner_dim, cfg.lora_rank
 
         def get(name, required=True):
@@ -168,11 +169,20 @@ class PackedQwenWeights:
                 return None
             return t.to(device=device, dtype=BF16)
 
-        def hold(t):
+        def hold(t, view_name=None):
             if t is None:
                 return None
             t = t.contiguous()
             self.keep.append(t)
+            if view_name is not None:
+                self.adapter_views[view_name] = t
+            return t.data_ptr()
+
+        def hold_packed(w_, lb_, prefix):
+            t = _cat_k(w_, lb_)
+            self.keep.append(t)
+            if lb_ is not None:
+                self.adapter_views[prefix + ".lora_B.weight"] = t[:, w_.shape[1]:]
             return t.data_ptr()
 
         def lora(prefix):
@@ -192,8 +202,8 @@ class PackedQwenWeights:
             setattr(w, f"t{li}_w", hold(get(pre + ".weight")))
             setattr(w, f"t{li}_b", hold(get(pre + ".bias")))
             a, b = lora(pre)
-            setattr(w, f"t{li}_la", hold(a))
-            setattr(w, f"t{li}_lb", hold(b))
+            setattr(w, f"t{li}_la", hold(a, pre + ".lora_A.weight"))
+            setattr(w, f"t{li}_lb", hold(b, pre + ".lora_B.weight"))
         mod_w, mod_b, mod_off = [], [], 0
 
         def add_mod(prefix):
@@ -218,18 +228,21 @@ class PackedQwenWeights:
                 setattr(k, f"{side}_out_w", hold(get(p + f"attn.{out_name}.weight")))
                 setattr(k, f"{side}_out_b", hold(get(p + f"attn.{out_name}.bias")))
                 la, lb = lora(p + f"{ff}.net.0.proj")
-                setattr(k, f"{side}_up_w", hold(_cat_k(get(p + f"{ff}.net.0.proj.weight"), lb)))
+                setattr(k, f"{side}_up_w", hold_packed(get(p + f"{ff}.net.0.proj.weight"), lb, p + f"{ff}.net.0.proj"))
                 setattr(k, f"{side}_up_b", hold(get(p + f"{ff}.net.0.proj.bias")))
-                setattr(k, f"{side}_up_la", hold(la))
+                setattr(k, f"{side}_up_la", hold(la, p + f"{ff}.net.0.proj.lora_A.weight"))
                 la, lb = lora(p + f"{ff}.net.2")
-                setattr(k, f"{side}_down_w", hold(_cat_k(get(p + f"{ff}.net.2.weight"), lb)))
+                setattr(k, f"{side}_down_w", hold_packed(get(p + f"{ff}.net.2.weight"), lb, p + f"{ff}.net.2"))
                 setattr(k, f"{side}_down_b", hold(get(p + f"{ff}.net.2.bias")))
-                setattr(k, f"{side}_down_la", hold(la))
+                setattr(k, f"{side}_down_la", hold(la, p + f"{ff}.net.2.lora_A.weight"))
             k.img_nq, k.img_nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
             k.txt_nq, k.txt_nk = hold(get(p + "attn.norm_added_q.weight")), hold(get(p + "attn.norm_added_k.weight"))
         self.sgl = (_lib.SingleBlock * 1)()
         w.norm_out_mod_off = add_mod("norm_out.linear")
-        w.mod_w, w.mod_b, w.mod_total = hold(torch.cat(mod_w, 0)), hold(torch.cat(mod_b, 0)), mod_off
+        mod_w_t, mod_b_t = torch.cat(mod_w, 0), torch.cat(mod_b, 0)
+        w.mod_w, w.mod_b, w.mod_total = hold(mod_w_t), hold(mod_b_t), mod_off
+        self.adapter_views["norm_out.linear.weight"] = mod_w_t[w.norm_out_mod_off:]
+        self.adapter_views["norm_out.linear.bias"] = mod_b_t[w.norm_out_mod_off:]
         del mod_w, mod_b
         hw = [get("proj_out_means.weight"), get("proj_out_logweights.weight"), get("proj_out_loggamma.weight")]
         hb = [get("proj_out_means.bias"), get("proj_out_logweights.bias"), get("proj_out_loggamma.bias")]
@@ -238,7 +251,14 @@ class PackedQwenWeights:
         if pad:
             hw.append(torch.zeros(pad, D, device=device, dtype=BF16))
             hb.append(torch.zeros(pad, device=device, dtype=BF16))
-        w.head_w, w.head_b, w.head_n = hold(torch.cat(hw, 0)), hold(torch.cat(hb, 0)), n + pad
+        self.head_w_tensor = torch.cat(hw, 0).contiguous()
+        head_b_tensor = torch.cat(hb, 0).contiguous()
+        row = 0
+        for hn, t in zip(("proj_out_means", "proj_out_logweights", "proj_out_loggamma"), hw):
+            self.adapter_views[hn + ".weight"] = self.head_w_tensor[row:row + t.shape[0]]
+            self.adapter_views[hn + ".bias"] = head_b_tensor[row:row + t.shape[0]]
+            row += t.shape[0]
+        w.head_w, w.head_b, w.head_n = hold(self.head_w_tensor), hold(head_b_tensor), n + pad
         self.head_n = n + pad
         w.dbl = C.cast(self.dbl, C.POINTER(_lib.DoubleBlock))
         w.sgl = C.cast(self.sgl, C.POINTER(_lib.SingleBlock))
@@ -254,7 +274,10 @@ def qwen_time_input(sigma: float) -> float:
 
 
 class ArcQwenEngineModel(EngineModelBase):
-    """ArcFlow-Qwen-Image student transformer + N-NFE sampler on the native engine (inference)."""
+    """ArcFlow-Qwen-Image student transformer + N-NFE sampler on the native engine (inference and training)."""
+    arch = "qwen"
+    _DBL_LORA = (("img_up", "img_mlp.net.0.proj"), ("img_down", "img_mlp.net.2"), ("txt_up", "txt_mlp.net.0.proj"),
+                 ("txt_down", "txt_mlp.net.2"))
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ArcQwenConfig, device="cuda",
                  consume_state_dict: bool = False):
@@ -284,18 +307,23 @@ class ArcQwenEngineModel(EngineModelBase):
             raise AfbError("inputs must be CUDA tensors (no CPU fallback exists)")
 
     @torch.no_grad()
-    def forward_heads(self, latents, txt, sigma: float, grid_hw: Sequence[int]) -> torch.Tensor:
+    def forward_heads(self, latents, txt, sigma, grid_hw: Sequence[int], train: bool = False) -> torch.Tensor:
+        """One network call; `sigma`: a scalar or per-sample values. train=True also stores the per-block checkpoints
+        `backward_trunk` recomputes from (see ArcFluxEngineModel.forward_heads)."""
         self._check(latents, txt, grid_hw)
         B, Si, _ = latents.shape
         lat, txt = latents.to(BF16).contiguous(), txt.to(BF16).contiguous()
         self._reserve(B, txt.shape[1], Si)
-        tdev = torch.full((B,), qwen_time_input(sigma), dtype=torch.float32, device=self.device)
+        sig = [float(v) for v in (sigma.tolist() if isinstance(sigma, torch.Tensor) else
+                                  (sigma if isinstance(sigma, (list, tuple)) else [sigma] * B))]
+        if len(sig) != B:
+            raise AfbError(f"sigma: expected a scalar or {B} per-sample values")
+        tdev = torch.tensor([qwen_time_input(v) for v in sig], dtype=torch.float32).to(self.device)
         cos, sin = self.rope(txt.shape[1], grid_hw[0], grid_hw[1])
         out = torch.empty(B, Si, self.weights.head_n, dtype=BF16, device=self.device)
         a = self._fwd_args(txt, None, tdev, None, cos, sin, B, Si)
         a.latents, a.head_out = lat.data_ptr(), out.data_ptr()
-        _lib.check(self.lib.afb_engine_forward(self.handle, C.byref(a), torch.cuda.current_stream().cuda_stream),
-                   "afb_engine_forward")
+        self._launch_forward(a, (lat, txt, tdev, cos, sin, out), train)
         return out
 
     @torch.no_grad()
@@ -319,3 +347,65 @@ class ArcQwenEngineModel(EngineModelBase):
         _lib.check(self.lib.afb_engine_denoise(self.handle, C.byref(d), torch.cuda.current_stream().cuda_stream),
                    "afb_engine_denoise")
         return x
+
+
+def make_qwen_teacher_extras(cfg: ArcQwenConfig, seed: int = 4321, device="cpu", dtype=BF16) -> Dict[str, torch.Tensor]:
+    """The teacher-only tensors of the stock Qwen-Image transformer (its `norm_out.linear` and `proj_out`); the trunk is
+    tied to the student's frozen base layers (lakonlab/models/base_diffusion.py:93-94)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    D = cfg.inner_dim
+    normal = lambda shape: torch.empty(shape, device=device, dtype=torch.float32).normal_(0.0, 0.02, generator=g).to(dtype)
+    return {"norm_out.linear.weight": normal((2 * D, D)), "norm_out.linear.bias": normal((2 * D,)),
+            "proj_out.weight": normal((cfg.out_channels, D)), "proj_out.bias": normal((cfg.out_channels,))}
+
+
+class QwenTeacherEngine(ArcQwenEngineModel):
+    """Stock Qwen-Image velocity network TIED to a student's frozen trunk (lakonlab/models/base_diffusion.py:93-94,
+    lakonlab/utils/misc.py:116-132), with true classifier-free guidance as the reference's teacher uses it
+    (GaussianFlow.forward_u, lakonlab/models/diffusions/gaussian_flow.py:224-254; teacher_guidance_scale = 4.0,
+    configs/qwen/arcqwen_2nfe_k16.py:100): ONE batch-doubled forward on [neg; pos] text, then
+    pos + (pos - neg)(g - 1) in fp32 (afb_cfg_combine). Forward = lakonlab/models/architecture/diffusers/qwen.py:107-139."""
+
+    def __init__(self, student: ArcQwenEngineModel, teacher_sd: Dict[str, torch.Tensor]):
+        from types import SimpleNamespace
+        cfg, dev = student.cfg, student.device
+        self.student = student   # keeps the shared packed tensors alive
+        keep = []
+
+        def hold(name):
+            if name not in teacher_sd:
+                raise AfbError(f"teacher state dict is missing '{name}'")
+            t = teacher_sd[name].to(device=dev, dtype=BF16).contiguous()
+            keep.append(t)
+            return t
+
+        w = _lib.Weights()
+        C.memmove(C.byref(w), C.byref(student.weights.struct), C.sizeof(w))
+        pw, pb = hold("proj_out.weight"), hold("proj_out.bias")
+        nw, nb = hold("norm_out.linear.weight"), hold("norm_out.linear.bias")
+        if pw.shape != (cfg.out_channels, cfg.inner_dim) or nw.shape != (2 * cfg.inner_dim, cfg.inner_dim):
+            raise AfbError("teacher proj_out / norm_out.linear have unexpected shapes")
+        w.head_w, w.head_b, w.head_n = pw.data_ptr(), pb.data_ptr(), cfg.out_channels
+        w.alt_norm_out_w, w.alt_norm_out_b = nw.data_ptr(), nb.data_ptr()
+        weights = SimpleNamespace(struct=w, keep=keep, head_n=cfg.out_channels, adapter_views={})
+        md = _lib.ModelDesc(
+            arch=_lib.AFB_ARCH_QWEN, num_double=cfg.num_layers, num_single=0, dim=cfg.inner_dim,
+            heads=cfg.num_attention_heads, mlp_dim=cfg.mlp_dim, in_channels=cfg.in_channels,
+            txt_dim=cfg.joint_attention_dim, pooled_dim=0, guidance=0, num_gaussians=cfg.num_gaussians,
+            lora_rank=cfg.lora_rank, head_mode=1, ignore_lora=1)
+        EngineModelBase.__init__(self, cfg, weights, md, dev)
+
+    def velocity(self, latents, txt_pos, txt_neg, sigma, guidance_scale: float, grid_hw) -> torch.Tensor:
+        """u(x_t, t) in packed-token layout [batch, tokens, 64]: bf16 without guidance, fp32 with true CFG."""
+        if not guidance_scale > 1.0:
+            return self.forward_heads(latents, txt_pos, sigma, grid_hw)
+        if txt_neg is None or txt_neg.shape != txt_pos.shape:
+            raise AfbError("true CFG needs negative text embeds of the positive ones' shape ([neg; pos] is one batch)")
+        B = latents.shape[0]
+        sig = [float(v) for v in (sigma.tolist() if isinstance(sigma, torch.Tensor) else
+                                  (sigma if isinstance(sigma, (list, tuple)) else [sigma] * B))]
+        both = self.forward_heads(torch.cat([latents, latents], 0), torch.cat([txt_neg, txt_pos], 0), sig + sig, grid_hw)
+        return ops.cfg_combine(both, guidance_scale)
+
+    def denoise(self, *a, **k):
+        raise AfbError("the teacher has no ArcFlow heads; denoise() is a student method")

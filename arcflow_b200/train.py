@@ -31,6 +31,9 @@ DEFAULT_TRAIN_CFG = dict(  # configs/flux/arcflux_2nfe_k16.py:89-99
     num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4,
     distilled_guidance_scale=3.5, teacher_distilled_guidance_scale=3.5, nfe=2, timestep_ratio=1.0,
     total_substeps=128, eps=1e-4)
+QWEN_TRAIN_CFG = dict(  # configs/qwen/arcqwen_2nfe_k16.py:96-106 — true CFG on the teacher, no guidance embedding
+    num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, teacher_guidance_scale=4.0,
+    nfe=2, timestep_ratio=1.0, total_substeps=128, eps=1e-4)
 
 
 def warp_t(t: torch.Tensor, shift: float) -> torch.Tensor:
@@ -48,7 +51,8 @@ def draw_rollout_randoms(batch: int, num_states: int, num_gaussians: int, genera
 class ArcFlowDistillStep:
     def __init__(self, student, teacher, train_cfg: Optional[Dict] = None, shift: float = 3.2, loss_scale: float = 30.0):
         self.student, self.teacher = student, teacher
-        self.cfg = dict(DEFAULT_TRAIN_CFG)
+        self.qwen = getattr(student, "arch", "flux") == "qwen"
+        self.cfg = dict(QWEN_TRAIN_CFG if self.qwen else DEFAULT_TRAIN_CFG)
         if train_cfg:
             self.cfg.update(train_cfg)
         self.shift, self.loss_scale = shift, loss_scale
@@ -60,9 +64,11 @@ class ArcFlowDistillStep:
     @torch.no_grad()
     def forward(self, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int], noise: torch.Tensor,
                 rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0, save_for_backward: bool = False,
-                step_hook=None):
+                step_hook=None, neg_txt: Optional[torch.Tensor] = None):
         """One train iteration, forward only. noise: fp32 packed tokens [B, S_i, 64] (the data-free x_t_src);
         rands: one dict of uniforms per student step (see draw_rollout_randoms). Returns (loss, log_vars, extras).
+        FLUX: pooled = pooled text projections. Qwen: pooled is None and neg_txt carries the negative-prompt embeds of
+        the teacher's true CFG (latent_diffusion_text_image.py:63-78).
         step_hook(saved): called after each student step's roll-out while that step's trunk checkpoints are still live
         (forward_backward() uses it to run the step's backward before the next student forward overwrites them)."""
         cfg, st, te = self.cfg, self.student, self.teacher
@@ -76,7 +82,14 @@ class ArcFlowDistillStep:
         base_seg = 1.0 / (nfe - 1 + ratio_t)
         n_states, total_sub = cfg["num_intermediate_states"], cfg["total_substeps"]
         K = st.num_gaussians
-        g_student, g_teacher = cfg["distilled_guidance_scale"], cfg["teacher_distilled_guidance_scale"]
+        if self.qwen:
+            g_true = cfg.get("teacher_guidance_scale") or 1.0
+            student_heads = lambda x_, sig_, train_: st.forward_heads(x_, txt, sig_, grid_hw, train=train_)
+            teacher_u = lambda x_, sig_: te.velocity(x_, txt, neg_txt, sig_, g_true, grid_hw)
+        else:
+            g_student, g_teacher = cfg["distilled_guidance_scale"], cfg["teacher_distilled_guidance_scale"]
+            student_heads = lambda x_, sig_, train_: st.forward_heads(x_, txt, pooled, sig_, g_student, grid_hw, train=train_)
+            teacher_u = lambda x_, sig_: te.velocity(x_, txt, pooled, sig_, g_teacher, grid_hw)
         teacher_ratio = self.teacher_ratio(iteration)
         log_vars = dict(teacher_ratio=teacher_ratio) if cfg.get("num_decay_iters", 0) > 0 else {}
 
@@ -92,7 +105,7 @@ class ArcFlowDistillStep:
             raw_t_dst = raw_t_src - seg
             sigma_src = warp_t(raw_t_src, self.shift)
 
-            head = st.forward_heads(x_src, txt, pooled, sigma_src, g_student, grid_hw, train=step_hook is not None)
+            head = student_heads(x_src, sigma_src, step_hook is not None)
             head2 = head.reshape(-1, head.shape[-1])
             saved = None
             if save_for_backward:
@@ -121,7 +134,7 @@ class ArcFlowDistillStep:
                 sigma_a, sigma_b = warp_t(raw_t_a, self.shift), warp_t(raw_t_b, self.shift)
                 x_a, x_a_bf = ops.policy_eval(head2, _lib.AFB_POLICY_INTEGRATE, sigma_src, sigma_t, sigma_a, x=x_t,
                                               batch=B, drop_mask=drop, num_gaussians=K, eps=eps, want_bf16=True)
-                tgt_u = te.velocity(x_a_bf, txt, pooled, sigma_a, g_teacher, grid_hw)
+                tgt_u = teacher_u(x_a_bf, sigma_a)
                 raw_end = raw_t_b - window
                 small = torch.round((raw_t_a - raw_end) * total_sub) < 2
                 pred_u = ops.policy_eval(head2, _lib.AFB_POLICY_AVERAGE_U, sigma_src, sigma_a, warp_t(raw_end, self.shift),
@@ -208,7 +221,7 @@ class ArcFlowDistillStep:
     @torch.no_grad()
     def forward_backward(self, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int], noise: torch.Tensor,
                          rands: Sequence[Dict[str, torch.Tensor]], iteration: int = 0,
-                         grads: Optional[Dict[str, torch.Tensor]] = None):
+                         grads: Optional[Dict[str, torch.Tensor]] = None, neg_txt: Optional[torch.Tensor] = None):
         """train_fwd_bwd (lakonlab/models/base_diffusion.py:14-62): forward + loss + the gradients of every adapter
         tensor: heads, norm_out.linear, the trunk's LoRA pairs, and — through the gradients of every AdaLN shift / scale /
         gate vector — the timestep embedder's LoRA pairs.
@@ -232,7 +245,7 @@ class ArcFlowDistillStep:
             st.backward_embed(d_mod, grads)
 
         loss, log_vars, extras = self.forward(txt, pooled, grid_hw, noise, rands, iteration, save_for_backward=True,
-                                              step_hook=hook)
+                                              step_hook=hook, neg_txt=neg_txt)
         for n, g in self._split_head_grads(acc).items():
             if n in grads:
                 grads[n] += g
@@ -279,10 +292,11 @@ class ArcFlowTrainer:
         return {n: self.opt.view(buf, n).to(torch.bfloat16).clone() for n in self.student.weights.adapter_views}
 
     @torch.no_grad()
-    def train_step(self, txt, pooled, grid_hw, noise, rands, iteration: Optional[int] = None):
+    def train_step(self, txt, pooled, grid_hw, noise, rands, iteration: Optional[int] = None, neg_txt=None):
         it = self.iteration if iteration is None else iteration
         self.opt.grads.zero_()
-        loss, log_vars, _ = self.distill.forward_backward(txt, pooled, grid_hw, noise, rands, it, grads=self.grads)
+        loss, log_vars, _ = self.distill.forward_backward(txt, pooled, grid_hw, noise, rands, it, grads=self.grads,
+                                                          neg_txt=neg_txt)
         log_vars.update(self.opt.step(it))
         self.write_back()
         self.iteration = it + 1

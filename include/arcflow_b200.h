@@ -217,8 +217,8 @@ int afb_policy_eval(const afb_policy_args* args, void* stream);
  *   L = coef/2 * sum (policy_average_u(head) - tgt)^2   ->   dhead[tokens, dh_ld] (fp32, same column layout as head)
  * gets dL/d(means | logits | loggamma); accumulate != 0 adds to the existing contents (the 4 roll-out states of one
  * student step share one head tensor). The rounding of the bf16 log-softmax is treated as straight-through. */
-int afb_policy_backward(const afb_policy_args* args, const void* tgt_bf16, float* dhead, int64_t dh_ld, float coef,
-                        int32_t accumulate, void* stream);
+int afb_policy_backward(const afb_policy_args* args, const void* tgt, float* dhead, int64_t dh_ld, float coef,
+                        int32_t accumulate, int32_t tgt_is_f32, void* stream);
 /* out[n] += sum_t x[t, n]; x fp32 [rows, ld] (bias gradients). out must be initialised by the caller. */
 int afb_colsum_f32(const float* x, int64_t ld, float* out, int64_t rows, int32_t n, void* stream);
 
@@ -255,11 +255,16 @@ int afb_rowlinear_param_grad(const float* de, int64_t de_ld, const void* t, int6
  * which = 0 final image hidden states [batch, img_len, dim], 1 head input (norm_out output) [batch, img_len, dim], 2 temb [batch, dim]. */
 int afb_engine_export(afb_engine* e, int32_t which, void* dst, int32_t batch, int32_t txt_len, int32_t img_len, void* stream);
 
-/* out[b, :] = x[b, :] + coef[b] * u[b, :]  (teacher Euler step, arcflow.py:190). x/out fp32, u bf16, coef host. */
-int afb_axpy_rows(const float* x, const void* u_bf16, const float* coef, float* out, void* out_bf16,
-                  int32_t batch, int64_t per_sample, void* stream);
-/* out[b] = mean_i (pred[b, i] - tgt[b, i])^2 — mmgen mse_loss(reduction='flatmean'); pred fp32, tgt bf16, out device fp32 [batch]. */
-int afb_mse_rows(const float* pred, const void* tgt_bf16, float* out, int32_t batch, int64_t per_sample, void* stream);
+/* Teacher targets u / tgt below are bf16 (a network output, FLUX) or fp32 when *_is_f32 != 0 (the true-CFG combination). */
+/* out[b, :] = x[b, :] + coef[b] * u[b, :]  (teacher Euler step, arcflow.py:190). x/out fp32, coef host. */
+int afb_axpy_rows(const float* x, const void* u, const float* coef, float* out, void* out_bf16,
+                  int32_t batch, int64_t per_sample, int32_t u_is_f32, void* stream);
+/* out[b] = mean_i (pred[b, i] - tgt[b, i])^2 — mmgen mse_loss(reduction='flatmean'); pred fp32, out device fp32 [batch]. */
+int afb_mse_rows(const float* pred, const void* tgt, float* out, int32_t batch, int64_t per_sample, int32_t tgt_is_f32,
+                 void* stream);
+/* True classifier-free guidance on a batch-doubled bf16 network output [neg; pos] (each `half` elements):
+ * out = pos + (pos - neg) * (guidance_scale - 1), fp32 (GaussianFlow.forward_u, gaussian_flow.py:18-26, 224-254). */
+int afb_cfg_combine(const void* both_bf16, float* out, int64_t half, float guidance_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Step glue over ONE flat fp32 arena of all trainable adapter tensors (reference

@@ -410,12 +410,12 @@ def qwen_block(sd, p: str, x: Tensor, c: Tensor, temb: Tensor, rope, heads: int,
     return c, x
 
 
-def qwen_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
-                 timestep: Tensor, grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0,
-                 bf16_quirks: bool = True) -> Dict[str, Tensor]:
-    """_ArcQwenImageTransformer2DModel.forward (arcqwen.py:106-174). `timestep` is sigma in [0, 1]
-    (arcqwen_pipeline.py:412); it is cast to the hidden dtype (:128, bf16 in deployment) and scaled by 1000
-    inside Timesteps(scale=1000) in fp32 (QwenTimestepProjEmbeddings)."""
+def qwen_trunk(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
+               timestep: Tensor, grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0,
+               bf16_quirks: bool = True):
+    """Everything of the Qwen-Image transformer up to (not including) norm_out: returns (image hidden states, temb).
+    Shared by the ArcFlow student (arcqwen.py:106-157) and the stock teacher (diffusers QwenImageTransformer2DModel
+    reached through lakonlab/models/architecture/diffusers/qwen.py:107-139)."""
     heads = cfg.num_attention_heads
     x = _lin(sd, "img_in", hidden_states.to(dtype), dtype)
     t = timestep.to(torch.bfloat16 if bf16_quirks else dtype)
@@ -427,6 +427,16 @@ def qwen_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidd
     rope = QwenEmbedRope(10000, cfg.axes_dims_rope, True)(1, grid_hw[0], grid_hw[1], c.shape[1])
     for i in range(cfg.num_layers):
         c, x = qwen_block(sd, f"transformer_blocks.{i}.", x, c, temb, rope, heads, dtype, lora_scale)
+    return x, temb
+
+
+def qwen_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
+                 timestep: Tensor, grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0,
+                 bf16_quirks: bool = True) -> Dict[str, Tensor]:
+    """_ArcQwenImageTransformer2DModel.forward (arcqwen.py:106-174). `timestep` is sigma in [0, 1]
+    (arcqwen_pipeline.py:412); it is cast to the hidden dtype (:128, bf16 in deployment) and scaled by 1000
+    inside Timesteps(scale=1000) in fp32 (QwenTimestepProjEmbeddings)."""
+    x, temb = qwen_trunk(sd, cfg, hidden_states, encoder_hidden_states, timestep, grid_hw, dtype, lora_scale, bf16_quirks)
     emb = _lin(sd, "norm_out.linear", F.silu(temb).to(x.dtype), dtype)
     scale, shift = emb.chunk(2, dim=1)
     x = _ln(x) * (1 + scale)[:, None, :] + shift[:, None, :]

@@ -203,8 +203,81 @@ def flux_train_forward(sd, teacher_extra, cfg, txt, pooled, grid_hw, noise_token
         step_loss, x_t_dst, raw_t_dst, tr = piid_segment(mp, x_t_src, raw_t_src, sigma_t_src, teacher_ratio, seg, teacher_u,
                                                          rands[step_id], train_cfg, shift, loss_scale)
         loss = loss + step_loss * seg
-        log_vars[f"loss_diffusion_step{step_id}"] = float(step_loss)
-        log_vars["loss_diffusion"] = log_vars.get("loss_diffusion", 0.0) + float(step_loss * seg)
+        log_vars[f"loss_diffusion_step{step_id}"] = float(step_loss.detach())
+        log_vars["loss_diffusion"] = log_vars.get("loss_diffusion", 0.0) + float((step_loss * seg).detach())
+        trace.append(dict(x_t_dst=x_t_dst, **tr))
+        x_t_src, raw_t_src = x_t_dst, raw_t_dst
+    return loss, log_vars, dict(leaves=leaves, trace=trace)
+
+
+def qwen_teacher_velocity(tsd, cfg, x_tokens: Tensor, txt, sigma: Tensor, grid_hw, dtype=torch.float32) -> Tensor:
+    """Stock Qwen-Image forward: same trunk, AdaLayerNormContinuous + proj_out (D -> 64)
+    (lakonlab/models/architecture/diffusers/qwen.py:107-139)."""
+    import torch.nn.functional as F
+    x, temb = O.qwen_trunk(tsd, cfg, x_tokens, txt, sigma, grid_hw, dtype=dtype)
+    emb = O._lin(tsd, "norm_out.linear", F.silu(temb).to(x.dtype), dtype)
+    scale, shift = emb.chunk(2, dim=1)
+    x = O._ln(x) * (1 + scale)[:, None, :] + shift[:, None, :]
+    return O._lin(tsd, "proj_out", x, dtype)
+
+
+def qwen_teacher_cfg_velocity(tsd, cfg, x_tokens: Tensor, txt_pos, txt_neg, sigma: Tensor, guidance_scale: float, grid_hw,
+                              dtype=torch.float32, net_dtype=torch.bfloat16) -> Tensor:
+    """GaussianFlow.forward_u with true classifier-free guidance (gaussian_flow.py:224-254): one batch-doubled call on
+    [neg; pos] text (latent_diffusion_text_image.py:75-78), `mean_pos + (mean_pos - mean_neg) * (g - 1)` in fp32 on the
+    network's bf16 outputs (pred() casts them back to the fp32 x_t dtype, :90-107)."""
+    if not guidance_scale > 1.0:
+        return qwen_teacher_velocity(tsd, cfg, x_tokens, txt_pos, sigma, grid_hw, dtype=dtype).to(net_dtype).to(torch.float32)
+    both = qwen_teacher_velocity(tsd, cfg, torch.cat([x_tokens, x_tokens], 0), torch.cat([txt_neg, txt_pos], 0),
+                                 torch.cat([sigma, sigma], 0), grid_hw, dtype=dtype).to(net_dtype).to(torch.float32)
+    neg, pos = both.chunk(2, dim=0)
+    return pos + (pos - neg) * (guidance_scale - 1)
+
+
+def qwen_train_forward(sd, teacher_extra, cfg, txt, txt_neg, grid_hw, noise_tokens: Tensor, rands: Sequence[Dict],
+                       iteration: int, train_cfg: Dict, shift: float = 3.2, loss_scale: float = 30.0,
+                       dtype=torch.float32, net_dtype=torch.bfloat16, require_grad: Sequence[str] = ()):
+    """flux_train_forward for the Qwen-Image student / teacher pair (configs/qwen/arcqwen_2nfe_k16.py: same roll-out,
+    teacher_guidance_scale = 4.0 true CFG, no distilled-guidance embedding, no pooled text)."""
+    gh, gw = grid_hw
+    B = noise_tokens.shape[0]
+    leaves = {}
+    if require_grad:
+        sd = dict(sd)
+        for k in require_grad:
+            leaves[k] = sd[k].detach().to(dtype).clone().requires_grad_(True)
+            sd[k] = leaves[k]
+    tsd = teacher_state_dict({k: (v.detach() if isinstance(v, Tensor) else v) for k, v in sd.items()}, teacher_extra)
+    num_decay = train_cfg.get("num_decay_iters", 0)
+    teacher_ratio = 1 - min(iteration, num_decay) / num_decay if num_decay > 0 else 0.0
+    nfe = train_cfg["nfe"]
+    eps = train_cfg.get("eps", 1e-4)
+    ratio = max(train_cfg.get("timestep_ratio", 1.0), eps)
+    base_seg = 1 / (nfe - 1 + ratio)
+    g_teacher = train_cfg.get("teacher_guidance_scale", 4.0)
+
+    def teacher_u(x_img, sigma):
+        with torch.no_grad():
+            v = qwen_teacher_cfg_velocity(tsd, cfg, O.pack_latents(x_img).to(net_dtype), txt, txt_neg, sigma, g_teacher,
+                                          grid_hw, dtype=dtype, net_dtype=net_dtype)
+        return O.unpack_latents(v, gh, gw)
+
+    x_t_src = O.unpack_latents(noise_tokens.to(torch.float32), gh, gw)
+    raw_t_src = torch.ones(B, dtype=torch.float32)
+    loss = 0
+    log_vars = dict(teacher_ratio=teacher_ratio) if num_decay > 0 else {}
+    trace = []
+    for step_id in range(nfe):
+        seg = base_seg * ratio if step_id == nfe - 1 else base_seg
+        sigma_t_src = warp_t(raw_t_src, shift).reshape(B, 1, 1, 1)
+        out = O.qwen_forward(sd, cfg, O.pack_latents(x_t_src).to(net_dtype), txt, sigma_t_src.flatten(), grid_hw, dtype=dtype)
+        out = {k: v + (v.to(net_dtype).to(v.dtype) - v).detach() for k, v in out.items()}
+        mp = O.unpack_mp({k: v.to(torch.float32) for k, v in out.items()}, gh, gw, cfg.num_gaussians)
+        step_loss, x_t_dst, raw_t_dst, tr = piid_segment(mp, x_t_src, raw_t_src, sigma_t_src, teacher_ratio, seg, teacher_u,
+                                                         rands[step_id], train_cfg, shift, loss_scale)
+        loss = loss + step_loss * seg
+        log_vars[f"loss_diffusion_step{step_id}"] = float(step_loss.detach())
+        log_vars["loss_diffusion"] = log_vars.get("loss_diffusion", 0.0) + float((step_loss * seg).detach())
         trace.append(dict(x_t_dst=x_t_dst, **tr))
         x_t_src, raw_t_src = x_t_dst, raw_t_dst
     return loss, log_vars, dict(leaves=leaves, trace=trace)

@@ -47,3 +47,25 @@ def test_dropout_mask_never_drops_everything():
     u = torch.tensor([[0.01] * 16, [0.5] * 15 + [0.01]])
     m = T.dropout_mask(u, 0.1)
     assert not m[0].any() and m[1].sum() == 1
+
+
+def test_qwen_true_cfg_teacher_identities():
+    """qwen_teacher_cfg_velocity: g <= 1 is the plain conditional velocity; neg == pos cancels the guidance term; the
+    general case is pos + (pos - neg)(g - 1) of two independent bf16-rounded calls (gaussian_flow.py:18-26, 224-254)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    from arcflow_b200.qwen import make_qwen_inputs, make_qwen_state_dict, make_qwen_teacher_extras, qwen_tiny
+    from oracle import arcflow_train_oracle as T
+    cfg = qwen_tiny(2, 2)
+    sd, extra = make_qwen_state_dict(cfg, seed=3), make_qwen_teacher_extras(cfg, seed=4)
+    x, txt = make_qwen_inputs(cfg, 2, 32, 32, txt_len=8, seed=5)
+    _, neg = make_qwen_inputs(cfg, 2, 32, 32, txt_len=8, seed=6)
+    tsd = T.teacher_state_dict(sd, extra)
+    sig = torch.tensor([0.9, 0.3])
+    plain = T.qwen_teacher_velocity(tsd, cfg, x.bfloat16(), txt, sig, (2, 2)).bfloat16().float()
+    plain_neg = T.qwen_teacher_velocity(tsd, cfg, x.bfloat16(), neg, sig, (2, 2)).bfloat16().float()
+    assert torch.equal(T.qwen_teacher_cfg_velocity(tsd, cfg, x.bfloat16(), txt, neg, sig, 1.0, (2, 2)), plain)
+    assert torch.allclose(T.qwen_teacher_cfg_velocity(tsd, cfg, x.bfloat16(), txt, txt, sig, 4.0, (2, 2)), plain, atol=1e-6)
+    got = T.qwen_teacher_cfg_velocity(tsd, cfg, x.bfloat16(), txt, neg, sig, 4.0, (2, 2))
+    assert torch.allclose(got, plain + (plain - plain_neg) * 3.0, atol=2e-2, rtol=2e-2)   # batch-doubled vs separate calls

@@ -1,11 +1,15 @@
 """Times the native train iteration at the reference's training shape: FLUX, bs 4 per GPU, latent 16x128x128
 (S_img = 4096, S_txt = 512) — BASELINE.json configs[3]: 2 student + 8 teacher forwards, roll-out kernels, the full
 adapter backward (per-block recompute), grad clip + AdamW + EMA and the bf16 write-back.
-Usage: python tools/train_step_time.py [batch] [--profile]"""
+Usage: python tools/train_step_time.py [batch] [--profile]
+   or: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step_time.py [batch]
+       (DDP: per-rank noise, ONE NCCL all-reduce of the flat gradient arena per iteration; time = max over ranks)"""
 import json
+import os
 import sys
 
 import torch
+import torch.distributed as dist
 
 sys.path.insert(0, ".")
 from arcflow_b200 import _lib  # noqa: E402
@@ -17,22 +21,29 @@ from arcflow_b200.train import ArcFlowTrainer, draw_rollout_randoms  # noqa: E40
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 B = int(args[0]) if args else 4
 profile = "--profile" in sys.argv
-dev = torch.device("cuda", 0)
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
 cfg = flux_dev()
 sd = make_flux_state_dict(cfg, 1234, dev)
 student = ArcFluxEngineModel(sd, cfg, dev, consume_state_dict=True)
 del sd
 teacher = FluxTeacherEngine(student, make_flux_teacher_extras(cfg, 99, dev))
-x, txt, pooled = make_flux_inputs(cfg, B, 1024, 1024, 512, 42, dev)
+x, txt, pooled = make_flux_inputs(cfg, B, 1024, 1024, 512, 42 + rank, dev)
 trainer = ArcFlowTrainer(student, teacher)
 step = trainer.distill
-g = torch.Generator().manual_seed(0)
+g = torch.Generator().manual_seed(rank)
 rands = [draw_rollout_randoms(B, 4, 16, g) for _ in range(2)]
 lib = _lib.load()
 
 
 def timed(fn, n):
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     n0 = lib.afb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -40,15 +51,18 @@ def timed(fn, n):
         out = fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n, (lib.afb_launch_count() - n0) // n, out
+    ms_ = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
+    return float(ms_.item()), (lib.afb_launch_count() - n0) // n, out
 
 
 trainer.train_step(txt, pooled, (64, 64), x, rands, iteration=500)   # warm-up (also sizes every workspace)
 fwd_ms, fwd_launches, (loss_f, _, _) = timed(lambda: step.forward(txt, pooled, (64, 64), x, rands, iteration=500), 2)
 ms, launches, (loss, lv) = timed(lambda: trainer.train_step(txt, pooled, (64, 64), x, rands, iteration=500), 2)
 fwd_flops = (2 * 78.77e12 + 8 * 74.36e12) * B
-out = dict(what="train iteration (fwd + bwd + optimizer)", batch=B, ms=ms, forward_only_ms=fwd_ms, backward_optim_ms=ms - fwd_ms,
-           samples_per_s=B / (ms / 1e3), loss=loss, fwd_tflops=fwd_flops / (fwd_ms * 1e9), launches=launches,
+out = dict(what="train iteration (fwd + bwd + optimizer)", n_gpus=world, batch=B, ms=ms, forward_only_ms=fwd_ms, backward_optim_ms=ms - fwd_ms,
+           samples_per_s=B * world / (ms / 1e3), loss=loss, fwd_tflops=fwd_flops / (fwd_ms * 1e9), launches=launches,
            fwd_launches=fwd_launches, mem_gb=torch.cuda.max_memory_allocated() / 2**30,
            log_vars={k: (float(v) if isinstance(v, (int, float)) else v) for k, v in lv.items()})
 if profile:
@@ -56,4 +70,13 @@ if profile:
     trainer.train_step(txt, pooled, (64, 64), x, rands, iteration=500)
     out["student_profile"] = student.read_profile()
     student.set_profiling(False)
-print(json.dumps(out))
+if world > 1:   # DDP invariant: every rank holds the same parameters after the step
+    chk = trainer.opt.params.double().sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out["params_identical_across_ranks"] = bool((lo == hi).item())
+if rank == 0:
+    print(json.dumps(out))
+if world > 1:
+    dist.destroy_process_group()
