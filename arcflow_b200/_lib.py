@@ -187,6 +187,8 @@ SIGNATURES = {
     "afb_cast_f32_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
     "afb_policy_eval": (C.c_int, [C.POINTER(PolicyArgs), _P]),
     "afb_policy_backward": (C.c_int, [C.POINTER(PolicyArgs), _P, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32, _P]),
+    "afb_dropout_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_uint64, C.c_uint32, C.c_float, C.c_int32, C.c_int32, _P]),
     "afb_cfg_combine": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P]),
     "afb_colsum_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P]),
     "afb_gemm_tn": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
@@ -202,6 +204,7 @@ SIGNATURES = {
     "afb_gelu_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, _P]),
     "afb_rmsnorm_rope_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, _P]),
+    "afb_engine_set_lora_dropout": (C.c_int, [_P, C.c_float, C.c_uint64]),
     "afb_engine_train_reserve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "afb_engine_forward_train": (C.c_int, [_P, C.POINTER(ForwardArgs), _P]),
     "afb_engine_backward": (C.c_int, [_P, C.POINTER(BackwardArgs), _P]),

@@ -27,6 +27,9 @@ int cast_f32_bf16_launch(const float* in, void* out, int64_t n, cudaStream_t str
 int policy_eval_launch(const afb_policy_args* a, cudaStream_t stream);
 int policy_backward_launch(const afb_policy_args* a, const void* tgt, float* dhead, int64_t dh_ld, float coef,
                            int accumulate, int tgt_f32, cudaStream_t stream);
+int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, int64_t out_ld, int64_t out_bs, int batches,
+                        int rows_per_batch, int cols, int logical_cols, int col0, uint64_t seed, uint32_t layer_id, float p,
+                        int silu_in, int accumulate, cudaStream_t stream);
 int cfg_combine_launch(const void* both_bf16, float* out, int64_t half, float guidance_scale, cudaStream_t stream);
 int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream);
@@ -108,6 +111,12 @@ int afb_policy_eval(const afb_policy_args* args, void* stream) {
 int afb_policy_backward(const afb_policy_args* args, const void* tgt, float* dhead, int64_t dh_ld, float coef,
                         int32_t accumulate, int32_t tgt_is_f32, void* stream) {
   return afb::policy_backward_launch(args, tgt, dhead, dh_ld, coef, accumulate, tgt_is_f32, static_cast<cudaStream_t>(stream));
+}
+int afb_dropout_rows(const void* x, int64_t x_ld, int64_t x_bs, void* out, int64_t out_ld, int64_t out_bs, int32_t batches,
+                     int32_t rows_per_batch, int32_t cols, int32_t logical_cols, int32_t col0, uint64_t seed, uint32_t layer_id,
+                     float p, int32_t silu_in, int32_t accumulate, void* stream) {
+  return afb::dropout_rows_launch(x, x_ld, x_bs, out, out_ld, out_bs, batches, rows_per_batch, cols, logical_cols, col0, seed,
+                                  layer_id, p, silu_in, accumulate, static_cast<cudaStream_t>(stream));
 }
 int afb_cfg_combine(const void* both_bf16, float* out, int64_t half, float guidance_scale, void* stream) {
   return afb::cfg_combine_launch(both_bf16, out, half, guidance_scale, static_cast<cudaStream_t>(stream));

@@ -734,6 +734,59 @@ rowlinear_param_grad_kernel(const float* __restrict__ de, long long de_ld, const
 }
 
 
+
+// ================================================================================================
+// LoRA input dropout (peft lora_dropout = 0.05, train only: result = base(x) + B(A(dropout(x)))).
+// Counter-based: keep(element) = hash(key, logical index) >= p * 2^32, so the checkpointed recompute and the backward
+// regenerate the same mask from (seed, layer id) with no stored mask. The hash is restated in numpy by the oracle.
+// ================================================================================================
+__device__ __forceinline__ uint32_t lowbias32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x7feb352dU;
+  h ^= h >> 15;
+  h *= 0x846ca68bU;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ bool dropout_keep(uint32_t key, unsigned long long idx, uint32_t thresh) {
+  uint32_t h = lowbias32(uint32_t(idx) ^ key);
+  h = lowbias32(h + uint32_t(idx >> 32) * 0x9E3779B1U + 0x85EBCA77U);
+  return h >= thresh;
+}
+
+struct DropParams {
+  int rows_per_batch, cols, logical_cols, col0;
+  uint32_t key, thresh;
+  float inv_keep;
+  int silu_in;      // forward: apply SiLU (rounded to bf16, as small_linear's SILU_IN does) before the mask
+  int accumulate;   // backward: out += mask * x / keep instead of out = ...
+};
+
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, long long x_bs, __nv_bfloat16* __restrict__ out,
+                    long long out_ld, long long out_bs, long long total_chunks, const DropParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int cpr = p.cols / 8;
+  const long long row = i / cpr;
+  const int c = int(i - row * cpr) * 8;
+  const int b = int(row / p.rows_per_batch);
+  const long long r = row - (long long)b * p.rows_per_batch;
+  float v[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(x + (long long)b * x_bs + r * x_ld + c), v);
+  __nv_bfloat16* op = out + (long long)b * out_bs + r * out_ld + c;
+  if (p.accumulate) unpack8(*reinterpret_cast<const uint4*>(op), o);
+  const unsigned long long base = (unsigned long long)row * p.logical_cols + p.col0 + c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float a = v[k];
+    if (p.silu_in) a = round_bf16(silu(a));
+    const float m = dropout_keep(p.key, base + k, p.thresh) ? a * p.inv_keep : 0.f;
+    o[k] = p.accumulate ? o[k] + m : m;
+  }
+  *reinterpret_cast<uint4*>(op) = pack8(o);
+}
+
 // ================================================================================================
 // Modulation-vector gradients (the only path to the timestep-embedder LoRA)
 // ================================================================================================
@@ -1452,6 +1505,67 @@ int silu_bwd_launch(float* d, int64_t d_ld, const void* x, int64_t x_ld, int row
   AFB_REQUIRE(d && x && rows >= 1 && cols >= 1, "silu_bwd: bad arguments");
   dim3 grid((cols + 255) / 256, rows);
   silu_bwd_kernel<<<grid, 256, 0, stream>>>(d, d_ld, static_cast<const __nv_bfloat16*>(x), x_ld, rows, cols);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+// dst[r, c] += mask * src[r, c] / (1 - p)   (fp32, the tiny timestep-embedder path); logical index = r * cols + c
+__global__ void __launch_bounds__(256)
+dropout_f32_add_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst, long long dst_ld, int rows,
+                       int cols, uint32_t key, uint32_t thresh, float inv_keep) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= cols || r >= rows) return;
+  if (dropout_keep(key, (unsigned long long)r * cols + c, thresh))
+    dst[(long long)r * dst_ld + c] += src[(long long)r * src_ld + c] * inv_keep;
+}
+
+uint32_t dropout_layer_key(uint64_t seed, uint32_t layer_id) {
+  auto mix = [](uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x7feb352dU;
+    h ^= h >> 15;
+    h *= 0x846ca68bU;
+    h ^= h >> 16;
+    return h;
+  };
+  return mix(uint32_t(seed) ^ mix(uint32_t(seed >> 32) + layer_id * 0x632BE5ABU + 1U));
+}
+
+// out (=|+=) dropout_mask (.) act(x) / (1 - p) on a [batches, rows, cols] view; the mask is indexed by the LOGICAL position
+// (batch*rows + row) * logical_cols + col0 + col, so column slices of one logical tensor can be processed separately.
+int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, int64_t out_ld, int64_t out_bs, int batches,
+                        int rows_per_batch, int cols, int logical_cols, int col0, uint64_t seed, uint32_t layer_id, float p,
+                        int silu_in, int accumulate, cudaStream_t stream) {
+  AFB_REQUIRE(x && out && batches >= 1 && rows_per_batch >= 1 && cols % 8 == 0 && x_ld % 8 == 0 && out_ld % 8 == 0,
+              "dropout_rows: bad arguments");
+  AFB_REQUIRE(p >= 0.f && p < 1.f && logical_cols >= col0 + cols, "dropout_rows: bad p / logical layout");
+  DropParams dp{};
+  dp.rows_per_batch = rows_per_batch;
+  dp.cols = cols;
+  dp.logical_cols = logical_cols;
+  dp.col0 = col0;
+  dp.key = dropout_layer_key(seed, layer_id);
+  dp.thresh = uint32_t(double(p) * 4294967296.0);
+  dp.inv_keep = 1.0f / (1.0f - p);
+  dp.silu_in = silu_in;
+  dp.accumulate = accumulate;
+  const long long chunks = (long long)batches * rows_per_batch * (cols / 8);
+  dropout_rows_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_bs,
+                                                                         static_cast<__nv_bfloat16*>(out), out_ld, out_bs,
+                                                                         chunks, dp);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int dropout_f32_add_launch(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int rows, int cols, uint64_t seed,
+                           uint32_t layer_id, float p, cudaStream_t stream) {
+  AFB_REQUIRE(src && dst && rows >= 1 && cols >= 1 && p >= 0.f && p < 1.f, "dropout_f32_add: bad arguments");
+  dim3 grid((cols + 255) / 256, rows);
+  dropout_f32_add_kernel<<<grid, 256, 0, stream>>>(src, src_ld, dst, dst_ld, rows, cols, dropout_layer_key(seed, layer_id),
+                                                   uint32_t(double(p) * 4294967296.0), 1.0f / (1.0f - p));
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

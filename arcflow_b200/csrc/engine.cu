@@ -66,6 +66,11 @@ int gate_res_launch(const void* res, int64_t res_bs, const void* u, int64_t u_bs
 int rowlinear_dx_launch(const float* de, int64_t de_ld, const void* w, int64_t w_ld, float* out, int64_t out_ld, int m, int J,
                         int N, cudaStream_t stream);
 int silu_bwd_launch(float* d, int64_t d_ld, const void* x, int64_t x_ld, int rows, int cols, cudaStream_t stream);
+int dropout_f32_add_launch(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int rows, int cols, uint64_t seed,
+                           uint32_t layer_id, float p, cudaStream_t stream);
+int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, int64_t out_ld, int64_t out_bs, int batches,
+                        int rows_per_batch, int cols, int logical_cols, int col0, uint64_t seed, uint32_t layer_id, float p,
+                        int silu_in, int accumulate, cudaStream_t stream);
 int ln_mod_param_grad_strided_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws,
                                      float* dscale, float* dshift, int64_t out_bs, int batches, int rows_per_batch, int dim,
                                      float eps, cudaStream_t stream);
@@ -100,6 +105,11 @@ struct afb_engine {
        *dattn = nullptr, *du = nullptr, *dy = nullptr, *dl = nullptr, *h_mid = nullptr, *u1 = nullptr, *u2 = nullptr,
        *tproj_t = nullptr, *tmp_t = nullptr, *ltv1 = nullptr, *ltv2 = nullptr;
   float *lse = nullptr, *delta = nullptr, *stats = nullptr, *dsilu = nullptr, *dtmp = nullptr, *dltv = nullptr;
+  // LoRA input dropout (train forward / backward only): p, seed, scratch for the dropped LoRA-branch inputs
+  float drop_p = 0.f;
+  uint64_t drop_seed = 0;
+  bf16 *xd = nullptr, *xd_small = nullptr;
+  float* dtmp2 = nullptr;
   // optional per-launch CUDA-event profiling of the two tensor-core kernels
   bool profiling = false;
   struct ProfRec { int cls; double flops; cudaEvent_t e0, e1; };
@@ -179,6 +189,9 @@ size_t carve_train(afb_engine* e, uint8_t* base, int B, int St, int Si) {
   e->dsilu = c.take<float>(B * D);
   e->dtmp = c.take<float>(B * D);
   e->dltv = c.take<float>(B * r);
+  e->xd = c.take<bf16>(B * S * (D + M));
+  e->xd_small = c.take<bf16>(B * D);
+  e->dtmp2 = c.take<float>(B * D);
   return c.off;
 }
 
@@ -289,6 +302,10 @@ int run_attention(afb_engine* e, const afb_attn_desc* at, cudaStream_t s) {
   return afb::attention_launch(at, s);
 }
 
+// LoRA layer ids for the dropout mask stream: 4 slots per block (double: img up/down, txt up/down; single: mlp, out),
+// double blocks first; the timestep embedder's two Linears use ids past any block.
+constexpr uint32_t DROP_ID_T1 = 0xFFFF0u, DROP_ID_T2 = 0xFFFF1u;
+
 #define AFB_TRY(expr)            \
   do {                           \
     int _rc = (expr);            \
@@ -310,26 +327,50 @@ int small_linear_rows(const bf16* x, int64_t x_ld, const void* w, int64_t w_ld, 
 // written (or accumulated) into e->temb.
 int embed_mlp(afb_engine* e, const bf16* in, int in_dim, const void* w1, const void* b1,
               const void* la1, const void* lb1, const void* w2, const void* b2, const void* la2,
-              const void* lb2, bool accumulate, int B, cudaStream_t s) {
+              const void* lb2, bool accumulate, int B, cudaStream_t s, bool drop = false) {
+  // drop: the LoRA branches see dropout(x) (train forward of the timestep embedder; mask ids DROP_ID_T1 / T2)
   const int D = e->desc.dim, r = e->desc.lora_rank;
   AFB_TRY(small_linear_rows(in, in_dim, w1, in_dim, b1, e->tmp, D, B, D, in_dim, 0, s));
   if (la1 && lb1) {
-    AFB_TRY(small_linear_rows(in, in_dim, la1, in_dim, nullptr, e->ltv, r, B, r, in_dim, 0, s));
+    const bf16* xin = in;
+    if (drop) {
+      AFB_TRY(afb::dropout_rows_launch(in, in_dim, int64_t(B) * in_dim, e->xd_small, in_dim, int64_t(B) * in_dim, 1, B, in_dim,
+                                       in_dim, 0, e->drop_seed, DROP_ID_T1, e->drop_p, 0, 0, s));
+      xin = e->xd_small;
+    }
+    AFB_TRY(small_linear_rows(xin, in_dim, la1, in_dim, nullptr, e->ltv, r, B, r, in_dim, 0, s));
     AFB_TRY(small_linear_rows(e->ltv, r, lb1, r, nullptr, e->tmp, D, B, D, r, AFB_SL_ACCUMULATE, s));
   }
   AFB_TRY(small_linear_rows(e->tmp, D, w2, D, b2, e->temb, D, B, D, D,
                             AFB_SL_SILU_IN | (accumulate ? AFB_SL_ACCUMULATE : 0), s));
   if (la2 && lb2) {
-    AFB_TRY(small_linear_rows(e->tmp, D, la2, D, nullptr, e->ltv, r, B, r, D, AFB_SL_SILU_IN, s));
+    if (drop) {
+      AFB_TRY(afb::dropout_rows_launch(e->tmp, D, int64_t(B) * D, e->xd_small, D, int64_t(B) * D, 1, B, D, D, 0, e->drop_seed,
+                                       DROP_ID_T2, e->drop_p, 1, 0, s));
+      AFB_TRY(small_linear_rows(e->xd_small, D, la2, D, nullptr, e->ltv, r, B, r, D, 0, s));
+    } else {
+      AFB_TRY(small_linear_rows(e->tmp, D, la2, D, nullptr, e->ltv, r, B, r, D, AFB_SL_SILU_IN, s));
+    }
     AFB_TRY(small_linear_rows(e->ltv, r, lb2, r, nullptr, e->temb, D, B, D, r, AFB_SL_ACCUMULATE, s));
   }
   return AFB_OK;
 }
 
+// dropout(x) of one LoRA branch input into the contiguous scratch e->xd, viewed [B, rows, logical_cols]; x may be one
+// column slice (col0, cols) of the logical input. Returns the scratch view of the whole logical tensor.
+View dropped_view(afb_engine* e, int rows, int logical_cols) {
+  return View{e->xd, logical_cols, int64_t(rows) * logical_cols};
+}
+int drop_into(afb_engine* e, View x, int B, int rows, int cols, int logical_cols, int col0, uint32_t layer, cudaStream_t s) {
+  return afb::dropout_rows_launch(x.p, x.ld, x.bs, e->xd + col0, logical_cols, int64_t(rows) * logical_cols, B, rows, cols,
+                                  logical_cols, col0, e->drop_seed, layer, e->drop_p, 0, 0, s);
+}
+
 // One MLP (Linear up + GELU-tanh + Linear down, both with optional LoRA K-extension), gated into res.
 int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v, int rows, int B,
                const void* up_w, const void* up_b, const void* up_la, const void* down_w,
-               const void* down_b, const void* down_la, const bf16* gate, cudaStream_t s) {
+               const void* down_b, const void* down_la, const bf16* gate, cudaStream_t s, bool drop = false,
+               uint32_t layer_up = 0) {
   // `*_la != NULL` means the packed weight is [W | lora_B] (leading dim in + rank). A teacher engine
   // (ignore_lora) shares those buffers with the student and simply never reads the extra K columns.
   const int D = e->desc.dim, M = e->desc.mlp_dim, r = e->desc.lora_rank;
@@ -337,13 +378,23 @@ int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v,
   const int64_t mod_bs = e->w.mod_total;
   const int64_t up_ld = D + (up_la ? r : 0), down_ld = M + (down_la ? r : 0);
   if (up_la && lora) {
-    AFB_TRY(Gemm(B, rows).a(yv, D).w(up_la, D, r, nullptr).out(lt0v, AFB_EPI_BIAS).run(e, s));
+    View xa = yv;
+    if (drop) {
+      AFB_TRY(drop_into(e, yv, B, rows, D, D, 0, layer_up, s));
+      xa = dropped_view(e, rows, D);
+    }
+    AFB_TRY(Gemm(B, rows).a(xa, D).w(up_la, D, r, nullptr).out(lt0v, AFB_EPI_BIAS).run(e, s));
     AFB_TRY(Gemm(B, rows).a(yv, D).a(lt0v, r).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
   } else {
     AFB_TRY(Gemm(B, rows).a(yv, D).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
   }
   if (down_la && lora) {
-    AFB_TRY(Gemm(B, rows).a(mlpv, M).w(down_la, M, r, nullptr).out(lt1v, AFB_EPI_BIAS).run(e, s));
+    View xa = mlpv;
+    if (drop) {
+      AFB_TRY(drop_into(e, mlpv, B, rows, M, M, 0, layer_up + 1, s));
+      xa = dropped_view(e, rows, M);
+    }
+    AFB_TRY(Gemm(B, rows).a(xa, M).w(down_la, M, r, nullptr).out(lt1v, AFB_EPI_BIAS).run(e, s));
     AFB_TRY(Gemm(B, rows).a(mlpv, M).a(lt1v, r).w(down_w, down_ld, D, down_b)
                 .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
   } else {
@@ -363,11 +414,12 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   const int r = d.ignore_lora ? 0 : d.lora_rank;   // rank actually computed (0: frozen trunk / teacher)
   const int64_t mod_bs = w.mod_total;
   const bool flux = d.arch == AFB_ARCH_FLUX;
+  const bool drop = save_ckpt && e->drop_p > 0.f && r > 0;  // LoRA input dropout: train forward only
 
   // ---- conditioning vector temb [B, D] ---------------------------------------------------------
   AFB_TRY(afb::timestep_embed_launch(a->timestep, e->tproj, B, s));
   AFB_TRY(embed_mlp(e, e->tproj, 256, w.t1_w, w.t1_b, r > 0 ? w.t1_la : nullptr, r > 0 ? w.t1_lb : nullptr,
-                    w.t2_w, w.t2_b, r > 0 ? w.t2_la : nullptr, r > 0 ? w.t2_lb : nullptr, false, B, s));
+                    w.t2_w, w.t2_b, r > 0 ? w.t2_la : nullptr, r > 0 ? w.t2_lb : nullptr, false, B, s, drop));
   if (flux && d.guidance) {
     AFB_REQUIRE(a->guidance != nullptr, "forward: model has guidance embeds but guidance is NULL");
     AFB_TRY(afb::timestep_embed_launch(a->guidance, e->tproj, B, s));
@@ -460,13 +512,13 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
                                     im + 3 * D, mod_bs, B, Si, D, LN_EPS, s));
     AFB_TRY(mlp_branch(e, y_img, h_img, mlp_img, l0_img, l1_img, Si, B, k.img_up_w, k.img_up_b,
                        k.img_up_la, k.img_down_w, k.img_down_b,
-                       k.img_down_la, im + 5 * D, s));
+                       k.img_down_la, im + 5 * D, s, drop, 4u * i));
     if (!last_qwen_txt) {
       AFB_TRY(afb::ln_modulate_launch(h_txt.p, h_txt.bs, const_cast<bf16*>(y_txt.p), y_txt.bs, tm + 4 * D,
                                       tm + 3 * D, mod_bs, B, St, D, LN_EPS, s));
       AFB_TRY(mlp_branch(e, y_txt, h_txt, mlp_txt, l0_txt, l1_txt, St, B, k.txt_up_w, k.txt_up_b,
                          k.txt_up_la, k.txt_down_w, k.txt_down_b,
-                         k.txt_down_la, tm + 5 * D, s));
+                         k.txt_down_la, tm + 5 * D, s, drop, 4u * i + 2));
     }
   }
 
@@ -489,14 +541,26 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
                                      k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     AFB_TRY(run_attention(e, &at, s));
     const int64_t mlp_ld = D + (k.mlp_la ? rpad : 0), out_ld = D + M + (k.out_la ? rpad : 0);
+    const uint32_t layer = 4u * (d.num_double + i);
     if (r > 0 && k.mlp_la) {
-      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
+      View xa = y_all;
+      if (drop) {
+        AFB_TRY(drop_into(e, y_all, B, S, D, D, 0, layer, s));
+        xa = dropped_view(e, S, D);
+      }
+      AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
       AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
     } else {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
     }
     if (r > 0 && k.out_la) {
-      AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+      if (drop) {
+        AFB_TRY(drop_into(e, at_all, B, S, D, D + M, 0, layer + 1, s));
+        AFB_TRY(drop_into(e, mlp_all, B, S, M, D + M, D, layer + 1, s));
+        AFB_TRY(Gemm(B, S).a(dropped_view(e, S, D + M), D + M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+      } else {
+        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+      }
       AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, out_ld, D, k.out_b)
                   .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
     } else {
@@ -534,37 +598,66 @@ int tn_rows(View a, int m, View b, int n, float* out, int64_t out_ld, int B, int
   return afb::gemm_tn_batched_launch(a.p, a.ld, a.bs, b.p, b.ld, b.bs, out, out_ld, B, rows, m, n, s);
 }
 
-// Backward of one LoRA-extended Linear  out = [x | t] [W | Bl]^T,  t = x A^T  (packed weight `w`, leading dim w_ld =
-// in + rank when `la` is set). dout -> dx (= dout W + dt A), dBl += dout^T t, dA += dt^T x. x may be two column
-// segments (FLUX single block: [attn | mlp]); dx is produced per segment.
+// Backward of one LoRA-extended Linear  out = [x | t] [W | Bl]^T,  t = dropout(x) A^T  (packed weight `w`, leading dim
+// w_ld = in + rank when the layer carries LoRA). dout -> dx = dout W + mask (.) (dt A) / keep, dBl += dout^T t,
+// dA += dt^T dropout(x). x may be two column segments (FLUX single block: [attn | mlp]); dx is produced per segment.
+// Without dropout the LoRA term of dx joins the main GEMM as a K-extension ([dout | dt] [W ; A]).
 struct LoraBwd {
   afb_engine* e;
   int B, rows;
   cudaStream_t s;
-  // dt = dout Bl   (rank columns after the `in` columns of the packed weight), and the two LoRA gradients
-  int lora_grads(View dout, int out_n, const bf16* w, int64_t w_ld, int in, View t, View dt, View x0, int k0, View x1, int k1,
-                 float* g_la, float* g_lb) {
+  bool drop;
+
+  struct Seg {
+    View x;    // forward input segment
+    View dx;   // where its gradient goes
+    int k;     // columns
+  };
+
+  int run(View dout, int out_n, const bf16* w, int64_t w_ld, const bf16* la, int in, View t, View dt, Seg s0, Seg s1,
+          uint32_t layer, float* g_la, float* g_lb, bool add_res = false) {
     const int r = e->desc.lora_rank;
-    AFB_TRY(tn_rows(dout, out_n, t, r, g_lb, r, B, rows, s));
-    AFB_TRY(Gemm(B, rows).a(dout, out_n).wt(w + in, w_ld, r, out_n).out(dt, AFB_EPI_BIAS).run(e, s));
-    AFB_TRY(tn_rows(dt, r, x0, k0, g_la, in, B, rows, s));
-    if (k1 > 0) AFB_TRY(tn_rows(dt, r, x1, k1, g_la ? g_la + k0 : nullptr, in, B, rows, s));
-    return AFB_OK;
-  }
-  // dx[:, col0 : col0 + n] = dout W[:, col0:...] (+ dt A[:, col0:...]) (+ res)
-  int dx(View dout, int out_n, const bf16* w, int64_t w_ld, const bf16* la, int64_t la_ld, View dt, int col0, int n, View out,
-         bool add_res) {
-    Gemm g(B, rows);
-    g.a(dout, out_n);
     if (la) {
-      g.a(dt, e->desc.lora_rank);
-      g.wt(w + col0, w_ld, n, out_n, la + col0, la_ld);
-    } else {
-      g.wt(w + col0, w_ld, n, out_n);
+      AFB_TRY(tn_rows(dout, out_n, t, r, g_lb, r, B, rows, s));                                    // dBl += dout^T t
+      AFB_TRY(Gemm(B, rows).a(dout, out_n).wt(w + in, w_ld, r, out_n).out(dt, AFB_EPI_BIAS).run(e, s));  // dt = dout Bl
+      if (drop) {  // dA += dt^T dropout(x): regenerate the dropped input (same mask as the forward)
+        AFB_TRY(drop_into(e, s0.x, B, rows, s0.k, in, 0, layer, s));
+        if (s1.k > 0) AFB_TRY(drop_into(e, s1.x, B, rows, s1.k, in, s0.k, layer, s));
+        AFB_TRY(tn_rows(dt, r, dropped_view(e, rows, in), in, g_la, in, B, rows, s));
+      } else {
+        AFB_TRY(tn_rows(dt, r, s0.x, s0.k, g_la, in, B, rows, s));
+        if (s1.k > 0) AFB_TRY(tn_rows(dt, r, s1.x, s1.k, g_la ? g_la + s0.k : nullptr, in, B, rows, s));
+      }
     }
-    g.out(out, add_res ? AFB_EPI_BIAS_RES : AFB_EPI_BIAS);
-    if (add_res) g.res(out);
-    return g.run(e, s);
+    const bool merged = la && !drop;
+    int col0 = 0;
+    for (const Seg* sg : {&s0, &s1}) {
+      if (sg->k == 0) continue;
+      Gemm g(B, rows);
+      g.a(dout, out_n);
+      if (merged) {
+        g.a(dt, r);
+        g.wt(w + col0, w_ld, sg->k, out_n, la + col0, in);
+      } else {
+        g.wt(w + col0, w_ld, sg->k, out_n);
+      }
+      g.out(sg->dx, add_res ? AFB_EPI_BIAS_RES : AFB_EPI_BIAS);
+      if (add_res) g.res(sg->dx);
+      AFB_TRY(g.run(e, s));
+      col0 += sg->k;
+    }
+    if (la && drop) {  // dx += mask (.) (dt A) / keep: the LoRA term goes through the scratch and a masked add
+      const View tmp = dropped_view(e, rows, in);
+      AFB_TRY(Gemm(B, rows).a(dt, r).wt(la, in, in, r).out(tmp, AFB_EPI_BIAS).run(e, s));
+      col0 = 0;
+      for (const Seg* sg : {&s0, &s1}) {
+        if (sg->k == 0) continue;
+        AFB_TRY(afb::dropout_rows_launch(tmp.p + col0, tmp.ld, tmp.bs, const_cast<bf16*>(sg->dx.p), sg->dx.ld, sg->dx.bs, B, rows,
+                                         sg->k, in, col0, e->drop_seed, layer, e->drop_p, 0, 1, s));
+        col0 += sg->k;
+      }
+    }
+    return AFB_OK;
   }
 };
 
@@ -637,7 +730,8 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
   const View raw_all{e->qkv_raw, 3 * D, bs3}, l0_all{e->lt0, rr, bsR}, l1_all{e->lt1, rr, bsR}, dl_all{e->dl, rr, bsR};
   const View dh_all{e->dh, D, bsD}, du_all{e->du, D, bsD}, dy_all{e->dy, D, bsD}, dat_all{e->dattn, D, bsD};
   const View dmlp_all{e->dmlp, M, bsM}, dqkv_all{e->dqkv, 3 * D, bs3}, u1_all{e->u1, D, bsD};
-  LoraBwd lb{e, B, S, s};
+  const bool drop = e->drop_p > 0.f && r > 0;
+  LoraBwd lb{e, B, S, s, drop};
   float* dmod = ba->d_mod;  // fp32 [B, mod_total] or NULL
 
   // ---- single-stream blocks, last to first ----------------------------------------------------------------------
@@ -657,14 +751,28 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, bs3, 0, D, B, S, H, 0, nullptr, nullptr, k.nq, k.nk, a->rope_cos,
                                      a->rope_sin, LN_EPS, s));
     AFB_TRY(run_attention(e, &at, s));
+    const uint32_t layer = 4u * (d.num_double + i);
     if (lm) {
-      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
+      View xa = y_all;
+      if (drop) {
+        AFB_TRY(drop_into(e, y_all, B, S, D, D, 0, layer, s));
+        xa = dropped_view(e, S, D);
+      }
+      AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
       AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
     } else {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
     }
     AFB_TRY(afb::gelu_fwd_launch(e->mlp_pre, M, e->mlp, M, int64_t(B) * S, M, s));
-    if (lo) AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+    if (lo) {
+      if (drop) {
+        AFB_TRY(drop_into(e, at_all, B, S, D, D + M, 0, layer + 1, s));
+        AFB_TRY(drop_into(e, mlp_all, B, S, M, D + M, D, layer + 1, s));
+        AFB_TRY(Gemm(B, S).a(dropped_view(e, S, D + M), D + M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+      } else {
+        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+      }
+    }
     // -- backward
     if (dmod) {  // the gate's gradient needs the branch output u = proj_out([attn | mlp]) the forward never stores
       if (lo)
@@ -676,17 +784,11 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     } else {
       AFB_TRY(afb::rowscale_launch(e->dh, D, bsD, m + 2 * D, mod_bs, e->du, D, bsD, B, S, D, s));
     }
-    if (lo)
-      AFB_TRY(lb.lora_grads(du_all, D, out_w, out_ld, D + M, l1_all, dl_all, at_all, D, mlp_all, M, g ? g->out_la : nullptr,
-                            g ? g->out_lb : nullptr));
-    const bf16* ola = lo ? static_cast<const bf16*>(k.out_la) : nullptr;
-    AFB_TRY(lb.dx(du_all, D, out_w, out_ld, ola, D + M, dl_all, 0, D, dat_all, false));
-    AFB_TRY(lb.dx(du_all, D, out_w, out_ld, ola, D + M, dl_all, D, M, dmlp_all, false));
+    AFB_TRY(lb.run(du_all, D, out_w, out_ld, lo ? static_cast<const bf16*>(k.out_la) : nullptr, D + M, l1_all, dl_all,
+                   {at_all, dat_all, D}, {mlp_all, dmlp_all, M}, layer + 1, g ? g->out_la : nullptr, g ? g->out_lb : nullptr));
     AFB_TRY(afb::gelu_bwd_launch(e->dmlp, M, e->mlp_pre, M, int64_t(B) * S, M, s));
-    if (lm)
-      AFB_TRY(lb.lora_grads(dmlp_all, M, mlp_w, mlp_ld, D, l0_all, dl_all, y_all, D, View{}, 0, g ? g->mlp_la : nullptr,
-                            g ? g->mlp_lb : nullptr));
-    AFB_TRY(lb.dx(dmlp_all, M, mlp_w, mlp_ld, lm ? static_cast<const bf16*>(k.mlp_la) : nullptr, D, dl_all, 0, D, dy_all, false));
+    AFB_TRY(lb.run(dmlp_all, M, mlp_w, mlp_ld, lm ? static_cast<const bf16*>(k.mlp_la) : nullptr, D, l0_all, dl_all,
+                   {y_all, dy_all, D}, {View{}, View{}, 0}, layer, g ? g->mlp_la : nullptr, g ? g->mlp_lb : nullptr));
     AFB_TRY(attention_bwd());
     AFB_TRY(afb::rmsnorm_rope_bwd_launch(e->dqkv, e->qkv_raw, 3 * D, bs3, 0, D, B, S, H, 0, nullptr, nullptr, k.nq, k.nk,
                                          a->rope_cos, a->rope_sin, LN_EPS, s));
@@ -770,7 +872,8 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
                                          size_t(t.rows) * D * sizeof(bf16), B, s));
         continue;
       }
-      LoraBwd sb{e, B, t.rows, s};
+      LoraBwd sb{e, B, t.rows, s, drop};
+      const uint32_t layer_up = 4u * i + (&t == &st2[0] ? 0u : 2u);
       const bool lu = r > 0 && t.up_la, ld_ = r > 0 && t.down_la;
       const int64_t up_ld = D + (t.up_la ? rpad : 0), down_ld = M + (t.down_la ? rpad : 0);
       const bf16* up_w = static_cast<const bf16*>(t.up_w);
@@ -786,7 +889,12 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       AFB_TRY(afb::ln_modulate_launch(t.h_mid.p, t.h_mid.bs, const_cast<bf16*>(t.y.p), t.y.bs, t.mod + 4 * D, t.mod + 3 * D,
                                       mod_bs, B, t.rows, D, LN_EPS, s));
       if (lu) {
-        AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.up_la, D, r, nullptr).out(t.l0, AFB_EPI_BIAS).run(e, s));
+        View xa = t.y;
+        if (drop) {
+          AFB_TRY(drop_into(e, t.y, B, t.rows, D, D, 0, layer_up, s));
+          xa = dropped_view(e, t.rows, D);
+        }
+        AFB_TRY(Gemm(B, t.rows).a(xa, D).w(t.up_la, D, r, nullptr).out(t.l0, AFB_EPI_BIAS).run(e, s));
         AFB_TRY(Gemm(B, t.rows).a(t.y, D).a(t.l0, r).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
       } else {
         AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
@@ -794,7 +902,14 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       for (int bi = 0; bi < B; ++bi)
         AFB_TRY(afb::gelu_fwd_launch(t.pre.p + int64_t(bi) * t.pre.bs, M, const_cast<bf16*>(t.mlp.p) + int64_t(bi) * t.mlp.bs, M,
                                      t.rows, M, s));
-      if (ld_) AFB_TRY(Gemm(B, t.rows).a(t.mlp, M).w(t.down_la, M, r, nullptr).out(t.l1, AFB_EPI_BIAS).run(e, s));
+      if (ld_) {
+        View xa = t.mlp;
+        if (drop) {
+          AFB_TRY(drop_into(e, t.mlp, B, t.rows, M, M, 0, layer_up + 1, s));
+          xa = dropped_view(e, t.rows, M);
+        }
+        AFB_TRY(Gemm(B, t.rows).a(xa, M).w(t.down_la, M, r, nullptr).out(t.l1, AFB_EPI_BIAS).run(e, s));
+      }
       // backward of  h_out = h_mid + gate_mlp * down(gelu(up(LNmod2(h_mid))))
       if (dmod) {
         if (ld_)
@@ -807,13 +922,13 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
         AFB_TRY(afb::rowscale_launch(t.dh.p, D, t.dh.bs, t.mod + 5 * D, mod_bs, const_cast<bf16*>(t.du.p), D, t.du.bs, B,
                                      t.rows, D, s));
       }
-      if (ld_) AFB_TRY(sb.lora_grads(t.du, D, down_w, down_ld, M, t.l1, t.dl, t.mlp, M, View{}, 0, t.g_down_la, t.g_down_lb));
-      AFB_TRY(sb.dx(t.du, D, down_w, down_ld, ld_ ? static_cast<const bf16*>(t.down_la) : nullptr, M, t.dl, 0, M, t.dmlp, false));
+      AFB_TRY(sb.run(t.du, D, down_w, down_ld, ld_ ? static_cast<const bf16*>(t.down_la) : nullptr, M, t.l1, t.dl,
+                     {t.mlp, t.dmlp, M}, {View{}, View{}, 0}, layer_up + 1, t.g_down_la, t.g_down_lb));
       for (int bi = 0; bi < B; ++bi)
         AFB_TRY(afb::gelu_bwd_launch(const_cast<bf16*>(t.dmlp.p) + int64_t(bi) * t.dmlp.bs, M, t.pre.p + int64_t(bi) * t.pre.bs,
                                      M, t.rows, M, s));
-      if (lu) AFB_TRY(sb.lora_grads(t.dmlp, M, up_w, up_ld, D, t.l0, t.dl, t.y, D, View{}, 0, t.g_up_la, t.g_up_lb));
-      AFB_TRY(sb.dx(t.dmlp, M, up_w, up_ld, lu ? static_cast<const bf16*>(t.up_la) : nullptr, D, t.dl, 0, D, t.dy, false));
+      AFB_TRY(sb.run(t.dmlp, M, up_w, up_ld, lu ? static_cast<const bf16*>(t.up_la) : nullptr, D, t.l0, t.dl,
+                     {t.y, t.dy, D}, {View{}, View{}, 0}, layer_up, t.g_up_la, t.g_up_lb));
       if (dmod)
         AFB_TRY(afb::ln_mod_param_grad_strided_launch(t.h_mid.p, t.h_mid.bs, t.dy.p, t.dy.bs, e->stats,
                                                       dmod + t.mod_off + 4 * D, dmod + t.mod_off + 3 * D, mod_bs, B, t.rows, D,
@@ -1065,26 +1180,55 @@ int afb_engine_backward_embed(afb_engine* e, const afb_forward_args* a, const fl
   AFB_CHECK_CUDA(cudaMemsetAsync(e->dsilu, 0, size_t(B) * D * sizeof(float), s));
   AFB_TRY(afb::rowlinear_dx_launch(d_mod, w.mod_total, w.mod_w, D, e->dsilu, D, B, int(w.mod_total), D, s));
   AFB_TRY(afb::silu_bwd_launch(e->dsilu, D, e->temb, D, B, D, s));
-  // recompute the timestep path's intermediates
+  // recompute the timestep path's intermediates (with the forward's dropout masks on the LoRA inputs)
+  const bool drop = e->drop_p > 0.f;
   AFB_TRY(afb::timestep_embed_launch(a->timestep, e->tproj_t, B, s));
   AFB_TRY(small_linear_rows(e->tproj_t, 256, w.t1_w, 256, w.t1_b, e->tmp_t, D, B, D, 256, 0, s));
-  AFB_TRY(small_linear_rows(e->tproj_t, 256, w.t1_la, 256, nullptr, e->ltv1, r, B, r, 256, 0, s));
+  const bf16* x1 = e->tproj_t;  // LoRA input of linear_1
+  if (drop) {
+    AFB_TRY(afb::dropout_rows_launch(e->tproj_t, 256, int64_t(B) * 256, e->tproj, 256, int64_t(B) * 256, 1, B, 256, 256, 0,
+                                     e->drop_seed, DROP_ID_T1, e->drop_p, 0, 0, s));
+    x1 = e->tproj;
+  }
+  AFB_TRY(small_linear_rows(x1, 256, w.t1_la, 256, nullptr, e->ltv1, r, B, r, 256, 0, s));
   AFB_TRY(small_linear_rows(e->ltv1, r, w.t1_lb, r, nullptr, e->tmp_t, D, B, D, r, AFB_SL_ACCUMULATE, s));
-  AFB_TRY(small_linear_rows(e->tmp_t, D, w.t2_la, D, nullptr, e->ltv2, r, B, r, D, AFB_SL_SILU_IN, s));
-  // linear_2: temb_t = W2 silu(tmp) + B2 (A2 silu(tmp))
+  if (drop) {
+    AFB_TRY(afb::dropout_rows_launch(e->tmp_t, D, int64_t(B) * D, e->xd_small, D, int64_t(B) * D, 1, B, D, D, 0, e->drop_seed,
+                                     DROP_ID_T2, e->drop_p, 1, 0, s));
+    AFB_TRY(small_linear_rows(e->xd_small, D, w.t2_la, D, nullptr, e->ltv2, r, B, r, D, 0, s));
+  } else {
+    AFB_TRY(small_linear_rows(e->tmp_t, D, w.t2_la, D, nullptr, e->ltv2, r, B, r, D, AFB_SL_SILU_IN, s));
+  }
+  // linear_2: temb_t = W2 silu(tmp) + B2 (A2 dropout(silu(tmp)))
   if (g->t2_lb) AFB_TRY(afb::rowlinear_param_grad_launch(e->dsilu, D, e->ltv2, r, g->t2_lb, r, nullptr, B, D, r, 0, s));
   AFB_CHECK_CUDA(cudaMemsetAsync(e->dltv, 0, size_t(B) * r * sizeof(float), s));
   AFB_TRY(afb::rowlinear_dx_launch(e->dsilu, D, w.t2_lb, r, e->dltv, r, B, D, r, s));
-  if (g->t2_la) AFB_TRY(afb::rowlinear_param_grad_launch(e->dltv, r, e->tmp_t, D, g->t2_la, D, nullptr, B, r, D, 1, s));
+  if (g->t2_la)
+    AFB_TRY(afb::rowlinear_param_grad_launch(e->dltv, r, drop ? e->xd_small : e->tmp_t, D, g->t2_la, D, nullptr, B, r, D,
+                                             drop ? 0 : 1, s));
   AFB_CHECK_CUDA(cudaMemsetAsync(e->dtmp, 0, size_t(B) * D * sizeof(float), s));
   AFB_TRY(afb::rowlinear_dx_launch(e->dsilu, D, w.t2_w, D, e->dtmp, D, B, D, D, s));
-  AFB_TRY(afb::rowlinear_dx_launch(e->dltv, r, w.t2_la, D, e->dtmp, D, B, r, D, s));
+  if (drop) {
+    AFB_CHECK_CUDA(cudaMemsetAsync(e->dtmp2, 0, size_t(B) * D * sizeof(float), s));
+    AFB_TRY(afb::rowlinear_dx_launch(e->dltv, r, w.t2_la, D, e->dtmp2, D, B, r, D, s));
+    AFB_TRY(afb::dropout_f32_add_launch(e->dtmp2, D, e->dtmp, D, B, D, e->drop_seed, DROP_ID_T2, e->drop_p, s));
+  } else {
+    AFB_TRY(afb::rowlinear_dx_launch(e->dltv, r, w.t2_la, D, e->dtmp, D, B, r, D, s));
+  }
   AFB_TRY(afb::silu_bwd_launch(e->dtmp, D, e->tmp_t, D, B, D, s));
-  // linear_1: tmp = W1 p + B1 (A1 p)
+  // linear_1: tmp = W1 p + B1 (A1 dropout(p))
   if (g->t1_lb) AFB_TRY(afb::rowlinear_param_grad_launch(e->dtmp, D, e->ltv1, r, g->t1_lb, r, nullptr, B, D, r, 0, s));
   AFB_CHECK_CUDA(cudaMemsetAsync(e->dltv, 0, size_t(B) * r * sizeof(float), s));
   AFB_TRY(afb::rowlinear_dx_launch(e->dtmp, D, w.t1_lb, r, e->dltv, r, B, D, r, s));
-  if (g->t1_la) AFB_TRY(afb::rowlinear_param_grad_launch(e->dltv, r, e->tproj_t, 256, g->t1_la, 256, nullptr, B, r, 256, 0, s));
+  if (g->t1_la) AFB_TRY(afb::rowlinear_param_grad_launch(e->dltv, r, x1, 256, g->t1_la, 256, nullptr, B, r, 256, 0, s));
+  return AFB_OK;
+}
+
+int afb_engine_set_lora_dropout(afb_engine* e, float p, uint64_t seed) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  AFB_REQUIRE(p >= 0.f && p < 1.f, "engine_set_lora_dropout: p=%f must be in [0, 1)", double(p));
+  e->drop_p = p;
+  e->drop_seed = seed;
   return AFB_OK;
 }
 

@@ -259,6 +259,12 @@ class EngineModelBase:
     _DBL_LORA: tuple = ()
     _SGL_LORA: tuple = ()
 
+    def set_lora_dropout(self, p: float, seed: int = 0):
+        """peft lora_dropout for the NEXT forward_heads(train=True) and its backward (counter-based mask, see
+        afb_engine_set_lora_dropout); p = 0 disables. Inference forwards never drop."""
+        _lib.check(self.lib.afb_engine_set_lora_dropout(self.handle, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF),
+                   "afb_engine_set_lora_dropout")
+
     def _launch_forward(self, a: "_lib.ForwardArgs", keep: tuple, train: bool):
         stream = torch.cuda.current_stream().cuda_stream
         if train:

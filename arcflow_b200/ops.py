@@ -543,3 +543,18 @@ def rmsnorm_rope_bwd(dqkv: torch.Tensor, raw: torch.Tensor, q_off: int, k_off: i
         wq_txt.data_ptr() if wq_txt is not None else None, wk_txt.data_ptr() if wk_txt is not None else None,
         wq_img.data_ptr(), wk_img.data_ptr(), cos.data_ptr(), sin.data_ptr(), eps, _stream()), "afb_rmsnorm_rope_bwd")
     return dqkv
+
+
+def dropout_rows(x: torch.Tensor, seed: int, layer_id: int, p: float, out: Optional[torch.Tensor] = None,
+                 logical_cols: Optional[int] = None, col0: int = 0, silu_in: bool = False, accumulate: bool = False):
+    """out (=|+=) keep (.) act(x) / (1 - p); x bf16 [batches, rows, cols] view, counter-based mask (afb_dropout_rows)."""
+    lib = _lib.load()
+    _chk(x, BF16, "dropout_rows x")
+    xp, xld, xbs, nb, nr, cols = _rows3(x, "dropout_rows x")
+    if out is None:
+        out = torch.zeros((nb, nr, cols), dtype=BF16, device=x.device)
+    _chk(out, BF16, "dropout_rows out")
+    op, old, obs, *_ = _rows3(out, "dropout_rows out")
+    _lib.check(lib.afb_dropout_rows(xp, xld, xbs, op, old, obs, nb, nr, cols, logical_cols or cols, col0, int(seed),
+                                    int(layer_id), float(p), int(silu_in), int(accumulate), _stream()), "afb_dropout_rows")
+    return out

@@ -30,10 +30,10 @@ from ._lib import AfbError
 DEFAULT_TRAIN_CFG = dict(  # configs/flux/arcflux_2nfe_k16.py:89-99
     num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4,
     distilled_guidance_scale=3.5, teacher_distilled_guidance_scale=3.5, nfe=2, timestep_ratio=1.0,
-    total_substeps=128, eps=1e-4)
+    total_substeps=128, eps=1e-4, lora_dropout=0.05)   # lora_dropout: configs/flux/arcflux_2nfe_k16.py:40-48
 QWEN_TRAIN_CFG = dict(  # configs/qwen/arcqwen_2nfe_k16.py:96-106 — true CFG on the teacher, no guidance embedding
     num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, teacher_guidance_scale=4.0,
-    nfe=2, timestep_ratio=1.0, total_substeps=128, eps=1e-4)
+    nfe=2, timestep_ratio=1.0, total_substeps=128, eps=1e-4, lora_dropout=0.05)
 
 
 def warp_t(t: torch.Tensor, shift: float) -> torch.Tensor:
@@ -45,7 +45,10 @@ def draw_rollout_randoms(batch: int, num_states: int, num_gaussians: int, genera
     """The three uniform draws of one student step, in the reference's order (policies/arcflow.py:100-101,
     arcflow.py:148-155)."""
     r = lambda *s: torch.rand(s, generator=generator)
-    return dict(drop_u=r(batch, num_gaussians), student_u=r(batch, num_states), teacher_u=r(batch, num_states - 1))
+    out = dict(drop_u=r(batch, num_gaussians), student_u=r(batch, num_states), teacher_u=r(batch, num_states - 1))
+    # seed of the student forward's LoRA-dropout mask stream (drawn last so the three reference draws keep their order)
+    out["lora_seed"] = int(torch.randint(0, 2 ** 62, (1,), generator=generator).item())
+    return out
 
 
 class ArcFlowDistillStep:
@@ -105,7 +108,12 @@ class ArcFlowDistillStep:
             raw_t_dst = raw_t_src - seg
             sigma_src = warp_t(raw_t_src, self.shift)
 
-            head = student_heads(x_src, sigma_src, step_hook is not None)
+            p_lora = float(cfg.get("lora_dropout", 0.0) or 0.0)
+            if p_lora > 0 and "lora_seed" not in rands[step_id]:
+                raise AfbError("lora_dropout > 0 needs rands[step]['lora_seed'] (see draw_rollout_randoms)")
+            st.set_lora_dropout(p_lora, rands[step_id].get("lora_seed", 0))
+            # the dropped forward IS the train forward (peft drops only in train mode), with or without a backward hook
+            head = student_heads(x_src, sigma_src, step_hook is not None or p_lora > 0)
             head2 = head.reshape(-1, head.shape[-1])
             saved = None
             if save_for_backward:

@@ -238,6 +238,13 @@ int afb_rmsnorm_rope_bwd(void* dqkv, const void* raw, int64_t ld, int64_t batch_
                          const void* wk_txt, const void* wq_img, const void* wk_img, const float* cos_tab,
                          const float* sin_tab, float eps, void* stream);
 
+/* out (=|+=) keep_mask (.) act(x) / (1 - p) on a bf16 [batches, rows, cols] view — the LoRA-branch input dropout. The mask
+ * is a counter-based hash of (seed, layer_id, logical index (batch*rows + row) * logical_cols + col0 + col); silu_in applies
+ * SiLU (rounded to bf16) first; accumulate adds into out (the backward's dx += mask (.) (dT A) / keep). */
+int afb_dropout_rows(const void* x, int64_t x_ld, int64_t x_batch_stride, void* out, int64_t out_ld, int64_t out_batch_stride,
+                     int32_t batches, int32_t rows_per_batch, int32_t cols, int32_t logical_cols, int32_t col0, uint64_t seed,
+                     uint32_t layer_id, float p, int32_t silu_in, int32_t accumulate, void* stream);
+
 /* Weight-gradient ("TN") GEMM: out[m, n] += sum_t a[t, m] * b[t, n]; a bf16 [tokens, m] (ld a_ld), b bf16 [tokens, n],
  * out fp32 [m, n] (must be initialised; results are ADDED). dW = dY^T X for the heads / LoRA pairs. */
 int afb_gemm_tn(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
@@ -431,6 +438,12 @@ typedef struct afb_backward_args {
   const afb_single_block_grads* sgl; /* [num_single] */
   float* d_mod;              /* optional fp32 [batch, mod_total] */
 } afb_backward_args;
+/* peft lora_dropout (configs/flux/arcflux_2nfe_k16.py:40-48: 0.05, train only): the LoRA branches of
+ * afb_engine_forward_train / afb_engine_backward(_embed) see dropout(x) with the keep mask
+ *   hash(seed, layer id, logical element index) >= p * 2^32   (counter-based: recompute and backward regenerate it).
+ * Set a fresh seed before every afb_engine_forward_train; p = 0 (default) disables it. afb_engine_forward / _denoise
+ * never drop. */
+int afb_engine_set_lora_dropout(afb_engine* e, float p, uint64_t seed);
 int afb_engine_train_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
 int afb_engine_forward_train(afb_engine* e, const afb_forward_args* args, void* stream);
 int afb_engine_backward(afb_engine* e, const afb_backward_args* args, void* stream);

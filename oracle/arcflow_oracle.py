@@ -116,13 +116,68 @@ def momentum_integration(mp: Dict[str, Tensor], x_t_start: Tensor, sigma_t_src: 
 # =================================================================================================
 # FLUX transformer — arcflux.py:134-257 over diffusers blocks
 # =================================================================================================
+# LoRA input dropout (peft `lora_dropout`, train mode only; configs/flux/arcflux_2nfe_k16.py:40-48 p = 0.05). torch's
+# Philox stream cannot be reproduced by another implementation, so the mask is DEFINED here as a counter-based hash of
+# (seed, layer id, element index) — the CUDA kernels use the same definition and are tested against this restatement.
+# Set to dict(p=..., seed=..., num_double=...) to enable (tests / training oracle only); None = eval mode.
+LORA_DROPOUT = None
+
+
+def _lowbias32(h):
+    import numpy as np
+    m = np.uint64(0xFFFFFFFF)
+    h = h ^ (h >> np.uint64(16))
+    h = (h * np.uint64(0x7FEB352D)) & m
+    h = h ^ (h >> np.uint64(15))
+    h = (h * np.uint64(0x846CA68B)) & m
+    return h ^ (h >> np.uint64(16))
+
+
+def lora_layer_id(name: str, num_double: int) -> int:
+    """Mask-stream id of a LoRA target: 4 slots per block (double blocks first), the timestep embedder past all blocks."""
+    if name.endswith("timestep_embedder.linear_1"):
+        return 0xFFFF0
+    if name.endswith("timestep_embedder.linear_2"):
+        return 0xFFFF1
+    parts = name.split(".")
+    i = int(parts[1])
+    tail = ".".join(parts[2:])
+    if parts[0] == "single_transformer_blocks":
+        return 4 * (num_double + i) + {"proj_mlp": 0, "proj_out": 1}[tail]
+    slot = {"ff.net.0.proj": 0, "ff.net.2": 1, "ff_context.net.0.proj": 2, "ff_context.net.2": 3,
+            "img_mlp.net.0.proj": 0, "img_mlp.net.2": 1, "txt_mlp.net.0.proj": 2, "txt_mlp.net.2": 3}[tail]
+    return 4 * i + slot
+
+
+def lora_dropout_mask(seed: int, layer_id: int, shape, p: float) -> Tensor:
+    """keep[idx] = hash(key(seed, layer), idx) >= floor(p * 2^32), idx = row-major index into `shape` (bool tensor)."""
+    import numpy as np
+    m = np.uint64(0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        inner = (np.uint64(seed >> 32) + np.uint64(layer_id) * np.uint64(0x632BE5AB) + np.uint64(1)) & m
+        key = _lowbias32((np.uint64(seed & 0xFFFFFFFF) ^ _lowbias32(inner)) & m)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        idx = np.arange(n, dtype=np.uint64)
+        h = _lowbias32(((idx & m) ^ key) & m)
+        h = _lowbias32((h + (idx >> np.uint64(32)) * np.uint64(0x9E3779B1) + np.uint64(0x85EBCA77)) & m)
+    keep = h >= np.uint64(int(float(p) * 4294967296.0))
+    return torch.from_numpy(keep).reshape(tuple(shape))
+
+
 def _lin(sd, name: str, x: Tensor, dtype, lora_scale: float = 1.0) -> Tensor:
     """nn.Linear, plus the peft LoRA branch when `<name>.lora_A/B.weight` exist (Appendix A.6):
-    result = base(x) + lora_B(lora_A(x)) * scaling, scaling = alpha / r = 1 (arcflux.py:295-301)."""
+    result = base(x) + lora_B(lora_A(dropout(x))) * scaling, scaling = alpha / r = 1 (arcflux.py:295-301)."""
     y = F.linear(x, sd[name + ".weight"].to(dtype), sd[name + ".bias"].to(dtype) if name + ".bias" in sd else None)
     if name + ".lora_A.weight" in sd:
         a, b = sd[name + ".lora_A.weight"].to(dtype), sd[name + ".lora_B.weight"].to(dtype)
-        y = y + F.linear(F.linear(x, a), b) * lora_scale
+        xin = x
+        if LORA_DROPOUT is not None and LORA_DROPOUT["p"] > 0:
+            d = LORA_DROPOUT
+            keep = lora_dropout_mask(d["seed"], lora_layer_id(name, d["num_double"]), x.shape, d["p"])
+            xin = x * keep.to(x.dtype) * (1.0 / (1.0 - d["p"]))
+        y = y + F.linear(F.linear(xin, a), b) * lora_scale
     return y
 
 

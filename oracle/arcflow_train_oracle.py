@@ -138,6 +138,21 @@ def piid_segment(mp, x_t_src, raw_t_src, sigma_t_src, teacher_ratio, segment_siz
     return loss, x_t_dst, raw_t_dst, dict(pred=all_pred, tgt=all_tgt)
 
 
+class _lora_dropout:
+    """Train-mode peft dropout on the student forward only (the tied teacher has no LoRA branches): enables
+    O.LORA_DROPOUT with this step's mask seed for the duration of the call."""
+
+    def __init__(self, train_cfg, rand, num_double):
+        p = float(train_cfg.get("lora_dropout", 0.0) or 0.0)
+        self.cfg = dict(p=p, seed=int(rand["lora_seed"]), num_double=num_double) if p > 0 else None
+
+    def __enter__(self):
+        O.LORA_DROPOUT = self.cfg
+
+    def __exit__(self, *exc):
+        O.LORA_DROPOUT = None
+
+
 def teacher_state_dict(sd: Dict[str, Tensor], teacher_extra: Dict[str, Tensor]) -> Dict[str, Tensor]:
     """The teacher is the stock trunk (weights tied to the student's frozen base layers, base_diffusion.py:93-94)
     with its own `norm_out` and `proj_out`."""
@@ -195,8 +210,9 @@ def flux_train_forward(sd, teacher_extra, cfg, txt, pooled, grid_hw, noise_token
     for step_id in range(nfe):
         seg = base_seg * ratio if step_id == nfe - 1 else base_seg
         sigma_t_src = warp_t(raw_t_src, shift).reshape(B, 1, 1, 1)
-        out = O.flux_forward(sd, cfg, O.pack_latents(x_t_src).to(net_dtype), txt, pooled, sigma_t_src.flatten(), guidance,
-                             grid_hw, dtype=dtype)
+        with _lora_dropout(train_cfg, rands[step_id], cfg.num_layers):
+            out = O.flux_forward(sd, cfg, O.pack_latents(x_t_src).to(net_dtype), txt, pooled, sigma_t_src.flatten(), guidance,
+                                 grid_hw, dtype=dtype)
         # network emits net_dtype (bf16); GaussianFlow.pred casts back to fp32. Straight-through for the grad path.
         out = {k: v + (v.to(net_dtype).to(v.dtype) - v).detach() for k, v in out.items()}
         mp = O.unpack_mp({k: v.to(torch.float32) for k, v in out.items()}, gh, gw, cfg.num_gaussians)
@@ -270,7 +286,9 @@ def qwen_train_forward(sd, teacher_extra, cfg, txt, txt_neg, grid_hw, noise_toke
     for step_id in range(nfe):
         seg = base_seg * ratio if step_id == nfe - 1 else base_seg
         sigma_t_src = warp_t(raw_t_src, shift).reshape(B, 1, 1, 1)
-        out = O.qwen_forward(sd, cfg, O.pack_latents(x_t_src).to(net_dtype), txt, sigma_t_src.flatten(), grid_hw, dtype=dtype)
+        with _lora_dropout(train_cfg, rands[step_id], cfg.num_layers):
+            out = O.qwen_forward(sd, cfg, O.pack_latents(x_t_src).to(net_dtype), txt, sigma_t_src.flatten(), grid_hw,
+                                 dtype=dtype)
         out = {k: v + (v.to(net_dtype).to(v.dtype) - v).detach() for k, v in out.items()}
         mp = O.unpack_mp({k: v.to(torch.float32) for k, v in out.items()}, gh, gw, cfg.num_gaussians)
         step_loss, x_t_dst, raw_t_dst, tr = piid_segment(mp, x_t_src, raw_t_src, sigma_t_src, teacher_ratio, seg, teacher_u,

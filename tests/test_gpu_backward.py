@@ -121,3 +121,24 @@ def test_gemm_transposed_weight(ops, B, R, K, N, K2):
     from arcflow_b200 import _lib
     ops.gemm(segs, w, out, transposed=True, w2=w2, epilogue=_lib.AFB_EPI_BIAS_RES, res=res)
     assert rel(out, ref + res.float()) < 4e-3
+
+
+def test_lora_dropout_mask_matches_oracle(ops):
+    """The counter-based keep mask of afb_dropout_rows is the oracle's `lora_dropout_mask`, including column slices of one
+    logical tensor (FLUX single-block proj_out input = [attn | mlp]) and the accumulate form used by the backward."""
+    g = torch.Generator().manual_seed(5)
+    B, R, C0, C1 = 2, 37, 128, 256
+    seed, layer, p = 0x1234_5678_9ABC_DEF, 11, 0.3
+    a = torch.randn(B, R, C0, generator=g).bfloat16()
+    b = torch.randn(B, R, C1, generator=g).bfloat16()
+    keep = O.lora_dropout_mask(seed, layer, (B, R, C0 + C1), p)
+    assert 0.25 < 1 - keep.float().mean().item() < 0.35
+    out = torch.zeros(B, R, C0 + C1, dtype=torch.bfloat16, device=DEV)
+    ops.dropout_rows(a.to(DEV), seed, layer, p, out=out[..., :C0], logical_cols=C0 + C1, col0=0)
+    ops.dropout_rows(b.to(DEV), seed, layer, p, out=out[..., C0:], logical_cols=C0 + C1, col0=C0)
+    ref = (torch.cat([a, b], -1).float() * keep / (1 - p)).bfloat16()
+    assert torch.equal(out.cpu(), ref)
+    base = torch.randn(B, R, C0, generator=g).bfloat16()
+    acc = ops.dropout_rows(a.to(DEV), seed, layer, p, out=base.clone().to(DEV), logical_cols=C0 + C1, col0=0, accumulate=True)
+    assert torch.equal(acc.cpu(), (base.float() + a.float() * keep[..., :C0] / (1 - p)).bfloat16())
+    assert not torch.equal(O.lora_dropout_mask(seed, layer + 1, (B, R, C0 + C1), p), keep)

@@ -156,7 +156,7 @@ def test_tied_teacher_velocity_parity(lib):
 def test_train_step_forward_loss_parity(lib, iteration, p_drop):
     from arcflow_b200.train import ArcFlowDistillStep, draw_rollout_randoms
     cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup()
-    tc = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=p_drop, num_intermediate_states=4, nfe=2,
+    tc = dict(lora_dropout=0.0, num_decay_iters=2000, window_substeps=3, gm_dropout=p_drop, num_intermediate_states=4, nfe=2,
               timestep_ratio=1.0, total_substeps=128, eps=1e-4)
     g = torch.Generator().manual_seed(5 + iteration)
     rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
@@ -206,7 +206,7 @@ def test_head_and_norm_out_gradients_match_autograd(lib):
     """backward_heads(): exact grads of the post-trunk adapter tensors vs torch autograd through the training oracle."""
     from arcflow_b200.train import ArcFlowDistillStep, draw_rollout_randoms
     cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup()
-    tc = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, nfe=2,
+    tc = dict(lora_dropout=0.0, num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, nfe=2,
               timestep_ratio=1.0, total_substeps=128, eps=1e-4)
     g = torch.Generator().manual_seed(77)
     rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
@@ -226,14 +226,16 @@ def test_head_and_norm_out_gradients_match_autograd(lib):
         assert e < 3e-2, f"{n}: rel-L2 {e:.3e} (|ref| {ref.norm():.3e})"
 
 
-def test_trunk_lora_gradients_match_autograd(lib):
+@pytest.mark.parametrize("p_lora", [0.0, 0.25])
+def test_trunk_lora_gradients_match_autograd(lib, p_lora):
     """forward_backward(): LoRA gradients through the frozen trunk (per-block recompute, tcgen05 attention backward,
     transposed-weight dX GEMMs, token-contraction dW GEMMs) vs torch autograd through the fp32 training oracle.
+    p_lora > 0: peft's LoRA-input dropout with the counter-based mask both sides share (oracle `lora_dropout_mask`).
     Tolerance: the native backward carries activations and activation gradients in bf16 (like the reference's bf16
     autocast run) while the oracle differentiates in fp32 -> rel-L2 <= 2e-2 per tensor, cosine >= 0.9995 (measured worst: 7.4e-3, 0.99997)."""
     from arcflow_b200.train import ArcFlowDistillStep, draw_rollout_randoms
     cfg, sd, extra, x, txt, pooled, grid, student, teacher = _setup(num_layers=2, num_single=2)
-    tc = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, nfe=2,
+    tc = dict(lora_dropout=p_lora, num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, nfe=2,
               timestep_ratio=1.0, total_substeps=128, eps=1e-4)
     g = torch.Generator().manual_seed(78)
     rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
@@ -243,7 +245,7 @@ def test_trunk_lora_gradients_match_autograd(lib):
     ref_loss, _, ex = T.flux_train_forward(sd, extra, cfg, txt, pooled, grid, x, rands, 700, tc, dtype=torch.float32,
                                            require_grad=names)
     ref_loss.backward()
-    assert abs(loss - float(ref_loss)) <= 2e-2 * abs(float(ref_loss))
+    assert abs(loss - float(ref_loss.detach())) <= 2e-2 * abs(float(ref_loss.detach()))
     worst = []
     for n in names:
         ref = ex["leaves"][n].grad

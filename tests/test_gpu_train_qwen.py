@@ -9,7 +9,7 @@ from oracle import arcflow_train_oracle as T  # noqa: E402
 
 DEV = "cuda"
 TC = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4, teacher_guidance_scale=4.0,
-          nfe=2, timestep_ratio=1.0, total_substeps=128, eps=1e-4)
+          nfe=2, timestep_ratio=1.0, total_substeps=128, eps=1e-4, lora_dropout=0.1)
 
 
 def rel(a, b):
