@@ -195,6 +195,7 @@ class EngineModelBase:
         self.handle = h
         _lib.check(self.lib.afb_engine_bind(self.handle, C.byref(self.weights.struct)), "afb_engine_bind")
         self._rope_cache = {}
+        self._graphs = {}            # captured denoise loops, keyed by shape + schedule (see denoise(cuda_graph=True))
         self._reserved = (0, 0, 0)
 
     def __del__(self):
@@ -220,6 +221,7 @@ class EngineModelBase:
             nb, nt, ni = max(batch, rb), max(txt_len, rt), max(img_len, ri)
             _lib.check(self.lib.afb_engine_reserve(self.handle, nb, nt, ni), "afb_engine_reserve")
             self._reserved = (nb, nt, ni)
+            self._graphs.clear()     # captured graphs point into the old workspace
 
     def set_profiling(self, on: bool):
         _lib.check(self.lib.afb_engine_set_profiling(self.handle, int(on)), "afb_engine_set_profiling")
@@ -451,9 +453,13 @@ class ArcFluxEngineModel(EngineModelBase):
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, txt: torch.Tensor, pooled: torch.Tensor, grid_hw: Sequence[int],
                 num_inference_steps: int = 2, total_substeps: int = 128, timestep_ratio: float = 1.0,
-                shift: float = 3.2, guidance_scale: float = 3.5, eps: float = 1e-4) -> torch.Tensor:
+                shift: float = 3.2, guidance_scale: float = 3.5, eps: float = 1e-4, cuda_graph: bool = False) -> torch.Tensor:
         """The whole N-NFE loop (network + analytic momentum integration) in one C-ABI call.
-        latents: fp32 packed tokens [batch, tokens, 64]; returns the final fp32 packed latents."""
+        latents: fp32 packed tokens [batch, tokens, 64]; returns the final fp32 packed latents.
+        cuda_graph=True captures the call's fixed kernel sequence once per (shape, schedule) and replays it — the engine
+        does no host sync and no allocation, so the ~670 launches per NFE collapse into one graph launch (what matters for
+        small batches / resolutions, where the step is launch-bound; replaces the reference's eager Python loop,
+        arcflux_pipeline.py:453-524)."""
         self._check_inputs(latents, txt, pooled, grid_hw)
         if latents.dtype != torch.float32:
             raise AfbError("denoise: latents must be fp32 (the sampler state is fp32, arcflux_pipeline.py:407)")
@@ -464,20 +470,44 @@ class ArcFluxEngineModel(EngineModelBase):
         sig = denoise_sigmas(num_inference_steps, total_substeps, timestep_ratio, shift)
         tin = [flux_time_inputs(s, guidance_scale)[0] for s in sig[:-1]]
         g_in = flux_time_inputs(sig[0], guidance_scale)[1]
-        gdev = torch.full((B,), g_in, dtype=torch.float32, device=self.device) if self.cfg.guidance_embeds else None
         cos, sin = self.rope(txt.shape[1], grid_hw[0], grid_hw[1])
-        x = latents.contiguous().clone()
-        d = _lib.DenoiseArgs()
-        d.fwd = self._fwd_args(txt, pooled, None, gdev, cos, sin, B, Si)
-        d.nfe = num_inference_steps
-        sig_arr = (C.c_float * len(sig))(*sig)
-        tin_arr = (C.c_float * len(tin))(*tin)
-        d.sigmas, d.timesteps = sig_arr, tin_arr
-        d.x = x.data_ptr()
-        d.eps = eps
-        _lib.check(self.lib.afb_engine_denoise(self.handle, C.byref(d), torch.cuda.current_stream().cuda_stream),
-                   "afb_engine_denoise")
-        return x
+
+        def launch(x, txt_, pooled_, gdev_):
+            d = _lib.DenoiseArgs()
+            d.fwd = self._fwd_args(txt_, pooled_, None, gdev_, cos, sin, B, Si)
+            d.nfe = num_inference_steps
+            sig_arr = (C.c_float * len(sig))(*sig)
+            tin_arr = (C.c_float * len(tin))(*tin)
+            d.sigmas, d.timesteps = sig_arr, tin_arr
+            d.x = x.data_ptr()
+            d.eps = eps
+            _lib.check(self.lib.afb_engine_denoise(self.handle, C.byref(d), torch.cuda.current_stream().cuda_stream),
+                       "afb_engine_denoise")
+
+        mk_g = lambda: (torch.full((B,), g_in, dtype=torch.float32, device=self.device)
+                        if self.cfg.guidance_embeds else None)
+        if not cuda_graph:
+            x = latents.contiguous().clone()
+            launch(x, txt, pooled, mk_g())
+            return x
+        key = (B, txt.shape[1], Si, tuple(grid_hw), tuple(sig), tuple(tin), g_in, eps, self._reserved)
+        ent = self._graphs.get(key)
+        if ent is None:
+            st = dict(x=torch.empty_like(latents, memory_format=torch.contiguous_format), txt=torch.empty_like(txt),
+                      pooled=torch.empty_like(pooled), g=mk_g())
+            st["x"].copy_(latents), st["txt"].copy_(txt), st["pooled"].copy_(pooled)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture: one-time function attributes, lazy module load
+                launch(st["x"], st["txt"], st["pooled"], st["g"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                launch(st["x"], st["txt"], st["pooled"], st["g"])
+            ent = self._graphs[key] = dict(graph=graph, **st)
+        ent["x"].copy_(latents), ent["txt"].copy_(txt), ent["pooled"].copy_(pooled)
+        ent["graph"].replay()
+        return ent["x"].clone()
 
 
 class FluxTeacherEngine(ArcFluxEngineModel):

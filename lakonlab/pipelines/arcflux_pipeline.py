@@ -51,6 +51,13 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
         self.vae_decode_fn = vae_decode_fn
         self._num_timesteps = 0
         self._interrupt = False
+        self.use_cuda_graph = False
+
+    def enable_cuda_graph(self, on: bool = True):
+        """Extension (not in the reference): replay the denoising loop as ONE captured CUDA graph per (shape, schedule)
+        instead of ~1300 kernel launches — for small batches / resolutions where the loop is launch-bound."""
+        self.use_cuda_graph = bool(on)
+        return self
 
     @property
     def num_timesteps(self):
@@ -138,7 +145,7 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
             # whole loop in one C-ABI call (transformer + sampler per NFE, no host round trips)
             latents = tr.denoise(latents, prompt_embeds, pooled_prompt_embeds, grid, num_inference_steps=num_inference_steps,
                                  total_substeps=total_substeps, timestep_ratio=timestep_ratio, shift=self.scheduler_shift,
-                                 guidance_scale=guidance_scale)
+                                 guidance_scale=guidance_scale, cuda_graph=self.use_cuda_graph)
         else:
             sig = denoise_sigmas(num_inference_steps, total_substeps, timestep_ratio, self.scheduler_shift)
             for i in range(num_inference_steps):

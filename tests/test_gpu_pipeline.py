@@ -129,3 +129,26 @@ def test_qwen_pipeline_adapter_roundtrip(lib, tmp_path):
                timestep_ratio=1.0, output_type="latent").images
     ref = O.qwen_denoise(sd, cfg, x, txt[:, :30], (4, 4), num_inference_steps=2)
     assert rel(out, ref) < 2e-2
+
+
+def test_cuda_graph_replay_equals_eager_loop(setup):
+    """pipe.enable_cuda_graph(): the captured denoising loop is bit-identical to the eager launch sequence, also when
+    replayed with new inputs of the same shape, and a different schedule gets its own graph."""
+    from lakonlab.pipelines.arcflux_pipeline import ArcFluxPipeline, FluxBaseTransformer
+    from arcflow_b200 import _lib
+    cfg, sd, base, root, x, txt, pooled = setup
+    pipe = ArcFluxPipeline(transformer=FluxBaseTransformer(base, device="cuda"))
+    pipe.load_arcflow_adapter(str(root), subfolder="arcflow-flux-2steps")
+    kw = dict(height=64, width=64, timestep_ratio=1.0, output_type="latent")
+    eager = pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, num_inference_steps=2, **kw).images
+    eager2 = pipe(prompt_embeds=txt * 0.5, pooled_prompt_embeds=pooled, latents=x.flip(0), num_inference_steps=2, **kw).images
+    eager4 = pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, num_inference_steps=4, **kw).images
+    pipe.enable_cuda_graph()
+    g1 = pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, num_inference_steps=2, **kw).images
+    lib_ = _lib.load()
+    n0 = lib_.afb_launch_count()
+    g2 = pipe(prompt_embeds=txt * 0.5, pooled_prompt_embeds=pooled, latents=x.flip(0), num_inference_steps=2, **kw).images
+    assert lib_.afb_launch_count() == n0          # replay: no kernel goes through the launchers again
+    g4 = pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, num_inference_steps=4, **kw).images
+    assert torch.equal(g1, eager) and torch.equal(g2, eager2) and torch.equal(g4, eager4)
+    assert len(pipe.transformer._graphs) == 2
