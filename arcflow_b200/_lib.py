@@ -46,6 +46,7 @@ class GemmDesc(C.Structure):
         ("w_k", C.c_int32),
         ("w2", C.c_void_p),
         ("w2_ld", C.c_int64),
+        ("alpha", C.c_float),
     ]
 
 

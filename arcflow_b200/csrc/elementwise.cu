@@ -1521,6 +1521,11 @@ dropout_f32_add_kernel(const float* __restrict__ src, long long src_ld, float* _
     dst[(long long)r * dst_ld + c] += src[(long long)r * src_ld + c] * inv_keep;
 }
 
+__global__ void scale_bf16_kernel(__nv_bfloat16* __restrict__ x, long long n, float s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = __float2bfloat16(__bfloat162float(x[i]) * s);
+}
+
 uint32_t dropout_layer_key(uint64_t seed, uint32_t layer_id) {
   auto mix = [](uint32_t h) {
     h ^= h >> 16;
@@ -1555,6 +1560,14 @@ int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, in
   dropout_rows_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_bs,
                                                                          static_cast<__nv_bfloat16*>(out), out_ld, out_bs,
                                                                          chunks, dp);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+int scale_bf16_launch(void* x, int64_t n, float s, cudaStream_t stream) {
+  AFB_REQUIRE(x && n >= 1, "scale_bf16: bad arguments");
+  scale_bf16_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(x), n, s);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

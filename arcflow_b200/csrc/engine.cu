@@ -66,6 +66,7 @@ int gate_res_launch(const void* res, int64_t res_bs, const void* u, int64_t u_bs
 int rowlinear_dx_launch(const float* de, int64_t de_ld, const void* w, int64_t w_ld, float* out, int64_t out_ld, int m, int J,
                         int N, cudaStream_t stream);
 int silu_bwd_launch(float* d, int64_t d_ld, const void* x, int64_t x_ld, int rows, int cols, cudaStream_t stream);
+int scale_bf16_launch(void* x, int64_t n, float s, cudaStream_t stream);
 int dropout_f32_add_launch(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int rows, int cols, uint64_t seed,
                            uint32_t layer_id, float p, cudaStream_t stream);
 int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, int64_t out_ld, int64_t out_bs, int batches,
@@ -266,6 +267,10 @@ struct Gemm {
     d.w2_ld = ld2;
     return *this;
   }
+  Gemm& alpha(float a) {
+    d.alpha = a;
+    return *this;
+  }
   Gemm& res(View v) {
     d.res = v.p;
     d.res_ld = v.ld;
@@ -339,6 +344,7 @@ int embed_mlp(afb_engine* e, const bf16* in, int in_dim, const void* w1, const v
       xin = e->xd_small;
     }
     AFB_TRY(small_linear_rows(xin, in_dim, la1, in_dim, nullptr, e->ltv, r, B, r, in_dim, 0, s));
+    if (e->lora_scale != 1.0f) AFB_TRY(afb::scale_bf16_launch(e->ltv, int64_t(B) * r, e->lora_scale, s));
     AFB_TRY(small_linear_rows(e->ltv, r, lb1, r, nullptr, e->tmp, D, B, D, r, AFB_SL_ACCUMULATE, s));
   }
   AFB_TRY(small_linear_rows(e->tmp, D, w2, D, b2, e->temb, D, B, D, D,
@@ -351,6 +357,7 @@ int embed_mlp(afb_engine* e, const bf16* in, int in_dim, const void* w1, const v
     } else {
       AFB_TRY(small_linear_rows(e->tmp, D, la2, D, nullptr, e->ltv, r, B, r, D, AFB_SL_SILU_IN, s));
     }
+    if (e->lora_scale != 1.0f) AFB_TRY(afb::scale_bf16_launch(e->ltv, int64_t(B) * r, e->lora_scale, s));
     AFB_TRY(small_linear_rows(e->ltv, r, lb2, r, nullptr, e->temb, D, B, D, r, AFB_SL_ACCUMULATE, s));
   }
   return AFB_OK;
@@ -383,7 +390,7 @@ int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v,
       AFB_TRY(drop_into(e, yv, B, rows, D, D, 0, layer_up, s));
       xa = dropped_view(e, rows, D);
     }
-    AFB_TRY(Gemm(B, rows).a(xa, D).w(up_la, D, r, nullptr).out(lt0v, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(xa, D).w(up_la, D, r, nullptr).alpha(e->lora_scale).out(lt0v, AFB_EPI_BIAS).run(e, s));
     AFB_TRY(Gemm(B, rows).a(yv, D).a(lt0v, r).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
   } else {
     AFB_TRY(Gemm(B, rows).a(yv, D).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
@@ -394,7 +401,7 @@ int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v,
       AFB_TRY(drop_into(e, mlpv, B, rows, M, M, 0, layer_up + 1, s));
       xa = dropped_view(e, rows, M);
     }
-    AFB_TRY(Gemm(B, rows).a(xa, M).w(down_la, M, r, nullptr).out(lt1v, AFB_EPI_BIAS).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(xa, M).w(down_la, M, r, nullptr).alpha(e->lora_scale).out(lt1v, AFB_EPI_BIAS).run(e, s));
     AFB_TRY(Gemm(B, rows).a(mlpv, M).a(lt1v, r).w(down_w, down_ld, D, down_b)
                 .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
   } else {
@@ -548,7 +555,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
         AFB_TRY(drop_into(e, y_all, B, S, D, D, 0, layer, s));
         xa = dropped_view(e, S, D);
       }
-      AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).alpha(e->lora_scale).out(l0_all, AFB_EPI_BIAS).run(e, s));
       AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
     } else {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
@@ -557,9 +564,9 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
       if (drop) {
         AFB_TRY(drop_into(e, at_all, B, S, D, D + M, 0, layer + 1, s));
         AFB_TRY(drop_into(e, mlp_all, B, S, M, D + M, D, layer + 1, s));
-        AFB_TRY(Gemm(B, S).a(dropped_view(e, S, D + M), D + M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(Gemm(B, S).a(dropped_view(e, S, D + M), D + M).w(k.out_la, D + M, r, nullptr).alpha(e->lora_scale).out(l1_all, AFB_EPI_BIAS).run(e, s));
       } else {
-        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).alpha(e->lora_scale).out(l1_all, AFB_EPI_BIAS).run(e, s));
       }
       AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, out_ld, D, k.out_b)
                   .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
@@ -758,7 +765,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
         AFB_TRY(drop_into(e, y_all, B, S, D, D, 0, layer, s));
         xa = dropped_view(e, S, D);
       }
-      AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).out(l0_all, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).alpha(e->lora_scale).out(l0_all, AFB_EPI_BIAS).run(e, s));
       AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
     } else {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
@@ -768,9 +775,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       if (drop) {
         AFB_TRY(drop_into(e, at_all, B, S, D, D + M, 0, layer + 1, s));
         AFB_TRY(drop_into(e, mlp_all, B, S, M, D + M, D, layer + 1, s));
-        AFB_TRY(Gemm(B, S).a(dropped_view(e, S, D + M), D + M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(Gemm(B, S).a(dropped_view(e, S, D + M), D + M).w(k.out_la, D + M, r, nullptr).alpha(e->lora_scale).out(l1_all, AFB_EPI_BIAS).run(e, s));
       } else {
-        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).out(l1_all, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).alpha(e->lora_scale).out(l1_all, AFB_EPI_BIAS).run(e, s));
       }
     }
     // -- backward
@@ -894,7 +901,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
           AFB_TRY(drop_into(e, t.y, B, t.rows, D, D, 0, layer_up, s));
           xa = dropped_view(e, t.rows, D);
         }
-        AFB_TRY(Gemm(B, t.rows).a(xa, D).w(t.up_la, D, r, nullptr).out(t.l0, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(Gemm(B, t.rows).a(xa, D).w(t.up_la, D, r, nullptr).alpha(e->lora_scale).out(t.l0, AFB_EPI_BIAS).run(e, s));
         AFB_TRY(Gemm(B, t.rows).a(t.y, D).a(t.l0, r).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
       } else {
         AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
@@ -908,7 +915,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
           AFB_TRY(drop_into(e, t.mlp, B, t.rows, M, M, 0, layer_up + 1, s));
           xa = dropped_view(e, t.rows, M);
         }
-        AFB_TRY(Gemm(B, t.rows).a(xa, M).w(t.down_la, M, r, nullptr).out(t.l1, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(Gemm(B, t.rows).a(xa, M).w(t.down_la, M, r, nullptr).alpha(e->lora_scale).out(t.l1, AFB_EPI_BIAS).run(e, s));
       }
       // backward of  h_out = h_mid + gate_mlp * down(gelu(up(LNmod2(h_mid))))
       if (dmod) {
@@ -1020,10 +1027,7 @@ int afb_engine_bind(afb_engine* e, const afb_weights* w) {
 
 int afb_engine_set_lora_scale(afb_engine* e, float scale) {
   AFB_REQUIRE(e != nullptr, "engine: null handle");
-  if (scale != 1.0f) {
-    afb::set_last_error("engine: runtime LoRA scale != 1 is not built yet (got %f)", double(scale));
-    return AFB_ERR_UNSUPPORTED;
-  }
+  AFB_REQUIRE(scale == scale && scale > -1e6f && scale < 1e6f, "engine_set_lora_scale: bad scale");
   e->lora_scale = scale;
   return AFB_OK;
 }
@@ -1142,6 +1146,11 @@ int afb_engine_forward_train(afb_engine* e, const afb_forward_args* a, void* str
               "engine_forward_train: null tensor argument");
   carve(e, static_cast<uint8_t*>(e->ws), a->batch, a->txt_len, a->img_len);
   carve_train(e, static_cast<uint8_t*>(e->tws), a->batch, a->txt_len, a->img_len);
+  if (e->lora_scale != 1.0f) {
+    afb::set_last_error("engine_forward_train: the training path is built for LoRA scale 1 (alpha = rank), got %f",
+                        double(e->lora_scale));
+    return AFB_ERR_UNSUPPORTED;
+  }
   e->saved_batch = a->batch;
   e->saved_txt = a->txt_len;
   e->saved_img = a->img_len;

@@ -48,6 +48,7 @@ struct GemmParams {
   int nk_end[3];  // cumulative K-block (64) boundaries of the A segments
   int num_m_tiles, num_n_tiles;
   int epi;
+  float alpha;   // accumulator scale (1 unless a runtime LoRA scale is set)
   int w_trans;   // W given as [K, N] row-major (dX = dY W): MN-major B operand (2-CTA kernel only)
   int nkb_w0;    // K blocks served by the first W buffer (the rest come from the second one; transposed mode)
   __nv_bfloat16* out;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
         if (n < p.N) {
           float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]) * p.alpha;
           if (p.bias) {
             const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n);
             const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -612,6 +613,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   p.num_m_tiles = p.tiles_per_batch * d->batches;
   p.num_n_tiles = (d->n + BN - 1) / BN;
   p.epi = d->epilogue;
+  p.alpha = d->alpha != 0.f ? d->alpha : 1.0f;
   p.out = static_cast<__nv_bfloat16*>(d->out);
   p.out_ld = d->out_ld;
   p.out_batch_stride = d->out_batch_stride;

@@ -261,6 +261,15 @@ class EngineModelBase:
     _DBL_LORA: tuple = ()
     _SGL_LORA: tuple = ()
 
+    def set_lora_scale(self, scale: float):
+        """Runtime adapter scale (peft `scaling` = alpha / r x the weight given to `pipe.set_adapters` /
+        `joint_attention_kwargs={'scale': s}`): every LoRA branch contributes scale x B(A(x)). Inference only."""
+        if float(scale) == getattr(self, "_lora_scale", 1.0):
+            return
+        _lib.check(self.lib.afb_engine_set_lora_scale(self.handle, float(scale)), "afb_engine_set_lora_scale")
+        self._lora_scale = float(scale)
+        self._graphs.clear()     # the captured A-projection launches carry the old scale
+
     def set_lora_dropout(self, p: float, seed: int = 0):
         """peft lora_dropout for the NEXT forward_heads(train=True) and its backward (counter-based mask, see
         afb_engine_set_lora_dropout); p = 0 disables. Inference forwards never drop."""

@@ -90,6 +90,9 @@ typedef struct afb_gemm_desc {
   int32_t w_k;
   const void* w2;
   int64_t w2_ld;
+  /* The accumulator is multiplied by alpha before bias / epilogue (0 means 1): the LoRA A-projection uses it for a
+   * runtime adapter scale, t = scale * x A^T (peft `scaling`). */
+  float alpha;
 } afb_gemm_desc;
 
 int afb_gemm(const afb_gemm_desc* desc, void* stream);

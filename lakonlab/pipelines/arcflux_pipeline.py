@@ -117,8 +117,8 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
         width = width or self.default_sample_size * self.vae_scale_factor
         if height % 16 or width % 16:
             raise ValueError(f"`height` and `width` have to be divisible by 16 but are {height} and {width}.")
-        if joint_attention_kwargs and joint_attention_kwargs.get("scale", 1.0) != 1.0:
-            raise NotImplementedError("runtime LoRA scale != 1.0 is not built yet")
+        # diffusers' `joint_attention_kwargs={"scale": s}` = runtime LoRA scale (scale_lora_layers, arcflux.py:150-156)
+        tr.set_lora_scale(float((joint_attention_kwargs or {}).get("scale", 1.0)))
         device = tr.device
         if prompt_embeds is None:
             if prompt is None:

@@ -61,8 +61,7 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
         width = width or self.default_sample_size * self.vae_scale_factor
         if height % 16 or width % 16:
             raise ValueError(f"`height` and `width` have to be divisible by 16 but are {height} and {width}.")
-        if attention_kwargs and attention_kwargs.get("scale", 1.0) != 1.0:
-            raise NotImplementedError("runtime LoRA scale != 1.0 is not built yet")
+        self.transformer.set_lora_scale(float((attention_kwargs or {}).get("scale", 1.0)))   # runtime LoRA scale
         device = tr.device
         if prompt_embeds is None:
             if prompt is None:
