@@ -63,6 +63,12 @@ __device__ __forceinline__ void trace_stamp(bool on, int t, int j, int slot) {
   if (on && j < 64) g_attn_trace[t][j][slot] = clock64();
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 template <int ID>
 __device__ __forceinline__ void named_bar_sync() {
   asm volatile("bar.sync %0, 256;" ::"n"(ID) : "memory");
@@ -105,8 +111,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* v_full = k_empty + K_STAGES;     // [V_STAGES]
   uint64_t* v_empty = v_full + V_STAGES;     // [V_STAGES]
   uint64_t* s_full = v_empty + V_STAGES;     // [NQT]  MMA -> softmax : S_t(j) ready
-  uint64_t* p_full = s_full + NQT;           // [NQT]  softmax -> MMA : P_t(j) written
-  uint64_t* o_done = p_full + NQT;           // [NQT]  MMA -> softmax : PV_t(j) retired
+  uint64_t* p_full = s_full + NQT;           // [NQT][2]  softmax -> MMA : columns [64 h, 64 h + 64) of P_t(j) written
+  uint64_t* o_done = p_full + 2 * NQT;       // [NQT]  MMA -> softmax : PV_t(j) retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + NQT);
 
   const int warp = threadIdx.x >> 5;
@@ -131,7 +137,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int t = 0; t < NQT; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);  // one arrive per softmax warp
+      mbar_init(&p_full[2 * t], 4);  // one arrive per softmax warp
+      mbar_init(&p_full[2 * t + 1], 4);
       mbar_init(&o_done[t], 1);
     }
     fence_barrier_init();
@@ -193,12 +200,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int t, int st, bool acc) {
+      // P_t is published in two 64-column halves, so the first half of the PV product overlaps the second half of
+      // the exp phase (the K = 128 contraction is 8 independent K = 16 MMAs anyway).
+      auto issue_pv = [&](int t, int st, int hf, bool acc) {
         if (skip_pv) return;
         const uint64_t b0 = v_desc + uint64_t((st * TILE_BYTES) >> 4);
         if (elect_one_sync()) {
 #pragma unroll
-          for (int kk = 0; kk < KT / 16; ++kk) {
+          for (int kk = hf * (KT / 32); kk < (hf + 1) * (KT / 32); ++kk) {
             // A = P_t (bf16, TMEM, 8 columns per K=16); B = V rows [16 kk, 16 kk + 16) of the stage
             umma_ts(tmem_base + NQT * KT + t * HD, tmem_base + t * KT + kk * 8, b0 + uint64_t((kk * 2048) >> 4),
                     idesc_pv, (acc || kk > 0) ? 1u : 0u);
@@ -228,9 +237,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&v_full[st], ph);
         if (has_next) mbar_wait(&k_full[nst], nph);
         for (int t = 0; t < NQT; ++t) {
-          if (!free_run) mbar_wait(&p_full[t], j & 1);
+          if (!free_run) mbar_wait(&p_full[2 * t], j & 1);
           tc_fence_after();
-          issue_pv(t, st, j > 0);
+          issue_pv(t, st, 0, j > 0);
+          if (!free_run) mbar_wait(&p_full[2 * t + 1], j & 1);
+          tc_fence_after();
+          issue_pv(t, st, 1, true);
           commit(&o_done[t]);
           if (has_next) {
             issue_qk(t, nst);
@@ -265,7 +277,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (p.debug_mode >= 2 && p.debug_mode < 7) {  // timing probe: MMA/TMA pipeline alone
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) {
+          mbar_arrive(&p_full[2 * t]);
+          mbar_arrive(&p_full[2 * t + 1]);
+        }
         continue;
       }
       uint32_t s[KT];
@@ -273,6 +288,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int i = 0; i < KT / 32; ++i)
         tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
       tmem_ld_wait();
+      trace_stamp(tr, t, j, 6);
 
       const int valid = p.seq - j * KT;
       if (valid < KT) {
@@ -280,15 +296,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < KT; ++i)
           if (i >= valid) s[i] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < KT; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float mx = fmaxf(mx0, mx1);
 
       if (j == 0) {
         m = mx;
@@ -327,17 +341,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float2 nm2 = make_float2(-m * c, -m * c);
       float2 lsum = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < KT; i += 2) {
-        float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
-        float2 pv;
-        if (((i >> 1) & 3) == 3) {
-          pv = exp2_poly2(x);
-        } else {
-          pv.x = fast_exp2(x.x);
-          pv.y = fast_exp2(x.y);
+      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int i = hf * (KT / 2); i < (hf + 1) * (KT / 2); i += 2) {
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
+          float2 pv;
+          if (((i >> 1) & 3) == 3) {
+            pv = exp2_poly2(x);
+          } else {
+            pv.x = fast_exp2(x.x);
+            pv.y = fast_exp2(x.y);
+          }
+          lsum = __fadd2_rn(lsum, pv);
+          s[i >> 1] = pack_bf16x2(pv.x, pv.y);
         }
-        lsum = __fadd2_rn(lsum, pv);
-        s[i >> 1] = pack_bf16x2(pv.x, pv.y);
+        if (hf == 0) {  // publish columns [0, 64) of P: 32 TMEM columns
+#pragma unroll
+          for (int i = 0; i < KT / 64; ++i)
+            tmem_st_32x16(tS + i * 16, reinterpret_cast<const uint32_t(&)[16]>(s[i * 16]));
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[2 * t]);
+        }
       }
       trace_stamp(tr, t, j, 4);
       if (use_turns) {
@@ -349,12 +375,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       l += lsum.x + lsum.y;
 #pragma unroll
-      for (int i = 0; i < KT / 32; ++i)
+      for (int i = KT / 64; i < KT / 32; ++i)
         tmem_st_32x16(tS + i * 16, reinterpret_cast<const uint32_t(&)[16]>(s[i * 16]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(&p_full[2 * t + 1]);
       trace_stamp(tr, t, j, 5);
     }
 

@@ -18,4 +18,4 @@ print("stamps: 0 loop-top | 1 S ready | 2 max done | 3 turn granted | 4 exp done
 for j in range(12, 18):
     for t in range(2):
         r = a[t, j, :6] - t0
-        print(f"j={j} wg={t}  top {r[0]:8d}  wait_S {r[1]-r[0]:5d}  ld+max {r[2]-r[1]:5d}  wait_turn {r[3]-r[2]:5d}  exp {r[4]-r[3]:5d}  store {r[5]-r[4]:5d}   iter {a[t,j+1,0]-a[t,j,0]:5d}")
+        print(f"j={j} wg={t}  top {r[0]:8d}  wait_S {r[1]-r[0]:5d}  ld {a[t,j,6]-t0-r[1]:5d} max {r[2]-(a[t,j,6]-t0):5d}  wait_turn {r[3]-r[2]:5d}  exp {r[4]-r[3]:5d}  store {r[5]-r[4]:5d}   iter {a[t,j+1,0]-a[t,j,0]:5d}")
