@@ -84,6 +84,20 @@ class FlatAdamW:
         self.ema.copy_(self.params)
         self.shadow.copy_(self.params)
 
+    def state_dict(self) -> Dict:
+        """fp32 arenas + layout, for bit-exact resume (lakonlab/runner/checkpoint.py)."""
+        return dict(params=self.params.cpu(), exp_avg=self.exp_avg.cpu(), exp_avg_sq=self.exp_avg_sq.cpu(), ema=self.ema.cpu(),
+                    steps_taken=self.steps_taken, layout={n: (o, list(s)) for n, (o, s) in self.views.items()}, hp=dict(self.hp))
+
+    def load_state_dict(self, sd: Dict):
+        layout = {n: (o, tuple(s)) for n, (o, s) in sd["layout"].items()}
+        if layout != self.views:
+            raise AfbError("optimizer checkpoint was written for a different set of adapter tensors")
+        for name in ("params", "exp_avg", "exp_avg_sq", "ema"):
+            getattr(self, name).copy_(sd[name].to(self.device))
+        self.shadow.copy_(self.params)
+        self.steps_taken = int(sd["steps_taken"])
+
     def all_reduce_grads(self):
         """DDP semantics: gradients averaged over ranks; one collective on the whole arena (NCCL on GPU, gloo in CPU tests)."""
         if dist.is_initialized() and dist.get_world_size() > 1:

@@ -1,0 +1,45 @@
+# ArcFlow-FLUX, 2 NFE, K = 16 mixture components, rank-256 adapter: data-free trajectory distillation.
+# Hyper-parameters follow the reference's configs/flux/arcflux_2nfe_k16.py (student :16-57, teacher :59-79,
+# train_cfg :89-99, EMA hook :141-151). `pretrained` must be a LOCAL path offline (the reference's huggingface:// URI
+# names black-forest-labs/FLUX.1-dev/transformer); 'synthetic://1234' trains on seeded random weights of that shape.
+_base_ = ['./_runtime_ddp.py', './_data_prompts.py']
+
+name = 'arcflux_k16_2nfe'
+flux_trunk = dict(in_channels=64, num_layers=19, num_single_layers=38, attention_head_dim=128, num_attention_heads=24,
+                  joint_attention_dim=4096, pooled_projection_dim=768, guidance_embeds=True, torch_dtype='bfloat16',
+                  patch_size=2, freeze=True, pretrained='synthetic://1234')
+
+model = dict(
+    type='LatentDiffusionTextImage',
+    diffusion=dict(
+        type='ArcFlowImitationDataFree',
+        policy_type='ArcFlow',
+        denoising=dict(
+            type='ArcFluxTransformer2DModel', num_gaussians=16, logweights_channels=4,
+            freeze_exclude=['proj_out_means', 'proj_out_logweights', 'proj_out_loggamma', 'norm_out', 'lora'],
+            checkpointing=True, use_lora=True, lora_rank=256, lora_dropout=0.05,
+            lora_target_modules=['proj_mlp', 'proj_out', 'ff.net.0.proj', 'ff.net.2', 'ff_context.net.0.proj',
+                                 'ff_context.net.2', 'timestep_embedder.linear_1', 'timestep_embedder.linear_2'],
+            **flux_trunk),
+        flow_loss=dict(type='DiffusionMSELoss', rescale_mode='constant', rescale_cfg=dict(scale=30.0)),
+        timestep_sampler=dict(type='ContinuousTimeStepSampler', shift=3.2, logit_normal_enable=False)),
+    diffusion_use_ema=True,
+    teacher=dict(type='GaussianFlow', denoising=dict(type='FluxTransformer2DModel', **flux_trunk)),
+    tie_teacher=True)
+
+train_cfg = dict(num_decay_iters=2000, window_substeps=3, gm_dropout=0.1, num_intermediate_states=4,
+                 distilled_guidance_scale=3.5, teacher_distilled_guidance_scale=3.5, nfe=2, timestep_ratio=1.0,
+                 total_substeps=128)
+test_cfg = dict(distilled_guidance_scale=3.5, nfe=2, timestep_ratio=1.0, total_substeps=128)
+
+total_iters = 10000
+save_interval = 500
+work_dir = f'work_dirs/{name}'
+checkpoint_config = dict(interval=save_interval, must_save_interval=1000, by_epoch=False, max_keep_ckpts=1,
+                         out_dir='checkpoints/')
+log_config = dict(interval=1, hooks=[dict(type='TextLoggerHook')])
+custom_hooks = [dict(type='ExponentialMovingAverageHookMod', module_keys=('diffusion_ema',), interp_mode='lerp', interval=1,
+                     start_iter=100, momentum_policy='karras', momentum_cfg=dict(gamma=7.0), priority='VERY_HIGH')]
+load_from = None
+resume_from = f'checkpoints/{name}/latest.pth'   # resume by default
+workflow = [('train', save_interval)]

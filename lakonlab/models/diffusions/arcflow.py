@@ -1,7 +1,9 @@
 """`ArcFlowImitationDataFree` — the reference's distillation model surface (lakonlab/models/diffusions/arcflow.py:339-426)
-on the native train-step forward (arcflow_b200.train.ArcFlowDistillStep). Forward + loss only this round: the
-`forward_initialize` / `forward_train` step-state protocol of train_fwd_bwd (lakonlab/models/base_diffusion.py:14-62)
-is kept so a runner can drive it; `backward` raises until the adapter-only backward lands."""
+on the native train step (arcflow_b200.train.ArcFlowDistillStep). The `forward_initialize` / `train_forward` step-state
+protocol of train_fwd_bwd (lakonlab/models/base_diffusion.py:14-62) is kept for callers that want the loss only;
+`forward_backward` is the whole multi-step forward + adapter-only backward (each student step's backward runs right after
+its roll-out, so the trunk checkpoints are never stale). The runner-facing object is
+lakonlab.models.LatentDiffusionTextImage."""
 from __future__ import annotations
 
 from typing import Dict, Optional
@@ -38,5 +40,12 @@ class ArcFlowImitationDataFree:
             rands = [draw_rollout_randoms(B, n, K, generator) for _ in range(self.train_cfg["nfe"])]
         return self.step.forward(prompt_embeds, pooled_prompt_embeds, grid_hw, noise, rands, iteration=it)
 
-    def backward(self, *a, **k):
-        return self.step.backward(*a, **k)
+    def forward_backward(self, prompt_embeds, pooled_prompt_embeds, grid_hw, noise, running_status=None, rands=None,
+                         generator=None, grads=None, neg_prompt_embeds=None):
+        """loss, log_vars, grads (fp32 tensors keyed by adapter state-dict name, accumulated into when given)."""
+        it = (running_status or {}).get("iteration", 0)
+        B, n, K = noise.shape[0], self.train_cfg["num_intermediate_states"], self.denoising.num_gaussians
+        if rands is None:
+            rands = [draw_rollout_randoms(B, n, K, generator) for _ in range(self.train_cfg["nfe"])]
+        return self.step.forward_backward(prompt_embeds, pooled_prompt_embeds, grid_hw, noise, rands, iteration=it,
+                                          grads=grads, neg_txt=neg_prompt_embeds)

@@ -37,6 +37,20 @@ class FluxBaseTransformer:
         return self._sd
 
 
+def _load_base_transformer(path: str, arch: str, device):
+    import os
+    if path.startswith("synthetic://"):
+        from lakonlab.models.builder import synthetic_base_state_dict
+        if arch == "flux":
+            from arcflow_b200.config import flux_dev as full_cfg
+        else:
+            from arcflow_b200.qwen import qwen_image as full_cfg
+        return synthetic_base_state_dict(arch, full_cfg(), int(path[len("synthetic://"):] or 1234), device)
+    from lakonlab.models.builder import load_transformer_weights
+    sub = os.path.join(path, "transformer")
+    return load_transformer_weights(sub if os.path.isdir(sub) else path)
+
+
 class ArcFluxPipeline(ArcFlowLoaderMixin):
     vae_scale_factor = 8
     default_sample_size = 128
@@ -52,6 +66,17 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
         self._num_timesteps = 0
         self._interrupt = False
         self.use_cuda_graph = False
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype=torch.bfloat16, device="cuda", **kwargs):
+        """`ArcFluxPipeline.from_pretrained('black-forest-labs/FLUX.1-dev', torch_dtype=bf16)` (inference_flux.py:5-7),
+        offline: a local diffusers-layout folder (its `transformer/` sub-folder, or the folder itself, holds the
+        `.safetensors` shards) or `synthetic://<seed>` for seeded weights of the FLUX.1-dev shape. Text encoders / VAE
+        are attached by the caller as `text_encoder_fn` / `vae_decode_fn` hooks."""
+        if torch_dtype not in (None, torch.bfloat16):
+            raise ValueError("this build computes in bf16 only")
+        return cls(transformer=FluxBaseTransformer(_load_base_transformer(pretrained_model_name_or_path, "flux", device),
+                                                   device=device), **kwargs)
 
     def enable_cuda_graph(self, on: bool = True):
         """Extension (not in the reference): replay the denoising loop as ONE captured CUDA graph per (shape, schedule)

@@ -38,6 +38,16 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
         self._num_timesteps = 0
         self._interrupt = False
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype=torch.bfloat16, device="cuda", **kwargs):
+        """`ArcQwenImagePipeline.from_pretrained('Qwen/Qwen-Image', torch_dtype=bf16)` (inference_qwen.py:5-7), offline:
+        see ArcFluxPipeline.from_pretrained."""
+        from .arcflux_pipeline import FluxBaseTransformer, _load_base_transformer
+        if torch_dtype not in (None, torch.bfloat16):
+            raise ValueError("this build computes in bf16 only")
+        return cls(transformer=FluxBaseTransformer(_load_base_transformer(pretrained_model_name_or_path, "qwen", device),
+                                                   device=device), **kwargs)
+
     @property
     def interrupt(self):
         return self._interrupt

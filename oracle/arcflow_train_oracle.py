@@ -162,10 +162,11 @@ def teacher_state_dict(sd: Dict[str, Tensor], teacher_extra: Dict[str, Tensor]) 
 
 
 def flux_teacher_velocity(tsd, cfg, x_tokens: Tensor, txt, pooled, sigma: Tensor, guidance: Tensor, grid_hw,
-                          dtype=torch.float32) -> Tensor:
-    """Stock FLUX forward: same trunk, AdaLayerNormContinuous + proj_out (D -> 64) (diffusers/flux.py:122-156)."""
+                          dtype=torch.float32, bf16_quirks: bool = True) -> Tensor:
+    """Stock FLUX forward: same trunk, AdaLayerNormContinuous + proj_out (D -> 64) (diffusers/flux.py:122-156).
+    Cross-checked against the original black-forest-labs FLUX model code (tests/test_oracle_bfl.py)."""
     import torch.nn.functional as F
-    out = O.flux_trunk(tsd, cfg, x_tokens, txt, pooled, sigma, guidance, grid_hw, dtype=dtype)
+    out = O.flux_trunk(tsd, cfg, x_tokens, txt, pooled, sigma, guidance, grid_hw, dtype=dtype, bf16_quirks=bf16_quirks)
     x, temb = out
     emb = O._lin(tsd, "norm_out.linear", F.silu(temb).to(x.dtype), dtype)
     scale, shift = emb.chunk(2, dim=1)
