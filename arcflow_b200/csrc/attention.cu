@@ -54,10 +54,9 @@ struct AttnParams {
   __nv_bfloat16* o;
   long long o_ld, o_batch_stride;
   float* lse;  // optional [batch, heads, seq]: log2-domain logsumexp of the scaled scores (for the backward)
-  int debug_mode;  // 0 = normal. Developer timing probes (results invalid): 1 = no exp, 2 = barriers only
 };
 
-// Developer trace (debug_mode 7): per-iteration clock stamps of one softmax thread per warpgroup of CTA 0.
+// Developer trace (TRACE instantiations): per-iteration clock stamps of one softmax thread per warpgroup of CTA 0.
 __device__ long long g_attn_trace[2][64][8];
 __device__ __forceinline__ void trace_stamp(bool on, int t, int j, int slot) {
   if (on && j < 64) g_attn_trace[t][j][slot] = clock64();
@@ -69,13 +68,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-template <int ID>
-__device__ __forceinline__ void named_bar_sync() {
-  asm volatile("bar.sync %0, 256;" ::"n"(ID) : "memory");
+__device__ __forceinline__ void named_bar_sync(int id) {
+  asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
 }
-template <int ID>
-__device__ __forceinline__ void named_bar_arrive() {
-  asm volatile("bar.arrive %0, 256;" ::"n"(ID) : "memory");
+__device__ __forceinline__ void named_bar_arrive(int id) {
+  asm volatile("bar.arrive %0, 256;" ::"r"(id) : "memory");
 }
 
 // 2^x for a pair, on the FMA/ALU pipes: x = floor(x) + f, 2^f by a cubic minimax on [0, 1)
@@ -95,6 +92,10 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return p;
 }
 
+// TRACE: record clock stamps of the softmax hand-shake (developer builds only; the product instantiation carries no
+// instrumentation — the probes' predicates and address arithmetic cost 8 % of the kernel). TURNS: the two warpgroups
+// alternate in the exp phase.
+template <bool TRACE, bool TURNS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -184,11 +185,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint64_t k_desc = make_sw128_desc(smem_u32(sK), 16, 1024);
       const uint64_t v_desc = make_sw128_desc(smem_u32(sV), HALF_BYTES, 1024);
 
-      const bool skip_qk = p.debug_mode == 4 || p.debug_mode == 6, skip_pv = p.debug_mode == 3 || p.debug_mode == 5 || p.debug_mode == 6;
-      const bool free_run = p.debug_mode == 5 || p.debug_mode == 6;  // probes 5/6: no softmax hand-shake at all
       // descriptor start addresses are in 16-byte units, so advancing is an add on the low word
       auto issue_qk = [&](int t, int st) {
-        if (skip_qk) return;
         const uint64_t a0 = q_desc + uint64_t((t * TILE_BYTES) >> 4);
         const uint64_t b0 = k_desc + uint64_t((st * TILE_BYTES) >> 4);
         if (elect_one_sync()) {
@@ -203,7 +201,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // P_t is published in two 64-column halves, so the first half of the PV product overlaps the second half of
       // the exp phase (the K = 128 contraction is 8 independent K = 16 MMAs anyway).
       auto issue_pv = [&](int t, int st, int hf, bool acc) {
-        if (skip_pv) return;
         const uint64_t b0 = v_desc + uint64_t((st * TILE_BYTES) >> 4);
         if (elect_one_sync()) {
 #pragma unroll
@@ -237,10 +234,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&v_full[st], ph);
         if (has_next) mbar_wait(&k_full[nst], nph);
         for (int t = 0; t < NQT; ++t) {
-          if (!free_run) mbar_wait(&p_full[2 * t], j & 1);
+          mbar_wait(&p_full[2 * t], j & 1);
           tc_fence_after();
           issue_pv(t, st, 0, j > 0);
-          if (!free_run) mbar_wait(&p_full[2 * t + 1], j & 1);
+          mbar_wait(&p_full[2 * t + 1], j & 1);
           tc_fence_after();
           issue_pv(t, st, 1, true);
           commit(&o_done[t]);
@@ -267,28 +264,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float m = -INFINITY;
     float l = 0.f;
 
-    const bool use_turns = p.debug_mode != 8;
-    const bool tr = (p.debug_mode == 7 || p.debug_mode == 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0;
-    for (int j = 0; j < ((p.debug_mode == 5 || p.debug_mode == 6) ? 0 : n_kv); ++j) {
-      trace_stamp(tr, t, j, 0);
+    const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0;
+    const int my_turn = t == 0 ? BAR_TURN_A : BAR_TURN_B;
+    const int next_turn = t == 0 ? BAR_TURN_B : BAR_TURN_A;
+    if (TURNS && t == 1) named_bar_arrive(BAR_TURN_A);  // warpgroup A owns the first turn
+    for (int j = 0; j < n_kv; ++j) {
+      if (TRACE) trace_stamp(tr, t, j, 0);
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      trace_stamp(tr, t, j, 1);
-      if (p.debug_mode >= 2 && p.debug_mode < 7) {  // timing probe: MMA/TMA pipeline alone
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&p_full[2 * t]);
-          mbar_arrive(&p_full[2 * t + 1]);
-        }
-        continue;
-      }
+      if (TRACE) trace_stamp(tr, t, j, 1);
       uint32_t s[KT];
 #pragma unroll
       for (int i = 0; i < KT / 32; ++i)
         tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
       tmem_ld_wait();
-      trace_stamp(tr, t, j, 6);
+      if (TRACE) trace_stamp(tr, t, j, 6);
 
       const int valid = p.seq - j * KT;
       if (valid < KT) {
@@ -328,15 +318,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
 
       // ---- exp phase: the two warpgroups alternate (MUFU is the shared, saturated resource) ----
-      trace_stamp(tr, t, j, 2);
-      if (use_turns) {
-        if (t == 0) {
-          if (j > 0) named_bar_sync<BAR_TURN_A>();
-        } else {
-          named_bar_sync<BAR_TURN_B>();
-        }
-      }
-      trace_stamp(tr, t, j, 3);
+      if (TRACE) trace_stamp(tr, t, j, 2);
+      if (TURNS) named_bar_sync(my_turn);
+      if (TRACE) trace_stamp(tr, t, j, 3);
       const float2 c2 = make_float2(c, c);
       const float2 nm2 = make_float2(-m * c, -m * c);
       float2 lsum = make_float2(0.f, 0.f);
@@ -365,14 +349,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (lane == 0) mbar_arrive(&p_full[2 * t]);
         }
       }
-      trace_stamp(tr, t, j, 4);
-      if (use_turns) {
-        if (t == 0) {
-          named_bar_arrive<BAR_TURN_B>();
-        } else {
-          named_bar_arrive<BAR_TURN_A>();
-        }
-      }
+      if (TRACE) trace_stamp(tr, t, j, 4);
+      if (TURNS) named_bar_arrive(next_turn);
       l += lsum.x + lsum.y;
 #pragma unroll
       for (int i = KT / 64; i < KT / 32; ++i)
@@ -381,13 +359,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[2 * t + 1]);
-      trace_stamp(tr, t, j, 5);
+      if (TRACE) trace_stamp(tr, t, j, 5);
     }
 
-    if (t == 0 && (p.debug_mode < 2 || p.debug_mode == 7)) named_bar_sync<BAR_TURN_A>();  // consume warpgroup B's last hand-off
+    if (TURNS && t == 0) named_bar_sync(BAR_TURN_A);  // consume warpgroup B's last hand-off
 
     // final: O / l -> bf16 -> global
-    if (p.debug_mode < 5 || p.debug_mode >= 7) mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    mbar_wait(&o_done[t], (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int qrow = q0 + t * QT + row;
@@ -459,24 +437,25 @@ int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
   p.o_ld = d->o_ld;
   p.o_batch_stride = d->o_batch_stride;
   p.lse = d->lse;
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("AFB_ATTN_DEBUG_MODE");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.debug_mode = dbg;
+  // Developer variants (env AFB_ATTN_DEBUG_MODE): 7 = clock-stamp trace, 8 = trace without warpgroup turn-taking,
+  // 9 = no turn-taking, no trace. Anything else is the product kernel, which carries no instrumentation.
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("AFB_ATTN_DEBUG_MODE");
+    dbg = e ? atoi(e) : 0;
   }
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        int(ATT_SMEM_BYTES)));
-    attr_set = true;
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
+  KernelFn fn = dbg == 7   ? attention_fwd_kernel<true, true>
+                : dbg == 8 ? attention_fwd_kernel<true, false>
+                : dbg == 9 ? attention_fwd_kernel<false, false>
+                           : attention_fwd_kernel<false, true>;
+  static KernelFn attr_set_for = nullptr;
+  if (attr_set_for != fn) {
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATT_SMEM_BYTES)));
+    attr_set_for = fn;
   }
   dim3 grid((d->seq + NQT * QT - 1) / (NQT * QT), d->heads, d->batch);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], p);
+  fn<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], p);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
