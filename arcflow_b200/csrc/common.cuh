@@ -109,16 +109,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin-wait with a watchdog: a protocol bug must trap instead of hanging the GPU.
+// Spin-wait with a watchdog: a protocol bug must trap (the launch fails with an error) instead of hanging the GPU.
+// No printf here: a device-side call in every wait site costs stack traffic and spills in the hot loops around it.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("arcflow_b200: mbarrier watchdog (block %d,%d,%d thread %d bar@%u parity %u)\n",
-             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");  // ~2 s at 2 GHz
   }
 }
 
