@@ -8,10 +8,14 @@ Parity status
   * Sampler side (schedule, token<->image layout, ArcFlowPolicy, momentum_integration): PINNED — checked in
     tests/test_oracle_golden.py against tests/golden/reference_sampler.npz, which tools/make_golden.py
     produced by executing the reference's own functions from /root/reference.
-  * Transformer block arithmetic: PARITY UNPINNED. It lives in diffusers==0.35.1 / peft==0.17.0
-    (requirements.txt:4-5 of the reference), which are not vendored under /root/reference and not
-    installable offline. It is restated from their published semantics as recorded in SURVEY.md
-    Appendix A and anchored on the reference's own call sites, cited per function below.
+  * Transformer block arithmetic: lives in diffusers==0.35.1 / peft==0.17.0 (requirements.txt:4-5 of the reference),
+    which are not vendored under /root/reference and not installable offline, so the reference's own classes cannot
+    pin it (PARITY UNPINNED against diffusers itself). It is restated from their published semantics as recorded in
+    SURVEY.md Appendix A, anchored on the reference's own call sites (cited per function below), and — for FLUX —
+    CROSS-CHECKED against an independent implementation: the original black-forest-labs FLUX model code shipped in this
+    image as torchtitan.experiments.flux (tests/test_oracle_bfl.py, tests/golden/bfl_flux_tiny.npz from
+    tools/make_golden_bfl.py, weights mapped with diffusers' published FLUX conversion). Embedders, double / single
+    blocks, RoPE, QK-RMSNorm, modulation order and the final AdaLN agree to 2e-5. Qwen-Image has no such second source.
 
 Every function cites the reference file:line it follows (paths relative to the upstream repo root).
 """
