@@ -106,6 +106,13 @@ struct afb_engine {
        *dattn = nullptr, *du = nullptr, *dy = nullptr, *dl = nullptr, *h_mid = nullptr, *u1 = nullptr, *u2 = nullptr,
        *tproj_t = nullptr, *tmp_t = nullptr, *ltv1 = nullptr, *ltv2 = nullptr;
   float *lse = nullptr, *delta = nullptr, *stats = nullptr, *dsilu = nullptr, *dtmp = nullptr, *dltv = nullptr;
+  // activation stash (afb_engine_set_activation_stash): per-block outputs of the train forward kept for the backward
+  // instead of being recomputed from the checkpoint (a B200 has the HBM for it: ~62 GB at FLUX bs 4, 1024 px)
+  bool stash_on = false;
+  void* stash = nullptr;
+  size_t stash_bytes = 0;
+  int scap_batch = 0, scap_txt = 0, scap_img = 0;
+  bool stash_valid = false;  // the stash holds the activations of the checkpoints currently saved
   // LoRA input dropout (train forward / backward only): p, seed, scratch for the dropped LoRA-branch inputs
   float drop_p = 0.f;
   uint64_t drop_seed = 0;
@@ -194,6 +201,50 @@ size_t carve_train(afb_engine* e, uint8_t* base, int B, int St, int Si) {
   e->xd_small = c.take<bf16>(B * D);
   e->dtmp2 = c.take<float>(B * D);
   return c.off;
+}
+
+// One block's slice of the activation stash: raw QKV, attention output + log-sum-exp, MLP pre-activation, the un-gated
+// branch outputs (u1: attention / single-block branch, u2: MLP branch) and, for double-stream blocks, the residual
+// stream between the two halves.
+struct StashSlot {
+  bf16 *qkv_raw, *attn, *pre, *u1, *u2, *h_mid;
+  float* lse;
+};
+size_t stash_slot_elems(const afb_model_desc& d, bool dbl, size_t tokens) {
+  const size_t D = d.dim, M = d.mlp_dim;
+  return tokens * (3 * D + D + M + D + (dbl ? 2 * D : 0));
+}
+size_t stash_total_bytes(const afb_model_desc& d, int B, int St, int Si) {
+  const size_t tokens = size_t(B) * (size_t(St) + Si);
+  const size_t lse = align_up(size_t(B) * d.heads * (size_t(St) + Si) * sizeof(float));
+  return size_t(d.num_double) * (align_up(stash_slot_elems(d, true, tokens) * sizeof(bf16)) + lse) +
+         size_t(d.num_single) * (align_up(stash_slot_elems(d, false, tokens) * sizeof(bf16)) + lse);
+}
+StashSlot stash_slot(const afb_engine* e, int block, int B, int St, int Si) {
+  const afb_model_desc& d = e->desc;
+  const size_t tokens = size_t(B) * (size_t(St) + Si), D = d.dim, M = d.mlp_dim;
+  const size_t lse = align_up(size_t(B) * d.heads * (size_t(St) + Si) * sizeof(float));
+  const size_t dslot = align_up(stash_slot_elems(d, true, tokens) * sizeof(bf16)) + lse;
+  const size_t sslot = align_up(stash_slot_elems(d, false, tokens) * sizeof(bf16)) + lse;
+  const bool dbl = block < d.num_double;
+  uint8_t* base = static_cast<uint8_t*>(e->stash) +
+                  (dbl ? size_t(block) * dslot : size_t(d.num_double) * dslot + size_t(block - d.num_double) * sslot);
+  StashSlot t{};
+  bf16* p = reinterpret_cast<bf16*>(base);
+  t.qkv_raw = p, p += tokens * 3 * D;
+  t.attn = p, p += tokens * D;
+  t.pre = p, p += tokens * M;
+  t.u1 = p, p += tokens * D;
+  if (dbl) {
+    t.u2 = p, p += tokens * D;
+    t.h_mid = p, p += tokens * D;
+  }
+  t.lse = reinterpret_cast<float*>(base + (dbl ? dslot : sslot) - lse);
+  return t;
+}
+int copy_bf16(bf16* dst, const bf16* src, size_t elems, cudaStream_t s) {
+  AFB_CHECK_CUDA(cudaMemcpyAsync(dst, src, elems * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+  return AFB_OK;
 }
 
 // [batches, rows, cols] view helper for the GEMM descriptor
@@ -377,7 +428,9 @@ int drop_into(afb_engine* e, View x, int B, int rows, int cols, int logical_cols
 int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v, int rows, int B,
                const void* up_w, const void* up_b, const void* up_la, const void* down_w,
                const void* down_b, const void* down_la, const bf16* gate, cudaStream_t s, bool drop = false,
-               uint32_t layer_up = 0) {
+               uint32_t layer_up = 0, const View* pre_v = nullptr, const View* u2_v = nullptr) {
+  // pre_v / u2_v (train forward with the activation stash): keep the MLP pre-activation and the un-gated branch output
+  // instead of fusing GELU and gate * y + residual into the GEMM epilogues.
   // `*_la != NULL` means the packed weight is [W | lora_B] (leading dim in + rank). A teacher engine
   // (ignore_lora) shares those buffers with the student and simply never reads the extra K columns.
   const int D = e->desc.dim, M = e->desc.mlp_dim, r = e->desc.lora_rank;
@@ -391,10 +444,18 @@ int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v,
       xa = dropped_view(e, rows, D);
     }
     AFB_TRY(Gemm(B, rows).a(xa, D).w(up_la, D, r, nullptr).alpha(e->lora_scale).out(lt0v, AFB_EPI_BIAS).run(e, s));
-    AFB_TRY(Gemm(B, rows).a(yv, D).a(lt0v, r).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(yv, D).a(lt0v, r).w(up_w, up_ld, M, up_b)
+                .out(pre_v ? *pre_v : mlpv, pre_v ? AFB_EPI_BIAS : AFB_EPI_BIAS_GELU).run(e, s));
   } else {
-    AFB_TRY(Gemm(B, rows).a(yv, D).w(up_w, up_ld, M, up_b).out(mlpv, AFB_EPI_BIAS_GELU).run(e, s));
+    AFB_TRY(Gemm(B, rows).a(yv, D).w(up_w, up_ld, M, up_b)
+                .out(pre_v ? *pre_v : mlpv, pre_v ? AFB_EPI_BIAS : AFB_EPI_BIAS_GELU).run(e, s));
   }
+  if (pre_v)
+    for (int bi = 0; bi < B; ++bi)
+      AFB_TRY(afb::gelu_fwd_launch(pre_v->p + int64_t(bi) * pre_v->bs, M, const_cast<bf16*>(mlpv.p) + int64_t(bi) * mlpv.bs, M,
+                                   rows, M, s));
+  const View down_out = u2_v ? *u2_v : hv;
+  const int down_epi = u2_v ? AFB_EPI_BIAS : AFB_EPI_BIAS_GATE_RES;
   if (down_la && lora) {
     View xa = mlpv;
     if (drop) {
@@ -403,11 +464,13 @@ int mlp_branch(afb_engine* e, View yv, View hv, View mlpv, View lt0v, View lt1v,
     }
     AFB_TRY(Gemm(B, rows).a(xa, M).w(down_la, M, r, nullptr).alpha(e->lora_scale).out(lt1v, AFB_EPI_BIAS).run(e, s));
     AFB_TRY(Gemm(B, rows).a(mlpv, M).a(lt1v, r).w(down_w, down_ld, D, down_b)
-                .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
+                .out(down_out, down_epi).gate_res(gate, mod_bs, hv).run(e, s));
   } else {
     AFB_TRY(Gemm(B, rows).a(mlpv, M).w(down_w, down_ld, D, down_b)
-                .out(hv, AFB_EPI_BIAS_GATE_RES).gate_res(gate, mod_bs, hv).run(e, s));
+                .out(down_out, down_epi).gate_res(gate, mod_bs, hv).run(e, s));
   }
+  if (u2_v)
+    AFB_TRY(afb::gate_res_launch(hv.p, hv.bs, u2_v->p, u2_v->bs, gate, mod_bs, const_cast<bf16*>(hv.p), hv.bs, B, rows, D, s));
   return AFB_OK;
 }
 
@@ -422,6 +485,8 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   const int64_t mod_bs = w.mod_total;
   const bool flux = d.arch == AFB_ARCH_FLUX;
   const bool drop = save_ckpt && e->drop_p > 0.f && r > 0;  // LoRA input dropout: train forward only
+  const bool stash = save_ckpt && e->stash_on && e->stash != nullptr;  // keep block outputs for the backward
+  const size_t tok = size_t(B) * S;
 
   // ---- conditioning vector temb [B, D] ---------------------------------------------------------
   AFB_TRY(afb::timestep_embed_launch(a->timestep, e->tproj, B, s));
@@ -485,6 +550,9 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   at.heads = H;
   at.scale = 0.f;
 
+  const View u1_txt{e->u1, D, int64_t(S) * D}, u1_img{e->u1 + int64_t(St) * D, D, int64_t(S) * D};
+  const View u2_txt{e->u2, D, int64_t(S) * D}, u2_img{e->u2 + int64_t(St) * D, D, int64_t(S) * D};
+  const View pre_txt{e->mlp_pre, M, int64_t(S) * M}, pre_img{e->mlp_pre + int64_t(St) * M, M, int64_t(S) * M};
   const size_t ckpt_elems = size_t(B) * S * D;
   auto save = [&](int idx) -> int {
     if (!save_ckpt) return AFB_OK;
@@ -506,26 +574,51 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
                                     mod_bs, B, St, D, LN_EPS, s));
     AFB_TRY(Gemm(B, Si).a(y_img, D).w(k.img_qkv_w, D, 3 * D, k.img_qkv_b).out(qkv_img, AFB_EPI_BIAS).run(e, s));
     AFB_TRY(Gemm(B, St).a(y_txt, D).w(k.txt_qkv_w, D, 3 * D, k.txt_qkv_b).out(qkv_txt, AFB_EPI_BIAS).run(e, s));
+    StashSlot sl{};
+    if (stash) {
+      sl = stash_slot(e, i, B, St, Si);
+      AFB_TRY(copy_bf16(sl.qkv_raw, e->qkv, tok * 3 * D, s));
+      at.lse = sl.lse;
+    }
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, St, k.txt_nq,
                                      k.txt_nk, k.img_nq, k.img_nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     AFB_TRY(run_attention(e, &at, s));
-    AFB_TRY(Gemm(B, Si).a(at_img, D).w(k.img_out_w, D, D, k.img_out_b)
-                .out(h_img, AFB_EPI_BIAS_GATE_RES).gate_res(im + 2 * D, mod_bs, h_img).run(e, s));
     const bool last_qwen_txt = !flux && i == d.num_double - 1;  // its text stream output is never read
-    if (!last_qwen_txt)
-      AFB_TRY(Gemm(B, St).a(at_txt, D).w(k.txt_out_w, D, D, k.txt_out_b)
-                  .out(h_txt, AFB_EPI_BIAS_GATE_RES).gate_res(tm + 2 * D, mod_bs, h_txt).run(e, s));
+    if (stash) {  // un-fused: the un-gated branch output and the mid-block residual stream are kept
+      AFB_TRY(copy_bf16(sl.attn, e->attn, tok * D, s));
+      AFB_TRY(Gemm(B, Si).a(at_img, D).w(k.img_out_w, D, D, k.img_out_b).out(u1_img, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(afb::gate_res_launch(h_img.p, h_img.bs, u1_img.p, u1_img.bs, im + 2 * D, mod_bs, const_cast<bf16*>(h_img.p),
+                                   h_img.bs, B, Si, D, s));
+      if (!last_qwen_txt) {
+        AFB_TRY(Gemm(B, St).a(at_txt, D).w(k.txt_out_w, D, D, k.txt_out_b).out(u1_txt, AFB_EPI_BIAS).run(e, s));
+        AFB_TRY(afb::gate_res_launch(h_txt.p, h_txt.bs, u1_txt.p, u1_txt.bs, tm + 2 * D, mod_bs, const_cast<bf16*>(h_txt.p),
+                                     h_txt.bs, B, St, D, s));
+      }
+      AFB_TRY(copy_bf16(sl.u1, e->u1, tok * D, s));
+      AFB_TRY(copy_bf16(sl.h_mid, e->h, tok * D, s));
+    } else {
+      AFB_TRY(Gemm(B, Si).a(at_img, D).w(k.img_out_w, D, D, k.img_out_b)
+                  .out(h_img, AFB_EPI_BIAS_GATE_RES).gate_res(im + 2 * D, mod_bs, h_img).run(e, s));
+      if (!last_qwen_txt)
+        AFB_TRY(Gemm(B, St).a(at_txt, D).w(k.txt_out_w, D, D, k.txt_out_b)
+                    .out(h_txt, AFB_EPI_BIAS_GATE_RES).gate_res(tm + 2 * D, mod_bs, h_txt).run(e, s));
+    }
     AFB_TRY(afb::ln_modulate_launch(h_img.p, h_img.bs, const_cast<bf16*>(y_img.p), y_img.bs, im + 4 * D,
                                     im + 3 * D, mod_bs, B, Si, D, LN_EPS, s));
     AFB_TRY(mlp_branch(e, y_img, h_img, mlp_img, l0_img, l1_img, Si, B, k.img_up_w, k.img_up_b,
                        k.img_up_la, k.img_down_w, k.img_down_b,
-                       k.img_down_la, im + 5 * D, s, drop, 4u * i));
+                       k.img_down_la, im + 5 * D, s, drop, 4u * i, stash ? &pre_img : nullptr, stash ? &u2_img : nullptr));
     if (!last_qwen_txt) {
       AFB_TRY(afb::ln_modulate_launch(h_txt.p, h_txt.bs, const_cast<bf16*>(y_txt.p), y_txt.bs, tm + 4 * D,
                                       tm + 3 * D, mod_bs, B, St, D, LN_EPS, s));
       AFB_TRY(mlp_branch(e, y_txt, h_txt, mlp_txt, l0_txt, l1_txt, St, B, k.txt_up_w, k.txt_up_b,
                          k.txt_up_la, k.txt_down_w, k.txt_down_b,
-                         k.txt_down_la, tm + 5 * D, s, drop, 4u * i + 2));
+                         k.txt_down_la, tm + 5 * D, s, drop, 4u * i + 2, stash ? &pre_txt : nullptr,
+                         stash ? &u2_txt : nullptr));
+    }
+    if (stash) {
+      AFB_TRY(copy_bf16(sl.pre, e->mlp_pre, tok * M, s));
+      AFB_TRY(copy_bf16(sl.u2, e->u2, tok * D, s));
     }
   }
 
@@ -544,9 +637,20 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     AFB_TRY(afb::ln_modulate_launch(e->h, int64_t(S) * D, e->y, int64_t(S) * D, m + D, m, mod_bs, B, S, D,
                                     LN_EPS, s));
     AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(qkv_all, AFB_EPI_BIAS).run(e, s));
+    StashSlot sl{};
+    if (stash) {
+      sl = stash_slot(e, d.num_double + i, B, St, Si);
+      AFB_TRY(copy_bf16(sl.qkv_raw, e->qkv, tok * 3 * D, s));
+      at.lse = sl.lse;
+    }
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, 0, nullptr, nullptr,
                                      k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     AFB_TRY(run_attention(e, &at, s));
+    if (stash) AFB_TRY(copy_bf16(sl.attn, e->attn, tok * D, s));
+    const View up_out = stash ? View{e->mlp_pre, M, int64_t(S) * M} : mlp_all;
+    const int up_epi = stash ? AFB_EPI_BIAS : AFB_EPI_BIAS_GELU;
+    const View proj_out_v = stash ? View{e->u1, D, int64_t(S) * D} : h_all;
+    const int proj_epi = stash ? AFB_EPI_BIAS : AFB_EPI_BIAS_GATE_RES;
     const int64_t mlp_ld = D + (k.mlp_la ? rpad : 0), out_ld = D + M + (k.out_la ? rpad : 0);
     const uint32_t layer = 4u * (d.num_double + i);
     if (r > 0 && k.mlp_la) {
@@ -556,9 +660,13 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
         xa = dropped_view(e, S, D);
       }
       AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).alpha(e->lora_scale).out(l0_all, AFB_EPI_BIAS).run(e, s));
-      AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
+      AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(up_out, up_epi).run(e, s));
     } else {
-      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(mlp_all, AFB_EPI_BIAS_GELU).run(e, s));
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(up_out, up_epi).run(e, s));
+    }
+    if (stash) {
+      AFB_TRY(afb::gelu_fwd_launch(e->mlp_pre, M, e->mlp, M, int64_t(B) * S, M, s));
+      AFB_TRY(copy_bf16(sl.pre, e->mlp_pre, tok * M, s));
     }
     if (r > 0 && k.out_la) {
       if (drop) {
@@ -569,14 +677,19 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
         AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_la, D + M, r, nullptr).alpha(e->lora_scale).out(l1_all, AFB_EPI_BIAS).run(e, s));
       }
       AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, out_ld, D, k.out_b)
-                  .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
+                  .out(proj_out_v, proj_epi).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
     } else {
       AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_w, out_ld, D, k.out_b)
-                  .out(h_all, AFB_EPI_BIAS_GATE_RES).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
+                  .out(proj_out_v, proj_epi).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
+    }
+    if (stash) {
+      AFB_TRY(copy_bf16(sl.u1, e->u1, tok * D, s));
+      AFB_TRY(afb::gate_res_launch(e->h, int64_t(S) * D, e->u1, int64_t(S) * D, m + 2 * D, mod_bs, e->h, int64_t(S) * D, B, S, D, s));
     }
   }
 
   AFB_TRY(save(d.num_double + d.num_single));
+  if (save_ckpt) e->stash_valid = stash;
 
   // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + heads ------------------------
   const bf16* nm = e->mod + w.norm_out_mod_off;
@@ -740,6 +853,10 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
   const bool drop = e->drop_p > 0.f && r > 0;
   LoraBwd lb{e, B, S, s, drop};
   float* dmod = ba->d_mod;  // fp32 [B, mod_total] or NULL
+  // With the activation stash the block outputs of the train forward are copied back instead of being recomputed: no
+  // QKV / MLP-up / branch-output GEMMs and no attention forward in the backward.
+  const bool stash = e->stash_on && e->stash != nullptr && e->stash_valid;
+  const size_t tok = size_t(B) * S;
 
   // ---- single-stream blocks, last to first ----------------------------------------------------------------------
   for (int i = d.num_single - 1; i >= 0; --i) {
@@ -751,13 +868,22 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     const int64_t mlp_ld = D + (k.mlp_la ? rpad : 0), out_ld = D + M + (k.out_la ? rpad : 0);
     const bf16* mlp_w = static_cast<const bf16*>(k.mlp_w);
     const bf16* out_w = static_cast<const bf16*>(k.out_w);
-    // -- recompute
+    // -- recompute (or restore from the stash)
     AFB_TRY(afb::ln_modulate_launch(h_in, bsD, e->y, bsD, m + D, m, mod_bs, B, S, D, LN_EPS, s));
-    AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(raw_all, AFB_EPI_BIAS).run(e, s));
+    if (stash) {
+      const StashSlot sl = stash_slot(e, d.num_double + i, B, St, Si);
+      AFB_TRY(copy_bf16(e->qkv_raw, sl.qkv_raw, tok * 3 * D, s));
+      AFB_TRY(copy_bf16(e->attn, sl.attn, tok * D, s));
+      AFB_TRY(copy_bf16(e->mlp_pre, sl.pre, tok * M, s));
+      AFB_TRY(copy_bf16(e->u1, sl.u1, tok * D, s));
+      ab.lse = sl.lse;
+    } else {
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(raw_all, AFB_EPI_BIAS).run(e, s));
+    }
     AFB_CHECK_CUDA(cudaMemcpyAsync(e->qkv, e->qkv_raw, size_t(B) * S * 3 * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, bs3, 0, D, B, S, H, 0, nullptr, nullptr, k.nq, k.nk, a->rope_cos,
                                      a->rope_sin, LN_EPS, s));
-    AFB_TRY(run_attention(e, &at, s));
+    if (!stash) AFB_TRY(run_attention(e, &at, s));
     const uint32_t layer = 4u * (d.num_double + i);
     if (lm) {
       View xa = y_all;
@@ -766,8 +892,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
         xa = dropped_view(e, S, D);
       }
       AFB_TRY(Gemm(B, S).a(xa, D).w(k.mlp_la, D, r, nullptr).alpha(e->lora_scale).out(l0_all, AFB_EPI_BIAS).run(e, s));
-      AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
-    } else {
+      if (!stash)
+        AFB_TRY(Gemm(B, S).a(y_all, D).a(l0_all, r).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
+    } else if (!stash) {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(pre_all, AFB_EPI_BIAS).run(e, s));
     }
     AFB_TRY(afb::gelu_fwd_launch(e->mlp_pre, M, e->mlp, M, int64_t(B) * S, M, s));
@@ -781,8 +908,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       }
     }
     // -- backward
-    if (dmod) {  // the gate's gradient needs the branch output u = proj_out([attn | mlp]) the forward never stores
-      if (lo)
+    if (dmod) {  // the gate's gradient needs the branch output u = proj_out([attn | mlp]) the fused forward never stores
+      if (stash) {
+      } else if (lo)
         AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).a(l1_all, r).w(k.out_w, out_ld, D, k.out_b).out(u1_all, AFB_EPI_BIAS).run(e, s));
       else
         AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_w, out_ld, D, k.out_b).out(u1_all, AFB_EPI_BIAS).run(e, s));
@@ -862,8 +990,19 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     // Qwen: the last block's text-stream output is never read (forward_impl skips its out-projection and MLP), so that
     // stream only contributes through its K / V rows: its dattn is zero and its MLP half has no gradient.
     const bool skip_txt_tail = d.arch != AFB_ARCH_FLUX && i == d.num_double - 1;
-    // -- recompute: attention half
+    // -- recompute (or restore from the stash): attention half
+    if (stash) {
+      const StashSlot sl = stash_slot(e, i, B, St, Si);
+      AFB_TRY(copy_bf16(e->qkv_raw, sl.qkv_raw, tok * 3 * D, s));
+      AFB_TRY(copy_bf16(e->attn, sl.attn, tok * D, s));
+      AFB_TRY(copy_bf16(e->mlp_pre, sl.pre, tok * M, s));
+      AFB_TRY(copy_bf16(e->u1, sl.u1, tok * D, s));
+      AFB_TRY(copy_bf16(e->u2, sl.u2, tok * D, s));
+      AFB_TRY(copy_bf16(e->h_mid, sl.h_mid, tok * D, s));
+      ab.lse = sl.lse;
+    }
     for (Stream& t : st2) {
+      if (stash) break;
       AFB_TRY(afb::ln_modulate_launch(t.h_in.p, t.h_in.bs, const_cast<bf16*>(t.y.p), t.y.bs, t.mod + D, t.mod, mod_bs, B,
                                       t.rows, D, LN_EPS, s));
       AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.qkv_w, D, 3 * D, t.qkv_b).out(t.qkv_raw, AFB_EPI_BIAS).run(e, s));
@@ -871,7 +1010,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_CHECK_CUDA(cudaMemcpyAsync(e->qkv, e->qkv_raw, size_t(B) * S * 3 * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, bs3, 0, D, B, S, H, St, k.txt_nq, k.txt_nk, k.img_nq, k.img_nk,
                                      a->rope_cos, a->rope_sin, LN_EPS, s));
-    AFB_TRY(run_attention(e, &at, s));
+    if (!stash) AFB_TRY(run_attention(e, &at, s));
     // -- recompute: h_mid and the MLP half; then the MLP half's backward (per stream)
     for (Stream& t : st2) {
       if (skip_txt_tail && &t == &st2[1]) {
@@ -885,7 +1024,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       const int64_t up_ld = D + (t.up_la ? rpad : 0), down_ld = M + (t.down_la ? rpad : 0);
       const bf16* up_w = static_cast<const bf16*>(t.up_w);
       const bf16* down_w = static_cast<const bf16*>(t.down_w);
-      if (dmod) {  // keep the un-gated attention branch output for the gate's gradient
+      if (stash) {
+        // h_mid and u1 were restored
+      } else if (dmod) {  // keep the un-gated attention branch output for the gate's gradient
         AFB_TRY(Gemm(B, t.rows).a(t.attn, D).w(t.out_w, D, D, t.out_b).out(t.u1, AFB_EPI_BIAS).run(e, s));
         AFB_TRY(afb::gate_res_launch(t.h_in.p, t.h_in.bs, t.u1.p, t.u1.bs, t.mod + 2 * D, mod_bs, const_cast<bf16*>(t.h_mid.p),
                                      t.h_mid.bs, B, t.rows, D, s));
@@ -902,8 +1043,9 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
           xa = dropped_view(e, t.rows, D);
         }
         AFB_TRY(Gemm(B, t.rows).a(xa, D).w(t.up_la, D, r, nullptr).alpha(e->lora_scale).out(t.l0, AFB_EPI_BIAS).run(e, s));
-        AFB_TRY(Gemm(B, t.rows).a(t.y, D).a(t.l0, r).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
-      } else {
+        if (!stash)
+          AFB_TRY(Gemm(B, t.rows).a(t.y, D).a(t.l0, r).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
+      } else if (!stash) {
         AFB_TRY(Gemm(B, t.rows).a(t.y, D).w(t.up_w, up_ld, M, t.up_b).out(t.pre, AFB_EPI_BIAS).run(e, s));
       }
       for (int bi = 0; bi < B; ++bi)
@@ -919,7 +1061,8 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       }
       // backward of  h_out = h_mid + gate_mlp * down(gelu(up(LNmod2(h_mid))))
       if (dmod) {
-        if (ld_)
+        if (stash) {
+        } else if (ld_)
           AFB_TRY(Gemm(B, t.rows).a(t.mlp, M).a(t.l1, r).w(t.down_w, down_ld, D, t.down_b).out(t.u2, AFB_EPI_BIAS).run(e, s));
         else
           AFB_TRY(Gemm(B, t.rows).a(t.mlp, M).w(t.down_w, down_ld, D, t.down_b).out(t.u2, AFB_EPI_BIAS).run(e, s));
@@ -1000,6 +1143,7 @@ void afb_engine_destroy(afb_engine* e) {
   if (!e) return;
   if (e->ws) cudaFree(e->ws);
   if (e->tws) cudaFree(e->tws);
+  if (e->stash) cudaFree(e->stash);
   for (auto& r : e->prof) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -1137,6 +1281,41 @@ int afb_engine_train_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int3
   return AFB_OK;
 }
 
+int64_t afb_engine_stash_bytes(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len) {
+  if (!e || batch < 1 || txt_len < 1 || img_len < 1) return 0;
+  return int64_t(stash_total_bytes(e->desc, batch, txt_len, img_len));
+}
+
+int afb_engine_set_activation_stash(afb_engine* e, int32_t on, int32_t batch, int32_t txt_len, int32_t img_len) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  if (!on) {
+    if (e->stash) {
+      AFB_CHECK_CUDA(cudaDeviceSynchronize());
+      AFB_CHECK_CUDA(cudaFree(e->stash));
+    }
+    e->stash = nullptr;
+    e->stash_bytes = 0;
+    e->stash_on = e->stash_valid = false;
+    return AFB_OK;
+  }
+  AFB_REQUIRE(e->bound, "engine_set_activation_stash: bind weights first");
+  AFB_REQUIRE(batch >= 1 && txt_len >= 1 && img_len >= 1, "engine_set_activation_stash: empty problem");
+  const size_t bytes = stash_total_bytes(e->desc, batch, txt_len, img_len);
+  if (!e->stash || bytes > e->stash_bytes) {
+    if (e->stash) {
+      AFB_CHECK_CUDA(cudaDeviceSynchronize());
+      AFB_CHECK_CUDA(cudaFree(e->stash));
+      e->stash = nullptr;
+      e->stash_bytes = 0;
+    }
+    AFB_CHECK_CUDA(cudaMalloc(&e->stash, bytes));
+    e->stash_bytes = bytes;
+  }
+  e->stash_on = true;
+  e->stash_valid = false;
+  return AFB_OK;
+}
+
 int afb_engine_forward_train(afb_engine* e, const afb_forward_args* a, void* stream) {
   AFB_REQUIRE(a != nullptr, "engine_forward_train: null args");
   AFB_TRY(check_shapes(e, a->batch, a->txt_len, a->img_len));
@@ -1151,6 +1330,8 @@ int afb_engine_forward_train(afb_engine* e, const afb_forward_args* a, void* str
                         double(e->lora_scale));
     return AFB_ERR_UNSUPPORTED;
   }
+  AFB_REQUIRE(!e->stash_on || stash_total_bytes(e->desc, a->batch, a->txt_len, a->img_len) <= e->stash_bytes,
+              "engine_forward_train: the activation stash was sized for a smaller problem");
   e->saved_batch = a->batch;
   e->saved_txt = a->txt_len;
   e->saved_img = a->img_len;

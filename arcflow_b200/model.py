@@ -276,10 +276,38 @@ class EngineModelBase:
         _lib.check(self.lib.afb_engine_set_lora_dropout(self.handle, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF),
                    "afb_engine_set_lora_dropout")
 
+    def set_activation_stash(self, mode="auto", headroom_bytes: int = 12 << 30):
+        """Keep each block's outputs of the train forward for the backward instead of recomputing the block
+        (afb_engine_set_activation_stash). mode: True / False / "auto" = on when the device has room for it plus
+        `headroom_bytes` (FLUX bs 4 at 1024 px: ~62 GB — fits a 180 GB B200 next to weights, checkpoints and optimizer)."""
+        self._stash_mode = mode
+        self._stash_shape = None      # decided per shape at the next train forward
+
+    def _apply_stash(self):
+        mode = getattr(self, "_stash_mode", "auto")
+        if getattr(self, "_stash_shape", None) == (mode, self._reserved):
+            return
+        on = False
+        if mode is True or mode == "auto":
+            need = int(self.lib.afb_engine_stash_bytes(self.handle, *self._reserved))
+            free, _ = torch.cuda.mem_get_info(self.device)
+            cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            on = mode is True or need + getattr(self, "_stash_headroom", 12 << 30) <= free + cached
+            if on and need > free:
+                torch.cuda.empty_cache()
+        rc = self.lib.afb_engine_set_activation_stash(self.handle, int(on), *self._reserved)
+        if rc != 0 and mode == "auto":     # the device could not hold it after all: keep recomputing
+            rc = self.lib.afb_engine_set_activation_stash(self.handle, 0, *self._reserved)
+            on = False
+        _lib.check(rc, "afb_engine_set_activation_stash")
+        self.activation_stash = on
+        self._stash_shape = (mode, self._reserved)
+
     def _launch_forward(self, a: "_lib.ForwardArgs", keep: tuple, train: bool):
         stream = torch.cuda.current_stream().cuda_stream
         if train:
             _lib.check(self.lib.afb_engine_train_reserve(self.handle, *self._reserved), "afb_engine_train_reserve")
+            self._apply_stash()
             _lib.check(self.lib.afb_engine_forward_train(self.handle, C.byref(a), stream), "afb_engine_forward_train")
             self._train_ctx = dict(args=a, keep=keep)   # inputs stay alive until the backward has run
         else:

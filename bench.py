@@ -32,6 +32,17 @@ METRIC = "images_per_sec_1024px_2nfe"
 UNIT = "images/s"
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the two tensor-core kernels from the committed `ncu --set full` capture (dram__bytes_read.sum
+    + dram__bytes_write.sum; profiles/r01_ncu_traffic.json names the launches) — a profiler figure cannot be taken live."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -277,6 +288,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
     peaks = _peaks()
+    traffic = _ncu_traffic()
     fl = flux_flops_per_image_nfe(grid[0] * grid[1], 512, cfg.lora_rank)
     step_flops = fl["total"] * args.nfe * args.batch
     gemm_tf = prof["gemm_flops"] / (prof["gemm_ms"] * 1e9) if prof["gemm_ms"] > 0 else 0.0
@@ -292,7 +304,8 @@ def run_ours(args):
         "roofline": {
             "kernel": "gemm_bf16_kernel (tcgen05, all Linear/LoRA launches of one step)",
             "bound": "tensor", "achieved": gemm_tf, "peak": peaks["bf16"], "unit": "TFLOP/s",
-            "frac": gemm_tf / peaks["bf16"], "traffic": None,
+            "frac": gemm_tf / peaks["bf16"], "traffic": traffic.get("gemm", {}).get("dram_bytes_per_launch"),
+            "traffic_launch": traffic.get("gemm", {}).get("launch"), "traffic_source": traffic.get("source"),
             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
             "launches": prof["gemm_launches"], "avg_launch_ms": prof["gemm_ms"] / max(prof["gemm_launches"], 1),
             "algorithmic_flops_per_step": prof["gemm_flops"],
@@ -303,6 +316,7 @@ def run_ours(args):
             "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": attn_tf / peaks["bf16"],
             "launches": prof["attn_launches"], "avg_launch_ms": prof["attn_ms"] / max(prof["attn_launches"], 1),
             "algorithmic_bytes_per_launch": 4 * (512 + grid[0] * grid[1]) * 3072 * 2 * args.batch,
+            "traffic": traffic.get("attention", {}).get("dram_bytes_per_launch"),
             "share_of_step": prof["attn_ms"] / step_ms if step_ms else None,
         },
         "step_tflops": step_flops / (step_ms * 1e9), "step_frac_of_peak": step_flops / (step_ms * 1e9) / peaks["bf16"],

@@ -448,6 +448,16 @@ typedef struct afb_backward_args {
  * never drop. */
 int afb_engine_set_lora_dropout(afb_engine* e, float p, uint64_t seed);
 int afb_engine_train_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
+/* Activation stash: with 180 GB of HBM the train forward can keep each block's expensive outputs (raw QKV, attention
+ * output + log-sum-exp, MLP pre-activation, the un-gated branch outputs and the mid-block residual stream: ~62 GB for FLUX
+ * at batch 4, 1024 px) so that afb_engine_backward copies them back instead of recomputing the block (no QKV / MLP-up /
+ * branch GEMMs and no attention forward in the backward) — what the reference's `checkpointing=True`
+ * (configs/flux/arcflux_2nfe_k16.py:38, torch.utils.checkpoint re-running every block) trades the other way on 80 GB
+ * parts. Gradients are identical to the recompute path up to the un-fused epilogues' extra bf16 rounding.
+ * afb_engine_stash_bytes: size for a shape. afb_engine_set_activation_stash(on = 1, shape): allocate (AFB_ERR_CUDA if the
+ * device cannot hold it; the engine then keeps recomputing) — on = 0 frees it. */
+int64_t afb_engine_stash_bytes(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
+int afb_engine_set_activation_stash(afb_engine* e, int32_t on, int32_t batch, int32_t txt_len, int32_t img_len);
 int afb_engine_forward_train(afb_engine* e, const afb_forward_args* args, void* stream);
 int afb_engine_backward(afb_engine* e, const afb_backward_args* args, void* stream);
 /* d_mod (fp32 [batch, mod_total]: afb_engine_backward's output plus the caller-written norm_out slot) -> temb ->

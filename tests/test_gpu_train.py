@@ -226,8 +226,8 @@ def test_head_and_norm_out_gradients_match_autograd(lib):
         assert e < 3e-2, f"{n}: rel-L2 {e:.3e} (|ref| {ref.norm():.3e})"
 
 
-@pytest.mark.parametrize("p_lora", [0.0, 0.25])
-def test_trunk_lora_gradients_match_autograd(lib, p_lora):
+@pytest.mark.parametrize("p_lora,stash", [(0.0, False), (0.25, False), (0.0, True), (0.25, True)])
+def test_trunk_lora_gradients_match_autograd(lib, p_lora, stash):
     """forward_backward(): LoRA gradients through the frozen trunk (per-block recompute, tcgen05 attention backward,
     transposed-weight dX GEMMs, token-contraction dW GEMMs) vs torch autograd through the fp32 training oracle.
     p_lora > 0: peft's LoRA-input dropout with the counter-based mask both sides share (oracle `lora_dropout_mask`).
@@ -240,7 +240,10 @@ def test_trunk_lora_gradients_match_autograd(lib, p_lora):
     g = torch.Generator().manual_seed(78)
     rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
     step = ArcFlowDistillStep(student, teacher, tc)
+    # stash = False: per-block recompute from the checkpoints; True: block outputs kept by the train forward
+    student.set_activation_stash(stash)
     loss, _, grads = step.forward_backward(txt.to(DEV), pooled.to(DEV), grid, x.to(DEV), rands, iteration=700)
+    assert student.activation_stash == stash
     names = student.trunk_lora_names() + list(student.embed_lora_shapes()) + ["proj_out_means.weight", "norm_out.linear.weight"]
     ref_loss, _, ex = T.flux_train_forward(sd, extra, cfg, txt, pooled, grid, x, rands, 700, tc, dtype=torch.float32,
                                            require_grad=names)

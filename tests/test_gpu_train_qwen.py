@@ -62,7 +62,8 @@ def test_qwen_train_step_forward_loss_parity(lib, iteration):
     assert lv["teacher_ratio"] == ref_lv["teacher_ratio"]
 
 
-def test_qwen_adapter_gradients_match_autograd(lib):
+@pytest.mark.parametrize("stash", [False, True])
+def test_qwen_adapter_gradients_match_autograd(lib, stash):
     """forward_backward() on the Qwen student: every LoRA pair (img_mlp of all blocks, txt_mlp of blocks 0..L-2 — the last
     block's text tail is skipped in the backward as in the forward), the timestep embedder's pairs, heads and norm_out."""
     from arcflow_b200.train import ArcFlowDistillStep, draw_rollout_randoms
@@ -70,6 +71,7 @@ def test_qwen_adapter_gradients_match_autograd(lib):
     g = torch.Generator().manual_seed(91)
     rands = [draw_rollout_randoms(2, 4, 16, g) for _ in range(2)]
     step = ArcFlowDistillStep(student, teacher, TC)
+    student.set_activation_stash(stash)   # False: per-block recompute; True: block outputs kept by the train forward
     loss, _, grads = step.forward_backward(txt.to(DEV), None, grid, x.to(DEV), rands, iteration=700, neg_txt=neg.to(DEV))
     names = student.trunk_lora_names() + list(student.embed_lora_shapes()) + ["proj_out_means.weight", "norm_out.linear.weight"]
     assert len(student.trunk_lora_names()) == 2 * (2 * cfg.num_layers + 2 * (cfg.num_layers - 1))

@@ -1,7 +1,7 @@
 """Times the native train iteration at the reference's training shape: FLUX, bs 4 per GPU, latent 16x128x128
 (S_img = 4096, S_txt = 512) — BASELINE.json configs[3]: 2 student + 8 teacher forwards, roll-out kernels, the full
 adapter backward (per-block recompute), grad clip + AdamW + EMA and the bf16 write-back.
-Usage: python tools/train_step_time.py [batch] [--profile]
+Usage: python tools/train_step_time.py [batch] [--profile] [--no-stash]
    or: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step_time.py [batch]
        (DDP: per-rank noise, ONE NCCL all-reduce of the flat gradient arena per iteration; time = max over ranks)"""
 import json
@@ -21,6 +21,7 @@ from arcflow_b200.train import ArcFlowTrainer, draw_rollout_randoms  # noqa: E40
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 B = int(args[0]) if args else 4
 profile = "--profile" in sys.argv
+no_stash = "--no-stash" in sys.argv   # per-block recompute in the backward instead of the activation stash
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
 dev = torch.device("cuda", local)
@@ -33,6 +34,7 @@ student = ArcFluxEngineModel(sd, cfg, dev, consume_state_dict=True)
 del sd
 teacher = FluxTeacherEngine(student, make_flux_teacher_extras(cfg, 99, dev))
 x, txt, pooled = make_flux_inputs(cfg, B, 1024, 1024, 512, 42 + rank, dev)
+student.set_activation_stash(False if no_stash else "auto")
 trainer = ArcFlowTrainer(student, teacher)
 step = trainer.distill
 g = torch.Generator().manual_seed(rank)
@@ -64,6 +66,8 @@ fwd_flops = (2 * 78.77e12 + 8 * 74.36e12) * B
 out = dict(what="train iteration (fwd + bwd + optimizer)", n_gpus=world, batch=B, ms=ms, forward_only_ms=fwd_ms, backward_optim_ms=ms - fwd_ms,
            samples_per_s=B * world / (ms / 1e3), loss=loss, fwd_tflops=fwd_flops / (fwd_ms * 1e9), launches=launches,
            fwd_launches=fwd_launches, mem_gb=torch.cuda.max_memory_allocated() / 2**30,
+           activation_stash=bool(student.activation_stash),
+           device_mem_used_gb=(torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 2**30,
            log_vars={k: (float(v) if isinstance(v, (int, float)) else v) for k, v in lv.items()})
 if profile:
     student.set_profiling(True)
