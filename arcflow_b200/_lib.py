@@ -206,6 +206,7 @@ SIGNATURES = {
     "afb_rmsnorm_rope_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, _P]),
     "afb_engine_set_lora_dropout": (C.c_int, [_P, C.c_float, C.c_uint64]),
+    "afb_engine_set_ignore_lora": (C.c_int, [_P, C.c_int32]),
     "afb_engine_train_reserve": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "afb_engine_stash_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "afb_engine_set_activation_stash": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

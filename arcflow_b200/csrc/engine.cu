@@ -1169,6 +1169,12 @@ int afb_engine_bind(afb_engine* e, const afb_weights* w) {
   return AFB_OK;
 }
 
+int afb_engine_set_ignore_lora(afb_engine* e, int32_t on) {
+  AFB_REQUIRE(e != nullptr, "engine: null handle");
+  e->desc.ignore_lora = on ? 1 : 0;
+  return AFB_OK;
+}
+
 int afb_engine_set_lora_scale(afb_engine* e, float scale) {
   AFB_REQUIRE(e != nullptr, "engine: null handle");
   AFB_REQUIRE(scale == scale && scale > -1e6f && scale < 1e6f, "engine_set_lora_scale: bad scale");

@@ -41,7 +41,7 @@ def _rows3(t: torch.Tensor, name: str):
 def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.Tensor,
          bias: Optional[torch.Tensor] = None, epilogue: int = _lib.AFB_EPI_BIAS,
          gate: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, transposed: bool = False,
-         w2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         w2: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
     """out[b, r, :] = epi(sum_s a_s[b, r, :] @ w[:, koff_s : koff_s + K_s].T).
 
     `a` is one tensor or up to three K-segments sharing [batches, rows]; `w` is [N, sum K_s] (torch
@@ -85,6 +85,7 @@ def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.T
     elif w2 is not None:
         raise AfbError("gemm: w2 needs transposed=True")
     d.epilogue = epilogue
+    d.alpha = float(alpha)      # scales the accumulator before bias / epilogue (0 in the struct means 1)
     d.out, d.out_ld, d.out_batch_stride = optr, old, obs
     if bias is not None:
         _chk(bias, BF16, "gemm bias")

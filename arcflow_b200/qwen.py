@@ -159,6 +159,7 @@ class PackedQwenWeights:
         self.cfg = cfg
         self.keep: List[torch.Tensor] = []
         self.adapter_views: Dict[str, torch.Tensor] = {}   # see PackedFluxWeights.adapter_views
+        self.lora_base: Dict[str, torch.Tensor] = {}
         D, r = cfg.inner_dim, cfg.lora_rank
 
         def get(name, required=True):
@@ -200,6 +201,7 @@ class PackedQwenWeights:
         for li in (1, 2):
             pre = f"time_text_embed.timestep_embedder.linear_{li}"
             setattr(w, f"t{li}_w", hold(get(pre + ".weight")))
+            self.lora_base[pre] = self.keep[-1]          # un-packed base weight of a LoRA target (fuse_lora)
             setattr(w, f"t{li}_b", hold(get(pre + ".bias")))
             a, b = lora(pre)
             setattr(w, f"t{li}_la", hold(a, pre + ".lora_A.weight"))

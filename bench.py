@@ -322,6 +322,23 @@ def run_ours(args):
         "step_tflops": step_flops / (step_ms * 1e9), "step_frac_of_peak": step_flops / (step_ms * 1e9) / peaks["bf16"],
         "tflop_per_image": fl["total"] * args.nfe / 1e12,
     }
+    if world == 1 and args.variants:
+        # Not the headline: the same step with the adapter merged into the base weights (pipe.fuse_lora(), one-way, so it
+        # runs last). The LoRA branches are 5.6 % of the algorithmic FLOPs counted above; images/s is what a deployment
+        # that accepts bf16-rounded merged weights gets.
+        pipe.fuse_lora()
+        for _ in range(2):
+            step_device()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            step_device()
+        f1.record()
+        torch.cuda.synchronize()
+        line["variants"] = {"fuse_lora": {"value": args.batch * args.steps / (f0.elapsed_time(f1) / 1000.0), "unit": UNIT,
+                                          "note": "adapter merged into the base weights (W + BA rounded to bf16); "
+                                                  "not comparable to the un-merged headline"}}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cb = cpu_sample_images_per_sec(args.px, args.nfe, threads)
@@ -343,6 +360,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--nfe", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", dest="variants", action="store_false",
+                    help="skip the extra (non-headline) fused-adapter measurement at N = 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

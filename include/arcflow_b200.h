@@ -384,6 +384,11 @@ int afb_engine_bind(afb_engine* e, const afb_weights* w);
 /* Runtime LoRA scale (joint_attention_kwargs['scale'] in the reference); 1.0 by default. The packed
  * [W | B] weights assume scale 1; other values are applied by scaling the A-projection output. */
 int afb_engine_set_lora_scale(afb_engine* e, float scale);
+/* Skip every LoRA branch at run time (the A-projection launches and the K-extension columns of the packed [W | B]
+ * weights are not read). Used after the adapter has been merged into the base weights, W <- W + scale * B A — diffusers'
+ * `fuse_lora()`; SURVEY.md §8f rank 4 — which the host does with afb_gemm (transposed-W mode, residual epilogue, in place
+ * on the packed buffers). Inference only: the training entry points need the separate branch. */
+int afb_engine_set_ignore_lora(afb_engine* e, int32_t on);
 /* Bytes of workspace the engine needs for (batch, txt_len, img_len); afb_engine_reserve allocates it. */
 size_t afb_engine_workspace_bytes(const afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);
 int afb_engine_reserve(afb_engine* e, int32_t batch, int32_t txt_len, int32_t img_len);

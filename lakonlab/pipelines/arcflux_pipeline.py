@@ -88,6 +88,13 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
     def num_timesteps(self):
         return self._num_timesteps
 
+    def fuse_lora(self, **_unused):
+        """diffusers' `pipe.fuse_lora()`: merge the ArcFlow adapter's low-rank branches into the base weights of
+        `pipe.transformer` (ArcFluxEngineModel.fuse_lora) — same images up to bf16 rounding of the merged weights, ~5 % less
+        work per step. Inference only, one-way."""
+        self.transformer.fuse_lora()
+        return self
+
     @property
     def interrupt(self):
         return self._interrupt

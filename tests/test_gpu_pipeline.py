@@ -152,3 +152,40 @@ def test_cuda_graph_replay_equals_eager_loop(setup):
     g4 = pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, num_inference_steps=4, **kw).images
     assert torch.equal(g1, eager) and torch.equal(g2, eager2) and torch.equal(g4, eager4)
     assert len(pipe.transformer._graphs) == 2
+
+
+def test_fuse_lora_equals_an_engine_built_from_merged_weights(lib):
+    """`fuse_lora()` (W <- W + B A on the GEMM kernel, LoRA branches switched off) against a fresh engine whose state dict
+    was merged on the host and carries no adapter branches; and against the un-merged path (bf16-level difference only)."""
+    import dataclasses
+    from arcflow_b200 import AfbError
+    from arcflow_b200.config import flux_tiny
+    from arcflow_b200.model import ArcFluxEngineModel
+    from arcflow_b200.synthetic import make_flux_inputs, make_flux_state_dict
+    cfg = flux_tiny(2, 2, 2)
+    sd = make_flux_state_dict(cfg, seed=1234, device="cpu")
+    x, txt, pooled = make_flux_inputs(cfg, 2, 64, 64, txt_len=64, seed=42)
+    args = (x.cuda(), txt.cuda(), pooled.cuda(), (4, 4))
+    model = ArcFluxEngineModel(sd, cfg, device="cuda")
+    unfused = model.denoise(args[0].clone(), *args[1:], num_inference_steps=2)
+    model.fuse_lora()
+    fused = model.denoise(args[0].clone(), *args[1:], num_inference_steps=2)
+    merged = {}
+    for k, v in sd.items():
+        if "lora" in k:
+            continue
+        pre = k[:-len(".weight")]
+        if k.endswith(".weight") and pre + ".lora_A.weight" in sd:
+            v = (v.float() + sd[pre + ".lora_B.weight"].float() @ sd[pre + ".lora_A.weight"].float()).bfloat16()
+        merged[k] = v
+    plain = ArcFluxEngineModel(merged, dataclasses.replace(cfg, lora_rank=0), device="cuda")
+    want = plain.denoise(args[0].clone(), *args[1:], num_inference_steps=2)
+
+    def rel(a, b):
+        return ((a - b).norm() / b.norm()).item()
+    assert rel(fused, want) < 2e-3, rel(fused, want)          # same merged bf16 weights up to fp32 summation order
+    assert 0 < rel(fused, unfused) < 2e-2, rel(fused, unfused)  # one extra bf16 rounding of the merged weights
+    with pytest.raises(AfbError):
+        model.set_lora_scale(0.5)
+    with pytest.raises(AfbError):
+        model.forward_heads(*args[:3], 0.7, 3.5, (4, 4), train=True)
