@@ -325,9 +325,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float2 nm2 = make_float2(-m * c, -m * c);
       float2 lsum = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
+      for (int qt = 0; qt < 4; ++qt) {  // quarters of 32 columns
 #pragma unroll
-        for (int i = hf * (KT / 2); i < (hf + 1) * (KT / 2); i += 2) {
+        for (int i = qt * (KT / 4); i < (qt + 1) * (KT / 4); i += 2) {
           float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
           float2 pv;
           if (((i >> 1) & 3) == 3) {
@@ -339,10 +339,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           lsum = __fadd2_rn(lsum, pv);
           s[i >> 1] = pack_bf16x2(pv.x, pv.y);
         }
-        if (hf == 0) {  // publish columns [0, 64) of P: 32 TMEM columns
+        if (qt == 1) {  // columns [0, 64) of P are complete: start their store (32 TMEM columns) ...
 #pragma unroll
           for (int i = 0; i < KT / 64; ++i)
             tmem_st_32x16(tS + i * 16, reinterpret_cast<const uint32_t(&)[16]>(s[i * 16]));
+        }
+        if (qt == 2) {  // ... and publish them one quarter later, when the store has drained behind the exponentials
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
