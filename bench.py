@@ -149,6 +149,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.model != "flux":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is implemented for the FLUX headline only"}),
+              flush=True)
+        return 0
     import torch
     threads = os.cpu_count() or 1
     for _ in range(args.warmup if args.warmup < 1 else 1):
@@ -171,7 +175,25 @@ def run_reference(args):
     return 0
 
 
+def qwen_flops_per_image_nfe(S_img: int, S_txt: int = 512, r: int = 256) -> dict:
+    """Algorithmic FLOPs of one ArcFlow-Qwen-Image forward: 60 double-stream blocks, LoRA on the MLPs
+    (text MLP of the last block excluded), heads and embedders."""
+    D, M, S = 3072, 12288, S_img + S_txt
+    linear = 60 * 2 * S * (4 * D * D + 2 * D * M)
+    attn = 60 * 4 * S * S * D
+    lora = 60 * S_img * 4 * r * (D + M) + 59 * S_txt * 4 * r * (D + M)
+    return {"total": linear + attn + lora + 2 * S_img * D * 1148 + 2 * S_img * 64 * D + 2 * S_txt * 3584 * D}
+
+
 def _config(args, world):
+    if getattr(args, "model", "flux") == "qwen":
+        return {"workload": f"ArcFlow-Qwen-Image {args.nfe}-NFE {args.px}x{args.px} batch {args.batch}/GPU, cached "
+                            f"Qwen2.5-VL embeds (BASELINE.json configs[2])",
+                "global_batch": args.batch * world, "txt_len": 512, "img_tokens": (args.px // 16) ** 2,
+                "nfe": args.nfe, "shift": 3.2, "timestep_ratio": 1.0,
+                "parallelism": f"batch-parallel dp{world}, weights replicated, all-gather of final latents",
+                "weights": "synthetic Qwen-Image shapes (60 blocks, D=3072) + rank-256 ArcFlow adapter, un-merged",
+                "l2": "working set (41 GB weights + activations) >> 126 MB L2; no explicit flush"}
     return {"workload": f"ArcFlow-FLUX {args.nfe}-NFE {args.px}x{args.px} batch {args.batch}/GPU, cached T5/CLIP embeds "
                         f"(BASELINE.json configs[1])",
             "global_batch": args.batch * world, "txt_len": 512, "img_tokens": (args.px // 16) ** 2,
@@ -206,18 +228,36 @@ def run_ours(args):
     build.build()
     lib = _lib.load()
 
-    cfg = flux_dev()
-    sd = make_flux_state_dict(cfg, seed=1234, device=dev)
-    model = ArcFluxEngineModel(sd, cfg, device=dev, consume_state_dict=True)
-    del sd
-    torch.cuda.empty_cache()
-    pipe = ArcFluxPipeline(transformer=model)
+    qwen = args.model == "qwen"
     grid = (args.px // 16, args.px // 16)
-    x, txt, pooled = make_flux_inputs(cfg, args.batch, args.px, args.px, seed=42 + rank, device=dev)
+    if qwen:   # BASELINE.json configs[2]; the headline (and the default) is FLUX
+        from arcflow_b200.qwen import ArcQwenEngineModel, make_qwen_inputs, make_qwen_state_dict, qwen_image
+        from lakonlab.pipelines.arcqwen_pipeline import ArcQwenImagePipeline
+        cfg = qwen_image()
+        sd = make_qwen_state_dict(cfg, seed=1234, device=dev)
+        model = ArcQwenEngineModel(sd, cfg, device=dev, consume_state_dict=True)
+        del sd
+        torch.cuda.empty_cache()
+        pipe = ArcQwenImagePipeline(transformer=model)
+        x, txt = make_qwen_inputs(cfg, args.batch, args.px, args.px, 512, 42 + rank, dev)
+        pooled = None
+    else:
+        cfg = flux_dev()
+        sd = make_flux_state_dict(cfg, seed=1234, device=dev)
+        model = ArcFluxEngineModel(sd, cfg, device=dev, consume_state_dict=True)
+        del sd
+        torch.cuda.empty_cache()
+        pipe = ArcFluxPipeline(transformer=model)
+        x, txt, pooled = make_flux_inputs(cfg, args.batch, args.px, args.px, seed=42 + rank, device=dev)
     gathered = torch.empty(world * args.batch, *x.shape[1:], device=dev) if world > 1 else None
 
+    def denoise_once():
+        if qwen:
+            return model.denoise(x, txt, grid, num_inference_steps=args.nfe)
+        return model.denoise(x, txt, pooled, grid, num_inference_steps=args.nfe)
+
     def step_device():
-        out = model.denoise(x, txt, pooled, grid, num_inference_steps=args.nfe)
+        out = denoise_once()
         if world > 1:   # sampler-boundary exchange: final packed latents of every rank
             dist.all_gather_into_tensor(gathered, out)
         return out
@@ -251,12 +291,18 @@ def run_ours(args):
     value = images / (ms_total / 1000.0)
 
     # ---- e2e: the public pipeline call with pinned HOST buffers, copies inside the timed region ----
-    hx, htxt, hpooled = [t_.cpu().pin_memory() for t_ in (x, txt, pooled)]
+    host_in = [t_.cpu().pin_memory() for t_ in (x, txt, pooled) if t_ is not None]
+    hx, htxt = host_in[0], host_in[1]
+    hpooled = host_in[2] if len(host_in) > 2 else None
     hout = torch.empty_like(hx).pin_memory()
 
     def step_e2e():
-        r = pipe(prompt_embeds=htxt, pooled_prompt_embeds=hpooled, latents=hx, height=args.px, width=args.px,
-                 num_inference_steps=args.nfe, timestep_ratio=1.0, guidance_scale=3.5, output_type="latent")
+        if qwen:
+            r = pipe(prompt_embeds=htxt, latents=hx, height=args.px, width=args.px, num_inference_steps=args.nfe,
+                     timestep_ratio=1.0, output_type="latent")
+        else:
+            r = pipe(prompt_embeds=htxt, pooled_prompt_embeds=hpooled, latents=hx, height=args.px, width=args.px,
+                     num_inference_steps=args.nfe, timestep_ratio=1.0, guidance_scale=3.5, output_type="latent")
         hout.copy_(r.images, non_blocking=True)
         if world > 1:
             dist.all_gather_into_tensor(gathered, r.images)
@@ -273,13 +319,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = images / (float(t.item()) / 1000.0)
     clock_info = clocks.stop() if rank == 0 else {}
-    h2d = sum(t_.numel() * t_.element_size() for t_ in (hx, htxt, hpooled))
+    h2d = sum(t_.numel() * t_.element_size() for t_ in host_in)
     d2h = hout.numel() * hout.element_size()
 
     # ---- roofline of the dominant kernel: one extra instrumented step (events around every launch) ----
     model.set_profiling(True)
     model.read_profile()
-    model.denoise(x, txt, pooled, grid, num_inference_steps=args.nfe)
+    denoise_once()
     prof = model.read_profile()
     model.set_profiling(False)
 
@@ -289,7 +335,7 @@ def run_ours(args):
         return 0
     peaks = _peaks()
     traffic = _ncu_traffic()
-    fl = flux_flops_per_image_nfe(grid[0] * grid[1], 512, cfg.lora_rank)
+    fl = (qwen_flops_per_image_nfe if qwen else flux_flops_per_image_nfe)(grid[0] * grid[1], 512, cfg.lora_rank)
     step_flops = fl["total"] * args.nfe * args.batch
     gemm_tf = prof["gemm_flops"] / (prof["gemm_ms"] * 1e9) if prof["gemm_ms"] > 0 else 0.0
     attn_tf = prof["attn_flops"] / (prof["attn_ms"] * 1e9) if prof["attn_ms"] > 0 else 0.0
@@ -339,7 +385,7 @@ def run_ours(args):
         line["variants"] = {"fuse_lora": {"value": args.batch * args.steps / (f0.elapsed_time(f1) / 1000.0), "unit": UNIT,
                                           "note": "adapter merged into the base weights (W + BA rounded to bf16); "
                                                   "not comparable to the un-merged headline"}}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not qwen:
         threads = os.cpu_count() or 1
         cb = cpu_sample_images_per_sec(args.px, args.nfe, threads)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": threads, "kind": "port",
@@ -356,6 +402,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="flux", choices=["flux", "qwen"],
+                    help="flux = the headline (BASELINE.json configs[1]); qwen = configs[2] (ArcFlow-Qwen-Image, batch-sharded)")
     ap.add_argument("--px", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--nfe", type=int, default=2)

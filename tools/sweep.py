@@ -7,15 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from bench import flux_flops_per_image_nfe, _peaks  # noqa: E402
-
-
-def qwen_flops_per_image_nfe(S_img, S_txt, r=256):
-    D, M, S = 3072, 12288, S_img + S_txt
-    linear = 60 * 2 * S * (4 * D * D + 2 * D * M)
-    attn = 60 * 4 * S * S * D
-    lora = 60 * S_img * 4 * r * (D + M) + 59 * S_txt * 4 * r * (D + M)
-    return linear + attn + lora + 2 * S_img * D * 1148 + 2 * S_img * 64 * D + 2 * S_txt * 3584 * D
+from bench import flux_flops_per_image_nfe, qwen_flops_per_image_nfe, _peaks  # noqa: E402
 
 
 def run(model_name, px, nfe, batch, txt_len, steps, warmup):
@@ -47,7 +39,7 @@ def run(model_name, px, nfe, batch, txt_len, steps, warmup):
         m = CACHE[key]
         x, txt = make_qwen_inputs(cfg, batch, px, px, txt_len, 42, dev)
         fn = lambda: m.denoise(x, txt, grid, num_inference_steps=nfe)
-        flops = qwen_flops_per_image_nfe(grid[0] * grid[1], txt_len)
+        flops = qwen_flops_per_image_nfe(grid[0] * grid[1], txt_len)["total"]
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
