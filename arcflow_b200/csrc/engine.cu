@@ -514,8 +514,8 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   const View y_img{e->y + int64_t(St) * D, D, int64_t(S) * D};
   const View qkv_txt{e->qkv, 3 * D, int64_t(S) * 3 * D};
   const View qkv_img{e->qkv + int64_t(St) * 3 * D, 3 * D, int64_t(S) * 3 * D};
-  const View at_txt{e->attn, D, int64_t(S) * D};
-  const View at_img{e->attn + int64_t(St) * D, D, int64_t(S) * D};
+  View at_txt{e->attn, D, int64_t(S) * D};
+  View at_img{e->attn + int64_t(St) * D, D, int64_t(S) * D};
   const View mlp_txt{e->mlp, M, int64_t(S) * M};
   const View mlp_img{e->mlp + int64_t(St) * M, M, int64_t(S) * M};
   const int rr = r > 0 ? r : 8;
@@ -550,9 +550,28 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   at.heads = H;
   at.scale = 0.f;
 
-  const View u1_txt{e->u1, D, int64_t(S) * D}, u1_img{e->u1 + int64_t(St) * D, D, int64_t(S) * D};
-  const View u2_txt{e->u2, D, int64_t(S) * D}, u2_img{e->u2 + int64_t(St) * D, D, int64_t(S) * D};
-  const View pre_txt{e->mlp_pre, M, int64_t(S) * M}, pre_img{e->mlp_pre + int64_t(St) * M, M, int64_t(S) * M};
+  View u1_txt{}, u1_img{}, u2_txt{}, u2_img{}, pre_txt{}, pre_img{}, at_all{};
+  // With the activation stash the GEMMs and the attention kernel write a block's kept outputs straight into its stash
+  // slice: the engine's buffer pointers are re-pointed per block and the views rebuilt (every entry point re-carves).
+  bf16 *const ws_attn = e->attn, *const ws_pre = e->mlp_pre, *const ws_u1 = e->u1, *const ws_u2 = e->u2;
+  auto retarget = [&](const StashSlot* sl) {
+    e->attn = sl ? sl->attn : ws_attn;
+    e->mlp_pre = sl ? sl->pre : ws_pre;
+    e->u1 = sl ? sl->u1 : ws_u1;
+    e->u2 = sl && sl->u2 ? sl->u2 : ws_u2;
+    at_txt = View{e->attn, D, int64_t(S) * D};
+    at_img = View{e->attn + int64_t(St) * D, D, int64_t(S) * D};
+    at_all = at_txt;
+    at.o = e->attn;
+    if (!e->u1) return;  // inference-only engine: no training workspace, the views below are never used
+    u1_txt = View{e->u1, D, int64_t(S) * D};
+    u1_img = View{e->u1 + int64_t(St) * D, D, int64_t(S) * D};
+    u2_txt = View{e->u2, D, int64_t(S) * D};
+    u2_img = View{e->u2 + int64_t(St) * D, D, int64_t(S) * D};
+    pre_txt = View{e->mlp_pre, M, int64_t(S) * M};
+    pre_img = View{e->mlp_pre + int64_t(St) * M, M, int64_t(S) * M};
+  };
+  retarget(nullptr);
   const size_t ckpt_elems = size_t(B) * S * D;
   auto save = [&](int idx) -> int {
     if (!save_ckpt) return AFB_OK;
@@ -577,6 +596,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     StashSlot sl{};
     if (stash) {
       sl = stash_slot(e, i, B, St, Si);
+      retarget(&sl);
       AFB_TRY(copy_bf16(sl.qkv_raw, e->qkv, tok * 3 * D, s));
       at.lse = sl.lse;
     }
@@ -585,7 +605,6 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     AFB_TRY(run_attention(e, &at, s));
     const bool last_qwen_txt = !flux && i == d.num_double - 1;  // its text stream output is never read
     if (stash) {  // un-fused: the un-gated branch output and the mid-block residual stream are kept
-      AFB_TRY(copy_bf16(sl.attn, e->attn, tok * D, s));
       AFB_TRY(Gemm(B, Si).a(at_img, D).w(k.img_out_w, D, D, k.img_out_b).out(u1_img, AFB_EPI_BIAS).run(e, s));
       AFB_TRY(afb::gate_res_launch(h_img.p, h_img.bs, u1_img.p, u1_img.bs, im + 2 * D, mod_bs, const_cast<bf16*>(h_img.p),
                                    h_img.bs, B, Si, D, s));
@@ -594,7 +613,6 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
         AFB_TRY(afb::gate_res_launch(h_txt.p, h_txt.bs, u1_txt.p, u1_txt.bs, tm + 2 * D, mod_bs, const_cast<bf16*>(h_txt.p),
                                      h_txt.bs, B, St, D, s));
       }
-      AFB_TRY(copy_bf16(sl.u1, e->u1, tok * D, s));
       AFB_TRY(copy_bf16(sl.h_mid, e->h, tok * D, s));
     } else {
       AFB_TRY(Gemm(B, Si).a(at_img, D).w(k.img_out_w, D, D, k.img_out_b)
@@ -616,17 +634,12 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
                          k.txt_down_la, tm + 5 * D, s, drop, 4u * i + 2, stash ? &pre_txt : nullptr,
                          stash ? &u2_txt : nullptr));
     }
-    if (stash) {
-      AFB_TRY(copy_bf16(sl.pre, e->mlp_pre, tok * M, s));
-      AFB_TRY(copy_bf16(sl.u2, e->u2, tok * D, s));
-    }
   }
 
   // ---- single-stream blocks (FLUX) on the joint buffer -----------------------------------------
   const View h_all{e->h, D, int64_t(S) * D};
   const View y_all{e->y, D, int64_t(S) * D};
   const View qkv_all{e->qkv, 3 * D, int64_t(S) * 3 * D};
-  const View at_all{e->attn, D, int64_t(S) * D};
   const View mlp_all{e->mlp, M, int64_t(S) * M};
   const View l0_all{e->lt0, rr, int64_t(S) * rr};
   const View l1_all{e->lt1, rr, int64_t(S) * rr};
@@ -640,13 +653,13 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     StashSlot sl{};
     if (stash) {
       sl = stash_slot(e, d.num_double + i, B, St, Si);
+      retarget(&sl);
       AFB_TRY(copy_bf16(sl.qkv_raw, e->qkv, tok * 3 * D, s));
       at.lse = sl.lse;
     }
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, 0, nullptr, nullptr,
                                      k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     AFB_TRY(run_attention(e, &at, s));
-    if (stash) AFB_TRY(copy_bf16(sl.attn, e->attn, tok * D, s));
     const View up_out = stash ? View{e->mlp_pre, M, int64_t(S) * M} : mlp_all;
     const int up_epi = stash ? AFB_EPI_BIAS : AFB_EPI_BIAS_GELU;
     const View proj_out_v = stash ? View{e->u1, D, int64_t(S) * D} : h_all;
@@ -664,10 +677,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     } else {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.mlp_w, mlp_ld, M, k.mlp_b).out(up_out, up_epi).run(e, s));
     }
-    if (stash) {
-      AFB_TRY(afb::gelu_fwd_launch(e->mlp_pre, M, e->mlp, M, int64_t(B) * S, M, s));
-      AFB_TRY(copy_bf16(sl.pre, e->mlp_pre, tok * M, s));
-    }
+    if (stash) AFB_TRY(afb::gelu_fwd_launch(e->mlp_pre, M, e->mlp, M, int64_t(B) * S, M, s));
     if (r > 0 && k.out_la) {
       if (drop) {
         AFB_TRY(drop_into(e, at_all, B, S, D, D + M, 0, layer + 1, s));
@@ -682,11 +692,11 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
       AFB_TRY(Gemm(B, S).a(at_all, D).a(mlp_all, M).w(k.out_w, out_ld, D, k.out_b)
                   .out(proj_out_v, proj_epi).gate_res(m + 2 * D, mod_bs, h_all).run(e, s));
     }
-    if (stash) {
-      AFB_TRY(copy_bf16(sl.u1, e->u1, tok * D, s));
+    if (stash)
       AFB_TRY(afb::gate_res_launch(e->h, int64_t(S) * D, e->u1, int64_t(S) * D, m + 2 * D, mod_bs, e->h, int64_t(S) * D, B, S, D, s));
-    }
   }
+  retarget(nullptr);
+  at.lse = nullptr;
 
   AFB_TRY(save(d.num_double + d.num_single));
   if (save_ckpt) e->stash_valid = stash;
@@ -846,17 +856,35 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
                                         bsD, nm, mod_bs, B, Si, D, LN_EPS, 0, s));
   }
 
-  const View y_all{e->y, D, bsD}, at_all{e->attn, D, bsD}, mlp_all{e->mlp, M, bsM}, pre_all{e->mlp_pre, M, bsM};
-  const View raw_all{e->qkv_raw, 3 * D, bs3}, l0_all{e->lt0, rr, bsR}, l1_all{e->lt1, rr, bsR}, dl_all{e->dl, rr, bsR};
+  const View y_all{e->y, D, bsD}, mlp_all{e->mlp, M, bsM};
+  View at_all{e->attn, D, bsD}, pre_all{e->mlp_pre, M, bsM}, raw_all{e->qkv_raw, 3 * D, bs3};
+  const View l0_all{e->lt0, rr, bsR}, l1_all{e->lt1, rr, bsR}, dl_all{e->dl, rr, bsR};
   const View dh_all{e->dh, D, bsD}, du_all{e->du, D, bsD}, dy_all{e->dy, D, bsD}, dat_all{e->dattn, D, bsD};
-  const View dmlp_all{e->dmlp, M, bsM}, dqkv_all{e->dqkv, 3 * D, bs3}, u1_all{e->u1, D, bsD};
+  const View dmlp_all{e->dmlp, M, bsM}, dqkv_all{e->dqkv, 3 * D, bs3};
+  View u1_all{e->u1, D, bsD};
   const bool drop = e->drop_p > 0.f && r > 0;
   LoraBwd lb{e, B, S, s, drop};
   float* dmod = ba->d_mod;  // fp32 [B, mod_total] or NULL
   // With the activation stash the block outputs of the train forward are copied back instead of being recomputed: no
   // QKV / MLP-up / branch-output GEMMs and no attention forward in the backward.
   const bool stash = e->stash_on && e->stash != nullptr && e->stash_valid;
-  const size_t tok = size_t(B) * S;
+  // the kept outputs are read in place: the engine's buffer pointers are re-pointed at the block's stash slice
+  bf16 *const ws_raw = e->qkv_raw, *const ws_attn = e->attn, *const ws_pre = e->mlp_pre, *const ws_u1 = e->u1,
+             *const ws_u2 = e->u2, *const ws_hmid = e->h_mid;
+  auto retarget = [&](const StashSlot* sl) {
+    e->qkv_raw = sl ? sl->qkv_raw : ws_raw;
+    e->attn = sl ? sl->attn : ws_attn;
+    e->mlp_pre = sl ? sl->pre : ws_pre;
+    e->u1 = sl ? sl->u1 : ws_u1;
+    e->u2 = sl && sl->u2 ? sl->u2 : ws_u2;
+    e->h_mid = sl && sl->h_mid ? sl->h_mid : ws_hmid;
+    at_all = View{e->attn, D, bsD};
+    pre_all = View{e->mlp_pre, M, bsM};
+    raw_all = View{e->qkv_raw, 3 * D, bs3};
+    u1_all = View{e->u1, D, bsD};
+    ab.o = e->attn;
+    ab.lse = sl ? sl->lse : e->lse;
+  };
 
   // ---- single-stream blocks, last to first ----------------------------------------------------------------------
   for (int i = d.num_single - 1; i >= 0; --i) {
@@ -872,11 +900,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_TRY(afb::ln_modulate_launch(h_in, bsD, e->y, bsD, m + D, m, mod_bs, B, S, D, LN_EPS, s));
     if (stash) {
       const StashSlot sl = stash_slot(e, d.num_double + i, B, St, Si);
-      AFB_TRY(copy_bf16(e->qkv_raw, sl.qkv_raw, tok * 3 * D, s));
-      AFB_TRY(copy_bf16(e->attn, sl.attn, tok * D, s));
-      AFB_TRY(copy_bf16(e->mlp_pre, sl.pre, tok * M, s));
-      AFB_TRY(copy_bf16(e->u1, sl.u1, tok * D, s));
-      ab.lse = sl.lse;
+      retarget(&sl);
     } else {
       AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(raw_all, AFB_EPI_BIAS).run(e, s));
     }
@@ -986,21 +1010,16 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
       }
       return t;
     };
+    StashSlot dsl{};
+    if (stash) {
+      dsl = stash_slot(e, i, B, St, Si);
+      retarget(&dsl);
+    }
     Stream st2[2] = {mk(true), mk(false)};
     // Qwen: the last block's text-stream output is never read (forward_impl skips its out-projection and MLP), so that
     // stream only contributes through its K / V rows: its dattn is zero and its MLP half has no gradient.
     const bool skip_txt_tail = d.arch != AFB_ARCH_FLUX && i == d.num_double - 1;
     // -- recompute (or restore from the stash): attention half
-    if (stash) {
-      const StashSlot sl = stash_slot(e, i, B, St, Si);
-      AFB_TRY(copy_bf16(e->qkv_raw, sl.qkv_raw, tok * 3 * D, s));
-      AFB_TRY(copy_bf16(e->attn, sl.attn, tok * D, s));
-      AFB_TRY(copy_bf16(e->mlp_pre, sl.pre, tok * M, s));
-      AFB_TRY(copy_bf16(e->u1, sl.u1, tok * D, s));
-      AFB_TRY(copy_bf16(e->u2, sl.u2, tok * D, s));
-      AFB_TRY(copy_bf16(e->h_mid, sl.h_mid, tok * D, s));
-      ab.lse = sl.lse;
-    }
     for (Stream& t : st2) {
       if (stash) break;
       AFB_TRY(afb::ln_modulate_launch(t.h_in.p, t.h_in.bs, const_cast<bf16*>(t.y.p), t.y.bs, t.mod + D, t.mod, mod_bs, B,
@@ -1106,6 +1125,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
                                           mod_bs, B, t.rows, D, LN_EPS, 1, s));
     }
   }
+  retarget(nullptr);
   return AFB_OK;
 }
 
