@@ -61,7 +61,8 @@ __device__ __forceinline__ void mma_ts_128(uint32_t d_tmem, uint32_t a_tmem, uin
 }
 
 // ------------------------------------------------------------------------------------------------
-// MODE 0: dQ kernel (outer = q tile, inner = kv tiles).  MODE 1: dK/dV kernel (outer = kv tile, inner = q tiles).
+// MODE 1: dK/dV kernel (outer = kv tile, inner = q tiles). MODE 0 is the un-pipelined dQ kernel, kept as the readable
+// statement of the algorithm; the launcher uses attention_bwd_dq_kernel below for dQ.
 // smem: R0, R1 resident tiles (Q,dO | K,V), ring of 2 x (X, Y) inner tiles (K,V | Q,dO).
 // TMEM: [0,128) S or S^T, [128,256) dP or dP^T, [256,384) dQ | dV, [384,512) dK.
 // ------------------------------------------------------------------------------------------------
@@ -276,6 +277,219 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dQ kernel, software-pipelined (supersedes attention_bwd_kernel<0>). The math leg of a tile (exp2, dS) is bound by
+// SM-wide MUFU / FMA throughput at ~1500 cycles and the three MMAs of a tile take 1536, so the only way to go faster is to
+// run them concurrently. TMEM has room for it here: S is double-buffered, S0 S1 dP dQ = 4 x 128 columns. The MMA warp
+// issues  S(j), dP(j), dQ += dS(j-1) K(j-1)  per iteration, so S(j) / dP(j) are computed while the math warps are still on
+// tile j-1 and dQ(j-1) runs under the exponentials of tile j. K tiles live until their dQ product has retired (3-stage
+// ring), V tiles only until dP (2-stage ring); Q and dO are resident.
+// ------------------------------------------------------------------------------------------------
+constexpr int DQ_K_STAGES = 3, DQ_V_STAGES = 2;
+constexpr size_t DQ_SMEM_BYTES = 1024 + size_t(2 + DQ_K_STAGES + DQ_V_STAGES) * TILE_BYTES + 256;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + TILE_BYTES;
+  uint8_t* sK = smem + 2 * TILE_BYTES;
+  uint8_t* sV = sK + DQ_K_STAGES * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + DQ_V_STAGES * TILE_BYTES);
+  uint64_t* r_full = bars;                       // Q, dO landed
+  uint64_t* k_full = r_full + 1;                 // [3]
+  uint64_t* k_empty = k_full + DQ_K_STAGES;      // [3]  dQ product of the tile retired
+  uint64_t* v_full = k_empty + DQ_K_STAGES;      // [2]
+  uint64_t* v_empty = v_full + DQ_V_STAGES;      // [2]  dP product of the tile retired
+  uint64_t* s_full = v_empty + DQ_V_STAGES;      // [2]  S(j) ready in buffer j & 1
+  uint64_t* dp_full = s_full + 2;                // dP(j) ready
+  uint64_t* dp_free = dp_full + 1;               // math warps hold dP(j) in registers
+  uint64_t* ds_full = dp_free + 1;               // [2]  dS(j) written over S(j)
+  uint64_t* acc_done = ds_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * T;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_inner = (p.seq + T - 1) / T;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmdO);
+    mbar_init(r_full, 1);
+    for (int s = 0; s < DQ_K_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < DQ_V_STAGES; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&ds_full[s], 4);
+    }
+    mbar_init(dp_full, 1);
+    mbar_init(dp_free, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t cS = 0, cdP = 256, cdQ = 384;  // TMEM columns: S buffers at 0 / 128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(r_full, 2 * TILE_BYTES);
+      load_tile(sQ, &tmQ, r_full, h, r0, b);
+      load_tile(sdO, &tmdO, r_full, h, r0, b);
+      for (int j = 0; j < n_inner; ++j) {
+        const int ks = j % DQ_K_STAGES, vs = j % DQ_V_STAGES;
+        mbar_wait(&k_empty[ks], ((j / DQ_K_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&k_full[ks], TILE_BYTES);
+        load_tile(sK + ks * TILE_BYTES, &tmK, &k_full[ks], h, j * T, b);
+        mbar_wait(&v_empty[vs], ((j / DQ_V_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&v_full[vs], TILE_BYTES);
+        load_tile(sV + vs * TILE_BYTES, &tmV, &v_full[vs], h, j * T, b);
+      }
+    }
+  } else if (warp == 1) {
+    const uint64_t q_k = make_sw128_desc(smem_u32(sQ), 16, 1024);
+    const uint64_t do_k = make_sw128_desc(smem_u32(sdO), 16, 1024);
+    const uint64_t k_k = make_sw128_desc(smem_u32(sK), 16, 1024);
+    const uint64_t v_k = make_sw128_desc(smem_u32(sV), 16, 1024);
+    const uint64_t k_mn = make_sw128_desc(smem_u32(sK), HALF_BYTES, 1024);
+    mbar_wait(r_full, 0);
+    for (int j = 0; j <= n_inner; ++j) {
+      if (j < n_inner) {
+        const int ks = j % DQ_K_STAGES, vs = j % DQ_V_STAGES;
+        mbar_wait(&k_full[ks], (j / DQ_K_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          mma_ss_128(tmem_base + cS + (j & 1) * 128, q_k, k_k + uint64_t((ks * TILE_BYTES) >> 4));   // S(j) = Q K_j^T
+          tc_commit(&s_full[j & 1]);
+        }
+        __syncwarp();
+        mbar_wait(&v_full[vs], (j / DQ_V_STAGES) & 1);
+        if (j > 0) mbar_wait(dp_free, (j - 1) & 1);  // dP(j-1) has left TMEM
+        tc_fence_after();
+        if (elect_one_sync()) {
+          mma_ss_128(tmem_base + cdP, do_k, v_k + uint64_t((vs * TILE_BYTES) >> 4));                  // dP(j) = dO V_j^T
+          tc_commit(dp_full);
+          tc_commit(&v_empty[vs]);
+        }
+        __syncwarp();
+      }
+      if (j > 0) {
+        const int i = j - 1, ks = i % DQ_K_STAGES;
+        mbar_wait(&ds_full[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          mma_ts_128(tmem_base + cdQ, tmem_base + cS + (i & 1) * 128, k_mn + uint64_t((ks * TILE_BYTES) >> 4), i > 0);
+          tc_commit(&k_empty[ks]);                                                                     // dQ += dS(i) K_i
+          if (i == n_inner - 1) tc_commit(acc_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    const int grow = r0 + row;
+    const long long bh = ((long long)b * p.heads + h) * p.seq;
+    const bool valid_row = grow < p.seq;
+    const float my_lse = valid_row ? p.lse[bh + grow] : 0.f;
+    const float my_delta = valid_row ? p.delta[bh + grow] : 0.f;
+    const float2 c2 = make_float2(p.scale_log2, p.scale_log2), nl = make_float2(-my_lse, -my_lse);
+    for (int j = 0; j < n_inner; ++j) {
+      const uint32_t tS = tmem_base + lane_base + cS + (j & 1) * 128;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[T];
+#pragma unroll
+      for (int i = 0; i < T / 32; ++i) tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
+      tmem_ld_wait();
+      const int valid = p.seq - j * T;
+      uint32_t pk[T / 2];
+#pragma unroll
+      for (int i = 0; i < T; i += 2) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nl);
+        float2 pv;
+        pv.x = fast_exp2(x.x);
+        pv.y = fast_exp2(x.y);
+        if (i >= valid || !valid_row) pv.x = 0.f;
+        if (i + 1 >= valid || !valid_row) pv.y = 0.f;
+        pk[i >> 1] = pack_bf16x2(pv.x, pv.y);
+      }
+      // dP(j): pull it into registers in one go and hand the TMEM columns back (the MMA warp is waiting to issue dP(j+1))
+      mbar_wait(dp_full, j & 1);
+      tc_fence_after();
+      uint32_t d[T];
+#pragma unroll
+      for (int i = 0; i < T / 32; ++i)
+        tmem_ld_32x32(tmem_base + lane_base + cdP + i * 32, reinterpret_cast<uint32_t(&)[32]>(d[i * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dp_free);
+      // dS = scale * P * (dP - delta), written as packed bf16 over S(j)
+#pragma unroll
+      for (int cidx = 0; cidx < T / 32; ++cidx) {
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int col = cidx * 32 + i;
+          const uint32_t pv = pk[col >> 1];
+          o[i >> 1] = pack_bf16x2(p.scale * bf16_lo(pv) * (__uint_as_float(d[col]) - my_delta),
+                                  p.scale * bf16_hi(pv) * (__uint_as_float(d[col + 1]) - my_delta));
+        }
+        tmem_st_32x16(tS + cidx * 16, o);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[j & 1]);
+    }
+    // epilogue: dQ -> bf16 -> global
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = p.out0 + (long long)b * p.out_bs + (long long)grow * p.out_ld + h * HD;
+    const uint32_t tA = tmem_base + lane_base + cdQ;
+#pragma unroll 1
+    for (int i = 0; i < HD / 32; ++i) {
+      uint32_t o[32];
+      tmem_ld_32x32(tA + i * 32, o);
+      tmem_ld_wait();
+      if (valid_row) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+          w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+          w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+          w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(orow + i * 32 + g * 8) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int make_view_map(CUtensorMap* tm, const void* ptr, int64_t ld, int64_t bs, int batch, int seq, int heads) {
   const uint64_t dims[3] = {uint64_t(heads) * HD, uint64_t(seq), uint64_t(batch)};
   const uint64_t bstride = batch > 1 ? uint64_t(bs) : uint64_t(seq) * uint64_t(ld);
@@ -316,14 +530,14 @@ int attention_backward_launch(const afb_attn_bwd_desc* d, cudaStream_t stream) {
   p.out_bs = d->dqkv_batch_stride;
   static bool attr_set = false;
   if (!attr_set) {
-    AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BWD_SMEM_BYTES)));
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DQ_SMEM_BYTES)));
     AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BWD_SMEM_BYTES)));
     attr_set = true;
   }
   dim3 grid((d->seq + T - 1) / T, d->heads, d->batch);
   p.out0 = static_cast<__nv_bfloat16*>(d->dq);
   p.out1 = nullptr;
-  attention_bwd_kernel<0><<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+  attention_bwd_dq_kernel<<<grid, BWD_THREADS, DQ_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
   AFB_CHECK_CUDA(cudaGetLastError());
   p.out0 = static_cast<__nv_bfloat16*>(d->dk);
   p.out1 = static_cast<__nv_bfloat16*>(d->dv);
