@@ -225,7 +225,12 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    build.build()
+    if rank == 0:       # one builder: concurrent ranks must not link the same .so
+        build.build()
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        build.build()   # no-op: the fingerprint matches what rank 0 just verified / built
     lib = _lib.load()
 
     qwen = args.model == "qwen"
