@@ -315,6 +315,7 @@ class EngineModelBase:
         (afb_engine_set_activation_stash). mode: True / False / "auto" = on when the device has room for it plus
         `headroom_bytes` (FLUX bs 4 at 1024 px: ~62 GB — fits a 180 GB B200 next to weights, checkpoints and optimizer)."""
         self._stash_mode = mode
+        self._stash_headroom = int(headroom_bytes)
         self._stash_shape = None      # decided per shape at the next train forward
 
     def _apply_stash(self):
