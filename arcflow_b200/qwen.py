@@ -330,7 +330,9 @@ class ArcQwenEngineModel(EngineModelBase):
 
     @torch.no_grad()
     def denoise(self, latents, txt, grid_hw: Sequence[int], num_inference_steps: int = 2, total_substeps: int = 128,
-                timestep_ratio: float = 1.0, shift: float = 3.2, eps: float = 1e-4) -> torch.Tensor:
+                timestep_ratio: float = 1.0, shift: float = 3.2, eps: float = 1e-4, cuda_graph: bool = False) -> torch.Tensor:
+        """The whole N-NFE loop in one C-ABI call (arcqwen_pipeline.py:399-463). cuda_graph=True captures the fixed kernel
+        sequence once per (shape, schedule) and replays it, as ArcFluxEngineModel.denoise does."""
         self._check(latents, txt, grid_hw)
         if latents.dtype != torch.float32:
             raise AfbError("denoise: latents must be fp32 packed tokens")
@@ -340,15 +342,37 @@ class ArcQwenEngineModel(EngineModelBase):
         sig = denoise_sigmas(num_inference_steps, total_substeps, timestep_ratio, shift)
         tin = [qwen_time_input(s) for s in sig[:-1]]
         cos, sin = self.rope(txt.shape[1], grid_hw[0], grid_hw[1])
-        x = latents.contiguous().clone()
-        d = _lib.DenoiseArgs()
-        d.fwd = self._fwd_args(txt, None, None, None, cos, sin, B, Si)
-        d.nfe = num_inference_steps
-        sig_arr, tin_arr = (C.c_float * len(sig))(*sig), (C.c_float * len(tin))(*tin)
-        d.sigmas, d.timesteps, d.x, d.eps = sig_arr, tin_arr, x.data_ptr(), eps
-        _lib.check(self.lib.afb_engine_denoise(self.handle, C.byref(d), torch.cuda.current_stream().cuda_stream),
-                   "afb_engine_denoise")
-        return x
+
+        def launch(x, txt_):
+            d = _lib.DenoiseArgs()
+            d.fwd = self._fwd_args(txt_, None, None, None, cos, sin, B, Si)
+            d.nfe = num_inference_steps
+            sig_arr, tin_arr = (C.c_float * len(sig))(*sig), (C.c_float * len(tin))(*tin)
+            d.sigmas, d.timesteps, d.x, d.eps = sig_arr, tin_arr, x.data_ptr(), eps
+            _lib.check(self.lib.afb_engine_denoise(self.handle, C.byref(d), torch.cuda.current_stream().cuda_stream),
+                       "afb_engine_denoise")
+
+        if not cuda_graph:
+            x = latents.contiguous().clone()
+            launch(x, txt)
+            return x
+        key = (B, txt.shape[1], Si, tuple(grid_hw), tuple(sig), tuple(tin), eps, self._reserved)
+        ent = self._graphs.get(key)
+        if ent is None:
+            st = dict(x=torch.empty_like(latents, memory_format=torch.contiguous_format), txt=torch.empty_like(txt))
+            st["x"].copy_(latents), st["txt"].copy_(txt)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture: one-time function attributes, lazy module load
+                launch(st["x"], st["txt"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                launch(st["x"], st["txt"])
+            ent = self._graphs[key] = dict(graph=graph, **st)
+        ent["x"].copy_(latents), ent["txt"].copy_(txt)
+        ent["graph"].replay()
+        return ent["x"].clone()
 
 
 def make_qwen_teacher_extras(cfg: ArcQwenConfig, seed: int = 4321, device="cpu", dtype=BF16) -> Dict[str, torch.Tensor]:

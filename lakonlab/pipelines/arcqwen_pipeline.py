@@ -37,6 +37,12 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
         self.vae_decode_fn = vae_decode_fn
         self._num_timesteps = 0
         self._interrupt = False
+        self.use_cuda_graph = False
+
+    def enable_cuda_graph(self, on: bool = True):
+        """Extension (not in the reference): replay the denoising loop as one captured CUDA graph per (shape, schedule)."""
+        self.use_cuda_graph = bool(on)
+        return self
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype=torch.bfloat16, device="cuda", **kwargs):
@@ -105,7 +111,8 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
         self._num_timesteps = retrieve_raw_timesteps(num_inference_steps, total_substeps, timestep_ratio)[2]
         if callback_on_step_end is None:
             latents = tr.denoise(latents, prompt_embeds, grid, num_inference_steps=num_inference_steps,
-                                 total_substeps=total_substeps, timestep_ratio=timestep_ratio, shift=self.scheduler_shift)
+                                 total_substeps=total_substeps, timestep_ratio=timestep_ratio, shift=self.scheduler_shift,
+                                 cuda_graph=self.use_cuda_graph)
         else:
             sig = denoise_sigmas(num_inference_steps, total_substeps, timestep_ratio, self.scheduler_shift)
             for i in range(num_inference_steps):

@@ -129,6 +129,19 @@ def test_qwen_pipeline_adapter_roundtrip(lib, tmp_path):
                timestep_ratio=1.0, output_type="latent").images
     ref = O.qwen_denoise(sd, cfg, x, txt[:, :30], (4, 4), num_inference_steps=2)
     assert rel(out, ref) < 2e-2
+    # captured loop = eager loop, bit for bit, also when replayed on new inputs of the same shape; fused adapter runs
+    pipe.enable_cuda_graph()
+    g1 = pipe(prompt_embeds=txt, prompt_embeds_mask=mask, latents=x, height=64, width=64, num_inference_steps=2,
+              timestep_ratio=1.0, output_type="latent").images
+    eager2 = pipe.enable_cuda_graph(False)(prompt_embeds=txt * 0.5, prompt_embeds_mask=mask, latents=x.flip(0), height=64,
+                                            width=64, num_inference_steps=2, timestep_ratio=1.0, output_type="latent").images
+    g2 = pipe.enable_cuda_graph()(prompt_embeds=txt * 0.5, prompt_embeds_mask=mask, latents=x.flip(0), height=64, width=64,
+                                  num_inference_steps=2, timestep_ratio=1.0, output_type="latent").images
+    assert torch.equal(g1, out) and torch.equal(g2, eager2)
+    fused = pipe.enable_cuda_graph(False).fuse_lora()(prompt_embeds=txt, prompt_embeds_mask=mask, latents=x, height=64,
+                                                      width=64, num_inference_steps=2, timestep_ratio=1.0,
+                                                      output_type="latent").images
+    assert 0 < rel(fused, out) < 2e-2
 
 
 def test_cuda_graph_replay_equals_eager_loop(setup):
