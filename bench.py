@@ -224,6 +224,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG=VERSION prints one) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:       # one builder: concurrent ranks must not link the same .so
         build.build()
