@@ -32,6 +32,29 @@ METRIC = "images_per_sec_1024px_2nfe"
 UNIT = "images/s"
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner through C
+    stdio). From here on file descriptor 1 points at stderr for everything — Python and C alike, including buffers flushed
+    at exit — and the result line is written to the original stdout by `_emit`."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def _ncu_traffic():
     """DRAM bytes per launch of the two tensor-core kernels from the committed `ncu --set full` capture (dram__bytes_read.sum
     + dram__bytes_write.sum; profiles/r01_ncu_traffic.json names the launches) — a profiler figure cannot be taken live."""
@@ -150,8 +173,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     if args.model != "flux":
-        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is implemented for the FLUX headline only"}),
-              flush=True)
+        _emit({"impl": "reference", "unavailable": "the CPU reference arm is implemented for the FLUX headline only"})
         return 0
     import torch
     threads = os.cpu_count() or 1
@@ -171,7 +193,7 @@ def run_reference(args):
         "note": "reference deps (diffusers/peft/mmcv) are not installable offline; this is the oracle port of its "
                 "torch path (oracle/arcflow_oracle.py) on the host cores",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -224,8 +246,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG=VERSION prints one) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:       # one builder: concurrent ranks must not link the same .so
         build.build()
@@ -397,7 +417,7 @@ def run_ours(args):
         cb = cpu_sample_images_per_sec(args.px, args.nfe, threads)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": cb["sample"]}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -418,6 +438,7 @@ def main():
     ap.add_argument("--no-variants", dest="variants", action="store_false",
                     help="skip the extra (non-headline) fused-adapter measurement at N = 1")
     args = ap.parse_args()
+    _claim_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     return run_reference(args) if args.impl == "reference" else run_ours(args)
