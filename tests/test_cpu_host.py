@@ -183,3 +183,24 @@ def test_qwen_packing_and_lora_targets():
     assert by_ptr[pk.dbl[2].txt_up_w].shape == (M, D) and not pk.dbl[2].txt_up_la
     assert pk.struct.mod_total == 3 * 12 * D + 2 * D
     assert qwen_time_input(0.7619047761) == pytest.approx(761.71875)      # bf16(sigma) * 1000, SURVEY App. D
+
+
+def test_bench_stdout_carries_only_the_result_line():
+    """bench.py's contract is ONE JSON line on stdout; library chatter (NCCL's version banner goes through C stdio) must land
+    on stderr even when it is flushed at exit."""
+    import subprocess
+    import sys as _sys
+    import textwrap
+    code = textwrap.dedent('''
+        import ctypes, sys
+        sys.argv = ["bench.py"]
+        import bench
+        bench._claim_stdout()
+        ctypes.CDLL(None).puts(b"NCCL version 0.0.0 (C stdio)")
+        print("python-level chatter")
+        bench._emit({"metric": "m", "value": 1.0})
+    ''')
+    r = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"metric": "m", "value": 1.0}\n'
+    assert "NCCL version 0.0.0" in r.stderr and "python-level chatter" in r.stderr

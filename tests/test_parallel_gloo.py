@@ -90,3 +90,94 @@ def test_gradient_arena_all_reduce_is_a_mean_world2():
         assert p.exitcode == 0
     for _, g in res:
         assert g == [1.5] * 10
+
+
+# ------------------------------------------------------------------------------------------------
+# lakonlab.apis.train_model under world_size 2 (gloo): rank-disjoint data shards, all ranks step together, only rank 0
+# writes checkpoints — the host protocol of `torchrun ... train.py --launcher pytorch` with the engine replaced by a stub.
+# ------------------------------------------------------------------------------------------------
+class _StubOpt:
+    def __init__(self):
+        self.v = torch.zeros(2)
+
+    def state_dict(self):
+        return dict(v=self.v.clone())
+
+    def load_state_dict(self, sd):
+        self.v.copy_(sd["v"])
+
+
+class _StubModel:
+    """train_step all-reduces a 'gradient' like FlatAdamW.all_reduce_grads does, so ranks must stay in lock-step."""
+
+    def __init__(self):
+        self.opt = _StubOpt()
+        self.generator = torch.Generator().manual_seed(0)
+        self.seen = []
+        self.trainer = type("T", (), {"iteration": 0, "write_back": lambda s: None, "opt": self.opt})()
+
+    def build_trainer(self, optimizer_cfg, lr_config=None, ema_cfg=None):
+        self.ema_cfg = ema_cfg
+        return {"diffusion": self.opt}
+
+    def train_step(self, data, optimizer, running_status=None):
+        ids = data["prompt_embed_kwargs"]["encoder_hidden_states"][:, 0, 0]
+        self.seen += [float(v) for v in ids]
+        g = ids.sum().reshape(1).clone()
+        dist.all_reduce(g)
+        optimizer["diffusion"].v += g / dist.get_world_size()
+        return dict(log_vars=dict(loss=float(g)), num_samples=len(ids))
+
+    def state_dict(self, trainable_only=True):
+        return {"diffusion.denoising.w": self.opt.v.clone()}
+
+
+class _IdDataset(torch.utils.data.Dataset):
+    def __len__(self):
+        return 16
+
+    def __getitem__(self, i):
+        return dict(prompt_embed_kwargs=dict(encoder_hidden_states=torch.full((2, 2), float(i))), latents=torch.zeros(16, 2, 2))
+
+
+def _train_worker(rank, world, port, work_dir, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lakonlab.apis import train_model
+        from lakonlab.utils import Config
+        cfg = Config(dict(
+            data=dict(workers_per_gpu=0, train_dataloader=dict(samples_per_gpu=2)), seed=3, module_wrapper="ddp",
+            optimizer=dict(diffusion=dict(type="AdamW8bit", lr=1e-4)), lr_config=dict(policy="fixed"),
+            runner=dict(type="DynamicIterBasedRunnerMod", pass_training_status=True), work_dir=work_dir, total_iters=4,
+            custom_hooks=[dict(type="ExponentialMovingAverageHookMod", module_keys=("diffusion_ema",), start_iter=2,
+                               momentum_policy="karras", momentum_cfg=dict(gamma=7.0))],
+            checkpoint_config=dict(interval=2, max_keep_ckpts=-1, out_dir=os.path.join(work_dir, "ck")), name="stub",
+            log_config=dict(interval=1, hooks=[dict(type="TextLoggerHook")]), workflow=[("train", 2)],
+            resume_from=os.path.join(work_dir, "ck", "stub", "latest.pth")))
+        model = _StubModel()
+        runner = train_model(model, [_IdDataset()], cfg, distributed=True)
+        q.put((rank, runner.iter, sorted(model.seen), model.opt.v.tolist(), model.ema_cfg))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_train_model_world2(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, it0, seen0, v0, ema0), (r1, it1, seen1, v1, ema1) = res
+    assert it0 == it1 == 4
+    assert len(seen0) == len(seen1) == 8 and not set(seen0) & set(seen1)      # DistributedSampler: disjoint shards
+    assert v0 == v1                                                           # the all-reduced update is identical
+    assert ema0 == dict(start_iter=2, momentum_cfg=dict(gamma=7.0))           # EMA hook config reaches the trainer
+    ck = tmp_path / "ck" / "stub"
+    assert sorted(p.name for p in ck.iterdir()) == ["iter_2.pth", "iter_4.pth", "latest.pth"]   # written once, by rank 0
