@@ -2,7 +2,7 @@
 # Hyper-parameters follow the reference's configs/flux/arcflux_2nfe_k16.py (student :16-57, teacher :59-79,
 # train_cfg :89-99, EMA hook :141-151). `pretrained` must be a LOCAL path offline (the reference's huggingface:// URI
 # names black-forest-labs/FLUX.1-dev/transformer); 'synthetic://1234' trains on seeded random weights of that shape.
-_base_ = ['./_runtime_ddp.py', './_data_prompts.py']
+_base_ = ['./_data_prompts.py']
 
 name = 'arcflux_k16_2nfe'
 flux_trunk = dict(in_channels=64, num_layers=19, num_single_layers=38, attention_head_dim=128, num_attention_heads=24,
@@ -43,3 +43,17 @@ custom_hooks = [dict(type='ExponentialMovingAverageHookMod', module_keys=('diffu
 load_from = None
 resume_from = f'checkpoints/{name}/latest.pth'   # resume by default
 workflow = [('train', save_interval)]
+
+# ---- optimisation / runtime (values of the reference's configs/flux/_ddp_train.py: clip :14-17, optimizer :18-26,
+# lr_config :27-31, runner :32-38; only the keys this build consumes) ----
+train_cfg.update(diffusion_grad_clip=50.0, diffusion_grad_clip_begin_iter=100)
+optimizer = dict(diffusion=dict(
+    type='AdamW8bit',   # moments are kept in fp32 here: same update rule, no 8-bit state
+    lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0,
+    paramwise_cfg=dict(custom_keys=dict(proj_out_loggamma=dict(lr_mult=0.1)))))
+lr_config = dict(policy='fixed', warmup='linear', warmup_iters=100, warmup_ratio=0.001)
+runner = dict(type='DynamicIterBasedRunnerMod', pass_training_status=True, ckpt_trainable_only=True, ckpt_fp16=True,
+              ckpt_fp16_ema=True, gc_interval=20)
+dist_params = dict(backend='nccl')
+module_wrapper = 'ddp'
+log_level = 'INFO'

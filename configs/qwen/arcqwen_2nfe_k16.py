@@ -1,7 +1,7 @@
 # ArcFlow-Qwen-Image (20B), 2 NFE, K = 16, rank-256 adapter: data-free trajectory distillation with a true-CFG teacher.
 # Hyper-parameters follow the reference's configs/qwen/arcqwen_2nfe_k16.py (student :24-62, teacher :64-80,
 # train_cfg :96-106). `pretrained`: see configs/flux/arcflux_2nfe_k16.py.
-_base_ = ['./_runtime_ddp.py', './_data_prompts.py']
+_base_ = ['./_data_prompts.py']
 
 name = 'arcqwen_k16_2nfe'
 qwen_trunk = dict(in_channels=64, num_layers=60, attention_head_dim=128, num_attention_heads=24, joint_attention_dim=3584,
@@ -39,3 +39,17 @@ custom_hooks = [dict(type='ExponentialMovingAverageHookMod', module_keys=('diffu
 load_from = None
 resume_from = f'checkpoints/{name}/latest.pth'
 workflow = [('train', save_interval)]
+
+# ---- optimisation / runtime (values of the reference's configs/qwen/_ddp_train.py: clip :14-17, optimizer :18-26,
+# lr_config :27-31, runner :32-38; only the keys this build consumes) ----
+train_cfg.update(diffusion_grad_clip=50.0, diffusion_grad_clip_begin_iter=100)
+optimizer = dict(diffusion=dict(
+    type='AdamW8bit',   # moments are kept in fp32 here: same update rule, no 8-bit state
+    lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0,
+    paramwise_cfg=dict(custom_keys=dict(proj_out_loggamma=dict(lr_mult=0.1)))))
+lr_config = dict(policy='fixed', warmup='linear', warmup_iters=100, warmup_ratio=0.001)
+runner = dict(type='DynamicIterBasedRunnerMod', pass_training_status=True, ckpt_trainable_only=True, ckpt_fp16=True,
+              ckpt_fp16_ema=True, gc_interval=20)
+dist_params = dict(backend='nccl')
+module_wrapper = 'ddp'
+log_level = 'INFO'
