@@ -1334,7 +1334,14 @@ int afb_engine_set_activation_stash(afb_engine* e, int32_t on, int32_t batch, in
       e->stash = nullptr;
       e->stash_bytes = 0;
     }
-    AFB_CHECK_CUDA(cudaMalloc(&e->stash, bytes));
+    const cudaError_t err = cudaMalloc(&e->stash, bytes);
+    if (err != cudaSuccess) {  // not fatal: the engine keeps recomputing; clear the error so later launch checks stay clean
+      cudaGetLastError();
+      e->stash = nullptr;
+      e->stash_on = e->stash_valid = false;
+      afb::set_last_error("engine_set_activation_stash: cannot allocate %zu bytes (%s)", bytes, cudaGetErrorString(err));
+      return AFB_ERR_CUDA;
+    }
     e->stash_bytes = bytes;
   }
   e->stash_on = true;
