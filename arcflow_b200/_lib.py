@@ -14,7 +14,7 @@ AFB_OK = 0
 AFB_EPI_BIAS, AFB_EPI_BIAS_GELU, AFB_EPI_BIAS_GATE_RES, AFB_EPI_BIAS_RES = 0, 1, 2, 3
 AFB_SL_SILU_IN, AFB_SL_ACCUMULATE = 1, 2
 AFB_ARCH_FLUX, AFB_ARCH_QWEN = 0, 1
-AFB_ABI_VERSION = 1
+AFB_ABI_VERSION = 2
 
 
 class AfbError(RuntimeError):
@@ -140,7 +140,7 @@ class AdamwArgs(C.Structure):
                 ("n", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("step", C.c_int32), ("max_norm", C.c_float), ("grad_norm_sq", _P),
                 ("skipped", _P), ("ema_momentum", C.c_float), ("ema_copy", C.c_int32),
-                ("lr_mult_begin", C.c_int64), ("lr_mult_end", C.c_int64), ("lr_mult", C.c_float)]
+                ("lr_mult_begin", C.c_int64), ("lr_mult_end", C.c_int64), ("lr_mult", C.c_float), ("skip_norm", C.c_float)]
 
 
 class DoubleBlockGrads(C.Structure):
@@ -214,6 +214,8 @@ SIGNATURES = {
     "afb_engine_backward": (C.c_int, [_P, C.POINTER(BackwardArgs), _P]),
     "afb_engine_backward_embed": (C.c_int, [_P, C.POINTER(ForwardArgs), _P, C.POINTER(EmbedGrads), _P]),
     "afb_grad_norm_sq": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "afb_grad_norm_scratch_floats": (C.c_int, []),
+    "afb_grad_norm_sq_ws": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P]),
     "afb_adamw_ema_step": (C.c_int, [C.POINTER(AdamwArgs), _P]),
     "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),
     "afb_mse_rows": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),

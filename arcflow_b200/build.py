@@ -46,12 +46,19 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+# what the last build() call in this process did: "compiled" (nvcc ran) or "reused" (sources + flags match the
+# fingerprint of the library already in the tree, e.g. the prebuilt .so that travelled to the GPU box)
+LAST_BUILD = None
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source for sm_100a and link the shared library. Returns its path."""
+    global LAST_BUILD
     LIB_DIR.mkdir(exist_ok=True)
     stamp = LIB_DIR / "build.stamp"
     fp = _fingerprint()
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == fp:
+        LAST_BUILD = "reused"
         return LIB_PATH
     objs = []
     procs = []
@@ -74,9 +81,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     link = [_nvcc(), "-shared", "-cudart", "static", "-o", str(LIB_PATH), *map(str, objs)]
     subprocess.run(link, check=True)
     stamp.write_text(fp)
+    LAST_BUILD = "compiled"
     return LIB_PATH
 
 
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    print(f"{LAST_BUILD} {path}")

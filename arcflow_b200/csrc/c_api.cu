@@ -33,6 +33,8 @@ int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, in
 int cfg_combine_launch(const void* both_bf16, float* out, int64_t half, float guidance_scale, cudaStream_t stream);
 int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream);
+int grad_norm_scratch_floats();
+int grad_norm_sq_ws_launch(const float* g, int64_t n, float* out, float* scratch, int64_t scratch_floats, cudaStream_t stream);
 int ln_modulate_bwd_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs,
                            const void* scale, int64_t mod_bs, int batches, int rows_per_batch, int dim, float eps,
                            int accumulate, cudaStream_t stream);
@@ -161,6 +163,10 @@ int afb_rmsnorm_rope_bwd(void* dqkv, const void* raw, int64_t ld, int64_t bs, in
 }
 int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream) {
   return afb::grad_norm_sq_launch(grads, n, out, static_cast<cudaStream_t>(stream));
+}
+int afb_grad_norm_scratch_floats(void) { return afb::grad_norm_scratch_floats(); }
+int afb_grad_norm_sq_ws(const float* grads, int64_t n, float* out, float* scratch, int64_t scratch_floats, void* stream) {
+  return afb::grad_norm_sq_ws_launch(grads, n, out, scratch, scratch_floats, static_cast<cudaStream_t>(stream));
 }
 int afb_adamw_ema_step(const afb_adamw_args* args, void* stream) {
   return afb::adamw_ema_launch(args, static_cast<cudaStream_t>(stream));

@@ -61,6 +61,7 @@ sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out, 
 struct AdamParams {
   float lr, beta1, beta2, eps, weight_decay, bias1, bias2;  // bias_k = 1 - beta_k^step
   float max_norm;      // <= 0: no clipping
+  float skip_norm;     // > 0: a norm above it skips the step like a non-finite one (grad_clip_skip_ratio * grad_clip)
   float ema_momentum;  // < 0: EMA not touched; ema = m * ema + (1 - m) * p
   int ema_copy;        // before start_iter: ema = p
   long long lo_begin, lo_end;  // element range that uses lr * lo_mult (proj_out_loggamma)
@@ -74,7 +75,7 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   float clip = 1.0f;
   if (a.max_norm > 0.f) {
     const float norm = sqrtf(*gnorm_sq);
-    if (!isfinite(norm)) {  // reference: zero_grad + skip the optimizer step; EMA still runs afterwards
+    if (!isfinite(norm) || (a.skip_norm > 0.f && norm > a.skip_norm)) {  // reference (base.py:91-95): zero_grad + skip the optimizer step; EMA still runs afterwards
       if (blockIdx.x == 0 && threadIdx.x == 0) *skipped = 1;
       clip = -1.0f;
     } else {
@@ -104,6 +105,27 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 }  // namespace
 
+int grad_norm_scratch_floats() { return device_sm_count() * 8 + 1; }
+
+// Caller-owned scratch ([grad_norm_scratch_floats()] floats, zeroed once by the caller): one scratch per optimizer
+// instance, so launches of different instances on different streams cannot race on the partials / ticket, and nothing is
+// allocated here (CUDA-graph capturable).
+int grad_norm_sq_ws_launch(const float* g, int64_t n, float* out, float* scratch, int64_t scratch_floats, cudaStream_t stream) {
+  AFB_REQUIRE(g && out && scratch && n >= 1, "grad_norm_sq: bad arguments");
+  const int cap = device_sm_count() * 8;
+  AFB_REQUIRE(scratch_floats >= int64_t(cap) + 1, "grad_norm_sq: scratch holds %lld floats, needs %d", (long long)scratch_floats,
+              cap + 1);
+  int blocks = int((n / 4 + 255) / 256);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<blocks, 256, 0, stream>>>(g, n, out, scratch, reinterpret_cast<unsigned int*>(scratch + cap));
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
+// Convenience form with one library-owned scratch per device: callers must not run it concurrently on two streams of the
+// same device (use the _ws form for that); the first call per device allocates and is not graph-capturable.
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream) {
   AFB_REQUIRE(g && out && n >= 1, "grad_norm_sq: bad arguments");
   int blocks = int((n / 4 + 255) / 256);
@@ -137,6 +159,7 @@ int adamw_ema_launch(const afb_adamw_args* a, cudaStream_t stream) {
   k.bias1 = 1.0f - powf(a->beta1, float(a->step));
   k.bias2 = 1.0f - powf(a->beta2, float(a->step));
   k.max_norm = a->max_norm;
+  k.skip_norm = a->skip_norm;
   k.ema_momentum = a->ema_momentum;
   k.ema_copy = a->ema_copy;
   k.lo_begin = a->lr_mult_begin;

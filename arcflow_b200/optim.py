@@ -38,7 +38,7 @@ def karras_momentum(iteration: int, start_iter: int = 100, gamma: float = 7.0, m
 class FlatAdamW:
     def __init__(self, shapes: Dict[str, Tuple[int, ...]], device, lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
                  weight_decay: float = 0.0, lr_mult_key: str = "proj_out_loggamma", lr_mult: float = 0.1,
-                 max_norm: float = 50.0, clip_begin_iter: int = 100, warmup_iters: int = 100, warmup_ratio: float = 0.001,
+                 max_norm: float = 50.0, clip_begin_iter: int = 100, clip_skip_ratio: float = 0.0, warmup_iters: int = 100, warmup_ratio: float = 0.001,
                  ema_gamma: float = 7.0, ema_start_iter: int = 100):
         self.lib = _lib.load()
         self.device = torch.device(device)
@@ -60,8 +60,11 @@ class FlatAdamW:
         self.shadow = z(torch.bfloat16)
         self.norm_sq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.skipped = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # partials + ticket of the deterministic norm reduction: one per optimizer instance (never shared across streams)
+        self.norm_scratch = torch.zeros(max(int(self.lib.afb_grad_norm_scratch_floats()), 1), dtype=torch.float32,
+                                        device=self.device) if self.device.type == "cuda" else None
         self.hp = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, lr_mult=lr_mult, max_norm=max_norm,
-                       clip_begin_iter=clip_begin_iter, warmup_iters=warmup_iters, warmup_ratio=warmup_ratio,
+                       clip_begin_iter=clip_begin_iter, clip_skip_ratio=clip_skip_ratio, warmup_iters=warmup_iters, warmup_ratio=warmup_ratio,
                        ema_gamma=ema_gamma, ema_start_iter=ema_start_iter)
         self.steps_taken = 0
 
@@ -112,7 +115,8 @@ class FlatAdamW:
         stream = torch.cuda.current_stream().cuda_stream
         self.all_reduce_grads()
         clip = hp["max_norm"] > 0 and iteration >= hp["clip_begin_iter"]
-        _lib.check(self.lib.afb_grad_norm_sq(self.grads.data_ptr(), self.n, self.norm_sq.data_ptr(), stream), "afb_grad_norm_sq")
+        _lib.check(self.lib.afb_grad_norm_sq_ws(self.grads.data_ptr(), self.n, self.norm_sq.data_ptr(),
+                                                self.norm_scratch.data_ptr(), self.norm_scratch.numel(), stream), "afb_grad_norm_sq_ws")
         a = _lib.AdamwArgs()
         a.params, a.grads = self.params.data_ptr(), self.grads.data_ptr()
         a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
@@ -121,6 +125,8 @@ class FlatAdamW:
         a.beta1, a.beta2, a.eps, a.weight_decay = hp["betas"][0], hp["betas"][1], hp["eps"], hp["weight_decay"]
         a.step = self.steps_taken + 1
         a.max_norm = hp["max_norm"] if clip else 0.0
+        ratio = hp.get("clip_skip_ratio", 0.0)
+        a.skip_norm = hp["max_norm"] * ratio if (clip and ratio > 0) else 0.0
         a.grad_norm_sq, a.skipped = self.norm_sq.data_ptr(), self.skipped.data_ptr()
         a.ema_copy = int(iteration < hp["ema_start_iter"])
         a.ema_momentum = karras_momentum(iteration, hp["ema_start_iter"], hp["ema_gamma"])

@@ -41,7 +41,7 @@ typedef struct afb_engine afb_engine;
 #define AFB_ERR_UNSUPPORTED (-3)
 
 /* ABI version; bumped on any incompatible change of the structs below. */
-#define AFB_ABI_VERSION 1
+#define AFB_ABI_VERSION 2
 int afb_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* afb_last_error(void);
@@ -282,6 +282,10 @@ int afb_cfg_combine(const void* both_bf16, float* out, int64_t half, float guida
  * ---------------------------------------------------------------------------------------------- */
 /* out[0] = sum g^2 (device scalar, fp32). */
 int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream);
+/* Same with caller-owned scratch (afb_grad_norm_scratch_floats() floats, zeroed once): one scratch per optimizer instance
+ * makes concurrent launches on different streams safe and the call CUDA-graph capturable (no allocation inside). */
+int afb_grad_norm_scratch_floats(void);
+int afb_grad_norm_sq_ws(const float* grads, int64_t n, float* out, float* scratch, int64_t scratch_floats, void* stream);
 
 typedef struct afb_adamw_args {
   float* params;          /* fp32 [n], updated in place */
@@ -300,6 +304,8 @@ typedef struct afb_adamw_args {
   int32_t ema_copy;       /* 1: ema = p (before the EMA start iteration) */
   int64_t lr_mult_begin, lr_mult_end; /* element range using lr * lr_mult (proj_out_loggamma: 0.1) */
   float lr_mult;
+  float skip_norm;        /* > 0 (with max_norm > 0): a gradient norm above it skips the update like a non-finite one —
+                             `<k>_grad_clip_skip_ratio` x `<k>_grad_clip`, lakonlab/models/base.py:81,91-95 */
 } afb_adamw_args;
 int afb_adamw_ema_step(const afb_adamw_args* args, void* stream);
 

@@ -44,7 +44,12 @@ def main(argv=None):
     ap.add_argument('--out', default=None)
     args = ap.parse_args(argv)
 
-    pipe = ArcQwenImagePipeline.from_pretrained(args.base, torch_dtype=torch.bfloat16)
+    # under `torchrun --nproc-per-node N` the batch (prompts x num_images_per_prompt) is split over the N GPUs inside
+    # pipe(...) and the final latents are all-gathered (lakonlab/parallel/batch_parallel.py); rank 0 writes the result
+    from lakonlab.parallel import init_from_env
+    rank, world, dev = init_from_env()
+
+    pipe = ArcQwenImagePipeline.from_pretrained(args.base, torch_dtype=torch.bfloat16, device=dev)
     adapter = args.adapter
     if adapter is None:
         if not args.synthetic_adapter:
@@ -53,7 +58,7 @@ def main(argv=None):
         adapter = _synthetic_adapter_folder(pipe, tempfile.mkdtemp(prefix='arcflow_adapter_'), args.seed)
     adapter_name = pipe.load_arcflow_adapter(adapter, subfolder=args.subfolder, target_module_name='transformer')
     pipe.scheduler_shift = 3.2   # FlowMatchEulerDiscreteScheduler(shift=3.2, use_dynamic_shifting=False), inference_qwen.py:14
-    pipe = pipe.to('cuda')
+    pipe = pipe.to(dev)
 
     mask = None
     if args.prompt_embeds:
@@ -68,14 +73,16 @@ def main(argv=None):
     else:
         g = torch.Generator().manual_seed(args.seed)
         prompt_embeds = torch.randn(1, 512, 3584, generator=g)
-    out = pipe(prompt_embeds=prompt_embeds.to('cuda', torch.bfloat16),
-               prompt_embeds_mask=mask.to('cuda') if mask is not None else None,
+    out = pipe(prompt_embeds=prompt_embeds.to(dev, torch.bfloat16),
+               prompt_embeds_mask=mask.to(dev) if mask is not None else None,
                num_images_per_prompt=args.num_images_per_prompt, width=args.width, height=args.height,
-               num_inference_steps=args.nfe, generator=torch.Generator(device='cuda').manual_seed(args.seed),
+               num_inference_steps=args.nfe, generator=torch.Generator(device=dev).manual_seed(args.seed),
                timestep_ratio=1.0, output_type='latent').images
     path = args.out or f'arcqwen_{args.nfe}nfe.pt'
-    torch.save(dict(latents=out.cpu(), adapter=adapter_name, nfe=args.nfe, height=args.height, width=args.width), path)
-    print(f'{adapter_name}: {tuple(out.shape)} latents -> {path}')
+    if rank == 0:
+        torch.save(dict(latents=out.cpu(), adapter=adapter_name, nfe=args.nfe, height=args.height, width=args.width), path)
+    if rank == 0:
+        print(f'{adapter_name}: {tuple(out.shape)} latents -> {path}' + (f' ({world} ranks)' if world > 1 else ''))
     return out
 
 

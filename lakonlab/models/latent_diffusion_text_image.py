@@ -42,6 +42,7 @@ class LatentDiffusionTextImage:
                   lr_mult=(keys.get(mult_key) or {}).get("lr_mult", 1.0) if keys else 0.1,
                   max_norm=self.train_cfg.get("diffusion_grad_clip", 0.0),
                   clip_begin_iter=self.train_cfg.get("diffusion_grad_clip_begin_iter", 0),
+                  clip_skip_ratio=self.train_cfg.get("diffusion_grad_clip_skip_ratio", 0.0),
                   warmup_iters=lr.get("warmup_iters", 0) if lr.get("warmup") else 0,
                   warmup_ratio=lr.get("warmup_ratio", 1.0),
                   ema_gamma=(ema.get("momentum_cfg") or {}).get("gamma", 7.0), ema_start_iter=ema.get("start_iter", 0))

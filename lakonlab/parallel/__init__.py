@@ -1,1 +1,1 @@
-from .batch_parallel import shard_batch, gather_latents  # noqa: F401
+from .batch_parallel import gather_latents, init_from_env, parallel_context, shard_batch, shard_bounds  # noqa: F401

@@ -41,3 +41,33 @@ def gather_latents(local: torch.Tensor, total: int) -> torch.Tensor:
     out = local.new_empty((world * mx, *local.shape[1:]))
     dist.all_gather_into_tensor(out, pad.contiguous())
     return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
+
+
+def parallel_context(enabled: bool = True) -> Tuple[int, int]:
+    """(rank, world) the pipelines shard a call over: the default process group when `torch.distributed` is initialised
+    (and sharding was not switched off with `pipe.enable_batch_parallel(False)`), else (0, 1)."""
+    if enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: str = None):
+    """Under `torchrun` (WORLD_SIZE > 1): bind this process to GPU LOCAL_RANK and initialise the default process group
+    (NCCL on GPUs, gloo otherwise; MASTER_ADDR defaults to 127.0.0.1 — one box). Returns (rank, world, device string).
+    A plain `python inference_*.py` run is (0, 1, 'cuda')."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, "cuda"
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        if cuda:
+            dist.init_process_group(backend or "nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend or "gloo")
+    return dist.get_rank(), world, (f"cuda:{local}" if cuda else "cpu")

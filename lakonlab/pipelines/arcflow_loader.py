@@ -76,6 +76,9 @@ class ArcFlowLoaderMixin:
         if base is None or not hasattr(base, "state_dict"):
             raise ValueError(f"pipeline has no module '{target_module_name}' with a state_dict() to adapt")
         base_sd = dict(base.state_dict())
+        # keys saved under the target module's name (`transformer.<key>`) are accepted as the reference does
+        # (arcflow_loader.py:246-250 strips f"{target_module_name}." before splitting LoRA from non-LoRA tensors)
+        adapter_sd = {k.removeprefix(target_module_name + "."): v for k, v in adapter_sd.items()}
         other, lora = split_adapter_keys(adapter_sd)
         if not lora:
             warnings.warn(f"No LoRA weights found in '{pretrained_model_name_or_path}'; adapter not loaded.")

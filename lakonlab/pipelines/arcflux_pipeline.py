@@ -17,6 +17,7 @@ import torch
 
 from arcflow_b200 import ops
 from arcflow_b200.schedule import denoise_sigmas, retrieve_raw_timesteps  # noqa: F401  (same public name)
+from lakonlab.parallel.batch_parallel import gather_latents, parallel_context, shard_bounds
 from .arcflow_loader import ArcFlowLoaderMixin
 
 
@@ -66,6 +67,7 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
         self._num_timesteps = 0
         self._interrupt = False
         self.use_cuda_graph = False
+        self.batch_parallel = True
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype=torch.bfloat16, device="cuda", **kwargs):
@@ -84,6 +86,14 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
         self.use_cuda_graph = bool(on)
         return self
 
+    def enable_batch_parallel(self, on: bool = True):
+        """Extension (the reference's README.md:39 To-Do): when `torch.distributed` is initialised, one `pipe(...)` call
+        made with the SAME arguments on every rank splits the batch over the ranks (weights replicated, nothing exchanged
+        inside the loop) and all-gathers the final packed latents, so every rank returns the full batch. On by default;
+        off = every rank denoises whatever it was given."""
+        self.batch_parallel = bool(on)
+        return self
+
     @property
     def num_timesteps(self):
         return self._num_timesteps
@@ -99,7 +109,15 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
     def interrupt(self):
         return self._interrupt
 
-    def to(self, device):
+    def to(self, device=None, *args, **kwargs):
+        """The engine packs its weights on the device given at load time; moving an engine-backed transformer is not
+        supported (there is no CPU path), so anything but that device is an error rather than a silent no-op."""
+        tr = self.transformer
+        if device is not None and tr is not None and hasattr(tr, "device") and not isinstance(device, torch.dtype):
+            want = torch.device(device)
+            have = torch.device(tr.device)
+            if want.type != have.type or (want.index is not None and have.index is not None and want.index != have.index):
+                raise RuntimeError(f"pipe.to({device!r}): the transformer lives on {have}; load the pipeline with device=")
         return self
 
     # -- layout helpers kept under the reference's names (arcflux_pipeline.py:163-193) ---------------
@@ -141,7 +159,12 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
                  output_type: Optional[str] = "pil", return_dict: bool = True,
                  joint_attention_kwargs: Optional[Dict[str, Any]] = None,
                  callback_on_step_end: Optional[Callable[[Any, int, Any, Dict], Dict]] = None,
-                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], max_sequence_length: int = 512):
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], max_sequence_length: int = 512,
+                 ip_adapter_image=None, ip_adapter_image_embeds=None):
+        if ip_adapter_image is not None or ip_adapter_image_embeds is not None:
+            # accepted for signature compatibility (arcflux_pipeline.py:268-269); the reference forwards them to the stock
+            # FluxPipeline image-projection path, which is outside the ArcFlow hot path
+            raise NotImplementedError("IP-Adapter inputs are out of scope of this build (SURVEY.md §8)")
         tr = self.transformer
         if tr is None or not hasattr(tr, "denoise"):
             raise RuntimeError("pipe.transformer is not an ArcFlow module — call pipe.load_arcflow_adapter(...) first")
@@ -161,19 +184,34 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
             prompt_embeds, pooled_prompt_embeds = self.text_encoder_fn(prompt, max_sequence_length)
         if pooled_prompt_embeds is None:
             raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
-        prompt_embeds = prompt_embeds.to(device, non_blocking=True)
-        pooled_prompt_embeds = pooled_prompt_embeds.to(device, non_blocking=True)
         if num_images_per_prompt and num_images_per_prompt > 1:
             prompt_embeds = prompt_embeds.repeat_interleave(num_images_per_prompt, 0)
             pooled_prompt_embeds = pooled_prompt_embeds.repeat_interleave(num_images_per_prompt, 0)
         batch = prompt_embeds.shape[0]
+        # batch-parallel call: this rank keeps images [lo, hi) — sliced on the HOST side of the copy, and
+        # noise is drawn for the whole batch from the caller's generator, so the result does not depend on the rank count
+        rank, world = parallel_context(self.batch_parallel)
+        lo, hi = shard_bounds(batch, rank, world)
         num_channels_latents = tr.cfg.in_channels // 4
-        latents = self.prepare_latents(batch, num_channels_latents, height, width, torch.float32, device, generator, latents)
+        if latents is not None:
+            latents = latents[lo:hi]
+        elif world > 1:
+            if isinstance(generator, list):
+                generator = generator[lo:hi]
+                latents = self.prepare_latents(hi - lo, num_channels_latents, height, width, torch.float32, device, generator)
+            else:
+                gdev = generator.device if generator is not None else torch.device("cpu")
+                latents = self.prepare_latents(batch, num_channels_latents, height, width, torch.float32, gdev, generator)[lo:hi]
+        prompt_embeds = prompt_embeds[lo:hi].to(device, non_blocking=True)
+        pooled_prompt_embeds = pooled_prompt_embeds[lo:hi].to(device, non_blocking=True)
+        latents = self.prepare_latents(hi - lo, num_channels_latents, height, width, torch.float32, device, generator, latents)
         grid = (height // 16, width // 16)
         _, _, total = retrieve_raw_timesteps(num_inference_steps, total_substeps, timestep_ratio)
         self._num_timesteps = total
 
-        if callback_on_step_end is None:
+        if hi == lo:
+            pass    # more ranks than images: this rank only takes part in the gather
+        elif callback_on_step_end is None:
             # whole loop in one C-ABI call (transformer + sampler per NFE, no host round trips)
             latents = tr.denoise(latents, prompt_embeds, pooled_prompt_embeds, grid, num_inference_steps=num_inference_steps,
                                  total_substeps=total_substeps, timestep_ratio=timestep_ratio, shift=self.scheduler_shift,
@@ -187,10 +225,13 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
                 latents = ops.sampler_step(head.reshape(-1, head.shape[-1]), latents, sig[i], sig[i], sig[i + 1],
                                            num_gaussians=tr.num_gaussians)
                 t_src = torch.tensor(sig[i] * 1000.0, device=device)
-                cb = callback_on_step_end(self, i, t_src, {k: locals()[k] for k in callback_on_step_end_tensor_inputs})
+                tensors = dict(latents=latents, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled_prompt_embeds)
+                cb = callback_on_step_end(self, i, t_src, {k: tensors[k] for k in callback_on_step_end_tensor_inputs})
                 latents = cb.pop("latents", latents)
                 prompt_embeds = cb.pop("prompt_embeds", prompt_embeds)
 
+        if world > 1:   # the sampler-boundary exchange: one all-gather of the final packed latents (1.05 MB / image)
+            latents = gather_latents(latents.contiguous(), batch)
         if output_type == "latent":
             image = latents
         else:

@@ -13,6 +13,7 @@ import torch
 
 from arcflow_b200 import ops
 from arcflow_b200.schedule import denoise_sigmas, retrieve_raw_timesteps
+from lakonlab.parallel.batch_parallel import gather_latents, parallel_context, shard_bounds
 from .arcflow_loader import ArcFlowLoaderMixin
 from .arcflux_pipeline import ArcFluxPipeline, FluxPipelineOutput
 
@@ -26,6 +27,8 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
     default_sample_size = 128
     _pack_latents = staticmethod(ArcFluxPipeline._pack_latents)
     _unpack_latents = staticmethod(ArcFluxPipeline._unpack_latents)
+    enable_batch_parallel = ArcFluxPipeline.enable_batch_parallel
+    to = ArcFluxPipeline.to
 
     def __init__(self, transformer=None, scheduler_shift: float = 3.2, text_encoder_fn: Optional[Callable] = None,
                  vae_decode_fn: Optional[Callable] = None, policy_type: str = "ArcFlow"):
@@ -38,6 +41,7 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
         self._num_timesteps = 0
         self._interrupt = False
         self.use_cuda_graph = False
+        self.batch_parallel = True
 
     def enable_cuda_graph(self, on: bool = True):
         """Extension (not in the reference): replay the denoising loop as one captured CUDA graph per (shape, schedule)."""
@@ -65,9 +69,6 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
     def interrupt(self):
         return self._interrupt
 
-    def to(self, device):
-        return self
-
     @torch.inference_mode()
     def __call__(self, prompt: Union[str, List[str]] = None, height: Optional[int] = None, width: Optional[int] = None,
                  num_inference_steps: int = 4, total_substeps: int = 128, timestep_ratio: float = 0.5,
@@ -93,23 +94,29 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
                 raise NotImplementedError("the text encoder is out of scope of this build: pass cached `prompt_embeds` "
                                           "(+ `prompt_embeds_mask`) or construct the pipeline with text_encoder_fn")
             prompt_embeds, prompt_embeds_mask = self.text_encoder_fn(prompt, max_sequence_length)
-        prompt_embeds = prompt_embeds.to(device, non_blocking=True)
         if prompt_embeds_mask is not None:   # trim to the longest prompt (arcqwen.py:325-330)
             max_len = int(prompt_embeds_mask.sum(dim=1).max().item())
             prompt_embeds = prompt_embeds[:, :max_len]
         if num_images_per_prompt > 1:
             prompt_embeds = prompt_embeds.repeat_interleave(num_images_per_prompt, 0)
         batch = prompt_embeds.shape[0]
+        # batch-parallel call: this rank keeps images [lo, hi); noise is drawn for the whole batch from
+        # the caller's generator so the result does not depend on the rank count
+        rank, world = parallel_context(self.batch_parallel)
+        lo, hi = shard_bounds(batch, rank, world)
+        prompt_embeds = prompt_embeds[lo:hi].to(device, non_blocking=True)
         h, w = 2 * (height // 16), 2 * (width // 16)
         if latents is None:
-            gdev = generator.device if generator is not None else device
-            noise = torch.randn((batch, 16, h, w), generator=generator, device=gdev, dtype=torch.float32).to(device)
-            latents = self._pack_latents(noise, batch, 16, h, w)
+            gdev = generator.device if generator is not None else (device if world == 1 else torch.device("cpu"))
+            noise = torch.randn((batch, 16, h, w), generator=generator, device=gdev, dtype=torch.float32)[lo:hi].to(device)
+            latents = self._pack_latents(noise, hi - lo, 16, h, w)
         else:
-            latents = latents.to(device=device, dtype=torch.float32, non_blocking=True)
+            latents = latents[lo:hi].to(device=device, dtype=torch.float32, non_blocking=True)
         grid = (height // 16, width // 16)
         self._num_timesteps = retrieve_raw_timesteps(num_inference_steps, total_substeps, timestep_ratio)[2]
-        if callback_on_step_end is None:
+        if hi == lo:
+            pass    # more ranks than images: this rank only takes part in the gather
+        elif callback_on_step_end is None:
             latents = tr.denoise(latents, prompt_embeds, grid, num_inference_steps=num_inference_steps,
                                  total_substeps=total_substeps, timestep_ratio=timestep_ratio, shift=self.scheduler_shift,
                                  cuda_graph=self.use_cuda_graph)
@@ -121,10 +128,13 @@ class ArcQwenImagePipeline(ArcFlowLoaderMixin):
                 head = tr.forward_heads(latents, prompt_embeds, sig[i], grid)
                 latents = ops.sampler_step(head.reshape(-1, head.shape[-1]), latents, sig[i], sig[i], sig[i + 1],
                                            num_gaussians=tr.num_gaussians)
+                tensors = dict(latents=latents, prompt_embeds=prompt_embeds)
                 cb = callback_on_step_end(self, i, torch.tensor(sig[i] * 1000.0, device=device),
-                                          {k: locals()[k] for k in callback_on_step_end_tensor_inputs})
+                                          {k: tensors[k] for k in callback_on_step_end_tensor_inputs})
                 latents = cb.pop("latents", latents)
                 prompt_embeds = cb.pop("prompt_embeds", prompt_embeds)
+        if world > 1:   # the sampler-boundary exchange: one all-gather of the final packed latents
+            latents = gather_latents(latents.contiguous(), batch)
         if output_type == "latent":
             image = latents
         else:

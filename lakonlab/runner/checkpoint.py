@@ -24,8 +24,36 @@ def get_checkpoint(model, optimizer=None, meta: Optional[Dict] = None) -> Dict:
     if optimizer is not None:
         ckpt["optimizer"] = {k: opt.state_dict() for k, opt in optimizer.items()}
     if hasattr(model, "generator"):   # noise / roll-out draws continue where they stopped (the reference re-seeds)
-        ckpt["rng_state"] = model.generator.get_state()
+        ckpt["rng_state"] = gather_rng_states(model.generator)
     return ckpt
+
+
+def gather_rng_states(generator) -> Dict[int, torch.Tensor]:
+    """{rank: generator state} of EVERY rank (collective: all ranks call get_checkpoint, rank 0 writes the file).
+    train.py --diff_seed gives each rank its own noise / roll-out stream (train.py:74-77,222-225 of the reference);
+    restoring rank 0's state everywhere would make all ranks draw identical x_T after a resume."""
+    import torch.distributed as dist
+    state = generator.get_state()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return {0: state}
+    states = [None] * dist.get_world_size()
+    dist.all_gather_object(states, state)
+    return {r: s for r, s in enumerate(states)}
+
+
+def restore_rng_state(generator, saved, rank: int, iteration: int = 0) -> str:
+    """Restore THIS rank's stream. `saved` is the {rank: state} dict written by get_checkpoint (a bare tensor from an
+    older checkpoint counts as rank 0's). A rank the checkpoint does not know (the world size grew) is re-seeded from
+    (rank 0's seed, rank, iteration) instead of cloning another rank's stream. Returns what was done."""
+    if isinstance(saved, torch.Tensor):
+        saved = {0: saved}
+    if rank in saved:
+        generator.set_state(saved[rank])
+        return "restored"
+    probe = torch.Generator()
+    probe.set_state(saved[min(saved)])
+    generator.manual_seed((probe.initial_seed() + 1000003 * rank + 7919 * int(iteration)) % (1 << 63))
+    return "reseeded"
 
 
 def write_checkpoint_to_file(checkpoint: Dict, filepath: str, create_symlink: bool = True):

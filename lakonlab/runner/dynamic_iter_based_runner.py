@@ -139,7 +139,8 @@ class DynamicIterBasedRunnerMod:
                                                 for k, v in adapter_from_checkpoint(ckpt, use_ema=False).items()})
             self.model.trainer.write_back()
         if resume_optimizer and "rng_state" in ckpt and hasattr(self.model, "generator"):
-            self.model.generator.set_state(ckpt["rng_state"])
+            from .checkpoint import restore_rng_state
+            restore_rng_state(self.model.generator, ckpt["rng_state"], self.rank, self._iter)
         self.logger.info("resumed from epoch: %d, iter %d", self._epoch, self._iter)
         return ckpt
 

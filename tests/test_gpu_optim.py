@@ -56,6 +56,40 @@ def test_nan_gradient_skips_the_step_but_not_the_ema(opt):
     assert torch.equal(o.params, before) and o.steps_taken == 0
 
 
+def test_grad_clip_skip_ratio_skips_large_norms(lib):
+    """`<k>_grad_clip_skip_ratio`: a norm above ratio x grad_clip skips the step like a non-finite one
+    (reference lakonlab/models/base.py:81,91-95)."""
+    from arcflow_b200.optim import FlatAdamW
+    shapes = {"proj_out_means.weight": (8, 33), "proj_out_loggamma.bias": (5,)}
+    o = FlatAdamW(shapes, "cuda", max_norm=1.0, clip_begin_iter=0, clip_skip_ratio=4.0)
+    o.load_params({n: torch.ones(s) for n, s in shapes.items()})
+    before = o.params.clone()
+    o.grads.fill_(1.0)                               # norm = sqrt(272) = 16.5 > 4 x 1
+    info = o.step(10)
+    assert info["skipped"] and math.isnan(info["diffusion_grad_norm"]) and torch.equal(o.params, before)
+    o.grads.fill_(0.2)                               # norm = 3.3: clipped to 1, not skipped
+    info = o.step(11)
+    assert not info["skipped"] and info["diffusion_grad_norm"] == pytest.approx(0.2 * math.sqrt(o.n), rel=1e-5)
+    assert not torch.equal(o.params, before) and o.steps_taken == 1
+
+
+def test_two_optimizers_on_two_streams_do_not_share_norm_scratch(lib):
+    from arcflow_b200.optim import FlatAdamW
+    a = FlatAdamW({"w.lora_A.weight": (512, 1024)}, "cuda", max_norm=0.0)
+    b = FlatAdamW({"w.lora_A.weight": (640, 1024)}, "cuda", max_norm=0.0)
+    assert a.norm_scratch.data_ptr() != b.norm_scratch.data_ptr()
+    a.grads.fill_(1.0), b.grads.fill_(2.0)
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(20):
+        with torch.cuda.stream(sa):
+            ia = a.step(0)
+        with torch.cuda.stream(sb):
+            ib = b.step(0)
+        assert ia["diffusion_grad_norm"] == pytest.approx(math.sqrt(a.n), rel=1e-6)
+        assert ib["diffusion_grad_norm"] == pytest.approx(2.0 * math.sqrt(b.n), rel=1e-6)
+
+
 def test_karras_ema(opt):
     from arcflow_b200.optim import karras_momentum
     o, shapes = opt

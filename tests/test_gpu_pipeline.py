@@ -102,6 +102,29 @@ def test_generator_latents_and_errors(setup):
         pipe(**{**kw, "output_type": "pil"})
     with pytest.raises(ValueError, match="divisible by 16"):
         pipe(**{**kw, "height": 72})
+    # reference signature kwargs outside the hot path are accepted by name and refused explicitly (arcflux_pipeline.py:268-269)
+    with pytest.raises(NotImplementedError, match="IP-Adapter"):
+        pipe(ip_adapter_image_embeds=[torch.zeros(1)], **kw)
+    assert pipe(ip_adapter_image=None, **kw, generator=torch.Generator("cuda").manual_seed(42)).images.equal(a)
+    assert pipe.to("cuda") is pipe and pipe.to(torch.bfloat16) is pipe
+    with pytest.raises(RuntimeError, match="lives on"):
+        pipe.to("cpu")
+
+
+def test_adapter_keys_prefixed_with_the_target_module_name(setup, tmp_path):
+    """Adapter files saved as `transformer.<key>` load like un-prefixed ones (reference arcflow_loader.py:246-250)."""
+    from lakonlab.pipelines.arcflow_loader import read_adapter_folder, write_adapter_folder
+    from lakonlab.pipelines.arcflux_pipeline import ArcFluxPipeline, FluxBaseTransformer
+    cfg, sd, base, root, x, txt, pooled = setup
+    _, adapter = read_adapter_folder(str(root), "arcflow-flux-2steps")
+    write_adapter_folder(tmp_path / "prefixed", cfg, {"transformer." + k: v for k, v in adapter.items()})
+    outs = []
+    for folder, sub in ((str(root), "arcflow-flux-2steps"), (str(tmp_path / "prefixed"), None)):
+        pipe = ArcFluxPipeline(transformer=FluxBaseTransformer(dict(base), device="cuda"))
+        assert pipe.load_arcflow_adapter(folder, subfolder=sub) == "transformer_arcflow"
+        outs.append(pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, latents=x, height=64, width=64,
+                         num_inference_steps=2, timestep_ratio=1.0, output_type="latent").images)
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_qwen_pipeline_adapter_roundtrip(lib, tmp_path):

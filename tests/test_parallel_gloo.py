@@ -181,3 +181,121 @@ def test_train_model_world2(tmp_path):
     assert ema0 == dict(start_iter=2, momentum_cfg=dict(gamma=7.0))           # EMA hook config reaches the trainer
     ck = tmp_path / "ck" / "stub"
     assert sorted(p.name for p in ck.iterdir()) == ["iter_2.pth", "iter_4.pth", "latest.pth"]   # written once, by rank 0
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharding through the PRODUCT API: pipe(...) called with the same arguments on every rank splits the batch, denoises its
+# shard and all-gathers the final latents (lakonlab/pipelines/arcflux_pipeline.py). The engine is replaced by a CPU stub
+# whose "denoise" is a per-image function, so what is tested is the host protocol: who gets which images, what noise.
+# ------------------------------------------------------------------------------------------------
+class _StubTransformer:
+    num_gaussians = 16
+    device = torch.device("cpu")
+    cfg = type("C", (), {"in_channels": 64})()
+
+    def __init__(self):
+        self.seen = []
+
+    def set_lora_scale(self, s):
+        pass
+
+    def denoise(self, latents, prompt_embeds, pooled, grid, **kw):
+        self.seen.append(latents.shape[0])
+        return latents * 2.0 + prompt_embeds.float().mean(dim=(1, 2))[:, None, None] + pooled.float().sum(1)[:, None, None]
+
+
+def _pipe_call(batch, seed, with_latents):
+    from lakonlab.pipelines.arcflux_pipeline import ArcFluxPipeline
+    g = torch.Generator().manual_seed(seed)
+    txt, pooled = torch.randn(batch, 4, 8, generator=g), torch.randn(batch, 8, generator=g)
+    kw = dict(latents=torch.randn(batch, 16, 64, generator=g)) if with_latents else dict(
+        generator=torch.Generator().manual_seed(seed + 1))
+    tr = _StubTransformer()
+    pipe = ArcFluxPipeline(transformer=tr)
+    out = pipe(prompt_embeds=txt, pooled_prompt_embeds=pooled, height=64, width=64, num_inference_steps=2,
+               timestep_ratio=1.0, output_type="latent", **kw).images
+    return out, tr.seen
+
+
+def _pipe_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = {}
+        for batch in (5, 2, 1):
+            for with_latents in (True, False):
+                out, seen = _pipe_call(batch, 11, with_latents)
+                res[(batch, with_latents)] = (out, seen)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipeline_call_shards_the_batch_and_is_rank_count_invariant():
+    single = {(b, w): _pipe_call(b, 11, w) for b in (5, 2, 1) for w in (True, False)}
+    for (b, w), (out, seen) in single.items():
+        assert seen == [b] and out.shape == (b, 16, 64)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipe_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for key, (want, _) in single.items():
+        b = key[0]
+        for rank in (0, 1):
+            out, seen = res[rank][key]
+            assert torch.equal(out, want), (key, rank)          # every rank returns the FULL batch, same as one process
+            lo, hi = shard_bounds(b, rank, 2)
+            assert seen == ([hi - lo] if hi > lo else [])       # ... having denoised only its own images
+
+
+def _rng_worker(rank, world, port, path, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lakonlab.runner.checkpoint import get_checkpoint, restore_rng_state, write_checkpoint_to_file, load_checkpoint
+        model = type("M", (), {})()
+        model.generator = torch.Generator().manual_seed(100 + rank)       # train.py --diff_seed: seed + rank
+        model.state_dict = lambda trainable_only=True: {}
+        torch.randn(3, generator=model.generator)                         # advance the streams
+        ck = get_checkpoint(model)                                        # collective
+        expect = torch.randn(4, generator=model.generator)                # what the uninterrupted run draws next
+        if rank == 0:
+            write_checkpoint_to_file(ck, path, create_symlink=False)
+        dist.barrier()
+        fresh = torch.Generator().manual_seed(0)
+        how = restore_rng_state(fresh, load_checkpoint(path)["rng_state"], rank, 7)
+        q.put((rank, how, torch.equal(torch.randn(4, generator=fresh), expect), expect.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_checkpoint_keeps_every_ranks_rng_stream(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    path = str(tmp_path / "ck.pth")
+    procs = [ctx.Process(target=_rng_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(how == "restored" and same for _, how, same, _ in res)     # each rank continues ITS OWN stream
+    assert res[0][3] != res[1][3]                                         # and the streams differ between ranks
+    # a rank the checkpoint does not know is re-seeded (distinct from every saved stream), an old bare-tensor state is rank 0's
+    from lakonlab.runner.checkpoint import load_checkpoint, restore_rng_state
+    saved = load_checkpoint(path)["rng_state"]
+    g2, g3 = torch.Generator(), torch.Generator()
+    assert restore_rng_state(g2, saved, 2, 7) == "reseeded" and restore_rng_state(g3, saved, 3, 7) == "reseeded"
+    assert not torch.equal(torch.randn(4, generator=g2), torch.randn(4, generator=g3))
+    g0 = torch.Generator()
+    assert restore_rng_state(g0, saved[0], 0) == "restored"
