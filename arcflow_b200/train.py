@@ -199,6 +199,16 @@ class ArcFlowDistillStep:
         for s in sv["states"]:
             dhead = ops.policy_backward(head2, s["tgt_u"], sv["sigma_src"], s["sigma_a"], s["sigma_end"], coef,
                                         dhead=dhead, small=s["small"], num_gaussians=st.num_gaussians, eps=eps)
+        return self.backward_from_dhead(sv, dhead, acc, d_mod)
+
+    @torch.no_grad()
+    def backward_from_dhead(self, sv, dhead: torch.Tensor, acc, d_mod: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """d(raw heads) (fp32 [B * tokens, head_n]) -> head / norm_out gradients (accumulated into acc) and dy, the gradient
+        w.r.t. the norm_out output. sv needs 'hidden', 'head_in', 'temb' of the forward (export_activation)."""
+        st = self.student
+        D, head_n, dev = st.cfg.inner_dim, st.weights.head_n, st.device
+        B = sv["temb"].shape[0]
+        tokens = dhead.shape[0] // B
         ops.colsum_f32(dhead, acc["g_b"])
         dhead_bf = dhead.to(torch.bfloat16)      # plumbing cast; the GEMM operands are bf16
         x_in = sv["head_in"].reshape(-1, D)

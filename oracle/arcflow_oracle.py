@@ -188,7 +188,7 @@ def _lin(sd, name: str, x: Tensor, dtype, lora_scale: float = 1.0) -> Tensor:
 def timestep_proj(t: Tensor, dim: int = 256, scale: float = 1.0) -> Tensor:
     """diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0) (Appendix A.5)."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     emb = t.float()[:, None] * torch.exp(exponent)[None, :] * scale
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
@@ -216,6 +216,19 @@ def flux_rope(txt_len: int, grid_h: int, grid_w: int, axes=(16, 56, 56), theta: 
         cos.append(ang.cos().repeat_interleave(2, dim=1).float())
         sin.append(ang.sin().repeat_interleave(2, dim=1).float())
     return torch.cat(cos, -1), torch.cat(sin, -1)
+
+
+_ROPE_CACHE: Dict = {}
+
+
+def _cached_rope(key, make):
+    """The tables depend on the shape only; the reference recomputes them every forward (arcflux.py:171-173) — caching them
+    here only makes the baseline arms that run this oracle (bench.py) faster, never different."""
+    if key not in _ROPE_CACHE:
+        if len(_ROPE_CACHE) > 16:
+            _ROPE_CACHE.clear()
+        _ROPE_CACHE[key] = make()
+    return _ROPE_CACHE[key]
 
 
 def apply_rope(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
@@ -317,7 +330,8 @@ def flux_trunk(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden
     temb = temb + mlp(te + "text_embedder", pooled)
     c = _lin(sd, "context_embedder", encoder_hidden_states.to(dtype), dtype)
 
-    cos, sin = flux_rope(c.shape[1], grid_hw[0], grid_hw[1], cfg.axes_dims_rope)
+    cos, sin = _cached_rope(("flux", c.shape[1], tuple(grid_hw), tuple(cfg.axes_dims_rope), str(x.device)),
+                            lambda: tuple(t.to(x.device) for t in flux_rope(c.shape[1], grid_hw[0], grid_hw[1], cfg.axes_dims_rope)))
     if bf16_quirks:
         cos, sin = cos.bfloat16().float(), sin.bfloat16().float()
     rope = (cos.to(dtype) if dtype != torch.bfloat16 else cos.bfloat16(),
@@ -333,8 +347,9 @@ def flux_trunk(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden
 def flux_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden_states: Tensor,
                  pooled_projections: Tensor, timestep: Tensor, guidance: Optional[Tensor],
                  grid_hw: Sequence[int], dtype=torch.float32, lora_scale: float = 1.0,
-                 bf16_quirks: bool = True) -> Dict[str, Tensor]:
-    """_ArcFluxTransformer2DModel.forward (arcflux.py:134-257).
+                 bf16_quirks: bool = True, return_raw: bool = False) -> Dict[str, Tensor]:
+    """_ArcFluxTransformer2DModel.forward (arcflux.py:134-257). return_raw adds 'raw': the three head Linears'
+    outputs concatenated [B, S_i, K*C + K*L + (K-1)*L] before the log-softmax (what the engine's head GEMM emits).
 
     `timestep` is sigma in [0, 1] as the pipeline passes it (arcflux_pipeline.py:472), `guidance` the
     guidance scale. `dtype` is the compute dtype (float32/float64 = oracle; bfloat16 = the reference's
@@ -350,10 +365,14 @@ def flux_forward(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidd
     x = _ln(x) * (1 + scale)[:, None, :] + shift[:, None, :]
     bs, seq, _ = x.shape
     K, C, L = cfg.num_gaussians, cfg.out_channels, cfg.logweights_channels
-    means = _lin(sd, "proj_out_means", x, dtype).reshape(bs, seq, K, C)
-    logw = _lin(sd, "proj_out_logweights", x, dtype).reshape(bs, seq, K, L).log_softmax(dim=-2)
-    gam = _lin(sd, "proj_out_loggamma", x, dtype).reshape(bs, seq, K - 1, L)
-    return dict(means=means, logweights=logw, loggammas=gam)
+    means = _lin(sd, "proj_out_means", x, dtype)
+    logits = _lin(sd, "proj_out_logweights", x, dtype)
+    gam = _lin(sd, "proj_out_loggamma", x, dtype)
+    out = dict(means=means.reshape(bs, seq, K, C), logweights=logits.reshape(bs, seq, K, L).log_softmax(dim=-2),
+               loggammas=gam.reshape(bs, seq, K - 1, L))
+    if return_raw:
+        out["raw"] = torch.cat([means, logits, gam], dim=-1)
+    return out
 
 
 # =================================================================================================
@@ -372,7 +391,8 @@ def flux_denoise(sd, cfg, latents: Tensor, prompt_embeds: Tensor, pooled: Tensor
     timesteps = scheduler_timesteps(raw, shift)
     assert len(timesteps) == total
     B = latents.shape[0]
-    guidance = torch.full([B], guidance_scale, dtype=torch.float32) if cfg.guidance_embeds else None
+    dev = latents.device
+    guidance = torch.full([B], guidance_scale, dtype=torch.float32, device=dev) if cfg.guidance_embeds else None
     tid = 0
     trace = []
     latents = latents.to(torch.float32)
@@ -380,7 +400,7 @@ def flux_denoise(sd, cfg, latents: Tensor, prompt_embeds: Tensor, pooled: Tensor
         t_src = timesteps[tid]
         sigma_src = t_src / 1000.0
         out = flux_forward(sd, cfg, latents.to(net_dtype), prompt_embeds, pooled,
-                           (t_src.expand(B) / 1000), guidance, grid_hw, dtype=dtype)
+                           (t_src.expand(B) / 1000).to(dev), guidance, grid_hw, dtype=dtype)
         out = {k: v.to(net_dtype).to(torch.float32) for k, v in out.items()}
         x_img = unpack_latents(latents, gh, gw)
         mp = unpack_mp(out, gh, gw, cfg.num_gaussians)
@@ -483,7 +503,9 @@ def qwen_trunk(sd: Dict[str, Tensor], cfg, hidden_states: Tensor, encoder_hidden
     te = "time_text_embed.timestep_embedder"
     tproj = timestep_proj(t, scale=1000.0).to(dtype)
     temb = _lin(sd, te + ".linear_2", F.silu(_lin(sd, te + ".linear_1", tproj, dtype, lora_scale)), dtype, lora_scale)
-    rope = QwenEmbedRope(10000, cfg.axes_dims_rope, True)(1, grid_hw[0], grid_hw[1], c.shape[1])
+    rope = _cached_rope(("qwen", c.shape[1], tuple(grid_hw), tuple(cfg.axes_dims_rope), str(x.device)),
+                        lambda: tuple(f.to(x.device) for f in QwenEmbedRope(10000, cfg.axes_dims_rope, True)(
+                            1, grid_hw[0], grid_hw[1], c.shape[1])))
     for i in range(cfg.num_layers):
         c, x = qwen_block(sd, f"transformer_blocks.{i}.", x, c, temb, rope, heads, dtype, lora_scale)
     return x, temb
@@ -519,7 +541,8 @@ def qwen_denoise(sd, cfg, latents: Tensor, prompt_embeds: Tensor, grid_hw: Seque
     for i in range(num_inference_steps):
         t_src = timesteps[tid]
         sigma_src = t_src / 1000.0
-        out = qwen_forward(sd, cfg, latents.to(net_dtype), prompt_embeds, t_src.expand(B) / 1000, grid_hw, dtype=dtype)
+        out = qwen_forward(sd, cfg, latents.to(net_dtype), prompt_embeds, (t_src.expand(B) / 1000).to(latents.device), grid_hw,
+                           dtype=dtype)
         out = {k: v.to(net_dtype).to(torch.float32) for k, v in out.items()}
         mp = unpack_mp(out, gh, gw, cfg.num_gaussians)
         tid += substeps[i]

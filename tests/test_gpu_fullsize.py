@@ -22,7 +22,7 @@ def rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-20)).item()
 
 
-def test_full_width_forward_parity(lib):
+def test_full_width_forward_parity(lib, parity):
     from arcflow_b200.config import ArcFluxConfig
     from arcflow_b200.model import ArcFluxEngineModel
     from arcflow_b200.synthetic import make_flux_inputs, make_flux_state_dict
@@ -37,7 +37,7 @@ def test_full_width_forward_parity(lib):
     ref_bf16 = O.flux_forward(sd, cfg, *args, dtype=torch.bfloat16)
     for key in ("means", "logweights", "loggammas"):
         e_ours, e_bf16 = rel(ours[key], ref[key]), rel(ref_bf16[key], ref[key])
-        assert e_ours < max(2e-2, 1.5 * e_bf16), f"{key}: ours {e_ours:.3e} vs reference-bf16 {e_bf16:.3e}"
+        parity(f"flux_fullwidth_fwd.{key}", e_ours, max(2e-2, 1.5 * e_bf16))
 
 
 @pytest.fixture(scope="module")
