@@ -19,7 +19,12 @@
 //    "accumulator full" barriers; the peer's epilogue warps release the accumulator with a remote arrive.
 //  * gemm_bf16_kernel (AFB_GEMM_1CTA=1, or tiny problems): one CTA per 128 x 256 tile, 4-stage ring.
 // Roles per CTA: warp 0 TMA producer, warp 1 MMA issuer (whole warp converged, one elected lane issues),
-// warps 2..5 epilogue (tcgen05.ld 32x32b -> bias / GELU-tanh / gate*y+residual -> 16-byte bf16 stores).
+// warps 2..5 epilogue (tcgen05.ld 32x32b -> bias / GELU-tanh / gate*y+residual -> bf16 into a swizzled shared-memory
+// staging tile -> TMA store of whole 128-byte rows, 32 rows x 64 columns per warp and bulk group, double-buffered).
+// Per-row 16-byte global stores (the first version, still selectable with AFB_GEMM_TMA_STORE=0) touch 32 half-written
+// sectors per warp instruction; ncu showed 2x the algorithmic DRAM traffic from the resulting sector fills.
+// W loads carry an L2 evict_last policy and the output stores evict_first: the streamed output (0.6-0.9 GB per launch)
+// must not push the 57-82 MB weight, which every M tile re-reads, out of the 126 MB L2.
 // The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile i overlaps the main
 // loop of tile i+1. Tiles are walked N-fastest so A is read from HBM once and W stays L2-resident.
 #include <stdlib.h>
@@ -39,8 +44,14 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
+// epilogue staging: per epilogue warp 2 buffers of 32 rows x 64 bf16 columns (128-byte rows, SWIZZLE_128B, 1 KiB-aligned)
+constexpr int EPI_COLS = 64;
+constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;           // 4 KiB
+constexpr int EPI_STAGE_BYTES = 4 * 2 * EPI_BUF_BYTES;     // 32 KiB per CTA
 constexpr size_t GEMM_SMEM_BYTES =
-    1024 /*align slack*/ + size_t(STAGES) * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/;
+    1024 /*align slack*/ + size_t(STAGES) * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + 256 /*barriers*/;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;  // createpolicy.fractional.L2::evict_first, fraction 1.0
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;   // createpolicy.fractional.L2::evict_last, fraction 1.0
 
 struct GemmParams {
   int batches, rows_per_batch, tiles_per_batch;
@@ -51,6 +62,8 @@ struct GemmParams {
   float alpha;   // accumulator scale (1 unless a runtime LoRA scale is set)
   int w_trans;   // W given as [K, N] row-major (dX = dY W): MN-major B operand (2-CTA kernel only)
   int nkb_w0;    // K blocks served by the first W buffer (the rest come from the second one; transposed mode)
+  int tma_store; // epilogue through shared memory + TMA store (0: per-row 16-byte global stores)
+  int l2_hints;  // W loads evict_last, output stores evict_first
   __nv_bfloat16* out;
   long long out_ld, out_batch_stride;
   const __nv_bfloat16* bias;
@@ -133,16 +146,118 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
   }
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, bool hint) {
+  if (hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+            reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(L2_EVICT_FIRST)
+        : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One warp = 32 accumulator rows; the tile's 256 columns go out as 4 chunks of 64: tcgen05.ld -> epilogue math -> bf16
+// into the warp's staging buffer (row r at r * 128 B, its 16-byte chunk j at ((j ^ (r & 7)) * 16): the SWIZZLE_128B
+// pattern, conflict-free for the per-row writes) -> one TMA store per chunk. TMA clips rows >= rows_per_batch and
+// columns >= N, so edge tiles need no masks on the store side; loads of bias / gate / residual stay guarded.
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmOut, uint32_t t_base, int n_tile,
+                                                  bool valid, int lane, int row0_warp, int b, uint8_t* stage,
+                                                  int& buf, const __nv_bfloat16* res_row, const __nv_bfloat16* gate_b) {
+  const bool store_rows = row0_warp < p.rows_per_batch;  // warp-uniform: anything of this warp's 32 rows inside the batch?
+#pragma unroll 1
+  for (int c = 0; c < BN / EPI_COLS; ++c) {
+    const int n0 = n_tile * BN + c * EPI_COLS;
+    if (n0 >= p.N) break;
+    uint8_t* sbuf = stage + buf * EPI_BUF_BYTES;
+    if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago (same buffer) has read its source
+    __syncwarp();
+    uint32_t v[2][32];
+    tmem_ld_32x32(t_base + c * EPI_COLS, v[0]);
+    tmem_ld_32x32(t_base + c * EPI_COLS + 32, v[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + hh * 32 + g * 8;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (valid && n < p.N) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[hh][g * 8 + i]) * p.alpha;
+          if (p.bias) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] += bf16_lo(bw[i]);
+              f[2 * i + 1] += bf16_hi(bw[i]);
+            }
+          }
+          if (p.epi == AFB_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_fast(f[i]);
+          } else if (p.epi == AFB_EPI_BIAS_RES) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] += bf16_lo(rw[i]);
+              f[2 * i + 1] += bf16_hi(rw[i]);
+            }
+          } else if (p.epi == AFB_EPI_BIAS_GATE_RES) {
+            const uint4 gv = *reinterpret_cast<const uint4*>(gate_b + n);
+            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] = bf16_lo(rw[i]) + bf16_lo(gw[i]) * f[2 * i];
+              f[2 * i + 1] = bf16_hi(rw[i]) + bf16_hi(gw[i]) * f[2 * i + 1];
+            }
+          }
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+        }
+        const int j = hh * 4 + g;  // 16-byte chunk of this row's 128 bytes
+        *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+      }
+    }
+    fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      if (store_rows) tma_store_3d(tmOut, sbuf, n0, row0_warp, b, p.l2_hints != 0);
+      bulk_commit();
+    }
+    buf ^= 1;
+  }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint8_t* sEpi = sB + STAGES * B_STAGE_BYTES;  // [4 warps][2][4 KiB], 1 KiB-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
@@ -157,6 +272,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     prefetch_tmap(&tmA1);
     prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -249,14 +365,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else {
     // ------------------------------- epilogue warps -----------------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
+    uint8_t* stage = sEpi + q * 2 * EPI_BUF_BYTES;
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int b = m_tile / p.tiles_per_batch;
-      const int r = (m_tile - b * p.tiles_per_batch) * BM + row;
+      const int r0w = (m_tile - b * p.tiles_per_batch) * BM + q * 32;
+      const int r = r0w + lane;
       const bool valid = r < p.rows_per_batch;
       __nv_bfloat16* out_row = p.out + (long long)b * p.out_batch_stride + (long long)r * p.out_ld;
       const __nv_bfloat16* res_row =
@@ -266,13 +384,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
+      if (p.tma_store)
+        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b);
+      else
+        epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();  // the stores' global writes are complete before the grid ends
   }
 
   tc_fence_before();
@@ -290,7 +412,8 @@ constexpr int STAGES2 = 6;
 constexpr int HALF_N = BN / 2;                    // W rows staged per CTA
 constexpr int B2_STAGE_BYTES = HALF_N * BK * 2;   // 16 KiB
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
-constexpr size_t GEMM2_SMEM_BYTES = 1024 + size_t(STAGES2) * STAGE2_BYTES + 256;
+constexpr size_t GEMM2_SMEM_BYTES = 1024 + size_t(STAGES2) * STAGE2_BYTES + EPI_STAGE_BYTES + 256;
+static_assert(GEMM2_SMEM_BYTES <= 232448 && GEMM_SMEM_BYTES <= 232448, "shared memory budget (227 KiB per CTA)");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -317,6 +440,14 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta_hint(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                      int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2cta(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
@@ -350,13 +481,15 @@ __device__ __forceinline__ void tc_commit_2cta_mcast(uint64_t* bar) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
+                      const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut,
+                      const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES2 * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES2 * B2_STAGE_BYTES);
+  uint8_t* sEpi = sB + STAGES2 * B2_STAGE_BYTES;  // [4 warps][2][4 KiB], 1 KiB-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                  // [STAGES2]  both CTAs' TMA -> leader's MMA (leader copy is used)
   uint64_t* empty_bar = bars + STAGES2;       // [STAGES2]  leader's MMA -> each CTA's producer (multicast)
   uint64_t* acc_full = bars + 2 * STAGES2;    // [2]        leader's MMA -> each CTA's epilogue (multicast)
@@ -374,6 +507,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmB1);
+    prefetch_tmap(&tmOut);
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx; bytes from both CTAs
       mbar_init(&empty_bar[s], 1);  // one multicast commit per phase
@@ -429,7 +563,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           }
           tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
           if (!p.w_trans) {
-            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+            if (p.l2_hints)
+              tma_load_2d_2cta_hint(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0, L2_EVICT_LAST);
+            else
+              tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
           } else {  // W is [K, N] row-major: two [64 k x 64 n] boxes, N contiguous (MN-major operand)
             const CUtensorMap* bm = kb < p.nkb_w0 ? &tmB : &tmB1;
             const int kr = (kb < p.nkb_w0 ? kb : kb - p.nkb_w0) * BK;
@@ -486,14 +623,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   } else {
     // ------------------------------- epilogue warps (both CTAs) -----------------------------
     const int q = warp & 3;
-    const int row = q * 32 + lane;
+    uint8_t* stage = sEpi + q * 2 * EPI_BUF_BYTES;
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int b = m_tile / p.tiles_per_batch;
-      const int r = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM + row;
+      const int r0w = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM + q * 32;
+      const int r = r0w + lane;
       const bool valid = r < p.rows_per_batch;
       __nv_bfloat16* out_row = p.out + (long long)b * p.out_batch_stride + (long long)r * p.out_ld;
       const __nv_bfloat16* res_row =
@@ -503,13 +642,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
+      if (p.tma_store)
+        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b);
+      else
+        epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();  // the stores' global writes are complete before the grid ends
   }
 
   tc_fence_before();
@@ -606,6 +749,26 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     tmB1 = tmB;
   }
 
+  // output map for the TMA-store epilogue: [N, rows, batches], box 64 columns x 32 rows (one epilogue warp's chunk)
+  static int tma_store_env = -1, l2_hint_env = -1;
+  if (tma_store_env < 0) {
+    const char* e = getenv("AFB_GEMM_TMA_STORE");
+    tma_store_env = (e && atoi(e) == 0) ? 0 : 1;
+    e = getenv("AFB_GEMM_L2_HINTS");
+    l2_hint_env = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  CUtensorMap tmOut = tmA[0];
+  const uint64_t out_bs = d->batches > 1 ? uint64_t(d->out_batch_stride) : uint64_t(d->rows_per_batch) * uint64_t(d->out_ld);
+  p.tma_store = tma_store_env && (out_bs % 8 == 0);
+  if (p.tma_store) {
+    const uint64_t dims[3] = {uint64_t(d->n), uint64_t(d->rows_per_batch), uint64_t(d->batches)};
+    const uint64_t strides[2] = {uint64_t(d->out_ld) * 2, out_bs * 2};
+    const uint32_t box[3] = {EPI_COLS, 32, 1};
+    int rc = make_tmap_bf16(&tmOut, d->out, 3, dims, strides, box);
+    if (rc != AFB_OK) return rc;
+  }
+  p.l2_hints = l2_hint_env;
+
   p.batches = d->batches;
   p.rows_per_batch = d->rows_per_batch;
   p.tiles_per_batch = (d->rows_per_batch + tile_m - 1) / tile_m;
@@ -638,10 +801,10 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     const int max_clusters = sms / 2;
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
     gemm_bf16_2cta_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2],
-                                                                                  tmB, tmB1, p);
+                                                                                  tmB, tmB1, tmOut, p);
   } else {
     const int grid = num_tiles < sms ? num_tiles : sms;
-    gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
+    gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmOut, p);
   }
   AFB_CHECK_CUDA(cudaGetLastError());
   return AFB_OK;

@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -19,7 +21,34 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+
+// Descriptor cache: the engine launches the same (pointer, shape, box) combinations every forward (1300+ launches x 4-6
+// tensor maps per step), so an encoded CUtensorMap is kept per key instead of calling cuTensorMapEncodeTiled each time.
+// A map depends on nothing but its key (the driver call is a pure function of these arguments).
+struct TmapKey {
+  uint64_t v[12];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t x : k.v) {
+      h ^= x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+      h *= 0xD6E8FEB86659FD93ull;
+    }
+    return size_t(h ^ (h >> 32));
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+std::atomic<uint64_t> g_tmap_hits{0}, g_tmap_misses{0};
+constexpr size_t TMAP_CACHE_MAX = 16384;
 }  // namespace
+
+void tmap_cache_stats(uint64_t* hits, uint64_t* misses) {
+  *hits = g_tmap_hits.load(std::memory_order_relaxed);
+  *misses = g_tmap_misses.load(std::memory_order_relaxed);
+}
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -59,6 +88,27 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     set_last_error("TMA base pointer %p not 16-byte aligned", base);
     return AFB_ERR_INVALID;
   }
+  if (rank < 1 || rank > 5) {
+    set_last_error("TMA rank %d out of range", rank);
+    return AFB_ERR_INVALID;
+  }
+  TmapKey key{};
+  key.v[0] = reinterpret_cast<uintptr_t>(base);
+  key.v[1] = uint64_t(rank);
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i] | (uint64_t(box[i]) << 40);
+    if (i > 0) key.v[7 + i - 1] = strides_bytes[i - 1];
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return AFB_OK;
+    }
+  }
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bx[5];
@@ -86,6 +136,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    (unsigned long long)(rank > 1 ? dims[1] : 0),
                    (unsigned long long)(rank > 2 ? dims[2] : 0));
     return AFB_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= TMAP_CACHE_MAX) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
   }
   return AFB_OK;
 }
