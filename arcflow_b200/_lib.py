@@ -57,7 +57,7 @@ class AttnDesc(C.Structure):
         ("q_batch_stride", C.c_int64), ("k_batch_stride", C.c_int64),
         ("v_batch_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32),
-        ("scale", C.c_float), ("lse", C.c_void_p),
+        ("scale", C.c_float), ("lse", C.c_void_p), ("score_bound", C.c_float),
     ]
 
 
@@ -84,13 +84,13 @@ class DoubleBlock(C.Structure):
         "img_up_w", "img_up_b", "img_up_la", "img_down_w", "img_down_b", "img_down_la",
         "txt_qkv_w", "txt_qkv_b", "txt_nq", "txt_nk", "txt_out_w", "txt_out_b",
         "txt_up_w", "txt_up_b", "txt_up_la", "txt_down_w", "txt_down_b", "txt_down_la")] + [
-        ("img_mod_off", C.c_int64), ("txt_mod_off", C.c_int64)]
+        ("img_mod_off", C.c_int64), ("txt_mod_off", C.c_int64), ("qk_bound", C.c_float), ("reserved0", C.c_float)]
 
 
 class SingleBlock(C.Structure):
     _fields_ = [(n, _P) for n in (
         "qkv_w", "qkv_b", "nq", "nk", "mlp_w", "mlp_b", "mlp_la", "out_w", "out_b", "out_la")] + [
-        ("mod_off", C.c_int64)]
+        ("mod_off", C.c_int64), ("qk_bound", C.c_float), ("reserved0", C.c_float)]
 
 
 class Weights(C.Structure):

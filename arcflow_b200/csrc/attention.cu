@@ -19,6 +19,13 @@
 //   * one pair in four is evaluated on the FMA pipe (Cody-Waite split + cubic minimax for 2^frac),
 //   * scale/subtract, the polynomial and the row sum use packed f32x2 instructions,
 //   * registers move from the producer warpgroup to the softmax warpgroups (setmaxnreg).
+//
+// BOUNDED variant (afb_attn_desc.score_bound > 0): the caller guarantees |scale * q.k| <= score_bound for every pair — the
+// MMDiT blocks RMS-normalise q and k per head, so ||q|| ||k|| / sqrt(128) is bounded by the norm weights alone. Then
+// P = 2^(c s - B) with the FIXED reference B = score_bound * log2(e) needs no row maximum at all: P <= 1 by construction,
+// P >= 2^(-2B) stays a normal bf16 / fp32 number for B <= 60, and O / l and lse = B + log2(l) are the same softmax. The
+// row-max leg (350-540 cycles of the serial S -> max -> exp -> P -> PV chain per Q tile), the lazy O rescale and its
+// branch leave the kernel; the exp phase starts on the first 64 columns while the second 64 are still being read from TMEM.
 #include <math.h>
 #include <stdlib.h>
 
@@ -51,6 +58,7 @@ constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: skip O rescale while m
 struct AttnParams {
   int seq, heads, batch;
   float scale_log2;  // softmax scale * log2(e)
+  float bound_log2;  // BOUNDED: fixed softmax reference point, score_bound * log2(e)
   __nv_bfloat16* o;
   long long o_ld, o_batch_stride;
   float* lse;  // optional [batch, heads, seq]: log2-domain logsumexp of the scaled scores (for the backward)
@@ -95,7 +103,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // TRACE: record clock stamps of the softmax hand-shake (developer builds only; the product instantiation carries no
 // instrumentation — the probes' predicates and address arithmetic cost 8 % of the kernel). TURNS: the two warpgroups
 // alternate in the exp phase.
-template <bool TRACE, bool TURNS>
+template <bool TRACE, bool TURNS, bool BOUNDED>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -274,46 +282,61 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       if (TRACE) trace_stamp(tr, t, j, 1);
       uint32_t s[KT];
+      if (BOUNDED) {  // first half now, second half lands behind the first half's exponentials
+        tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(s[0]));
+        tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(s[32]));
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + 64, reinterpret_cast<uint32_t(&)[32]>(s[64]));
+        tmem_ld_32x32(tS + 96, reinterpret_cast<uint32_t(&)[32]>(s[96]));
+      } else {
 #pragma unroll
-      for (int i = 0; i < KT / 32; ++i)
-        tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
-      tmem_ld_wait();
+        for (int i = 0; i < KT / 32; ++i)
+          tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
+        tmem_ld_wait();
+      }
       if (TRACE) trace_stamp(tr, t, j, 6);
 
       const int valid = p.seq - j * KT;
-      if (valid < KT) {
+      if (BOUNDED && valid < KT / 2) {
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
-          if (i >= valid) s[i] = 0xff800000u;  // -inf
+        for (int i = 0; i < KT / 2; ++i)
+          if (i >= valid) s[i] = 0xff800000u;
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (!BOUNDED) {
+        if (valid < KT) {
 #pragma unroll
-      for (int i = 0; i < KT; i += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-      }
-      const float mx = fmaxf(mx0, mx1);
+          for (int i = 0; i < KT; ++i)
+            if (i >= valid) s[i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < KT; i += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        }
+        const float mx = fmaxf(mx0, mx1);
 
-      if (j == 0) {
-        m = mx;
-      } else {
-        const bool need = (mx - m) * c > RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, need)) {
-          const float f = need ? fast_exp2((m - mx) * c) : 1.0f;
-          if (need) m = mx;
-          l *= f;
-          mbar_wait(&o_done[t], (j - 1) & 1);  // PV_t(j-1) must have retired before O is touched
-          tc_fence_after();
+        if (j == 0) {
+          m = mx;
+        } else {
+          const bool need = (mx - m) * c > RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? fast_exp2((m - mx) * c) : 1.0f;
+            if (need) m = mx;
+            l *= f;
+            mbar_wait(&o_done[t], (j - 1) & 1);  // PV_t(j-1) must have retired before O is touched
+            tc_fence_after();
 #pragma unroll 1
-          for (int i = 0; i < HD / 32; ++i) {
-            uint32_t o[32];
-            tmem_ld_32x32(tO + i * 32, o);
-            tmem_ld_wait();
+            for (int i = 0; i < HD / 32; ++i) {
+              uint32_t o[32];
+              tmem_ld_32x32(tO + i * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
-            tmem_st_32x32(tO + i * 32, o);
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+              tmem_st_32x32(tO + i * 32, o);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
         }
       }
 
@@ -322,10 +345,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (TURNS) named_bar_sync(my_turn);
       if (TRACE) trace_stamp(tr, t, j, 3);
       const float2 c2 = make_float2(c, c);
-      const float2 nm2 = make_float2(-m * c, -m * c);
+      const float2 nm2 = BOUNDED ? make_float2(-p.bound_log2, -p.bound_log2) : make_float2(-m * c, -m * c);
       float2 lsum = make_float2(0.f, 0.f);
 #pragma unroll
       for (int qt = 0; qt < 4; ++qt) {  // quarters of 32 columns
+        if (BOUNDED && qt == 2) {
+          tmem_ld_wait();  // columns [64, 128) have arrived
+          if (valid < KT) {  // last KV tile: columns past the sequence contribute exp2(-inf) = 0
+#pragma unroll
+            for (int i = KT / 2; i < KT; ++i)
+              if (i >= valid) s[i] = 0xff800000u;
+          }
+        }
 #pragma unroll
         for (int i = qt * (KT / 4); i < (qt + 1) * (KT / 4); i += 2) {
           float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
@@ -372,7 +403,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float inv_l = 1.0f / l;
     const int qrow = q0 + t * QT + row;
     const bool valid_row = qrow < p.seq;
-    if (p.lse && valid_row) p.lse[((long long)b * p.heads + h) * p.seq + qrow] = m * c + log2f(l);
+    if (p.lse && valid_row)
+      p.lse[((long long)b * p.heads + h) * p.seq + qrow] = (BOUNDED ? p.bound_log2 : m * c) + log2f(l);
     __nv_bfloat16* orow =
         p.o + (long long)b * p.o_batch_stride + (long long)qrow * p.o_ld + h * HD;
 #pragma unroll 1
@@ -439,22 +471,34 @@ int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
   p.o_ld = d->o_ld;
   p.o_batch_stride = d->o_batch_stride;
   p.lse = d->lse;
+  // score_bound > 0: the caller guarantees |scale * q.k| <= score_bound -> fixed-reference softmax (no row max, no O
+  // rescale). Only used while 2 B stays far inside the fp32 / bf16 exponent range; otherwise the running-max kernel runs.
+  const float bound_log2 = d->score_bound > 0.f ? d->score_bound * 1.4426950408889634f : 0.f;
+  static int bounded_env = -1;
   // Developer variants (env AFB_ATTN_DEBUG_MODE): 7 = clock-stamp trace, 8 = trace without warpgroup turn-taking,
-  // 9 = no turn-taking, no trace. Anything else is the product kernel, which carries no instrumentation.
+  // 9 = no turn-taking, no trace, 10 = ignore score_bound (always the running-max kernel), 11 = bounded without
+  // turn-taking. Anything else is the product kernel, which carries no instrumentation.
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("AFB_ATTN_DEBUG_MODE");
     dbg = e ? atoi(e) : 0;
+    bounded_env = dbg == 10 ? 0 : 1;
   }
+  const bool bounded = bounded_env && bound_log2 > 0.f && bound_log2 <= 60.0f;
+  p.bound_log2 = bounded ? bound_log2 : 0.f;
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
-  KernelFn fn = dbg == 7   ? attention_fwd_kernel<true, true>
-                : dbg == 8 ? attention_fwd_kernel<true, false>
-                : dbg == 9 ? attention_fwd_kernel<false, false>
-                           : attention_fwd_kernel<false, true>;
-  static KernelFn attr_set_for = nullptr;
-  if (attr_set_for != fn) {
+  KernelFn fn;
+  if (bounded)
+    fn = dbg == 11 ? attention_fwd_kernel<false, false, true> : attention_fwd_kernel<false, true, true>;
+  else
+    fn = dbg == 7   ? attention_fwd_kernel<true, true, false>
+         : dbg == 8 ? attention_fwd_kernel<true, false, false>
+         : dbg == 9 ? attention_fwd_kernel<false, false, false>
+                    : attention_fwd_kernel<false, true, false>;
+  static KernelFn attr_set_for[2] = {nullptr, nullptr};
+  if (attr_set_for[bounded] != fn) {
     AFB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATT_SMEM_BYTES)));
-    attr_set_for = fn;
+    attr_set_for[bounded] = fn;
   }
   dim3 grid((d->seq + NQT * QT - 1) / (NQT * QT), d->heads, d->batch);
   fn<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], p);

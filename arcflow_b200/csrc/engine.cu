@@ -602,6 +602,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     }
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, St, k.txt_nq,
                                      k.txt_nk, k.img_nq, k.img_nk, a->rope_cos, a->rope_sin, LN_EPS, s));
+    at.score_bound = k.qk_bound;
     AFB_TRY(run_attention(e, &at, s));
     const bool last_qwen_txt = !flux && i == d.num_double - 1;  // its text stream output is never read
     if (stash) {  // un-fused: the un-gated branch output and the mid-block residual stream are kept
@@ -659,6 +660,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     }
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, 0, nullptr, nullptr,
                                      k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
+    at.score_bound = k.qk_bound;
     AFB_TRY(run_attention(e, &at, s));
     const View up_out = stash ? View{e->mlp_pre, M, int64_t(S) * M} : mlp_all;
     const int up_epi = stash ? AFB_EPI_BIAS : AFB_EPI_BIAS_GELU;
@@ -907,6 +909,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_CHECK_CUDA(cudaMemcpyAsync(e->qkv, e->qkv_raw, size_t(B) * S * 3 * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, bs3, 0, D, B, S, H, 0, nullptr, nullptr, k.nq, k.nk, a->rope_cos,
                                      a->rope_sin, LN_EPS, s));
+    at.score_bound = k.qk_bound;
     if (!stash) AFB_TRY(run_attention(e, &at, s));
     const uint32_t layer = 4u * (d.num_double + i);
     if (lm) {
@@ -1029,6 +1032,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
     AFB_CHECK_CUDA(cudaMemcpyAsync(e->qkv, e->qkv_raw, size_t(B) * S * 3 * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
     AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, bs3, 0, D, B, S, H, St, k.txt_nq, k.txt_nk, k.img_nq, k.img_nk,
                                      a->rope_cos, a->rope_sin, LN_EPS, s));
+    at.score_bound = k.qk_bound;
     if (!stash) AFB_TRY(run_attention(e, &at, s));
     // -- recompute: h_mid and the MLP half; then the MLP half's backward (per stream)
     for (Stream& t : st2) {

@@ -63,7 +63,8 @@ struct GemmParams {
   int w_trans;   // W given as [K, N] row-major (dX = dY W): MN-major B operand (2-CTA kernel only)
   int nkb_w0;    // K blocks served by the first W buffer (the rest come from the second one; transposed mode)
   int tma_store; // epilogue through shared memory + TMA store (0: per-row 16-byte global stores)
-  int l2_hints;  // W loads evict_last, output stores evict_first
+  int l2_hints;  // W loads evict_last, output stores evict_first; 2: A loads evict_first as well
+  int gn;        // tile raster: N tiles per column group (0 / >= num_n_tiles: plain N-fastest order)
   __nv_bfloat16* out;
   long long out_ld, out_batch_stride;
   const __nv_bfloat16* bias;
@@ -72,6 +73,27 @@ struct GemmParams {
   const __nv_bfloat16* res;
   long long res_ld, res_batch_stride;
 };
+
+// Tile raster. Tiles are handed out round-robin, so tiles [i * G, (i + 1) * G) (G = CTAs or clusters in flight) run
+// together. Plain order walks N fastest: a wave spans all N tiles, i.e. streams ALL of W, every wave — for the MLP
+// weights (77-96 MB, more than the part of the 126 MB L2 a streamed operand can hold) that re-reads W from DRAM ~20 times
+// (ncu: 3.8 GB read for 0.3 GB of operands). With column groups of `gn` N-tiles the order is: group by group, inside a
+// group M-major with N fastest — a wave spans gn N-tiles x (G / gn) M-rows, the group's W panels (gn x 256 x K x 2 B) stay
+// L2-resident while the sweep goes down M, and A is streamed once per group.
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_tile, int& n_tile) {
+  if (p.gn <= 0 || p.gn >= p.num_n_tiles) {
+    m_tile = tile / p.num_n_tiles;
+    n_tile = tile - m_tile * p.num_n_tiles;
+    return;
+  }
+  const int per_group = p.gn * p.num_m_tiles;
+  const int g = tile / per_group;
+  const int r = tile - g * per_group;
+  const int rest = p.num_n_tiles - g * p.gn;
+  const int width = rest < p.gn ? rest : p.gn;  // the last group may be narrower
+  m_tile = r / width;
+  n_tile = g * p.gn + (r - m_tile * width);
+}
 
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -298,8 +320,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        int m_tile, n_tile;
+        tile_coords(p, tile, m_tile, n_tile);
         const int b = m_tile / p.tiles_per_batch;
         const int r0 = (m_tile - b * p.tiles_per_batch) * BM;
         for (int kb = 0; kb < nk; ++kb) {
@@ -370,8 +392,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      int m_tile, n_tile;
+      tile_coords(p, tile, m_tile, n_tile);
       const int b = m_tile / p.tiles_per_batch;
       const int r0w = (m_tile - b * p.tiles_per_batch) * BM + q * 32;
       const int r = r0w + lane;
@@ -448,6 +470,14 @@ __device__ __forceinline__ void tma_load_2d_2cta_hint(void* dst, const CUtensorM
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta_hint(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                      int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2cta(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
@@ -540,8 +570,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        int m_tile, n_tile;
+        tile_coords(p, tile, m_tile, n_tile);
         const int b = m_tile / p.tiles_per_batch;
         const int r0 = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM;
         const int n0 = n_tile * BN + int(rank) * HALF_N;
@@ -561,7 +591,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             am = &tmA2;
             kk = kb - p.nk_end[1];
           }
-          tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
+          if (p.l2_hints == 2)
+            tma_load_3d_2cta_hint(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b, L2_EVICT_FIRST);
+          else
+            tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
           if (!p.w_trans) {
             if (p.l2_hints)
               tma_load_2d_2cta_hint(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0, L2_EVICT_LAST);
@@ -628,8 +661,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      int m_tile, n_tile;
+      tile_coords(p, tile, m_tile, n_tile);
       const int b = m_tile / p.tiles_per_batch;
       const int r0w = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM + q * 32;
       const int r = r0w + lane;
@@ -755,7 +788,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     const char* e = getenv("AFB_GEMM_TMA_STORE");
     tma_store_env = (e && atoi(e) == 0) ? 0 : 1;
     e = getenv("AFB_GEMM_L2_HINTS");
-    l2_hint_env = (e && atoi(e) == 0) ? 0 : 1;
+    l2_hint_env = e ? atoi(e) : 1;
   }
   CUtensorMap tmOut = tmA[0];
   const uint64_t out_bs = d->batches > 1 ? uint64_t(d->out_batch_stride) : uint64_t(d->rows_per_batch) * uint64_t(d->out_ld);
@@ -768,6 +801,26 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     if (rc != AFB_OK) return rc;
   }
   p.l2_hints = l2_hint_env;
+  // column-group raster (see tile_coords): keep a group's W panels within ~32 MB; AFB_GEMM_GN overrides (0 = plain order)
+  static int gn_env = -2;
+  if (gn_env == -2) {
+    const char* e = getenv("AFB_GEMM_GN");
+    gn_env = e ? atoi(e) : -1;
+  }
+  {
+    const int ntiles = (d->n + BN - 1) / BN;
+    const double panel = double(BN) * ktot * 2.0, w_total = double(d->n) * ktot * 2.0;
+    int gn = 0;
+    if (gn_env >= 0) {
+      gn = gn_env;
+    } else if (two_cta && !d->w_transposed && w_total > 40e6) {
+      gn = int(32e6 / panel);
+      if (gn < 2) gn = 2;
+      const int groups = (ntiles + gn - 1) / gn;  // even out the group widths
+      gn = (ntiles + groups - 1) / groups;
+    }
+    p.gn = gn >= ntiles ? 0 : gn;
+  }
 
   p.batches = d->batches;
   p.rows_per_batch = d->rows_per_batch;

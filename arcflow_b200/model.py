@@ -19,6 +19,7 @@ import torch
 from . import _lib
 from ._lib import AfbError
 from .config import ArcFluxConfig
+from .ops import qk_score_bound
 from .rope import flux_rope_tables
 from .schedule import denoise_sigmas, flux_time_inputs
 
@@ -132,8 +133,11 @@ class PackedFluxWeights:
                 setattr(k, f"{side}_down_w", hold_packed(get(p + f"{ff}.net.2.weight"), lb, p + f"{ff}.net.2"))
                 setattr(k, f"{side}_down_b", hold(get(p + f"{ff}.net.2.bias")))
                 setattr(k, f"{side}_down_la", hold(la, p + f"{ff}.net.2.lora_A.weight"))
-            k.img_nq, k.img_nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
-            k.txt_nq, k.txt_nk = hold(get(p + "attn.norm_added_q.weight")), hold(get(p + "attn.norm_added_k.weight"))
+            norms = [get(p + f"attn.{n}.weight") for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k")]
+            k.img_nq, k.img_nk, k.txt_nq, k.txt_nk = (hold(t) for t in norms)
+            # q and k are RMS-normalised per head, so the attention scores of the joint sequence are bounded by the norm
+            # weights alone -> fixed-reference softmax in the attention kernel (afb_attn_desc.score_bound)
+            k.qk_bound = qk_score_bound((norms[0], norms[1]), (norms[2], norms[3]))
 
         self.sgl = (_lib.SingleBlock * max(cfg.num_single_layers, 1))()
         for i in range(cfg.num_single_layers):
@@ -142,7 +146,9 @@ class PackedFluxWeights:
             k.mod_off = add_mod(p + "norm.linear")
             k.qkv_w = hold(torch.cat([get(p + f"attn.{n}.weight") for n in ("to_q", "to_k", "to_v")], 0))
             k.qkv_b = hold(torch.cat([get(p + f"attn.{n}.bias") for n in ("to_q", "to_k", "to_v")], 0))
-            k.nq, k.nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
+            nq_t, nk_t = get(p + "attn.norm_q.weight"), get(p + "attn.norm_k.weight")
+            k.nq, k.nk = hold(nq_t), hold(nk_t)
+            k.qk_bound = qk_score_bound((nq_t, nk_t))
             la, lb = lora(p + "proj_mlp")
             k.mlp_w = hold_packed(get(p + "proj_mlp.weight"), lb, p + "proj_mlp")
             k.mlp_b, k.mlp_la = hold(get(p + "proj_mlp.bias")), hold(la, p + "proj_mlp.lora_A.weight")

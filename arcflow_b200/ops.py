@@ -106,9 +106,10 @@ def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.T
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None,
-              scale: float = 0.0, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+              scale: float = 0.0, lse: Optional[torch.Tensor] = None, score_bound: float = 0.0) -> torch.Tensor:
     """Joint non-causal attention. q/k/v: [batch, seq, heads*128] views (last dim contiguous).
-    lse (optional, fp32 [batch, heads, seq]) receives the log2-domain logsumexp needed by attention_backward."""
+    lse (optional, fp32 [batch, heads, seq]) receives the log2-domain logsumexp needed by attention_backward.
+    score_bound > 0: a guaranteed bound on |scale * q.k| (see qk_score_bound) -> the fixed-reference softmax kernel."""
     lib = _lib.load()
     d = AttnDesc()
     shp = None
@@ -134,6 +135,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[t
     d.o, d.o_ld, d.o_batch_stride = optr, old, obs
     d.batch, d.seq, d.heads = nb, ns, nc // 128
     d.scale = scale
+    d.score_bound = float(score_bound)
     if lse is not None:
         _chk(lse, torch.float32, "attention lse")
         if tuple(lse.shape) != (nb, nc // 128, ns) or not lse.is_contiguous():
@@ -141,6 +143,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[t
         d.lse = lse.data_ptr()
     _lib.check(lib.afb_attention(C.byref(d), _stream()), "afb_attention")
     return out
+
+
+def qk_score_bound(*norm_weight_pairs, head_dim: int = 128, margin: float = 1.05) -> float:
+    """Bound on |q . k| / sqrt(head_dim) for per-head RMS-normalised, rotated q and k: RMSNorm makes ||q_hat||^2 <= head_dim,
+    the elementwise weight scales it by at most max|w|, RoPE is a rotation of pairs — so
+    |q . k| <= ||q|| ||k|| <= head_dim * max|w_q| * max|w_k|. Arguments: (w_q, w_k) tensors per stream of the joint sequence
+    (the bound must hold for every query against every key, so the maxima are taken over all streams). `margin` covers the
+    bf16 roundings after the norm, the weight multiply and the rotation (each < 0.4 %)."""
+    wq = max(float(p[0].float().abs().max()) for p in norm_weight_pairs)
+    wk = max(float(p[1].float().abs().max()) for p in norm_weight_pairs)
+    return margin * head_dim * wq * wk / (head_dim ** 0.5)
 
 
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor,

@@ -237,8 +237,10 @@ class PackedQwenWeights:
                 setattr(k, f"{side}_down_w", hold_packed(get(p + f"{ff}.net.2.weight"), lb, p + f"{ff}.net.2"))
                 setattr(k, f"{side}_down_b", hold(get(p + f"{ff}.net.2.bias")))
                 setattr(k, f"{side}_down_la", hold(la, p + f"{ff}.net.2.lora_A.weight"))
-            k.img_nq, k.img_nk = hold(get(p + "attn.norm_q.weight")), hold(get(p + "attn.norm_k.weight"))
-            k.txt_nq, k.txt_nk = hold(get(p + "attn.norm_added_q.weight")), hold(get(p + "attn.norm_added_k.weight"))
+            norms = [get(p + f"attn.{n}.weight") for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k")]
+            k.img_nq, k.img_nk, k.txt_nq, k.txt_nk = (hold(t) for t in norms)
+            # per-head RMSNorm on q and k bounds the joint attention scores (see PackedFluxWeights)
+            k.qk_bound = ops.qk_score_bound((norms[0], norms[1]), (norms[2], norms[3]))
         self.sgl = (_lib.SingleBlock * 1)()
         w.norm_out_mod_off = add_mod("norm_out.linear")
         mod_w_t, mod_b_t = torch.cat(mod_w, 0), torch.cat(mod_b, 0)

@@ -113,6 +113,10 @@ typedef struct afb_attn_desc {
   int32_t batch, seq, heads;
   float scale; /* 0 -> 1/sqrt(128) */
   float* lse;  /* optional fp32 [batch, heads, seq]: log2-domain logsumexp of the scaled scores, saved for afb_attention_backward */
+  float score_bound; /* optional, > 0: the caller guarantees |scale * q_i . k_j| <= score_bound for every pair (e.g. from
+                        per-head RMSNorm weights: sqrt(128) * max|w_q| * max|w_k|). The kernel then evaluates
+                        P = exp(s - score_bound) against this FIXED reference — same softmax, no running row maximum, no
+                        O rescale. 0 = unknown: running-max kernel. Bounds above ~41 (2^60) fall back to it too. */
 } afb_attn_desc;
 
 int afb_attention(const afb_attn_desc* desc, void* stream);
@@ -352,6 +356,9 @@ typedef struct afb_double_block {
   const void *txt_up_w, *txt_up_b, *txt_up_la;
   const void *txt_down_w, *txt_down_b, *txt_down_la;
   int64_t img_mod_off, txt_mod_off; /* column offset of this block's 6*D modulation chunk */
+  float qk_bound;  /* > 0: upper bound on |q . k| / sqrt(128) after RMSNorm + RoPE over BOTH streams of the joint sequence
+                      (afb_attn_desc.score_bound); 0 = not provided */
+  float reserved0;
 } afb_double_block;
 
 typedef struct afb_single_block {
@@ -360,6 +367,8 @@ typedef struct afb_single_block {
   const void *mlp_w, *mlp_b, *mlp_la;     /* [M, D(+r)], [M], [r, D] */
   const void *out_w, *out_b, *out_la;     /* [D, D+M(+r)], [D], [r, D+M] */
   int64_t mod_off;                        /* 3*D chunk */
+  float qk_bound;                         /* as in afb_double_block */
+  float reserved0;
 } afb_single_block;
 
 typedef struct afb_weights {
