@@ -161,6 +161,13 @@ class EmbedGrads(C.Structure):
     _fields_ = [(n, _P) for n in ("t1_la", "t1_lb", "t2_la", "t2_lb")]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [("x", _P), ("w", _P), ("bias", _P), ("res", _P), ("out", _P),
+                ("x_ld", C.c_int64), ("out_ld", C.c_int64), ("res_ld", C.c_int64),
+                ("n", C.c_int32), ("h", C.c_int32), ("w_px", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32),
+                ("epilogue", C.c_int32)]
+
+
 class Profile(C.Structure):
     _fields_ = [("gemm_ms", C.c_double), ("attn_ms", C.c_double), ("gemm_flops", C.c_double),
                 ("attn_flops", C.c_double), ("gemm_launches", C.c_int64), ("attn_launches", C.c_int64)]
@@ -213,6 +220,13 @@ SIGNATURES = {
     "afb_engine_forward_train": (C.c_int, [_P, C.POINTER(ForwardArgs), _P]),
     "afb_engine_backward": (C.c_int, [_P, C.POINTER(BackwardArgs), _P]),
     "afb_engine_backward_embed": (C.c_int, [_P, C.POINTER(ForwardArgs), _P, C.POINTER(EmbedGrads), _P]),
+    "afb_conv3x3": (C.c_int, [C.POINTER(ConvDesc), _P]),
+    "afb_groupnorm_ws_floats": (C.c_int, [C.c_int32, C.c_int64]),
+    "afb_groupnorm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
+    "afb_upsample2x": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "afb_softmax_rows": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P]),
+    "afb_vae_pre": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
+    "afb_vae_post": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "afb_grad_norm_sq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "afb_grad_norm_scratch_floats": (C.c_int, []),
     "afb_grad_norm_sq_ws": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P]),

@@ -18,7 +18,7 @@ LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libarcflow_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["host.cu", "gemm.cu", "gemm_tn.cu", "attention.cu", "attention_bwd.cu", "elementwise.cu", "optim.cu", "engine.cu", "c_api.cu"]
+SOURCES = ["host.cu", "gemm.cu", "gemm_tn.cu", "attention.cu", "attention_bwd.cu", "elementwise.cu", "optim.cu", "vae.cu", "engine.cu", "c_api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

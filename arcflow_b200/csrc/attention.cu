@@ -434,6 +434,256 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// ================================================================================================================
+// SPLIT variant of the bounded-score kernel: TWO threads per query row. The fixed-reference softmax has no row maximum, so a
+// row's 128 columns need no communication while the tile is processed — each of 4 softmax warpgroups (2 per Q tile) owns a
+// 64-column half: tcgen05.ld 64 columns -> 2^(c s - B) -> packed bf16 P into ITS OWN columns of the S region -> one arrive.
+// Why: in the one-thread-per-row kernel a tile's softmax is ~780 dependent-ish instructions in ONE warp per scheduler
+// (measured: S ready -> P published ~1900 cycles, IPC 0.4), and that latency sits in the serial chain
+// QK -> softmax -> PV -> QK of its tile (period ~2830 cycles per KV tile vs 2048 of tensor work). Two warps per scheduler
+// working on the same tile halve the chain's softmax leg; the MUFU unit sees the same total work.
+//   warps 0..3    as above (TMA, MMA, 2 idle)
+//   warps 4..19   softmax: tile t = (warp - 4) / 8, column half hf = ((warp - 4) / 4) & 1, TMEM lane quarter warp & 3
+// P layout in TMEM: half hf of tile t lives in columns [t * 128 + hf * 64, + 32) (inside the S columns its own warpgroup
+// read), so no warpgroup overwrites S data another one may still be loading.
+// ================================================================================================================
+constexpr int ATT_SPLIT_THREADS = 32 * (4 + 8 * NQT);
+// 640 threads x 96 registers fill the register file; the 64-column softmax fits in 96 (no spills in its loop), so no
+// setmaxnreg hand-off is needed here (moving registers away from the MMA-issue warp made IT spill)
+constexpr int SPLIT_SOFTMAX_REGS = 96;
+constexpr int SPLIT_PRODUCER_REGS = 96;
+static_assert((SPLIT_SOFTMAX_REGS - 96) * 512 <= (96 - SPLIT_PRODUCER_REGS) * 128, "register hand-off does not balance");
+
+__global__ void __launch_bounds__(ATT_SPLIT_THREADS, 1)
+attention_fwd_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + NQT * TILE_BYTES;
+  uint8_t* sV = sK + K_STAGES * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + V_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;                   // [1]
+  uint64_t* k_full = q_full + 1;             // [K_STAGES]
+  uint64_t* k_empty = k_full + K_STAGES;     // [K_STAGES]
+  uint64_t* v_full = k_empty + K_STAGES;     // [V_STAGES]
+  uint64_t* v_empty = v_full + V_STAGES;     // [V_STAGES]
+  uint64_t* s_full = v_empty + V_STAGES;     // [NQT]  MMA -> softmax : S_t(j) ready
+  uint64_t* p_full = s_full + NQT;           // [NQT][2]  softmax -> MMA : half hf of P_t(j) written
+  uint64_t* o_done = p_full + 2 * NQT;       // [NQT]  MMA -> softmax : PV_t(j) retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + NQT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (NQT * QT);
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_kv = (p.seq + KT - 1) / KT;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < K_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < V_STAGES; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < NQT; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[2 * t], 4);  // one arrive per warp of the half's warpgroup
+      mbar_init(&p_full[2 * t + 1], 4);
+      mbar_init(&o_done[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    if (SPLIT_PRODUCER_REGS < 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SPLIT_PRODUCER_REGS));
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_expect_tx(q_full, NQT * TILE_BYTES);
+        for (int t = 0; t < NQT; ++t)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sQ + t * TILE_BYTES + hf * HALF_BYTES, &tmQ, q_full, h * HD + hf * 64, q0 + t * QT, b);
+        for (int j = 0; j < n_kv; ++j) {
+          const int ks = j % K_STAGES, vs = j % V_STAGES;
+          const uint32_t kph = (j / K_STAGES) & 1, vph = (j / V_STAGES) & 1;
+          mbar_wait(&k_empty[ks], kph ^ 1);
+          mbar_expect_tx(&k_full[ks], TILE_BYTES);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sK + ks * TILE_BYTES + hf * HALF_BYTES, &tmK, &k_full[ks], h * HD + hf * 64, j * KT, b);
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          mbar_expect_tx(&v_full[vs], TILE_BYTES);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sV + vs * TILE_BYTES + hf * HALF_BYTES, &tmV, &v_full[vs], h * HD + hf * 64, j * KT, b);
+        }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KT, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(QT, HD, false, true);  // V is MN-major
+      const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
+      const uint64_t k_desc = make_sw128_desc(smem_u32(sK), 16, 1024);
+      const uint64_t v_desc = make_sw128_desc(smem_u32(sV), HALF_BYTES, 1024);
+      auto issue_qk = [&](int t, int st) {
+        const uint64_t a0 = q_desc + uint64_t((t * TILE_BYTES) >> 4);
+        const uint64_t b0 = k_desc + uint64_t((st * TILE_BYTES) >> 4);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint32_t off = ((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4;
+            umma_ss(tmem_base + t * KT, a0 + off, b0 + off, idesc_qk, kk > 0);
+          }
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int t, int st, int hf, bool acc) {
+        const uint64_t b0 = v_desc + uint64_t((st * TILE_BYTES) >> 4);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kl = 0; kl < KT / 32; ++kl) {
+            const int kk = hf * (KT / 32) + kl;  // K = 16 step: V rows [16 kk, 16 kk + 16); P half hf starts at column hf * 64
+            umma_ts(tmem_base + NQT * KT + t * HD, tmem_base + t * KT + hf * 64 + kl * 8, b0 + uint64_t((kk * 2048) >> 4),
+                    idesc_pv, (acc || kk > 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one_sync()) tc_commit(bar);
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < NQT; ++t) {
+        issue_qk(t, 0);
+        commit(&s_full[t]);
+      }
+      commit(&k_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % V_STAGES;
+        const uint32_t ph = (j / V_STAGES) & 1;
+        const bool has_next = (j + 1) < n_kv;
+        const int nst = (j + 1) % K_STAGES;
+        const uint32_t nph = ((j + 1) / K_STAGES) & 1;
+        mbar_wait(&v_full[st], ph);
+        if (has_next) mbar_wait(&k_full[nst], nph);
+        for (int t = 0; t < NQT; ++t) {
+          mbar_wait(&p_full[2 * t], j & 1);
+          tc_fence_after();
+          issue_pv(t, st, 0, j > 0);
+          mbar_wait(&p_full[2 * t + 1], j & 1);
+          tc_fence_after();
+          issue_pv(t, st, 1, true);
+          commit(&o_done[t]);
+          if (has_next) {
+            issue_qk(t, nst);
+            commit(&s_full[t]);
+          }
+        }
+        commit(&v_empty[st]);
+        if (has_next) commit(&k_empty[nst]);
+      }
+    }
+  } else {
+    if (SPLIT_SOFTMAX_REGS > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SPLIT_SOFTMAX_REGS));
+    const int sw = warp - 4;
+    const int t = sw >> 3;         // which Q tile
+    const int hf = (sw >> 2) & 1;  // which 64-column half of the tile
+    const int qd = warp & 3;       // TMEM lane quarter
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * KT + hf * 64;  // this thread's 64 S columns; P goes to the first 32
+    const uint32_t tO = tmem_base + lane_base + NQT * KT + t * HD + hf * 64;
+    const float c = p.scale_log2;
+    const float2 c2 = make_float2(c, c);
+    const float2 nm2 = make_float2(-p.bound_log2, -p.bound_log2);
+    float l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(s[0]));
+      tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(s[32]));
+      tmem_ld_wait();
+      const int valid = p.seq - j * KT - hf * 64;  // columns of this half inside the sequence
+      if (valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf -> exp2 = 0
+      }
+      float2 lsum = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
+        float2 pv;
+        if (((i >> 1) & 3) == 3) {
+          pv = exp2_poly2(x);
+        } else {
+          pv.x = fast_exp2(x.x);
+          pv.y = fast_exp2(x.y);
+        }
+        lsum = __fadd2_rn(lsum, pv);
+        s[i >> 1] = pack_bf16x2(pv.x, pv.y);
+      }
+      l += lsum.x + lsum.y;
+      tmem_st_32x32(tS, reinterpret_cast<const uint32_t(&)[32]>(s[0]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[2 * t + hf]);
+    }
+
+    // row sum of the two halves through shared memory (the Q tiles are dead once the last QK^T has retired)
+    mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    tc_fence_after();
+    float* sL = reinterpret_cast<float*>(sQ + t * TILE_BYTES);  // [2][128]
+    sL[hf * 128 + row] = l;
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");   // the 256 threads of this tile
+    const float l_tot = sL[row] + sL[128 + row];
+    const float inv_l = 1.0f / l_tot;
+    const int qrow = q0 + t * QT + row;
+    const bool valid_row = qrow < p.seq;
+    if (p.lse && valid_row && hf == 0) p.lse[((long long)b * p.heads + h) * p.seq + qrow] = p.bound_log2 + log2f(l_tot);
+    __nv_bfloat16* orow = p.o + (long long)b * p.o_batch_stride + (long long)qrow * p.o_ld + h * HD + hf * 64;
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      uint32_t o[32];
+      tmem_ld_32x32(tO + i * 32, o);
+      tmem_ld_wait();
+      if (valid_row) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + i * 32 + g * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int attention_read_trace(long long* out, int n) {
@@ -476,8 +726,9 @@ int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
   const float bound_log2 = d->score_bound > 0.f ? d->score_bound * 1.4426950408889634f : 0.f;
   static int bounded_env = -1;
   // Developer variants (env AFB_ATTN_DEBUG_MODE): 7 = clock-stamp trace, 8 = trace without warpgroup turn-taking,
-  // 9 = no turn-taking, no trace, 10 = ignore score_bound (always the running-max kernel), 11 = bounded without
-  // turn-taking. Anything else is the product kernel, which carries no instrumentation.
+  // 9 = no turn-taking, no trace, 10 = ignore score_bound (always the running-max kernel), 11 / 12 = bounded scores with ONE
+  // thread per row, without / with turn-taking (the first bounded kernel). Anything else is the product path, which
+  // carries no instrumentation.
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("AFB_ATTN_DEBUG_MODE");
@@ -488,7 +739,11 @@ int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
   p.bound_log2 = bounded ? bound_log2 : 0.f;
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
   KernelFn fn;
-  if (bounded)
+  int threads = ATT_THREADS;
+  if (bounded && dbg != 11 && dbg != 12) {  // product path for bounded scores: two threads per row
+    fn = attention_fwd_split_kernel;
+    threads = ATT_SPLIT_THREADS;
+  } else if (bounded)   // 11: one thread per row, no turn-taking; 12: one thread per row with turn-taking
     fn = dbg == 11 ? attention_fwd_kernel<false, false, true> : attention_fwd_kernel<false, true, true>;
   else
     fn = dbg == 7   ? attention_fwd_kernel<true, true, false>
@@ -501,7 +756,7 @@ int attention_launch(const afb_attn_desc* d, cudaStream_t stream) {
     attr_set_for[bounded] = fn;
   }
   dim3 grid((d->seq + NQT * QT - 1) / (NQT * QT), d->heads, d->batch);
-  fn<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], p);
+  fn<<<grid, threads, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], p);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

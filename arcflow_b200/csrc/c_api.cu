@@ -34,6 +34,14 @@ int cfg_combine_launch(const void* both_bf16, float* out, int64_t half, float gu
 int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream);
 int grad_norm_scratch_floats();
+int conv3x3_launch(const afb_conv_desc* d, cudaStream_t stream);
+int vae_pre_launch(const float* z, void* out, int n, int c_in, int h, int w, int c_pad, float scale, float shift, cudaStream_t stream);
+int vae_post_launch(const void* x, int64_t x_ld, float* out, int n, int c_out, int h, int w, cudaStream_t stream);
+int groupnorm_ws_floats(int n, long long hw);
+int groupnorm_launch(const void* x, void* y, const float* gamma, const float* beta, float* ws, int64_t ws_floats, int n,
+                     long long hw, int c, float eps, int silu_on, cudaStream_t stream);
+int upsample2x_launch(const void* x, void* y, int n, int h, int w, int c, cudaStream_t stream);
+int softmax_rows_launch(void* x, int64_t ld, long long rows, int cols, cudaStream_t stream);
 int grad_norm_sq_ws_launch(const float* g, int64_t n, float* out, float* scratch, int64_t scratch_floats, cudaStream_t stream);
 int ln_modulate_bwd_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, void* dh, int64_t dh_bs,
                            const void* scale, int64_t mod_bs, int batches, int rows_per_batch, int dim, float eps,
@@ -163,6 +171,29 @@ int afb_rmsnorm_rope_bwd(void* dqkv, const void* raw, int64_t ld, int64_t bs, in
 }
 int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream) {
   return afb::grad_norm_sq_launch(grads, n, out, static_cast<cudaStream_t>(stream));
+}
+int afb_conv3x3(const afb_conv_desc* desc, void* stream) {
+  int rc = afb::conv3x3_launch(desc, static_cast<cudaStream_t>(stream));
+  if (rc == AFB_OK) afb::count_launch(1);
+  return rc;
+}
+int afb_groupnorm_ws_floats(int32_t n, int64_t hw) { return afb::groupnorm_ws_floats(n, hw); }
+int afb_groupnorm(const void* x, void* y, const float* gamma, const float* beta, float* ws, int64_t ws_floats, int32_t n,
+                  int64_t hw, int32_t c, float eps, int32_t silu, void* stream) {
+  return afb::groupnorm_launch(x, y, gamma, beta, ws, ws_floats, n, hw, c, eps, silu, static_cast<cudaStream_t>(stream));
+}
+int afb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream) {
+  return afb::upsample2x_launch(x, y, n, h, w, c, static_cast<cudaStream_t>(stream));
+}
+int afb_softmax_rows(void* x, int64_t ld, int64_t rows, int32_t cols, void* stream) {
+  return afb::softmax_rows_launch(x, ld, rows, cols, static_cast<cudaStream_t>(stream));
+}
+int afb_vae_pre(const float* z, void* out, int32_t n, int32_t c_in, int32_t h, int32_t w, int32_t c_pad, float scale,
+                float shift, void* stream) {
+  return afb::vae_pre_launch(z, out, n, c_in, h, w, c_pad, scale, shift, static_cast<cudaStream_t>(stream));
+}
+int afb_vae_post(const void* x, int64_t x_ld, float* out, int32_t n, int32_t c_out, int32_t h, int32_t w, void* stream) {
+  return afb::vae_post_launch(x, x_ld, out, n, c_out, h, w, static_cast<cudaStream_t>(stream));
 }
 int afb_grad_norm_scratch_floats(void) { return afb::grad_norm_scratch_floats(); }
 int afb_grad_norm_sq_ws(const float* grads, int64_t n, float* out, float* scratch, int64_t scratch_floats, void* stream) {

@@ -65,6 +65,11 @@ struct GemmParams {
   int tma_store; // epilogue through shared memory + TMA store (0: per-row 16-byte global stores)
   int l2_hints;  // W loads evict_last, output stores evict_first; 2: A loads evict_first as well
   int gn;        // tile raster: N tiles per column group (0 / >= num_n_tiles: plain N-fastest order)
+  int bn;        // N extent of a tile: 256, or 128 for narrow outputs (CTA-pair kernel, K-major W only)
+  // implicit-GEMM 3x3 convolution (CTA-pair kernel): A is an NHWC image read through a 4-D map, an M tile is a 16 x 16 pixel
+  // patch (each CTA: 8 rows of 16 pixels), K runs over 9 taps x (channels / 64) chunks — tap (dy, dx) is the same box
+  // shifted by (dy - 1, dx - 1), zero-filled outside the image by the TMA unit
+  int conv, conv_h, conv_w, conv_tw, conv_cpt;
   __nv_bfloat16* out;
   long long out_ld, out_batch_stride;
   const __nv_bfloat16* bias;
@@ -111,8 +116,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
                                               __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
                                               const __nv_bfloat16* gate_b) {
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    const int n0 = n_tile * BN + c * 32;
+  for (int c = 0; c < p.bn / 32; ++c) {
+    const int n0 = n_tile * p.bn + c * 32;
     if (n0 >= p.N) break;
     uint32_t v[32];
     tmem_ld_32x32(t_base + c * 32, v);
@@ -182,6 +187,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                  : "memory");
   }
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // at most N of this thread's bulk groups may still be READING their shared-memory source
 template <int N>
@@ -196,11 +207,13 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // columns >= N, so edge tiles need no masks on the store side; loads of bias / gate / residual stay guarded.
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmOut, uint32_t t_base, int n_tile,
                                                   bool valid, int lane, int row0_warp, int b, uint8_t* stage,
-                                                  int& buf, const __nv_bfloat16* res_row, const __nv_bfloat16* gate_b) {
-  const bool store_rows = row0_warp < p.rows_per_batch;  // warp-uniform: anything of this warp's 32 rows inside the batch?
+                                                  int& buf, const __nv_bfloat16* res_row, const __nv_bfloat16* gate_b,
+                                                  int conv_w0 = -1) {
+  // warp-uniform: anything of this warp's 32 rows inside the batch? (conv: row0_warp is the first of the warp's 2 image rows)
+  const bool store_rows = row0_warp < (conv_w0 >= 0 ? p.conv_h : p.rows_per_batch);
 #pragma unroll 1
-  for (int c = 0; c < BN / EPI_COLS; ++c) {
-    const int n0 = n_tile * BN + c * EPI_COLS;
+  for (int c = 0; c < p.bn / EPI_COLS; ++c) {
+    const int n0 = n_tile * p.bn + c * EPI_COLS;
     if (n0 >= p.N) break;
     uint8_t* sbuf = stage + buf * EPI_BUF_BYTES;
     if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago (same buffer) has read its source
@@ -262,7 +275,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
     __syncwarp();
     if (lane == 0) {
-      if (store_rows) tma_store_3d(tmOut, sbuf, n0, row0_warp, b, p.l2_hints != 0);
+      if (store_rows) {
+        if (conv_w0 >= 0)
+          tma_store_4d(tmOut, sbuf, n0, conv_w0, row0_warp, b);
+        else
+          tma_store_3d(tmOut, sbuf, n0, row0_warp, b, p.l2_hints != 0);
+      }
       bulk_commit();
     }
     buf ^= 1;
@@ -488,6 +506,14 @@ __device__ __forceinline__ void tma_load_3d_2cta(void* dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -573,12 +599,31 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         int m_tile, n_tile;
         tile_coords(p, tile, m_tile, n_tile);
         const int b = m_tile / p.tiles_per_batch;
-        const int r0 = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM;
-        const int n0 = n_tile * BN + int(rank) * HALF_N;
+        const int t_in = m_tile - b * p.tiles_per_batch;
+        const int r0 = t_in * (2 * BM) + int(rank) * BM;
+        const int half_n = p.bn >> 1;
+        const int n0 = n_tile * p.bn + int(rank) * half_n;
+        const uint32_t stage_tx = 2u * uint32_t(A_STAGE_BYTES + half_n * BK * 2);
+        const int conv_th = p.conv ? t_in / p.conv_tw : 0;
+        const int conv_w0 = p.conv ? (t_in - conv_th * p.conv_tw) * 16 : 0;
+        const int conv_h0 = conv_th * 16 + int(rank) * 8;
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+          if (p.conv) {
+            const int tap = kb / p.conv_cpt;
+            const int cc = kb - tap * p.conv_cpt;
+            const int dy = tap / 3;
+            const int dx = tap - dy * 3;
+            tma_load_4d_2cta(sA + stage * A_STAGE_BYTES, &tmA0, leader_full, cc * BK, conv_w0 + dx - 1, conv_h0 + dy - 1, b);
+            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           const CUtensorMap* am;
           int kk;
           if (kb < p.nk_end[0]) {
@@ -616,7 +661,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (leader CTA only) ---------------------------
     if (leader) {
-      const uint32_t idesc = p.w_trans ? make_idesc_bf16(2 * BM, BN, false, true) : make_idesc_bf16(2 * BM, BN, false, false);
+      const uint32_t idesc = p.w_trans ? make_idesc_bf16(2 * BM, BN, false, true) : make_idesc_bf16(2 * BM, p.bn, false, false);
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 16, 1024);
       // K-major W: 16-element k step = 32 bytes; MN-major W: 64-n chunks 8 KiB apart, k step = 16 rows of 128 bytes
       const uint64_t b_desc0 = p.w_trans ? make_sw128_desc(smem_u32(sB), HALF_N * BK, 1024) : make_sw128_desc(smem_u32(sB), 16, 1024);
@@ -664,9 +709,19 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       int m_tile, n_tile;
       tile_coords(p, tile, m_tile, n_tile);
       const int b = m_tile / p.tiles_per_batch;
-      const int r0w = (m_tile - b * p.tiles_per_batch) * (2 * BM) + int(rank) * BM + q * 32;
-      const int r = r0w + lane;
-      const bool valid = r < p.rows_per_batch;
+      const int t_in = m_tile - b * p.tiles_per_batch;
+      int r0w = t_in * (2 * BM) + int(rank) * BM + q * 32;
+      int r = r0w + lane;
+      bool valid = r < p.rows_per_batch;
+      int conv_w0 = -1;
+      if (p.conv) {  // this warp's 32 accumulator rows = 2 image rows x 16 pixels of the CTA's 8 x 16 patch
+        const int th = t_in / p.conv_tw;
+        conv_w0 = (t_in - th * p.conv_tw) * 16;
+        r0w = th * 16 + int(rank) * 8 + q * 2;  // first image row of the warp
+        const int hh = r0w + (lane >> 4), ww = conv_w0 + (lane & 15);
+        valid = hh < p.conv_h && ww < p.conv_w;
+        r = hh * p.conv_w + ww;  // pixel index inside the image (row of the NHWC matrix)
+      }
       __nv_bfloat16* out_row = p.out + (long long)b * p.out_batch_stride + (long long)r * p.out_ld;
       const __nv_bfloat16* res_row =
           p.res ? p.res + (long long)b * p.res_batch_stride + (long long)r * p.res_ld : nullptr;
@@ -676,7 +731,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       if (p.tma_store)
-        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b);
+        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b, conv_w0);
       else
         epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
       tc_fence_before();
@@ -720,6 +775,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   }
   const bool two_cta = !force_1cta || d->w_transposed;
   const int tile_m = two_cta ? 2 * BM : BM;
+  const int bn = (two_cta && !d->w_transposed && d->n <= 128) ? 128 : BN;  // narrow outputs: half-width tiles
 
   GemmParams p{};
   CUtensorMap tmA[3];
@@ -775,7 +831,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     AFB_REQUIRE(d->w2 == nullptr, "gemm: a second W buffer needs w_transposed");
     const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->n)};
     const uint64_t strides[1] = {uint64_t(d->w_ld) * 2};
-    const uint32_t box[2] = {BK, uint32_t(two_cta ? HALF_N : BN)};
+    const uint32_t box[2] = {BK, uint32_t(two_cta ? bn / 2 : BN)};
     AFB_REQUIRE(d->w_ld >= ktot, "gemm: w_ld=%lld < total K=%d", (long long)d->w_ld, ktot);
     int rc = make_tmap_bf16(&tmB, d->w, 2, dims, strides, box);
     if (rc != AFB_OK) return rc;
@@ -808,17 +864,19 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     gn_env = e ? atoi(e) : -1;
   }
   {
-    const int ntiles = (d->n + BN - 1) / BN;
-    const double panel = double(BN) * ktot * 2.0, w_total = double(d->n) * ktot * 2.0;
+    const int ntiles = (d->n + bn - 1) / bn;
+    const double panel = double(bn) * ktot * 2.0, w_total = double(d->n) * ktot * 2.0;
     int gn = 0;
     if (gn_env >= 0) {
       gn = gn_env;
-    } else if (two_cta && !d->w_transposed && w_total > 40e6) {
-      gn = int(32e6 / panel);
-      if (gn < 2) gn = 2;
-      const int groups = (ntiles + gn - 1) / gn;  // even out the group widths
+    } else if (two_cta && !d->w_transposed && w_total > 40e6 && ntiles >= 24) {
+      // measured (profiles/r02_gemm_raster_sweep.json): QKV (36 N-tiles, W 57 MB) and MLP-up (48 N-tiles, W 82 MB) drop from
+      // 1.1 / 4.0 GB to 0.6 / 0.9 GB of DRAM reads with groups of 12-24 N-tiles; the K-heavy MLP-down / proj_out launches
+      // (12 N-tiles, 6-8 MB panels) gain nothing from grouping and keep the plain order
+      const int groups = int((w_total + 32e6 - 1) / 32e6);
       gn = (ntiles + groups - 1) / groups;
     }
+    (void)panel;
     p.gn = gn >= ntiles ? 0 : gn;
   }
 
@@ -827,7 +885,8 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   p.tiles_per_batch = (d->rows_per_batch + tile_m - 1) / tile_m;
   p.N = d->n;
   p.num_m_tiles = p.tiles_per_batch * d->batches;
-  p.num_n_tiles = (d->n + BN - 1) / BN;
+  p.num_n_tiles = (d->n + bn - 1) / bn;
+  p.bn = bn;
   p.epi = d->epilogue;
   p.alpha = d->alpha != 0.f ? d->alpha : 1.0f;
   p.out = static_cast<__nv_bfloat16*>(d->out);
@@ -859,6 +918,84 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     const int grid = num_tiles < sms ? num_tiles : sms;
     gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmOut, p);
   }
+  AFB_CHECK_CUDA(cudaGetLastError());
+  return AFB_OK;
+}
+
+// 3x3 convolution, stride 1, zero padding 1, NHWC bf16, as an implicit GEMM on the CTA-pair kernel (see GemmParams::conv).
+int conv3x3_launch(const afb_conv_desc* d, cudaStream_t stream) {
+  AFB_REQUIRE(d != nullptr && d->x && d->w && d->out, "conv3x3: null pointer");
+  AFB_REQUIRE(d->n >= 1 && d->h >= 1 && d->w_px >= 1, "conv3x3: empty image (%d x %d x %d)", d->n, d->h, d->w_px);
+  AFB_REQUIRE(d->c_in >= 64 && d->c_in % 64 == 0, "conv3x3: c_in=%d must be a positive multiple of 64 (pad the input)", d->c_in);
+  AFB_REQUIRE(d->c_out >= 8 && d->c_out % 8 == 0, "conv3x3: c_out=%d must be a positive multiple of 8 (pad the weight)", d->c_out);
+  AFB_REQUIRE(d->epilogue == AFB_EPI_BIAS || d->epilogue == AFB_EPI_BIAS_RES, "conv3x3: epilogue %d not supported", d->epilogue);
+  if (d->epilogue == AFB_EPI_BIAS_RES) AFB_REQUIRE(d->res, "conv3x3: residual epilogue needs the res pointer");
+  const int64_t x_ld = d->x_ld ? d->x_ld : d->c_in, out_ld = d->out_ld ? d->out_ld : d->c_out;
+  const int64_t res_ld = d->res_ld ? d->res_ld : d->c_out;
+  AFB_REQUIRE(x_ld % 8 == 0 && out_ld % 8 == 0 && res_ld % 8 == 0, "conv3x3: pixel strides must be multiples of 8 elements");
+  const int ktot = 9 * d->c_in;
+  const int bn = d->c_out <= 128 ? 128 : BN;
+
+  CUtensorMap tmA, tmB, tmOut;
+  {
+    const uint64_t dims[4] = {uint64_t(d->c_in), uint64_t(d->w_px), uint64_t(d->h), uint64_t(d->n)};
+    const uint64_t strides[3] = {uint64_t(x_ld) * 2, uint64_t(d->w_px) * x_ld * 2, uint64_t(d->h) * d->w_px * x_ld * 2};
+    const uint32_t box[4] = {BK, 16, 8, 1};
+    int rc = make_tmap_bf16(&tmA, d->x, 4, dims, strides, box);
+    if (rc != AFB_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->c_out)};
+    const uint64_t strides[1] = {uint64_t(ktot) * 2};
+    const uint32_t box[2] = {BK, uint32_t(bn / 2)};
+    int rc = make_tmap_bf16(&tmB, d->w, 2, dims, strides, box);
+    if (rc != AFB_OK) return rc;
+  }
+  {
+    const uint64_t dims[4] = {uint64_t(d->c_out), uint64_t(d->w_px), uint64_t(d->h), uint64_t(d->n)};
+    const uint64_t strides[3] = {uint64_t(out_ld) * 2, uint64_t(d->w_px) * out_ld * 2, uint64_t(d->h) * d->w_px * out_ld * 2};
+    const uint32_t box[4] = {EPI_COLS, 16, 2, 1};
+    int rc = make_tmap_bf16(&tmOut, d->out, 4, dims, strides, box);
+    if (rc != AFB_OK) return rc;
+  }
+  GemmParams p{};
+  p.conv = 1;
+  p.conv_h = d->h;
+  p.conv_w = d->w_px;
+  p.conv_tw = (d->w_px + 15) / 16;
+  p.conv_cpt = d->c_in / BK;
+  const int tiles_h = (d->h + 15) / 16;
+  p.batches = d->n;
+  p.rows_per_batch = d->h * d->w_px;
+  p.tiles_per_batch = tiles_h * p.conv_tw;
+  p.N = d->c_out;
+  p.nk_end[0] = p.nk_end[1] = p.nk_end[2] = ktot / BK;
+  p.nkb_w0 = ktot / BK;
+  p.num_m_tiles = p.tiles_per_batch * d->n;
+  p.num_n_tiles = (d->c_out + bn - 1) / bn;
+  p.bn = bn;
+  p.epi = d->epilogue;
+  p.alpha = 1.0f;
+  p.tma_store = 1;
+  p.l2_hints = 0;
+  p.gn = 0;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_ld = out_ld;
+  p.out_batch_stride = int64_t(d->h) * d->w_px * out_ld;
+  p.bias = static_cast<const __nv_bfloat16*>(d->bias);
+  p.res = static_cast<const __nv_bfloat16*>(d->res);
+  p.res_ld = res_ld;
+  p.res_batch_stride = int64_t(d->h) * d->w_px * res_ld;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(GEMM2_SMEM_BYTES)));
+    attr_set = true;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int max_clusters = device_sm_count() / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  gemm_bf16_2cta_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmA, tmA, tmB, tmB, tmOut, p);
   AFB_CHECK_CUDA(cudaGetLastError());
   return AFB_OK;
 }

@@ -572,3 +572,121 @@ def dropout_rows(x: torch.Tensor, seed: int, layer_id: int, p: float, out: Optio
     _lib.check(lib.afb_dropout_rows(xp, xld, xbs, op, old, obs, nb, nr, cols, logical_cols or cols, col0, int(seed),
                                     int(layer_id), float(p), int(silu_in), int(accumulate), _stream()), "afb_dropout_rows")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FLUX VAE decoder building blocks (NHWC bf16 activations) — see arcflow_b200/vae.py
+# ------------------------------------------------------------------------------------------------------------------
+def _nhwc(t: torch.Tensor, name: str):
+    _chk(t, BF16, name)
+    if t.dim() != 4 or t.stride(3) != 1 or t.stride(1) != t.shape[2] * t.stride(2) or t.stride(0) != t.shape[1] * t.stride(1):
+        raise AfbError(f"{name}: need a dense-pixel NHWC tensor [n, h, w, c] (channel slices allowed), got {tuple(t.shape)} "
+                       f"strides {t.stride()}")
+    return t.data_ptr(), t.stride(2)
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 convolution, stride 1, zero padding 1. x: NHWC bf16 [n, h, w, c_in] (c_in % 64 == 0); w: [c_out, 9 * c_in] packed
+    tap-major (`pack_conv3x3_weight`); res: added to the output (may alias out). Implicit GEMM on the tcgen05 kernel."""
+    lib = _lib.load()
+    xp, xld = _nhwc(x, "conv3x3 x")
+    _chk(w, BF16, "conv3x3 w")
+    n, h, wpx, cin = x.shape
+    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != 9 * cin:
+        raise AfbError(f"conv3x3: w must be contiguous [c_out, {9 * cin}], got {tuple(w.shape)}")
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty((n, h, wpx, cout), dtype=BF16, device=x.device)
+    op, old = _nhwc(out, "conv3x3 out")
+    if tuple(out.shape) != (n, h, wpx, cout):
+        raise AfbError("conv3x3: out shape mismatch")
+    d = _lib.ConvDesc()
+    d.x, d.w, d.out, d.x_ld, d.out_ld = xp, w.data_ptr(), op, xld, old
+    d.n, d.h, d.w_px, d.c_in, d.c_out = n, h, wpx, cin, cout
+    d.epilogue = _lib.AFB_EPI_BIAS
+    if bias is not None:
+        _chk(bias, BF16, "conv3x3 bias")
+        d.bias = bias.data_ptr()
+    if res is not None:
+        rp, rld = _nhwc(res, "conv3x3 res")
+        if tuple(res.shape) != tuple(out.shape):
+            raise AfbError("conv3x3: res shape mismatch")
+        d.res, d.res_ld, d.epilogue = rp, rld, _lib.AFB_EPI_BIAS_RES
+    _lib.check(lib.afb_conv3x3(C.byref(d), _stream()), "afb_conv3x3")
+    return out
+
+
+def pack_conv3x3_weight(w: torch.Tensor, c_in_pad: Optional[int] = None, c_out_pad: Optional[int] = None) -> torch.Tensor:
+    """torch Conv2d weight [c_out, c_in, 3, 3] -> [c_out_pad, 9 * c_in_pad] bf16, tap-major / channel-minor, zero-padded."""
+    co, ci = w.shape[:2]
+    cip, cop = c_in_pad or ci, c_out_pad or co
+    p = torch.zeros((cop, 3, 3, cip), dtype=BF16, device=w.device)
+    p[:co, :, :, :ci] = w.permute(0, 2, 3, 1).to(BF16)
+    return p.reshape(cop, 9 * cip).contiguous()
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool = True, out: Optional[torch.Tensor] = None,
+              eps: float = 1e-6) -> torch.Tensor:
+    """GroupNorm(32, affine) (+ swish) over NHWC bf16 [n, h, w, c] (contiguous); gamma / beta fp32 [c]."""
+    lib = _lib.load()
+    _chk(x, BF16, "groupnorm x")
+    _chk(gamma, torch.float32, "groupnorm gamma")
+    _chk(beta, torch.float32, "groupnorm beta")
+    if x.dim() != 4 or not x.is_contiguous():
+        raise AfbError("groupnorm: x must be a contiguous NHWC tensor")
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _chk(out, BF16, "groupnorm out")
+    if out.shape != x.shape or not out.is_contiguous():
+        raise AfbError("groupnorm: out must be contiguous with x's shape")
+    nws = int(lib.afb_groupnorm_ws_floats(n, h * w))
+    ws = torch.empty(nws, dtype=torch.float32, device=x.device)
+    _lib.check(lib.afb_groupnorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ws.data_ptr(), nws, n, h * w,
+                                 c, eps, int(silu), _stream()), "afb_groupnorm")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, BF16, "upsample2x x")
+    if x.dim() != 4 or not x.is_contiguous():
+        raise AfbError("upsample2x: x must be a contiguous NHWC tensor")
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    _lib.check(lib.afb_upsample2x(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()), "afb_upsample2x")
+    return out
+
+
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    """In-place softmax over the last dim of a bf16 matrix [rows, cols]."""
+    lib = _lib.load()
+    _chk(x, BF16, "softmax_rows x")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise AfbError("softmax_rows: need [rows, cols] with a contiguous last dim")
+    _lib.check(lib.afb_softmax_rows(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], _stream()), "afb_softmax_rows")
+    return x
+
+
+def vae_pre(latents: torch.Tensor, c_pad: int, scale: float, shift: float) -> torch.Tensor:
+    """fp32 NCHW latents [n, c, h, w] -> (z / scale + shift) as NHWC bf16 [n, h, w, c_pad] (zero-padded channels)."""
+    lib = _lib.load()
+    _chk(latents, torch.float32, "vae_pre latents")
+    if latents.dim() != 4 or not latents.is_contiguous():
+        raise AfbError("vae_pre: latents must be contiguous fp32 [n, c, h, w]")
+    n, c, h, w = latents.shape
+    out = torch.empty((n, h, w, c_pad), dtype=BF16, device=latents.device)
+    _lib.check(lib.afb_vae_pre(latents.data_ptr(), out.data_ptr(), n, c, h, w, c_pad, float(scale), float(shift), _stream()),
+               "afb_vae_pre")
+    return out
+
+
+def vae_post(x: torch.Tensor, c_out: int = 3) -> torch.Tensor:
+    """NHWC bf16 [n, h, w, >= 8] -> fp32 NCHW [n, c_out, h, w] (first c_out channels)."""
+    lib = _lib.load()
+    xp, xld = _nhwc(x, "vae_post x")
+    n, h, w, _ = x.shape
+    out = torch.empty((n, c_out, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.afb_vae_post(xp, xld, out.data_ptr(), n, c_out, h, w, _stream()), "afb_vae_post")
+    return out

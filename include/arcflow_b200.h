@@ -281,6 +281,39 @@ int afb_mse_rows(const float* pred, const void* tgt, float* out, int32_t batch, 
 int afb_cfg_combine(const void* both_bf16, float* out, int64_t half, float guidance_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * FLUX VAE decoder building blocks. Replaces what the reference reaches through diffusers'
+ * AutoencoderKL.decode (lakonlab/pipelines/arcflux_pipeline.py:531-534; lakonlab/models/architecture/diffusers/
+ * pretrained.py:69-76): 3x3 convolutions as implicit GEMMs on the tcgen05 kernel, GroupNorm(32) + swish, nearest 2x
+ * upsampling, the row softmax of the single-head attention block. Activations are NHWC bf16 (pixel-major rows).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct afb_conv_desc {
+  const void* x;      /* bf16 [n, h, w_px, c_in] (pixel stride x_ld, 0 -> c_in); c_in % 64 == 0 */
+  const void* w;      /* bf16 [c_out, 3, 3, c_in] = [c_out, 9 * c_in]: tap-major, channel-minor rows (pack of the torch
+                         [c_out, c_in, 3, 3] weight via permute(0, 2, 3, 1)) */
+  const void* bias;   /* bf16 [c_out] or NULL */
+  const void* res;    /* bf16 [n, h, w_px, c_out] added to the output (AFB_EPI_BIAS_RES), may alias out */
+  void* out;          /* bf16 [n, h, w_px, c_out] (pixel stride out_ld, 0 -> c_out); c_out % 8 == 0 */
+  int64_t x_ld, out_ld, res_ld;
+  int32_t n, h, w_px, c_in, c_out;
+  int32_t epilogue;   /* AFB_EPI_BIAS or AFB_EPI_BIAS_RES */
+} afb_conv_desc;
+int afb_conv3x3(const afb_conv_desc* desc, void* stream);
+/* GroupNorm(32 groups, affine) over NHWC bf16 [n, hw, c] (+ swish when silu != 0): y may alias x. gamma / beta fp32 [c];
+ * ws: fp32 scratch of afb_groupnorm_ws_floats(n, hw) floats. c in {64, 128, 256, 512, 1024, 2048}. Deterministic. */
+int afb_groupnorm_ws_floats(int32_t n, int64_t hw);
+int afb_groupnorm(const void* x, void* y, const float* gamma, const float* beta, float* ws, int64_t ws_floats, int32_t n,
+                  int64_t hw, int32_t c, float eps, int32_t silu, void* stream);
+/* nearest-neighbour 2x upsampling, NHWC bf16 [n, h, w, c] -> [n, 2h, 2w, c] */
+int afb_upsample2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+/* in-place softmax over the last dim of a bf16 matrix [rows, cols] (row stride ld) */
+int afb_softmax_rows(void* x, int64_t ld, int64_t rows, int32_t cols, void* stream);
+/* latents fp32 NCHW [n, c_in, h, w] -> (z / scale + shift) bf16 NHWC [n, h, w, c_pad], channels >= c_in zero-filled */
+int afb_vae_pre(const float* z, void* out, int32_t n, int32_t c_in, int32_t h, int32_t w, int32_t c_pad, float scale,
+                float shift, void* stream);
+/* bf16 NHWC rows (pixel stride x_ld >= 8) -> fp32 NCHW [n, c_out, h, w], first c_out <= 8 channels */
+int afb_vae_post(const void* x, int64_t x_ld, float* out, int32_t n, int32_t c_out, int32_t h, int32_t w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Step glue over ONE flat fp32 arena of all trainable adapter tensors (reference
  * lakonlab/models/base.py:76-103 + configs/flux/_ddp_train.py:13-26 + lakonlab/runner/hooks/ema_hook.py:86-121).
  * ---------------------------------------------------------------------------------------------- */

@@ -57,13 +57,14 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
     default_sample_size = 128
 
     def __init__(self, transformer=None, scheduler_shift: float = 3.2, text_encoder_fn: Optional[Callable] = None,
-                 vae_decode_fn: Optional[Callable] = None, policy_type: str = "ArcFlow"):
+                 vae_decode_fn: Optional[Callable] = None, policy_type: str = "ArcFlow", vae=None):
         if policy_type != "ArcFlow":
             raise ValueError(f"Invalid policy: {policy_type}. Supported policies are ['ArcFlow'].")
         self.transformer = transformer
         self.scheduler_shift = scheduler_shift
         self.text_encoder_fn = text_encoder_fn
         self.vae_decode_fn = vae_decode_fn
+        self.vae = vae      # arcflow_b200.vae.FluxVAEDecoder (native decode, arcflux_pipeline.py:531-534 of the reference)
         self._num_timesteps = 0
         self._interrupt = False
         self.use_cuda_graph = False
@@ -136,6 +137,21 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
         h, w = int(height) // (vae_scale_factor * patch_size), int(width) // (vae_scale_factor * patch_size)
         x = latents.view(b, h, w, ch // (s * s), s, s).permute(0, 3, 1, 4, 2, 5)
         return x.reshape(b, ch // (s * s), h * s, w * s)
+
+    @staticmethod
+    def postprocess_image(image: torch.Tensor, output_type: str = "pil"):
+        """diffusers VaeImageProcessor.postprocess: denormalise to [0, 1]; 'pt' -> fp32 [B, 3, H, W]; 'np' -> [B, H, W, 3];
+        'pil' -> list of PIL images."""
+        image = (image / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return image
+        arr = image.permute(0, 2, 3, 1).float().cpu().numpy()
+        if output_type == "np":
+            return arr
+        if output_type != "pil":
+            raise ValueError(f"unsupported output_type '{output_type}' (latent, pt, np, pil)")
+        from PIL import Image
+        return [Image.fromarray((a * 255).round().astype("uint8")) for a in arr]
 
     def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
         h, w = 2 * (int(height) // (self.vae_scale_factor * 2)), 2 * (int(width) // (self.vae_scale_factor * 2))
@@ -234,10 +250,15 @@ class ArcFluxPipeline(ArcFlowLoaderMixin):
             latents = gather_latents(latents.contiguous(), batch)
         if output_type == "latent":
             image = latents
+        elif self.vae is not None:
+            # latents / scaling_factor + shift_factor -> vae.decode -> image_processor.postprocess (reference :531-534);
+            # the affine map runs inside the decoder's first kernel
+            image = self.postprocess_image(self.vae.decode(self._unpack_latents(latents, height, width, self.vae_scale_factor)),
+                                           output_type)
         else:
             if self.vae_decode_fn is None:
-                raise NotImplementedError("the VAE is out of scope of this build: use output_type='latent' "
-                                          "or construct the pipeline with vae_decode_fn")
+                raise NotImplementedError("no VAE attached: use output_type='latent', or construct the pipeline with "
+                                          "vae=arcflow_b200.vae.FluxVAEDecoder(...) or a vae_decode_fn hook")
             image = self.vae_decode_fn(self._unpack_latents(latents, height, width, self.vae_scale_factor), output_type)
         if not return_dict:
             return (image,)
