@@ -11,7 +11,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libarcflow_b200.so"
 
 AFB_OK = 0
-AFB_EPI_BIAS, AFB_EPI_BIAS_GELU, AFB_EPI_BIAS_GATE_RES, AFB_EPI_BIAS_RES = 0, 1, 2, 3
+AFB_EPI_BIAS, AFB_EPI_BIAS_GELU, AFB_EPI_BIAS_GATE_RES, AFB_EPI_BIAS_RES, AFB_EPI_BIAS_QKNORM_ROPE = 0, 1, 2, 3, 4
 AFB_SL_SILU_IN, AFB_SL_ACCUMULATE = 1, 2
 AFB_ARCH_FLUX, AFB_ARCH_QWEN = 0, 1
 AFB_ABI_VERSION = 2
@@ -47,6 +47,8 @@ class GemmDesc(C.Structure):
         ("w2", C.c_void_p),
         ("w2_ld", C.c_int64),
         ("alpha", C.c_float),
+        ("norm_q", C.c_void_p), ("norm_k", C.c_void_p), ("rope", C.c_void_p),
+        ("rope_row0", C.c_int32), ("qk_cols", C.c_int32), ("norm_eps", C.c_float),
     ]
 
 
@@ -220,6 +222,7 @@ SIGNATURES = {
     "afb_engine_forward_train": (C.c_int, [_P, C.POINTER(ForwardArgs), _P]),
     "afb_engine_backward": (C.c_int, [_P, C.POINTER(BackwardArgs), _P]),
     "afb_engine_backward_embed": (C.c_int, [_P, C.POINTER(ForwardArgs), _P, C.POINTER(EmbedGrads), _P]),
+    "afb_rope_pack": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "afb_conv3x3": (C.c_int, [C.POINTER(ConvDesc), _P]),
     "afb_groupnorm_ws_floats": (C.c_int, [C.c_int32, C.c_int64]),
     "afb_groupnorm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),

@@ -34,6 +34,7 @@ int cfg_combine_launch(const void* both_bf16, float* out, int64_t half, float gu
 int colsum_f32_launch(const float* x, int64_t ld, float* out, int64_t rows, int n, cudaStream_t stream);
 int grad_norm_sq_launch(const float* g, int64_t n, float* out, cudaStream_t stream);
 int grad_norm_scratch_floats();
+int rope_pack_launch(const float* cos_tab, const float* sin_tab, float* out, int64_t rows, cudaStream_t stream);
 int conv3x3_launch(const afb_conv_desc* d, cudaStream_t stream);
 int vae_pre_launch(const float* z, void* out, int n, int c_in, int h, int w, int c_pad, float scale, float shift, cudaStream_t stream);
 int vae_post_launch(const void* x, int64_t x_ld, float* out, int n, int c_out, int h, int w, cudaStream_t stream);
@@ -171,6 +172,9 @@ int afb_rmsnorm_rope_bwd(void* dqkv, const void* raw, int64_t ld, int64_t bs, in
 }
 int afb_grad_norm_sq(const float* grads, int64_t n, float* out, void* stream) {
   return afb::grad_norm_sq_launch(grads, n, out, static_cast<cudaStream_t>(stream));
+}
+int afb_rope_pack(const float* cos_tab, const float* sin_tab, float* out, int64_t rows, void* stream) {
+  return afb::rope_pack_launch(cos_tab, sin_tab, out, rows, static_cast<cudaStream_t>(stream));
 }
 int afb_conv3x3(const afb_conv_desc* desc, void* stream) {
   int rc = afb::conv3x3_launch(desc, static_cast<cudaStream_t>(stream));

@@ -1157,6 +1157,21 @@ int ln_modulate_launch(const void* x, int64_t x_bs, void* y, int64_t y_bs, const
   return AFB_OK;
 }
 
+__global__ void __launch_bounds__(256) rope_pack_kernel(const float* __restrict__ c, const float* __restrict__ sn,
+                                                         float2* __restrict__ out, long long pairs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pairs) out[i] = make_float2(c[2 * i], sn[2 * i]);
+}
+
+int rope_pack_launch(const float* cos_tab, const float* sin_tab, float* out, int64_t rows, cudaStream_t stream) {
+  AFB_REQUIRE(cos_tab && sin_tab && out && rows >= 1, "rope_pack: bad arguments");
+  const long long pairs = rows * 64;
+  rope_pack_kernel<<<unsigned((pairs + 255) / 256), 256, 0, stream>>>(cos_tab, sin_tab, reinterpret_cast<float2*>(out), pairs);
+  AFB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return AFB_OK;
+}
+
 int rmsnorm_rope_launch(void* qkv, int64_t ld, int64_t bs, int q_off, int k_off, int batches, int seq,
                         int heads, int txt_rows, const void* wq_txt, const void* wk_txt,
                         const void* wq_img, const void* wk_img, const float* cos_tab,

@@ -19,8 +19,12 @@
 //   lt0/1 [B, S, r]    LoRA A-projections (the K-extension operands)
 //   mod   [B, mod_total] every AdaLN vector of the forward, from ONE weight-streaming launch
 //   head  [B*Si, head_n] raw ArcFlow heads (means | logits | loggamma), consumed by the sampler kernel
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: a no-op stub unless a profiler injects itself (nsys / ncu --nvtx)
 
 #include "common.cuh"
 
@@ -34,6 +38,7 @@ int rmsnorm_rope_launch(void* qkv, int64_t ld, int64_t bs, int q_off, int k_off,
                         int heads, int txt_rows, const void* wq_txt, const void* wk_txt,
                         const void* wq_img, const void* wk_img, const float* cos_tab,
                         const float* sin_tab, float eps, cudaStream_t stream);
+int rope_pack_launch(const float* cos_tab, const float* sin_tab, float* out, int64_t rows, cudaStream_t stream);
 int small_linear_launch(const void* x, int64_t x_ld, const void* w, int64_t w_ld, const void* bias,
                         void* y, int64_t y_ld, int m, int n, int k, int flags, cudaStream_t stream);
 int timestep_embed_launch(const float* t, void* out, int m, cudaStream_t stream);
@@ -97,6 +102,8 @@ struct afb_engine {
        *lt1 = nullptr, *mod = nullptr, *temb = nullptr, *tmp = nullptr, *tproj = nullptr,
        *ltv = nullptr, *head = nullptr, *x_bf16 = nullptr, *txtn = nullptr, *alt_nm = nullptr;
   float *t_dev = nullptr, *g_dev = nullptr;
+  float* rope_cs = nullptr;   // [S, 64, 2] packed (cos, sin) pairs for the fused QK-norm + RoPE epilogue
+  bool fuse_qk_rope = true;   // inference forwards: RMSNorm + RoPE inside the QKV GEMM epilogue (AFB_ENGINE_FUSE_QK_ROPE=0: separate kernel)
   // training workspace (afb_engine_train_reserve): checkpoints + recompute / gradient buffers
   void* tws = nullptr;
   size_t tws_bytes = 0;
@@ -165,6 +172,7 @@ size_t carve(afb_engine* e, uint8_t* base, int B, int St, int Si) {
   e->alt_nm = c.take<bf16>(size_t(B) * 2 * D);
   e->t_dev = c.take<float>(B);
   e->g_dev = c.take<float>(B);
+  e->rope_cs = c.take<float>(S * 128);
   return c.off;
 }
 
@@ -285,6 +293,25 @@ struct ProfScope {
   }
 };
 
+// NVTX push/pop range: names the forward / backward, every transformer block and the launch kinds inside it,
+// so profiler timelines and `ncu --nvtx --nvtx-include "afb_forward/single_block_3/"` filters address launches by name.
+struct NvtxRange {
+  bool open = true;
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  NvtxRange(const char* fmt, int i) {
+    char buf[48];
+    snprintf(buf, sizeof(buf), fmt, i);
+    nvtxRangePushA(buf);
+  }
+  void end() {
+    if (open) nvtxRangePop();
+    open = false;
+  }
+  ~NvtxRange() { end(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 struct Gemm {
   afb_gemm_desc d{};
   int nseg = 0;
@@ -335,6 +362,17 @@ struct Gemm {
     d.epilogue = epi;
     return *this;
   }
+  // fused per-head RMSNorm + RoPE on the first qk_cols output columns (q heads then k heads)
+  Gemm& qk_norm_rope(const void* nq, const void* nk, const float* rope, int row0, int qk_cols, float eps) {
+    d.epilogue = AFB_EPI_BIAS_QKNORM_ROPE;
+    d.norm_q = nq;
+    d.norm_k = nk;
+    d.rope = rope;
+    d.rope_row0 = row0;
+    d.qk_cols = qk_cols;
+    d.norm_eps = eps;
+    return *this;
+  }
   Gemm& gate_res(const bf16* gate, int64_t gate_bs, View res) {
     d.gate = gate;
     d.gate_batch_stride = gate_bs;
@@ -347,6 +385,7 @@ struct Gemm {
     double k = 0;
     for (int i = 0; i < nseg; ++i) k += d.a_k[i];
     ProfScope ps(e, s, 0, 2.0 * d.batches * d.rows_per_batch * double(d.n) * k);
+    NvtxRange nv(d.w_transposed ? "gemm_dx" : (d.n <= 256 ? "gemm_lora_a" : "gemm"));
     int rc = afb::gemm_launch(&d, s);
     if (rc == AFB_OK) afb::count_launch(1);
     return rc;
@@ -355,6 +394,7 @@ struct Gemm {
 
 int run_attention(afb_engine* e, const afb_attn_desc* at, cudaStream_t s) {
   ProfScope ps(e, s, 1, 4.0 * at->batch * at->heads * double(at->seq) * at->seq * 128.0);
+  NvtxRange nv("attention");
   return afb::attention_launch(at, s);
 }
 
@@ -487,8 +527,14 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   const bool drop = save_ckpt && e->drop_p > 0.f && r > 0;  // LoRA input dropout: train forward only
   const bool stash = save_ckpt && e->stash_on && e->stash != nullptr;  // keep block outputs for the backward
   const size_t tok = size_t(B) * S;
+  NvtxRange nvtx_fwd(save_ckpt ? "afb_forward_train" : "afb_forward");
+  // Inference forwards normalise + rotate q and k inside the QKV GEMM epilogue (no separate pass over the QKV buffer); the
+  // train forward keeps the stand-alone kernel: the backward needs the raw projections.
+  const bool fuse_qk = e->fuse_qk_rope && !save_ckpt && D % 256 == 0;
+  if (fuse_qk) AFB_TRY(afb::rope_pack_launch(a->rope_cos, a->rope_sin, e->rope_cs, S, s));
 
   // ---- conditioning vector temb [B, D] ---------------------------------------------------------
+  NvtxRange nvtx_embed("embedders");
   AFB_TRY(afb::timestep_embed_launch(a->timestep, e->tproj, B, s));
   AFB_TRY(embed_mlp(e, e->tproj, 256, w.t1_w, w.t1_b, r > 0 ? w.t1_la : nullptr, r > 0 ? w.t1_lb : nullptr,
                     w.t2_w, w.t2_b, r > 0 ? w.t2_la : nullptr, r > 0 ? w.t2_lb : nullptr, false, B, s, drop));
@@ -580,8 +626,10 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
     return AFB_OK;
   };
 
+  nvtx_embed.end();
   // ---- double-stream blocks --------------------------------------------------------------------
   for (int i = 0; i < d.num_double; ++i) {
+    NvtxRange nvtx_block("double_block_%d", i);
     const afb_double_block& k = e->dbl[i];
     AFB_TRY(save(i));
     // chunk(6): shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
@@ -591,8 +639,15 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
                                     mod_bs, B, Si, D, LN_EPS, s));
     AFB_TRY(afb::ln_modulate_launch(h_txt.p, h_txt.bs, const_cast<bf16*>(y_txt.p), y_txt.bs, tm + D, tm,
                                     mod_bs, B, St, D, LN_EPS, s));
-    AFB_TRY(Gemm(B, Si).a(y_img, D).w(k.img_qkv_w, D, 3 * D, k.img_qkv_b).out(qkv_img, AFB_EPI_BIAS).run(e, s));
-    AFB_TRY(Gemm(B, St).a(y_txt, D).w(k.txt_qkv_w, D, 3 * D, k.txt_qkv_b).out(qkv_txt, AFB_EPI_BIAS).run(e, s));
+    if (fuse_qk) {
+      AFB_TRY(Gemm(B, Si).a(y_img, D).w(k.img_qkv_w, D, 3 * D, k.img_qkv_b).out(qkv_img, AFB_EPI_BIAS)
+                  .qk_norm_rope(k.img_nq, k.img_nk, e->rope_cs, St, 2 * D, LN_EPS).run(e, s));
+      AFB_TRY(Gemm(B, St).a(y_txt, D).w(k.txt_qkv_w, D, 3 * D, k.txt_qkv_b).out(qkv_txt, AFB_EPI_BIAS)
+                  .qk_norm_rope(k.txt_nq, k.txt_nk, e->rope_cs, 0, 2 * D, LN_EPS).run(e, s));
+    } else {
+      AFB_TRY(Gemm(B, Si).a(y_img, D).w(k.img_qkv_w, D, 3 * D, k.img_qkv_b).out(qkv_img, AFB_EPI_BIAS).run(e, s));
+      AFB_TRY(Gemm(B, St).a(y_txt, D).w(k.txt_qkv_w, D, 3 * D, k.txt_qkv_b).out(qkv_txt, AFB_EPI_BIAS).run(e, s));
+    }
     StashSlot sl{};
     if (stash) {
       sl = stash_slot(e, i, B, St, Si);
@@ -600,8 +655,9 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
       AFB_TRY(copy_bf16(sl.qkv_raw, e->qkv, tok * 3 * D, s));
       at.lse = sl.lse;
     }
-    AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, St, k.txt_nq,
-                                     k.txt_nk, k.img_nq, k.img_nk, a->rope_cos, a->rope_sin, LN_EPS, s));
+    if (!fuse_qk)
+      AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, St, k.txt_nq,
+                                       k.txt_nk, k.img_nq, k.img_nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     at.score_bound = k.qk_bound;
     AFB_TRY(run_attention(e, &at, s));
     const bool last_qwen_txt = !flux && i == d.num_double - 1;  // its text stream output is never read
@@ -645,12 +701,17 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   const View l0_all{e->lt0, rr, int64_t(S) * rr};
   const View l1_all{e->lt1, rr, int64_t(S) * rr};
   for (int i = 0; i < d.num_single; ++i) {
+    NvtxRange nvtx_block("single_block_%d", i);
     const afb_single_block& k = e->sgl[i];
     const bf16* m = e->mod + k.mod_off;  // chunk(3): shift, scale, gate
     AFB_TRY(save(d.num_double + i));
     AFB_TRY(afb::ln_modulate_launch(e->h, int64_t(S) * D, e->y, int64_t(S) * D, m + D, m, mod_bs, B, S, D,
                                     LN_EPS, s));
-    AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(qkv_all, AFB_EPI_BIAS).run(e, s));
+    if (fuse_qk)
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(qkv_all, AFB_EPI_BIAS)
+                  .qk_norm_rope(k.nq, k.nk, e->rope_cs, 0, 2 * D, LN_EPS).run(e, s));
+    else
+      AFB_TRY(Gemm(B, S).a(y_all, D).w(k.qkv_w, D, 3 * D, k.qkv_b).out(qkv_all, AFB_EPI_BIAS).run(e, s));
     StashSlot sl{};
     if (stash) {
       sl = stash_slot(e, d.num_double + i, B, St, Si);
@@ -658,8 +719,9 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
       AFB_TRY(copy_bf16(sl.qkv_raw, e->qkv, tok * 3 * D, s));
       at.lse = sl.lse;
     }
-    AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, 0, nullptr, nullptr,
-                                     k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
+    if (!fuse_qk)
+      AFB_TRY(afb::rmsnorm_rope_launch(e->qkv, 3 * D, int64_t(S) * 3 * D, 0, D, B, S, H, 0, nullptr, nullptr,
+                                       k.nq, k.nk, a->rope_cos, a->rope_sin, LN_EPS, s));
     at.score_bound = k.qk_bound;
     AFB_TRY(run_attention(e, &at, s));
     const View up_out = stash ? View{e->mlp_pre, M, int64_t(S) * M} : mlp_all;
@@ -704,6 +766,7 @@ int forward_impl(afb_engine* e, const afb_forward_args* a, const bf16* latents, 
   if (save_ckpt) e->stash_valid = stash;
 
   // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + heads ------------------------
+  NvtxRange nvtx_heads("norm_out_heads");
   const bf16* nm = e->mod + w.norm_out_mod_off;
   int64_t nm_bs = mod_bs;
   if (w.alt_norm_out_w) {  // tied teacher: shares the trunk but has its own (frozen) norm_out Linear
@@ -805,6 +868,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
   const int64_t mod_bs = w.mod_total;
   const size_t ckpt_elems = size_t(B) * S * D;
   const int64_t bsD = int64_t(S) * D, bs3 = int64_t(S) * 3 * D, bsM = int64_t(S) * M, bsR = int64_t(S) * rr;
+  NvtxRange nvtx_bwd("afb_backward");
 
   auto img = [&](bf16* p, int64_t ld) { return View{p + int64_t(St) * ld, ld, int64_t(S) * ld}; };
   auto txt = [&](bf16* p, int64_t ld) { return View{p, ld, int64_t(S) * ld}; };
@@ -890,6 +954,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
 
   // ---- single-stream blocks, last to first ----------------------------------------------------------------------
   for (int i = d.num_single - 1; i >= 0; --i) {
+    NvtxRange nvtx_block("bwd_single_block_%d", i);
     const afb_single_block& k = e->sgl[i];
     const afb_single_block_grads* g = ba->sgl ? &ba->sgl[i] : nullptr;
     const bf16* m = e->mod + k.mod_off;  // shift, scale, gate
@@ -963,6 +1028,7 @@ int backward_impl(afb_engine* e, const afb_backward_args* ba, cudaStream_t s) {
 
   // ---- double-stream blocks, last to first ----------------------------------------------------------------------
   for (int i = d.num_double - 1; i >= 0; --i) {
+    NvtxRange nvtx_block("bwd_double_block_%d", i);
     const afb_double_block& k = e->dbl[i];
     const afb_double_block_grads* g = ba->dbl ? &ba->dbl[i] : nullptr;
     const bf16* im = e->mod + k.img_mod_off;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
@@ -1159,6 +1225,7 @@ int afb_engine_create(const afb_model_desc* desc, afb_engine** out) {
   afb_engine* e = new (std::nothrow) afb_engine();
   AFB_REQUIRE(e != nullptr, "engine_create: out of host memory");
   e->desc = *desc;
+  if (const char* env = getenv("AFB_ENGINE_FUSE_QK_ROPE")) e->fuse_qk_rope = atoi(env) != 0;  // A/B switch (default on)
   *out = e;
   return AFB_OK;
 }
@@ -1471,7 +1538,9 @@ int afb_engine_denoise(afb_engine* e, const afb_denoise_args* a, void* stream) {
   const int64_t tokens = int64_t(f.batch) * f.img_len;
   float* x = static_cast<float*>(a->x);
   AFB_TRY(afb::cast_f32_bf16_launch(x, e->x_bf16, tokens * e->desc.in_channels, s));
+  NvtxRange nvtx_loop("afb_denoise");
   for (int i = 0; i < a->nfe; ++i) {
+    NvtxRange nvtx_nfe("nfe_%d", i);
     afb_forward_args fa = f;
     AFB_TRY(afb::fill_f32_launch(e->t_dev, a->timesteps[i], f.batch, s));
     fa.timestep = e->t_dev;

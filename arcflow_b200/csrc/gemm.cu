@@ -70,6 +70,12 @@ struct GemmParams {
   // patch (each CTA: 8 rows of 16 pixels), K runs over 9 taps x (channels / 64) chunks — tap (dy, dx) is the same box
   // shifted by (dy - 1, dx - 1), zero-filled outside the image by the TMA unit
   int conv, conv_h, conv_w, conv_tw, conv_cpt;
+  // AFB_EPI_BIAS_QKNORM_ROPE: per-head RMSNorm (x weight) + rotary embedding on output columns [0, qk_cols) — the q heads
+  // then the k heads of a fused QKV projection, 128 columns per head — fused into the epilogue
+  const __nv_bfloat16 *norm_q, *norm_k;  // [128] RMSNorm weights
+  const float2* rope;                    // [positions, 64] (cos, sin) per adjacent pair
+  int rope_row0, qk_cols;
+  float norm_eps;
   __nv_bfloat16* out;
   long long out_ld, out_batch_stride;
   const __nv_bfloat16* bias;
@@ -211,11 +217,45 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
                                                   int conv_w0 = -1) {
   // warp-uniform: anything of this warp's 32 rows inside the batch? (conv: row0_warp is the first of the warp's 2 image rows)
   const bool store_rows = row0_warp < (conv_w0 >= 0 ? p.conv_h : p.rows_per_batch);
+  float qk_rstd = 0.f;
+  // this row's rotary table entry (QKNORM_ROPE): 64 (cos, sin) pairs; the chunk's 32 pairs are read per 16-byte load
+  const float2* rope_row = p.rope ? p.rope + (long long)(p.rope_row0 + row0_warp + lane) * 64 : nullptr;
 #pragma unroll 1
   for (int c = 0; c < p.bn / EPI_COLS; ++c) {
     const int n0 = n_tile * p.bn + c * EPI_COLS;
     if (n0 >= p.N) break;
     uint8_t* sbuf = stage + buf * EPI_BUF_BYTES;
+    const bool qk = p.epi == AFB_EPI_BIAS_QKNORM_ROPE && n0 < p.qk_cols;
+    if (qk && (c & 1) == 0) {
+      // first 64-column chunk of a head: sum of squares over the head's 128 (bias-added, bf16-rounded) columns. The
+      // accumulator is simply read twice from TMEM — the statistics pass keeps nothing but the sum.
+      float ss = 0.f;
+#pragma unroll 1
+      for (int hh = 0; hh < 4; ++hh) {
+        uint32_t t[32];
+        tmem_ld_32x32(t_base + c * EPI_COLS + hh * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (p.bias) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n0 + hh * 32 + g * 8);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              bb[2 * i] = bf16_lo(bw[i]);
+              bb[2 * i + 1] = bf16_hi(bw[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f = round_bf16(__uint_as_float(t[g * 8 + i]) * p.alpha + bb[i]);
+            ss = fmaf(f, f, ss);
+          }
+        }
+      }
+      qk_rstd = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
+    }
     if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago (same buffer) has read its source
     __syncwarp();
     uint32_t v[2][32];
@@ -261,6 +301,22 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
             for (int i = 0; i < 4; ++i) {
               f[2 * i] = bf16_lo(rw[i]) + bf16_lo(gw[i]) * f[2 * i];
               f[2 * i + 1] = bf16_hi(rw[i]) + bf16_hi(gw[i]) * f[2 * i + 1];
+            }
+          } else if (qk) {
+            // the reference's rounding chain (diffusers RMSNorm + apply_rotary_emb on a bf16 Linear output): Linear ->
+            // bf16; x * rstd -> bf16; * weight -> bf16; rotation in fp32 -> bf16. Same order as rmsnorm_rope_kernel.
+            const int hc = (c & 1) * EPI_COLS + hh * 32 + g * 8;  // column inside the 128-wide head
+            const uint4 wv = *reinterpret_cast<const uint4*>((n0 < (p.qk_cols >> 1) ? p.norm_q : p.norm_k) + hc);
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+            const float4 r0 = *reinterpret_cast<const float4*>(rope_row + (hc >> 1));      // pairs hc/2, hc/2 + 1
+            const float4 r1 = *reinterpret_cast<const float4*>(rope_row + (hc >> 1) + 2);  // pairs hc/2 + 2, + 3
+            const float cs[4] = {r0.x, r0.z, r1.x, r1.z}, sn[4] = {r0.y, r0.w, r1.y, r1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float x0 = round_bf16(round_bf16(round_bf16(f[2 * i]) * qk_rstd) * bf16_lo(ww[i]));
+              const float x1 = round_bf16(round_bf16(round_bf16(f[2 * i + 1]) * qk_rstd) * bf16_hi(ww[i]));
+              f[2 * i] = x0 * cs[i] - x1 * sn[i];
+              f[2 * i + 1] = x1 * cs[i] + x0 * sn[i];
             }
           }
           o.x = pack_bf16x2(f[0], f[1]);
@@ -760,8 +816,14 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   AFB_REQUIRE(d->batches >= 1 && d->rows_per_batch >= 1, "gemm: empty M (batches=%d rows=%d)",
               d->batches, d->rows_per_batch);
   AFB_REQUIRE(d->n >= 8 && d->n % 8 == 0, "gemm: N=%d must be a positive multiple of 8", d->n);
-  AFB_REQUIRE(d->epilogue >= AFB_EPI_BIAS && d->epilogue <= AFB_EPI_BIAS_RES,
+  AFB_REQUIRE(d->epilogue >= AFB_EPI_BIAS && d->epilogue <= AFB_EPI_BIAS_QKNORM_ROPE,
               "gemm: unknown epilogue %d", d->epilogue);
+  if (d->epilogue == AFB_EPI_BIAS_QKNORM_ROPE) {
+    AFB_REQUIRE(d->norm_q && d->norm_k && d->rope, "gemm: the QK-norm + RoPE epilogue needs norm_q, norm_k and the rope table");
+    AFB_REQUIRE(d->qk_cols > 0 && d->qk_cols % 256 == 0 && d->qk_cols <= d->n,
+                "gemm: qk_cols=%d must be a positive multiple of 256 (q heads then k heads, 128 columns each) <= N", d->qk_cols);
+    AFB_REQUIRE(!d->w_transposed, "gemm: the QK-norm + RoPE epilogue is a forward-projection epilogue");
+  }
   if (d->epilogue == AFB_EPI_BIAS_GATE_RES)
     AFB_REQUIRE(d->gate && d->res, "gemm: gate/residual epilogue needs gate and res pointers");
   if (d->epilogue == AFB_EPI_BIAS_RES) AFB_REQUIRE(d->res, "gemm: residual epilogue needs the res pointer");
@@ -849,6 +911,15 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   CUtensorMap tmOut = tmA[0];
   const uint64_t out_bs = d->batches > 1 ? uint64_t(d->out_batch_stride) : uint64_t(d->rows_per_batch) * uint64_t(d->out_ld);
   p.tma_store = tma_store_env && (out_bs % 8 == 0);
+  if (d->epilogue == AFB_EPI_BIAS_QKNORM_ROPE) {
+    AFB_REQUIRE(p.tma_store && two_cta, "gemm: the QK-norm + RoPE epilogue needs the TMA-store CTA-pair kernel");
+    p.norm_q = static_cast<const __nv_bfloat16*>(d->norm_q);
+    p.norm_k = static_cast<const __nv_bfloat16*>(d->norm_k);
+    p.rope = static_cast<const float2*>(d->rope);
+    p.rope_row0 = d->rope_row0;
+    p.qk_cols = d->qk_cols;
+    p.norm_eps = d->norm_eps > 0.f ? d->norm_eps : 1e-6f;
+  }
   if (p.tma_store) {
     const uint64_t dims[3] = {uint64_t(d->n), uint64_t(d->rows_per_batch), uint64_t(d->batches)};
     const uint64_t strides[2] = {uint64_t(d->out_ld) * 2, out_bs * 2};

@@ -41,7 +41,7 @@ def _rows3(t: torch.Tensor, name: str):
 def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.Tensor,
          bias: Optional[torch.Tensor] = None, epilogue: int = _lib.AFB_EPI_BIAS,
          gate: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, transposed: bool = False,
-         w2: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+         w2: Optional[torch.Tensor] = None, alpha: float = 1.0, qk_norm_rope: Optional[dict] = None) -> torch.Tensor:
     """out[b, r, :] = epi(sum_s a_s[b, r, :] @ w[:, koff_s : koff_s + K_s].T).
 
     `a` is one tensor or up to three K-segments sharing [batches, rows]; `w` is [N, sum K_s] (torch
@@ -85,6 +85,20 @@ def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.T
     elif w2 is not None:
         raise AfbError("gemm: w2 needs transposed=True")
     d.epilogue = epilogue
+    if qk_norm_rope is not None:
+        # fused QKV projection epilogue: dict(norm_q=bf16 [128], norm_k=bf16 [128], rope=fp32 [positions, 64, 2] from
+        # rope_pack(), qk_cols=leading q + k columns, row0=table row of output row 0 of each batch)
+        q = qk_norm_rope
+        _chk(q["norm_q"], BF16, "gemm norm_q")
+        _chk(q["norm_k"], BF16, "gemm norm_k")
+        _chk(q["rope"], torch.float32, "gemm rope")
+        if q["rope"].dim() != 3 or tuple(q["rope"].shape[1:]) != (64, 2) or not q["rope"].is_contiguous():
+            raise AfbError("gemm: rope must be contiguous fp32 [positions, 64, 2]")
+        if q["rope"].shape[0] < int(q.get("row0", 0)) + rows:
+            raise AfbError("gemm: rope table has fewer positions than row0 + rows")
+        d.epilogue = _lib.AFB_EPI_BIAS_QKNORM_ROPE
+        d.norm_q, d.norm_k, d.rope = q["norm_q"].data_ptr(), q["norm_k"].data_ptr(), q["rope"].data_ptr()
+        d.rope_row0, d.qk_cols, d.norm_eps = int(q.get("row0", 0)), int(q["qk_cols"]), float(q.get("eps", 1e-6))
     d.alpha = float(alpha)      # scales the accumulator before bias / epilogue (0 in the struct means 1)
     d.out, d.out_ld, d.out_batch_stride = optr, old, obs
     if bias is not None:
@@ -142,6 +156,18 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[t
             raise AfbError("attention: lse must be contiguous fp32 [batch, heads, seq]")
         d.lse = lse.data_ptr()
     _lib.check(lib.afb_attention(C.byref(d), _stream()), "afb_attention")
+    return out
+
+
+def rope_pack(cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, 128] cos / sin tables (adjacent-pair layout) -> fp32 [rows, 64, 2] (cos, sin) per pair."""
+    lib = _lib.load()
+    _chk(cos, torch.float32, "rope_pack cos")
+    _chk(sin, torch.float32, "rope_pack sin")
+    if cos.dim() != 2 or cos.shape[1] != 128 or cos.shape != sin.shape or not cos.is_contiguous() or not sin.is_contiguous():
+        raise AfbError("rope_pack: cos / sin must be contiguous fp32 [rows, 128]")
+    out = torch.empty((cos.shape[0], 64, 2), dtype=torch.float32, device=cos.device)
+    _lib.check(lib.afb_rope_pack(cos.data_ptr(), sin.data_ptr(), out.data_ptr(), cos.shape[0], _stream()), "afb_rope_pack")
     return out
 
 

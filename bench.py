@@ -597,6 +597,40 @@ def run_ours(args):
         "step_tflops": step_flops / (step_ms * 1e9), "step_frac_of_peak": step_flops / (step_ms * 1e9) / peaks["bf16"],
         "tflop_per_image": fl["total"] * args.nfe / 1e12,
     }
+    if world == 1 and args.variants and not qwen:
+        # Not the headline (BASELINE.json's metric is latents out): the public call with the native VAE decoder attached
+        # and output_type='pt' — host embeds / latents in, decoded fp32 images on the host out, everything in the timed region.
+        try:
+            from arcflow_b200.vae import FluxVAEDecoder
+            from arcflow_b200.synthetic import make_vae_decoder_state_dict  # seeded synthetic decoder weights (no checkpoint offline)
+            pipe.vae = FluxVAEDecoder(make_vae_decoder_state_dict(seed=7, device=dev), device=dev)
+            himg = torch.empty((args.batch, 3, args.px, args.px), dtype=torch.float32).pin_memory()
+
+            def step_decode():
+                r = pipe(prompt_embeds=htxt, pooled_prompt_embeds=hpooled, latents=hx, height=args.px, width=args.px,
+                         num_inference_steps=args.nfe, timestep_ratio=1.0, guidance_scale=3.5, output_type="pt")
+                himg.copy_(r.images, non_blocking=True)
+
+            step_decode()
+            torch.cuda.synchronize()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(args.steps):
+                step_decode()
+            v1.record()
+            torch.cuda.synchronize()
+            vms = v0.elapsed_time(v1) / args.steps
+            line.setdefault("variants", {})["e2e_with_vae_decode"] = {
+                "value": args.batch / (vms / 1000.0), "unit": UNIT, "ms_per_step": vms,
+                "d2h_bytes_per_step": himg.numel() * 4,
+                "vae_tflop_per_image": FluxVAEDecoder.flops(args.px // 8, args.px // 8) / 1e12,
+                "note": "pipe(..., output_type='pt'): 2-NFE denoise + native FLUX VAE decode (implicit-GEMM convolutions on the "
+                        "tcgen05 kernel) + fp32 image read-back; synthetic decoder weights"}
+            pipe.vae = None
+            del himg
+        except Exception as ex:
+            line.setdefault("variants", {})["e2e_with_vae_decode"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
     if world == 1 and args.variants:
         # Not the headline: the same step with the adapter merged into the base weights (pipe.fuse_lora(), one-way, so it
         # runs last). The LoRA branches are 5.6 % of the algorithmic FLOPs counted above; images/s is what a deployment
@@ -611,9 +645,9 @@ def run_ours(args):
             step_device()
         f1.record()
         torch.cuda.synchronize()
-        line["variants"] = {"fuse_lora": {"value": args.batch * args.steps / (f0.elapsed_time(f1) / 1000.0), "unit": UNIT,
-                                          "note": "adapter merged into the base weights (W + BA rounded to bf16); "
-                                                  "not comparable to the un-merged headline"}}
+        line.setdefault("variants", {})["fuse_lora"] = {
+            "value": args.batch * args.steps / (f0.elapsed_time(f1) / 1000.0), "unit": UNIT,
+            "note": "adapter merged into the base weights (W + BA rounded to bf16); not comparable to the un-merged headline"}
     if world == 1 and not args.no_torch_cuda:
         # the same-GPU library baseline (cuBLASLt + SDPA through the oracle port), timed in this run on this box; the full
         # 3 + 10 protocol is `--impl torch_cuda`

@@ -55,7 +55,11 @@ enum {
   AFB_EPI_BIAS = 0,          /* y + bias                                   (bias may be NULL)        */
   AFB_EPI_BIAS_GELU = 1,     /* gelu_tanh(y + bias)                                                   */
   AFB_EPI_BIAS_GATE_RES = 2, /* res + gate[b, n] * (y + bias)              (AdaLN-Zero gate+residual) */
-  AFB_EPI_BIAS_RES = 3       /* res + y + bias                             (gradient accumulation)   */
+  AFB_EPI_BIAS_RES = 3,      /* res + y + bias                             (gradient accumulation)   */
+  AFB_EPI_BIAS_QKNORM_ROPE = 4 /* fused QKV projection: columns [0, qk_cols) are q heads then k heads (128 each):
+                                  RMSNorm over the head (x norm_q / norm_k) + rotary embedding; the rest: y + bias.
+                                  diffusers FluxAttention / QwenDoubleStreamAttnProcessor q/k norm + apply_rotary_emb
+                                  (reached from arcflux.py:191-197, arcqwen.py:147-155), same bf16 rounding chain */
 };
 
 typedef struct afb_gemm_desc {
@@ -93,9 +97,21 @@ typedef struct afb_gemm_desc {
   /* The accumulator is multiplied by alpha before bias / epilogue (0 means 1): the LoRA A-projection uses it for a
    * runtime adapter scale, t = scale * x A^T (peft `scaling`). */
   float alpha;
+  /* AFB_EPI_BIAS_QKNORM_ROPE only: RMSNorm weights bf16 [128] for the q and the k heads, rotary table fp32 [positions, 64, 2]
+   * ((cos, sin) per adjacent pair, afb_rope_pack), table row of the first output row of a batch (the image stream of a
+   * joint sequence starts at txt_len), number of leading q + k columns, RMSNorm eps (0 -> 1e-6). */
+  const void* norm_q;
+  const void* norm_k;
+  const void* rope;
+  int32_t rope_row0;
+  int32_t qk_cols;
+  float norm_eps;
 } afb_gemm_desc;
 
 int afb_gemm(const afb_gemm_desc* desc, void* stream);
+/* fp32 [rows, 128] cos / sin tables (adjacent-pair layout, each value repeated twice) -> fp32 [rows, 64, 2] (cos, sin) pairs:
+ * the rotary table the AFB_EPI_BIAS_QKNORM_ROPE epilogue reads. */
+int afb_rope_pack(const float* cos_tab, const float* sin_tab, float* out, int64_t rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Joint (text+image) non-causal attention, head_dim 128:

@@ -9,7 +9,7 @@ restatement on that module (same state dict, fp32, <= 1e-5) the way tests/test_o
 
 State-dict names are the BFL ones (`decoder.conv_in`, `decoder.mid.block_1`, `decoder.mid.attn_1.{norm,q,k,v,proj_out}`,
 `decoder.up.<level>.block.<i>.{norm1,conv1,norm2,conv2,nin_shortcut}`, `decoder.up.<level>.upsample.conv`,
-`decoder.norm_out`, `decoder.conv_out`); `diffusers_to_bfl_keys` maps diffusers' AutoencoderKL names onto them.
+`decoder.norm_out`, `decoder.conv_out`); the product side (arcflow_b200/vae.py::diffusers_vae_to_bfl) maps diffusers' names onto them.
 """
 from __future__ import annotations
 
@@ -78,42 +78,5 @@ def vae_decode(sd: Dict[str, Tensor], latents: Tensor, dtype=torch.float32, scal
     return _conv(sd, "decoder.conv_out", h, dtype, 1)
 
 
-def make_vae_decoder_state_dict(ch: int = 128, ch_mult: Sequence[int] = (1, 2, 4, 4), z_channels: int = 16, out_ch: int = 3,
-                                num_res_blocks: int = 2, seed: int = 7, device="cpu", dtype=torch.bfloat16) -> Dict[str, Tensor]:
-    """Seeded synthetic decoder weights of the BFL layout (no checkpoint exists offline): conv weights N(0, 1/fan_in) so the
-    activations keep O(1) scale through the 30 convolutions, biases N(0, 0.02^2), GroupNorm scales 1 + N(0, 0.05^2)."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    sd: Dict[str, Tensor] = {}
-
-    def conv(name, cin, cout, k):
-        std = (1.0 / (cin * k * k)) ** 0.5
-        sd[name + ".weight"] = (torch.randn(cout, cin, k, k, generator=g, device=device) * std).to(dtype)
-        sd[name + ".bias"] = (torch.randn(cout, generator=g, device=device) * 0.02).to(dtype)
-
-    def norm(name, c):
-        sd[name + ".weight"] = (1 + torch.randn(c, generator=g, device=device) * 0.05).to(dtype)
-        sd[name + ".bias"] = (torch.randn(c, generator=g, device=device) * 0.05).to(dtype)
-
-    def res(p, cin, cout):
-        norm(p + "norm1", cin), conv(p + "conv1", cin, cout, 3), norm(p + "norm2", cout), conv(p + "conv2", cout, cout, 3)
-        if cin != cout:
-            conv(p + "nin_shortcut", cin, cout, 1)
-
-    levels = len(ch_mult)
-    block_in = ch * ch_mult[-1]
-    conv("decoder.conv_in", z_channels, block_in, 3)
-    res("decoder.mid.block_1.", block_in, block_in)
-    norm("decoder.mid.attn_1.norm", block_in)
-    for n in ("q", "k", "v", "proj_out"):
-        conv("decoder.mid.attn_1." + n, block_in, block_in, 1)
-    res("decoder.mid.block_2.", block_in, block_in)
-    for level in reversed(range(levels)):
-        block_out = ch * ch_mult[level]
-        for i in range(num_res_blocks + 1):
-            res(f"decoder.up.{level}.block.{i}.", block_in, block_out)
-            block_in = block_out
-        if level != 0:
-            conv(f"decoder.up.{level}.upsample.conv", block_in, block_in, 3)
-    norm("decoder.norm_out", block_in)
-    conv("decoder.conv_out", block_in, out_ch, 3)
-    return sd
+# seeded synthetic decoder weights of the BFL layout live with the other synthetic factories
+from arcflow_b200.synthetic import make_vae_decoder_state_dict  # noqa: E402,F401
