@@ -12,6 +12,8 @@ from arcflow_b200.optim import karras_momentum
 class ExponentialMovingAverageHookMod:
     def __init__(self, module_keys=("diffusion_ema",), interp_mode="lerp", interval=1, start_iter=0,
                  momentum_policy="karras", momentum_cfg=None, priority="VERY_HIGH", **_unused):
+        if interp_mode != "lerp":    # the fused pass computes ema = lerp(param, ema, momentum) — mmgen's default interpolation
+            raise NotImplementedError(f"interp_mode='{interp_mode}': only 'lerp' is fused into the optimizer pass")
         if momentum_policy != "karras":
             raise NotImplementedError("only momentum_policy='karras' is fused into the optimizer pass")
         if interval != 1:
