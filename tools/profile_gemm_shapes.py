@@ -54,6 +54,13 @@ TYPES = [
     ("lora_a_up", [y], r, _lib.AFB_EPI_BIAS, False, "LoRA A-projection of an MLP-up: M 36864 x N 256 x K 3072"),
 ]
 
+nq = (1 + 0.05 * torch.randn(128, device=dev, generator=g)).bfloat16()
+nk = (1 + 0.05 * torch.randn(128, device=dev, generator=g)).bfloat16()
+ang = torch.rand(S, 64, device=dev, generator=g) * 50.0
+rope = ops.rope_pack(torch.cos(ang).repeat_interleave(2, 1).contiguous(), torch.sin(ang).repeat_interleave(2, 1).contiguous())
+TYPES.append(("img_qkv_fused_norm_rope", [img(y)], 3 * D, _lib.AFB_EPI_BIAS, False,
+              "image QKV with the fused RMSNorm + RoPE epilogue: M 32768 x N 9216 x K 3072"))
+
 entries = []
 for name, segs, N, epi, gated, desc in TYPES:
     K = sum(s.shape[-1] for s in segs)
@@ -70,8 +77,10 @@ for name, segs, N, epi, gated, desc in TYPES:
     flops = 2.0 * Mrows * N * K
     bytes_alg = 2 * (Mrows * K + N * K + Mrows * N + (Mrows * N if gated else 0) + (N if bias is not None else 0))
 
-    def launch(segs=segs, w=w, out=out, bias=bias, epi=epi, res=res):
-        ops.gemm(segs, w, out, bias=bias, epilogue=epi, gate=gate if res is not None else None, res=res)
+    qk = dict(norm_q=nq, norm_k=nk, rope=rope, qk_cols=2 * D, row0=St) if name.endswith("fused_norm_rope") else None
+
+    def launch(segs=segs, w=w, out=out, bias=bias, epi=epi, res=res, qk=qk):
+        ops.gemm(segs, w, out, bias=bias, epilogue=epi, gate=gate if res is not None else None, res=res, qk_norm_rope=qk)
 
     entries.append(dict(name=name, desc=desc, M=Mrows, N=N, K=K, flops=flops, algorithmic_bytes=bytes_alg, launch=launch))
 
