@@ -279,6 +279,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int j = 0; j < n_kv; ++j) {
       if (TRACE) trace_stamp(tr, t, j, 0);
       mbar_wait(&s_full[t], j & 1);
+      // PV_t(j-1) was issued before QK_t(j) and the tensor pipe retires in order, so this phase has already completed: the
+      // wait is one try_wait that observes it (every o_done phase gets its consumer; the O rescale below relies on it)
+      if (j > 0) mbar_wait(&o_done[t], (j - 1) & 1);
       tc_fence_after();
       if (TRACE) trace_stamp(tr, t, j, 1);
       uint32_t s[KT];
@@ -324,8 +327,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const float f = need ? fast_exp2((m - mx) * c) : 1.0f;
             if (need) m = mx;
             l *= f;
-            mbar_wait(&o_done[t], (j - 1) & 1);  // PV_t(j-1) must have retired before O is touched
-            tc_fence_after();
 #pragma unroll 1
             for (int i = 0; i < HD / 32; ++i) {
               uint32_t o[32];
@@ -612,6 +613,7 @@ attention_fwd_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     float l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
+      if (j > 0) mbar_wait(&o_done[t], (j - 1) & 1);  // already complete (in-order tensor pipe): observes the phase
       tc_fence_after();
       uint32_t s[64];
       tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(s[0]));
@@ -762,6 +764,7 @@ attention_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   }
   tc_fence_before();
   cluster_sync_all();  // peer barriers initialised, both TMEM allocations done
+  __syncthreads();     // (ordering is the cluster barrier's; this one is what compute-sanitizer racecheck models)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -873,6 +876,7 @@ attention_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     float l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
+      if (j > 0) mbar_wait(&o_done[t], (j - 1) & 1);  // already complete (in-order tensor pipe): observes the phase
       tc_fence_after();
       uint32_t s[KT];
       tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(s[0]));

@@ -211,6 +211,19 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // into the warp's staging buffer (row r at r * 128 B, its 16-byte chunk j at ((j ^ (r & 7)) * 16): the SWIZZLE_128B
 // pattern, conflict-free for the per-row writes) -> one TMA store per chunk. TMA clips rows >= rows_per_batch and
 // columns >= N, so edge tiles need no masks on the store side; loads of bias / gate / residual stay guarded.
+// Two bf16-rounded values at once (one F2FP instead of two F2F + shifts): lo / hi come back as fp32.
+__device__ __forceinline__ void round_bf16_pair(float& a, float& b) {
+  const uint32_t pk = pack_bf16x2(a, b);
+  a = bf16_lo(pk);
+  b = bf16_hi(pk);
+}
+
+// Latency note (ncu source view of the fused QKV launch, profiles/r02_ncu_qkv_fused_stalls.txt): every global load the
+// epilogue issued right before its use — bias, gate, norm weights: one address for the whole warp — cost an L2 round trip
+// (the L1 is almost entirely carved out as shared memory), 8-16 of them per 64-column chunk, serialised; 60 % of the
+// samples of that launch sat on such a first use. Now each per-column vector is fetched ONCE per chunk as one coalesced
+// 4-byte load per lane (lane i holds columns 2 i, 2 i + 1) before the TMEM load and handed out by warp shuffles; per-row
+// data (residual, rotary pairs) is prefetched for the whole chunk.
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmOut, uint32_t t_base, int n_tile,
                                                   bool valid, int lane, int row0_warp, int b, uint8_t* stage,
                                                   int& buf, const __nv_bfloat16* res_row, const __nv_bfloat16* gate_b,
@@ -218,17 +231,21 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   // warp-uniform: anything of this warp's 32 rows inside the batch? (conv: row0_warp is the first of the warp's 2 image rows)
   const bool store_rows = row0_warp < (conv_w0 >= 0 ? p.conv_h : p.rows_per_batch);
   float qk_rstd = 0.f;
-  // this row's rotary table entry (QKNORM_ROPE): 64 (cos, sin) pairs; the chunk's 32 pairs are read per 16-byte load
+  // this row's rotary table entry (QKNORM_ROPE): 64 (cos, sin) pairs
   const float2* rope_row = p.rope ? p.rope + (long long)(p.rope_row0 + row0_warp + lane) * 64 : nullptr;
+  const bool has_res = p.epi == AFB_EPI_BIAS_RES || p.epi == AFB_EPI_BIAS_GATE_RES;
 #pragma unroll 1
   for (int c = 0; c < p.bn / EPI_COLS; ++c) {
     const int n0 = n_tile * p.bn + c * EPI_COLS;
     if (n0 >= p.N) break;
     uint8_t* sbuf = stage + buf * EPI_BUF_BYTES;
     const bool qk = p.epi == AFB_EPI_BIAS_QKNORM_ROPE && n0 < p.qk_cols;
+    const int ncol = n0 + 2 * lane;  // the two columns this lane fetches for the warp (N is a multiple of 8)
     if (qk && (c & 1) == 0) {
       // first 64-column chunk of a head: sum of squares over the head's 128 (bias-added, bf16-rounded) columns. The
       // accumulator is simply read twice from TMEM — the statistics pass keeps nothing but the sum.
+      uint2 b128 = make_uint2(0u, 0u);  // bias of columns n0 + 4 lane .. + 3
+      if (p.bias) b128 = *reinterpret_cast<const uint2*>(p.bias + n0 + 4 * lane);
       float ss = 0.f;
 #pragma unroll 1
       for (int hh = 0; hh < 4; ++hh) {
@@ -236,34 +253,36 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         tmem_ld_32x32(t_base + c * EPI_COLS + hh * 32, t);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (p.bias) {
-            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n0 + hh * 32 + g * 8);
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              bb[2 * i] = bf16_lo(bw[i]);
-              bb[2 * i + 1] = bf16_hi(bw[i]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float f = round_bf16(__uint_as_float(t[g * 8 + i]) * p.alpha + bb[i]);
-            ss = fmaf(f, f, ss);
-          }
+        for (int i = 0; i < 8; ++i) {  // 4 columns per step: bias words from lane hh * 8 + i
+          const uint32_t w0 = __shfl_sync(0xffffffffu, b128.x, hh * 8 + i), w1 = __shfl_sync(0xffffffffu, b128.y, hh * 8 + i);
+          float f0 = __uint_as_float(t[4 * i]) * p.alpha + bf16_lo(w0), f1 = __uint_as_float(t[4 * i + 1]) * p.alpha + bf16_hi(w0);
+          float f2 = __uint_as_float(t[4 * i + 2]) * p.alpha + bf16_lo(w1), f3 = __uint_as_float(t[4 * i + 3]) * p.alpha + bf16_hi(w1);
+          round_bf16_pair(f0, f1);
+          round_bf16_pair(f2, f3);
+          ss = fmaf(f0, f0, ss);
+          ss = fmaf(f1, f1, ss);
+          ss = fmaf(f2, f2, ss);
+          ss = fmaf(f3, f3, ss);
         }
       }
       qk_rstd = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
     }
-    // QKNORM_ROPE: this row's 32 (cos, sin) pairs of the chunk, all 16 loads issued back to back BEFORE anything depends on
-    // them — each lane reads its own table row (32 scattered sectors per instruction), and loading them one group at a
-    // time inside the arithmetic below exposed 16 dependent L2 round trips per chunk (measured: QKV launches 16 % slower)
-    float4 rp[16];
+    // ---- everything this chunk needs from global memory, issued before the TMEM load -------------------------------
+    uint32_t bias_pk = 0u, gate_pk = 0u, nw_pk = 0u;
+    if (ncol < p.N) {
+      if (p.bias) bias_pk = *reinterpret_cast<const uint32_t*>(p.bias + ncol);
+      if (p.epi == AFB_EPI_BIAS_GATE_RES) gate_pk = *reinterpret_cast<const uint32_t*>(gate_b + ncol);
+    }
+    if (qk) nw_pk = *reinterpret_cast<const uint32_t*>((n0 < (p.qk_cols >> 1) ? p.norm_q : p.norm_k) + (c & 1) * EPI_COLS + 2 * lane);
+    float4 pre[16];  // qk: this row's 32 (cos, sin) pairs of the chunk; residual epilogues: pre[0..7] = the row's 64 bf16
     if (qk && valid) {
       const float4* src = reinterpret_cast<const float4*>(rope_row + (c & 1) * 32);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) rp[i] = __ldg(src + i);
+      for (int i = 0; i < 16; ++i) pre[i] = __ldg(src + i);
+    } else if (has_res && valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (n0 + i * 8 < p.N) pre[i] = *reinterpret_cast<const float4*>(res_row + n0 + i * 8);
     }
     if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago (same buffer) has read its source
     __syncwarp();
@@ -276,53 +295,56 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n = n0 + hh * 32 + g * 8;
+        const int j = hh * 4 + g;  // 16-byte chunk of this row's 128 bytes = 8 columns = the words of lanes 4 j .. 4 j + 3
+        uint32_t bw[4], gw[4], ww[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // shuffles are warp-collective: outside the per-row predicate
+          bw[i] = __shfl_sync(0xffffffffu, bias_pk, 4 * j + i);
+          if (p.epi == AFB_EPI_BIAS_GATE_RES) gw[i] = __shfl_sync(0xffffffffu, gate_pk, 4 * j + i);
+          if (qk) ww[i] = __shfl_sync(0xffffffffu, nw_pk, 4 * j + i);
+        }
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (valid && n < p.N) {
           float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[hh][g * 8 + i]) * p.alpha;
-          if (p.bias) {
-            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + n);
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f[2 * i] += bf16_lo(bw[i]);
-              f[2 * i + 1] += bf16_hi(bw[i]);
-            }
+          for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(v[hh][g * 8 + 2 * i]) * p.alpha + bf16_lo(bw[i]);
+            f[2 * i + 1] = __uint_as_float(v[hh][g * 8 + 2 * i + 1]) * p.alpha + bf16_hi(bw[i]);
           }
           if (p.epi == AFB_EPI_BIAS_GELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_fast(f[i]);
-          } else if (p.epi == AFB_EPI_BIAS_RES) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+          } else if (has_res) {
+            const uint32_t rw[4] = {__float_as_uint(pre[j].x), __float_as_uint(pre[j].y), __float_as_uint(pre[j].z),
+                                    __float_as_uint(pre[j].w)};
+            if (p.epi == AFB_EPI_BIAS_RES) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f[2 * i] += bf16_lo(rw[i]);
-              f[2 * i + 1] += bf16_hi(rw[i]);
-            }
-          } else if (p.epi == AFB_EPI_BIAS_GATE_RES) {
-            const uint4 gv = *reinterpret_cast<const uint4*>(gate_b + n);
-            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + n);
-            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+              for (int i = 0; i < 4; ++i) {
+                f[2 * i] += bf16_lo(rw[i]);
+                f[2 * i + 1] += bf16_hi(rw[i]);
+              }
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f[2 * i] = bf16_lo(rw[i]) + bf16_lo(gw[i]) * f[2 * i];
-              f[2 * i + 1] = bf16_hi(rw[i]) + bf16_hi(gw[i]) * f[2 * i + 1];
+              for (int i = 0; i < 4; ++i) {
+                f[2 * i] = bf16_lo(rw[i]) + bf16_lo(gw[i]) * f[2 * i];
+                f[2 * i + 1] = bf16_hi(rw[i]) + bf16_hi(gw[i]) * f[2 * i + 1];
+              }
             }
           } else if (qk) {
             // the reference's rounding chain (diffusers RMSNorm + apply_rotary_emb on a bf16 Linear output): Linear ->
             // bf16; x * rstd -> bf16; * weight -> bf16; rotation in fp32 -> bf16. Same order as rmsnorm_rope_kernel.
-            const int hc = (c & 1) * EPI_COLS + hh * 32 + g * 8;  // column inside the 128-wide head
-            const uint4 wv = *reinterpret_cast<const uint4*>((n0 < (p.qk_cols >> 1) ? p.norm_q : p.norm_k) + hc);
-            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-            const float4 r0 = rp[(hh * 4 + g) * 2], r1 = rp[(hh * 4 + g) * 2 + 1];  // pairs hc/2 .. hc/2 + 3
+            const float4 r0 = pre[2 * j], r1 = pre[2 * j + 1];  // this group's 4 (cos, sin) pairs
             const float cs[4] = {r0.x, r0.z, r1.x, r1.z}, sn[4] = {r0.y, r0.w, r1.y, r1.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float x0 = round_bf16(round_bf16(round_bf16(f[2 * i]) * qk_rstd) * bf16_lo(ww[i]));
-              const float x1 = round_bf16(round_bf16(round_bf16(f[2 * i + 1]) * qk_rstd) * bf16_hi(ww[i]));
+              float x0 = f[2 * i], x1 = f[2 * i + 1];
+              round_bf16_pair(x0, x1);
+              x0 *= qk_rstd;
+              x1 *= qk_rstd;
+              round_bf16_pair(x0, x1);
+              x0 *= bf16_lo(ww[i]);
+              x1 *= bf16_hi(ww[i]);
+              round_bf16_pair(x0, x1);
               f[2 * i] = x0 * cs[i] - x1 * sn[i];
               f[2 * i + 1] = x1 * cs[i] + x0 * sn[i];
             }
@@ -332,7 +354,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
           o.z = pack_bf16x2(f[4], f[5]);
           o.w = pack_bf16x2(f[6], f[7]);
         }
-        const int j = hh * 4 + g;  // 16-byte chunk of this row's 128 bytes
         *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
       }
     }
@@ -567,6 +588,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   }
   tc_fence_before();
   cluster_sync_all();  // peer barriers initialised + both TMEM allocations done
+  __syncthreads();     // (ordering is the cluster barrier's; this one is what compute-sanitizer racecheck models)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
