@@ -102,7 +102,7 @@ struct afb_engine {
        *lt1 = nullptr, *mod = nullptr, *temb = nullptr, *tmp = nullptr, *tproj = nullptr,
        *ltv = nullptr, *head = nullptr, *x_bf16 = nullptr, *txtn = nullptr, *alt_nm = nullptr;
   float *t_dev = nullptr, *g_dev = nullptr;
-  float* rope_cs = nullptr;   // [S, 64, 2] packed (cos, sin) pairs for the fused QK-norm + RoPE epilogue
+  float* rope_cs = nullptr;   // afb_rope_pack layout: (cos, sin) pairs for the fused QK-norm + RoPE epilogue
   bool fuse_qk_rope = true;   // inference forwards: RMSNorm + RoPE inside the QKV GEMM epilogue (AFB_ENGINE_FUSE_QK_ROPE=0: separate kernel)
   // training workspace (afb_engine_train_reserve): checkpoints + recompute / gradient buffers
   void* tws = nullptr;
@@ -172,7 +172,7 @@ size_t carve(afb_engine* e, uint8_t* base, int B, int St, int Si) {
   e->alt_nm = c.take<bf16>(size_t(B) * 2 * D);
   e->t_dev = c.take<float>(B);
   e->g_dev = c.take<float>(B);
-  e->rope_cs = c.take<float>(S * 128);
+  e->rope_cs = c.take<float>((S + 31) / 32 * 32 * 128);
   return c.off;
 }
 

@@ -73,7 +73,7 @@ struct GemmParams {
   // AFB_EPI_BIAS_QKNORM_ROPE: per-head RMSNorm (x weight) + rotary embedding on output columns [0, qk_cols) — the q heads
   // then the k heads of a fused QKV projection, 128 columns per head — fused into the epilogue
   const __nv_bfloat16 *norm_q, *norm_k;  // [128] RMSNorm weights
-  const float2* rope;                    // [positions, 64] (cos, sin) per adjacent pair
+  const float4* rope;                    // afb_rope_pack layout: [positions / 32][2 halves][16][32 lanes] x (cos, sin, cos, sin)
   int rope_row0, qk_cols;
   float norm_eps;
   __nv_bfloat16* out;
@@ -231,8 +231,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   // warp-uniform: anything of this warp's 32 rows inside the batch? (conv: row0_warp is the first of the warp's 2 image rows)
   const bool store_rows = row0_warp < (conv_w0 >= 0 ? p.conv_h : p.rows_per_batch);
   float qk_rstd = 0.f;
-  // this row's rotary table entry (QKNORM_ROPE): 64 (cos, sin) pairs
-  const float2* rope_row = p.rope ? p.rope + (long long)(p.rope_row0 + row0_warp + lane) * 64 : nullptr;
+  // this row's rotary table entries (QKNORM_ROPE), afb_rope_pack layout: block of 32 positions, lane inside the block
+  const long long rope_s = (long long)p.rope_row0 + row0_warp + lane;
+  const float4* rope_row = p.rope ? p.rope + (rope_s >> 5) * (2 * 16 * 32) + (rope_s & 31) : nullptr;
   const bool has_res = p.epi == AFB_EPI_BIAS_RES || p.epi == AFB_EPI_BIAS_GATE_RES;
 #pragma unroll 1
   for (int c = 0; c < p.bn / EPI_COLS; ++c) {
@@ -276,9 +277,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     if (qk) nw_pk = *reinterpret_cast<const uint32_t*>((n0 < (p.qk_cols >> 1) ? p.norm_q : p.norm_k) + (c & 1) * EPI_COLS + 2 * lane);
     float4 pre[16];  // qk: this row's 32 (cos, sin) pairs of the chunk; residual epilogues: pre[0..7] = the row's 64 bf16
     if (qk && valid) {
-      const float4* src = reinterpret_cast<const float4*>(rope_row + (c & 1) * 32);
+      const float4* src = rope_row + (c & 1) * (16 * 32);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pre[i] = __ldg(src + i);
+      for (int i = 0; i < 16; ++i) pre[i] = __ldg(src + i * 32);  // 32 lanes x 16 B contiguous per instruction
     } else if (has_res && valid) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -866,7 +867,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
     AFB_REQUIRE(p.tma_store && two_cta, "gemm: the QK-norm + RoPE epilogue needs the TMA-store CTA-pair kernel");
     p.norm_q = static_cast<const __nv_bfloat16*>(d->norm_q);
     p.norm_k = static_cast<const __nv_bfloat16*>(d->norm_k);
-    p.rope = static_cast<const float2*>(d->rope);
+    p.rope = static_cast<const float4*>(d->rope);
     p.rope_row0 = d->rope_row0;
     p.qk_cols = d->qk_cols;
     p.norm_eps = d->norm_eps > 0.f ? d->norm_eps : 1e-6f;

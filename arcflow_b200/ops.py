@@ -86,15 +86,15 @@ def gemm(a: Sequence[torch.Tensor] | torch.Tensor, w: torch.Tensor, out: torch.T
         raise AfbError("gemm: w2 needs transposed=True")
     d.epilogue = epilogue
     if qk_norm_rope is not None:
-        # fused QKV projection epilogue: dict(norm_q=bf16 [128], norm_k=bf16 [128], rope=fp32 [positions, 64, 2] from
-        # rope_pack(), qk_cols=leading q + k columns, row0=table row of output row 0 of each batch)
+        # fused QKV projection epilogue: dict(norm_q=bf16 [128], norm_k=bf16 [128], rope=rope_pack(cos, sin),
+        # qk_cols=leading q + k columns, row0=table position of output row 0 of each batch)
         q = qk_norm_rope
         _chk(q["norm_q"], BF16, "gemm norm_q")
         _chk(q["norm_k"], BF16, "gemm norm_k")
         _chk(q["rope"], torch.float32, "gemm rope")
-        if q["rope"].dim() != 3 or tuple(q["rope"].shape[1:]) != (64, 2) or not q["rope"].is_contiguous():
-            raise AfbError("gemm: rope must be contiguous fp32 [positions, 64, 2]")
-        if q["rope"].shape[0] < int(q.get("row0", 0)) + rows:
+        if q["rope"].dim() != 5 or tuple(q["rope"].shape[1:]) != (2, 16, 32, 4) or not q["rope"].is_contiguous():
+            raise AfbError("gemm: rope must be the contiguous fp32 table rope_pack() returns")
+        if q["rope"].shape[0] * 32 < int(q.get("row0", 0)) + rows:
             raise AfbError("gemm: rope table has fewer positions than row0 + rows")
         d.epilogue = _lib.AFB_EPI_BIAS_QKNORM_ROPE
         d.norm_q, d.norm_k, d.rope = q["norm_q"].data_ptr(), q["norm_k"].data_ptr(), q["rope"].data_ptr()
@@ -160,13 +160,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[t
 
 
 def rope_pack(cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
-    """fp32 [rows, 128] cos / sin tables (adjacent-pair layout) -> fp32 [rows, 64, 2] (cos, sin) per pair."""
+    """fp32 [rows, 128] cos / sin tables (adjacent-pair layout) -> the warp-coalesced table the fused QK-norm + RoPE GEMM
+    epilogue reads: fp32 [ceil(rows / 32), 2, 16, 32, 4] (see afb_rope_pack)."""
     lib = _lib.load()
     _chk(cos, torch.float32, "rope_pack cos")
     _chk(sin, torch.float32, "rope_pack sin")
     if cos.dim() != 2 or cos.shape[1] != 128 or cos.shape != sin.shape or not cos.is_contiguous() or not sin.is_contiguous():
         raise AfbError("rope_pack: cos / sin must be contiguous fp32 [rows, 128]")
-    out = torch.empty((cos.shape[0], 64, 2), dtype=torch.float32, device=cos.device)
+    out = torch.empty(((cos.shape[0] + 31) // 32, 2, 16, 32, 4), dtype=torch.float32, device=cos.device)
     _lib.check(lib.afb_rope_pack(cos.data_ptr(), sin.data_ptr(), out.data_ptr(), cos.shape[0], _stream()), "afb_rope_pack")
     return out
 

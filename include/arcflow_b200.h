@@ -97,8 +97,8 @@ typedef struct afb_gemm_desc {
   /* The accumulator is multiplied by alpha before bias / epilogue (0 means 1): the LoRA A-projection uses it for a
    * runtime adapter scale, t = scale * x A^T (peft `scaling`). */
   float alpha;
-  /* AFB_EPI_BIAS_QKNORM_ROPE only: RMSNorm weights bf16 [128] for the q and the k heads, rotary table fp32 [positions, 64, 2]
-   * ((cos, sin) per adjacent pair, afb_rope_pack), table row of the first output row of a batch (the image stream of a
+  /* AFB_EPI_BIAS_QKNORM_ROPE only: RMSNorm weights bf16 [128] for the q and the k heads, rotary table in the afb_rope_pack
+   * layout, table position of the first output row of a batch (the image stream of a
    * joint sequence starts at txt_len), number of leading q + k columns, RMSNorm eps (0 -> 1e-6). */
   const void* norm_q;
   const void* norm_k;
@@ -109,8 +109,10 @@ typedef struct afb_gemm_desc {
 } afb_gemm_desc;
 
 int afb_gemm(const afb_gemm_desc* desc, void* stream);
-/* fp32 [rows, 128] cos / sin tables (adjacent-pair layout, each value repeated twice) -> fp32 [rows, 64, 2] (cos, sin) pairs:
- * the rotary table the AFB_EPI_BIAS_QKNORM_ROPE epilogue reads. */
+/* fp32 [rows, 128] cos / sin tables (adjacent-pair layout, each value repeated twice) -> the rotary table the
+ * AFB_EPI_BIAS_QKNORM_ROPE epilogue reads: fp32 [ceil(rows / 32)][2][16][32][4], i.e. for each block of 32 positions and each
+ * half of the head the (cos, sin, cos, sin) of pair 2 i, 2 i + 1 of the 32 positions side by side (warp-coalesced for a
+ * one-row-per-thread reader). out holds ceil(rows / 32) * 32 * 128 floats. */
 int afb_rope_pack(const float* cos_tab, const float* sin_tab, float* out, int64_t rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
