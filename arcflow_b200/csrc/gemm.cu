@@ -120,9 +120,10 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 // One thread = one accumulator row: 256 fp32 columns from TMEM in 8 chunks of 32.
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_base, int n_tile, bool valid,
                                               __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
-                                              const __nv_bfloat16* gate_b) {
+                                              const __nv_bfloat16* gate_b, int c_begin = 0, int c_end = 1 << 30) {
+  if (c_end > p.bn / 32) c_end = p.bn / 32;
 #pragma unroll 1
-  for (int c = 0; c < p.bn / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const int n0 = n_tile * p.bn + c * 32;
     if (n0 >= p.N) break;
     uint32_t v[32];
@@ -227,7 +228,8 @@ __device__ __forceinline__ void round_bf16_pair(float& a, float& b) {
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmOut, uint32_t t_base, int n_tile,
                                                   bool valid, int lane, int row0_warp, int b, uint8_t* stage,
                                                   int& buf, const __nv_bfloat16* res_row, const __nv_bfloat16* gate_b,
-                                                  int conv_w0 = -1) {
+                                                  int conv_w0 = -1, int c_begin = 0, int c_end = 1 << 30,
+                                                  bool single_buf = false) {
   // warp-uniform: anything of this warp's 32 rows inside the batch? (conv: row0_warp is the first of the warp's 2 image rows)
   const bool store_rows = row0_warp < (conv_w0 >= 0 ? p.conv_h : p.rows_per_batch);
   float qk_rstd = 0.f;
@@ -235,8 +237,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   const long long rope_s = (long long)p.rope_row0 + row0_warp + lane;
   const float4* rope_row = p.rope ? p.rope + (rope_s >> 5) * (2 * 16 * 32) + (rope_s & 31) : nullptr;
   const bool has_res = p.epi == AFB_EPI_BIAS_RES || p.epi == AFB_EPI_BIAS_GATE_RES;
+  if (c_end > p.bn / EPI_COLS) c_end = p.bn / EPI_COLS;
 #pragma unroll 1
-  for (int c = 0; c < p.bn / EPI_COLS; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const int n0 = n_tile * p.bn + c * EPI_COLS;
     if (n0 >= p.N) break;
     uint8_t* sbuf = stage + buf * EPI_BUF_BYTES;
@@ -285,7 +288,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       for (int i = 0; i < 8; ++i)
         if (n0 + i * 8 < p.N) pre[i] = *reinterpret_cast<const float4*>(res_row + n0 + i * 8);
     }
-    if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago (same buffer) has read its source
+    if (lane == 0) {  // the previous store out of this buffer has read its source
+      if (single_buf)
+        bulk_wait_read<0>();
+      else
+        bulk_wait_read<1>();
+    }
     __syncwarp();
     uint32_t v[2][32];
     tmem_ld_32x32(t_base + c * EPI_COLS, v[0]);
@@ -369,7 +377,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       }
       bulk_commit();
     }
-    buf ^= 1;
+    if (!single_buf) buf ^= 1;
   }
 }
 
@@ -539,9 +547,14 @@ constexpr int HALF_N = BN / 2;                    // W rows staged per CTA
 constexpr int B2_STAGE_BYTES = HALF_N * BK * 2;   // 16 KiB
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
 constexpr size_t GEMM2_SMEM_BYTES = 1024 + size_t(STAGES2) * STAGE2_BYTES + EPI_STAGE_BYTES + 256;
+// CTA-pair kernel: EIGHT epilogue warps — two per TMEM lane quarter, each taking half of the tile's 64-column chunks (one head
+// of a fused-QKV tile). The epilogue is a dependent chain per thread (TMEM load -> convert -> shared memory -> TMA store) with a
+// single warp per scheduler; with the fused norm + rotation it no longer fit under the K = 3072 main loop (QKV launches 25 %
+// slower). Each warp has ONE 4 KiB staging buffer (8 x 4 KiB = the same 32 KiB).
+constexpr int GEMM2_THREADS = 32 * (2 + 8);
 static_assert(GEMM2_SMEM_BYTES <= 232448 && GEMM_SMEM_BYTES <= 232448, "shared memory budget (227 KiB per CTA)");
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)  // 320 threads x 200 registers = 64 000 of the SM's 65 536
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut,
@@ -577,7 +590,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&acc_empty[a], 16);  // 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -708,8 +721,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     }
   } else {
     // ------------------------------- epilogue warps (both CTAs) -----------------------------
-    const int q = warp & 3;
-    uint8_t* stage = sEpi + q * 2 * EPI_BUF_BYTES;
+    const int q = warp & 3;               // TMEM lane quarter (warps 2..9: each quarter twice)
+    const int chalf = (warp - 2) >> 2;    // which half of the tile's chunks this warp takes
+    uint8_t* stage = sEpi + (warp - 2) * EPI_BUF_BYTES;
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -739,9 +753,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       if (p.tma_store)
-        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b, conv_w0);
+        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b, conv_w0,
+                          chalf * (p.bn / (2 * EPI_COLS)), (chalf + 1) * (p.bn / (2 * EPI_COLS)), true);
       else
-        epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
+        epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b, chalf * (p.bn / 64), (chalf + 1) * (p.bn / 64));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
@@ -935,7 +950,7 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   if (two_cta) {
     const int max_clusters = sms / 2;
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-    gemm_bf16_2cta_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2],
+    gemm_bf16_2cta_kernel<<<2 * clusters, GEMM2_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2],
                                                                                   tmB, tmB1, tmOut, p);
   } else {
     const int grid = num_tiles < sms ? num_tiles : sms;
@@ -1018,7 +1033,7 @@ int conv3x3_launch(const afb_conv_desc* d, cudaStream_t stream) {
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = device_sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  gemm_bf16_2cta_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmA, tmA, tmB, tmB, tmOut, p);
+  gemm_bf16_2cta_kernel<<<2 * clusters, GEMM2_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmA, tmA, tmB, tmB, tmOut, p);
   AFB_CHECK_CUDA(cudaGetLastError());
   return AFB_OK;
 }
