@@ -554,7 +554,7 @@ constexpr size_t GEMM2_SMEM_BYTES = 1024 + size_t(STAGES2) * STAGE2_BYTES + EPI_
 constexpr int GEMM2_THREADS = 32 * (2 + 8);
 static_assert(GEMM2_SMEM_BYTES <= 232448 && GEMM_SMEM_BYTES <= 232448, "shared memory budget (227 KiB per CTA)");
 
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)  // 320 threads x 200 registers = 64 000 of the SM's 65 536
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(192)  // 320 threads x 192 registers (register files are handed out 512 per warp: 200 did not launch)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut,
