@@ -295,12 +295,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         bulk_wait_read<1>();
     }
     __syncwarp();
-    uint32_t v[2][32];
-    tmem_ld_32x32(t_base + c * EPI_COLS, v[0]);
-    tmem_ld_32x32(t_base + c * EPI_COLS + 32, v[1]);
-    tmem_ld_wait();
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[32];  // 32 columns at a time: the 320-thread kernel has 168 registers per thread
+      tmem_ld_32x32(t_base + c * EPI_COLS + hh * 32, v);
+      tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n = n0 + hh * 32 + g * 8;
@@ -317,8 +316,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
           float f[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            f[2 * i] = __uint_as_float(v[hh][g * 8 + 2 * i]) * p.alpha + bf16_lo(bw[i]);
-            f[2 * i + 1] = __uint_as_float(v[hh][g * 8 + 2 * i + 1]) * p.alpha + bf16_hi(bw[i]);
+            f[2 * i] = __uint_as_float(v[g * 8 + 2 * i]) * p.alpha + bf16_lo(bw[i]);
+            f[2 * i + 1] = __uint_as_float(v[g * 8 + 2 * i + 1]) * p.alpha + bf16_hi(bw[i]);
           }
           if (p.epi == AFB_EPI_BIAS_GELU) {
 #pragma unroll
@@ -554,7 +553,8 @@ constexpr size_t GEMM2_SMEM_BYTES = 1024 + size_t(STAGES2) * STAGE2_BYTES + EPI_
 constexpr int GEMM2_THREADS = 32 * (2 + 8);
 static_assert(GEMM2_SMEM_BYTES <= 232448 && GEMM_SMEM_BYTES <= 232448, "shared memory budget (227 KiB per CTA)");
 
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(192)  // 320 threads x 192 registers (register files are handed out 512 per warp: 200 did not launch)
+// 10 warps are allocated as 12 (registers go out in groups of 4 warps): 65536 / (12 x 32) = 170 -> 168 registers per thread
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut,
