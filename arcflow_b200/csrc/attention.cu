@@ -83,23 +83,6 @@ __device__ __forceinline__ void named_bar_arrive(int id) {
   asm volatile("bar.arrive %0, 256;" ::"r"(id) : "memory");
 }
 
-// 2^x for a pair, on the FMA/ALU pipes: x = floor(x) + f, 2^f by a cubic minimax on [0, 1)
-// (max rel. error ~9e-5, far below the bf16 rounding of P), exponent patched in by integer add.
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  const float magic = 12582912.0f;  // 1.5 * 2^23: float add with round-down leaves floor(x) in the low mantissa bits
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 sh = __fadd2_rd(x, make_float2(magic, magic));
-  const float2 fl = __fadd2_rn(sh, make_float2(-magic, -magic));
-  const float2 f = __fadd2_rn(x, make_float2(-fl.x, -fl.y));
-  float2 p = __ffma2_rn(make_float2(0.07711909f, 0.07711909f), f, make_float2(0.22756439f, 0.22756439f));
-  p = __ffma2_rn(p, f, make_float2(0.69514614f, 0.69514614f));
-  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
-  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(sh.x) << 23));
-  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(sh.y) << 23));
-  return p;
-}
-
 // TRACE: record clock stamps of the softmax hand-shake (developer builds only; the product instantiation carries no
 // instrumentation — the probes' predicates and address arithmetic cost 8 % of the kernel). TURNS: the two warpgroups
 // alternate in the exp phase.

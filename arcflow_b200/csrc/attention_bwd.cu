@@ -11,6 +11,7 @@
 // of the TS products are the resident [rows, 128] tiles read MN-major (as V in the forward).
 // lse is the forward's log2-domain logsumexp, delta[b,h,s] = sum_d dO O (attn_delta_kernel).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/arcflow_b200.h"
@@ -490,6 +491,287 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dK/dV kernel with the tensor pipe and the math warps overlapped (supersedes attention_bwd_kernel<1>, which stays
+// selectable with AFB_ATTN_BWD_LEGACY=1 for A/B). S^T, dP^T, dV and dK fill the 512 TMEM columns, so nothing can be
+// double-buffered — but nothing has to be: a tile's math has two legs that depend on different products (the
+// exponentials need S^T, dS^T needs dP^T), and each leg's result feeds a different accumulating product. Issuing
+//      dV += P^T(j) dO(j),   S^T(j+1) = K Q(j+1)^T,   dK += dS^T(j) Q(j),   dP^T(j+1) = V dO(j+1)^T
+// in THAT order (the tensor pipe executes in issue order, so S^T(j+1) may overwrite the columns P^T(j) was read from, and
+// dP^T(j+1) those of dS^T(j)) keeps 1024 cycles of independent tensor work queued behind each leg: the exponentials of
+// tile j+1 run under dK(j) and dP^T(j+1), the dS leg under dV(j+1) and S^T(j+2). Q tiles are needed twice, two products
+// apart (3-stage ring); dO tiles are released by dV (2-stage ring); K and V are resident.
+// The math leg: P is kept in fp32 registers between the legs (no unpacking), a quarter of the exponentials run as a cubic
+// on the FMA pipe (the leg is MUFU-bound: 128 x 128 ex2 = 1024 cycles of the 16 lanes an SM has), and the softmax scale is
+// applied once to the dK accumulator instead of to every dS element. Columns / rows beyond the sequence need no masking:
+// TMA zero-fills them, so the out-of-range rows of Q and dO contribute exact zeros to both accumulators.
+// ------------------------------------------------------------------------------------------------
+constexpr int KV_Q_STAGES = 3, KV_DO_STAGES = 2;
+constexpr size_t DKDV_SMEM_BYTES = size_t(2 + KV_Q_STAGES + KV_DO_STAGES) * TILE_BYTES + 2048 + 256;
+static_assert(DKDV_SMEM_BYTES <= 232448, "dK/dV kernel: shared memory over the 227 KiB a CTA can have");
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attention_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdParams p) {
+  // No alignment slack to spare (224 KiB of tiles): the dynamic shared memory of a kernel without static shared memory
+  // starts on a 1 KiB boundary; checked, not assumed.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;
+  uint8_t* sdO = sQ + KV_Q_STAGES * TILE_BYTES;
+  float* sNl = reinterpret_cast<float*>(sdO + KV_DO_STAGES * TILE_BYTES);  // [2][128]  -lse of the inner tile's queries
+  float* sNd = sNl + 256;                                                  // [2][128]  -delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sNd + 256);
+  uint64_t* r_full = bars;                        // K, V landed
+  uint64_t* q_full = r_full + 1;                  // [3]
+  uint64_t* q_empty = q_full + KV_Q_STAGES;       // [3]  dK product of the tile retired
+  uint64_t* do_full = q_empty + KV_Q_STAGES;      // [2]
+  uint64_t* do_empty = do_full + KV_DO_STAGES;    // [2]  dV product of the tile retired
+  uint64_t* s_full = do_empty + KV_DO_STAGES;     // S^T(j) ready
+  uint64_t* p_full = s_full + 1;                  // P^T(j) written over S^T(j)
+  uint64_t* dp_full = p_full + 1;                 // dP^T(j) ready
+  uint64_t* ds_full = dp_full + 1;                // dS^T(j) written over dP^T(j)
+  uint64_t* acc_done = ds_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * T;  // this CTA's KV rows
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_inner = (p.seq + T - 1) / T;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmdO);
+    mbar_init(r_full, 1);
+    for (int s = 0; s < KV_Q_STAGES; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
+    for (int s = 0; s < KV_DO_STAGES; ++s) {
+      mbar_init(&do_full[s], 1);
+      mbar_init(&do_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(dp_full, 1);
+    mbar_init(ds_full, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t cdV = 0, cdK = 128, cS = 256, cdP = 384;  // TMEM columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(r_full, 2 * TILE_BYTES);
+      load_tile(sK, &tmK, r_full, h, r0, b);
+      load_tile(sV, &tmV, r_full, h, r0, b);
+      for (int j = 0; j < n_inner; ++j) {
+        const int qs = j % KV_Q_STAGES, ds = j % KV_DO_STAGES;
+        mbar_wait(&q_empty[qs], ((j / KV_Q_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], TILE_BYTES);
+        load_tile(sQ + qs * TILE_BYTES, &tmQ, &q_full[qs], h, j * T, b);
+        mbar_wait(&do_empty[ds], ((j / KV_DO_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&do_full[ds], TILE_BYTES);
+        load_tile(sdO + ds * TILE_BYTES, &tmdO, &do_full[ds], h, j * T, b);
+      }
+    }
+  } else if (warp == 1) {
+    const uint64_t k_k = make_sw128_desc(smem_u32(sK), 16, 1024);            // K-major views (contraction over d)
+    const uint64_t v_k = make_sw128_desc(smem_u32(sV), 16, 1024);
+    const uint64_t q_k = make_sw128_desc(smem_u32(sQ), 16, 1024);
+    const uint64_t do_k = make_sw128_desc(smem_u32(sdO), 16, 1024);
+    const uint64_t q_mn = make_sw128_desc(smem_u32(sQ), HALF_BYTES, 1024);   // MN-major views (contraction over rows)
+    const uint64_t do_mn = make_sw128_desc(smem_u32(sdO), HALF_BYTES, 1024);
+    const uint32_t tS = tmem_base + cS, tdP = tmem_base + cdP;
+    auto stage = [](int st) { return uint64_t((st * TILE_BYTES) >> 4); };
+    mbar_wait(r_full, 0);
+    mbar_wait(&q_full[0], 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      mma_ss_128(tS, k_k, q_k);                                              // S^T(0) = K Q_0^T
+      tc_commit(s_full);
+    }
+    __syncwarp();
+    mbar_wait(&do_full[0], 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      mma_ss_128(tdP, v_k, do_k);                                            // dP^T(0) = V dO_0^T
+      tc_commit(dp_full);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_inner; ++j) {
+      const int qs = j % KV_Q_STAGES, ds = j % KV_DO_STAGES;
+      const bool has_next = j + 1 < n_inner;
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        mma_ts_128(tmem_base + cdV, tS, do_mn + stage(ds), j > 0);           // dV += P^T(j) dO_j
+        tc_commit(&do_empty[ds]);
+      }
+      __syncwarp();
+      if (has_next) {
+        const int qn = (j + 1) % KV_Q_STAGES;
+        mbar_wait(&q_full[qn], ((j + 1) / KV_Q_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          mma_ss_128(tS, k_k, q_k + stage(qn));                              // S^T(j+1), over the columns of P^T(j)
+          tc_commit(s_full);
+        }
+        __syncwarp();
+      }
+      mbar_wait(ds_full, j & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        mma_ts_128(tmem_base + cdK, tdP, q_mn + stage(qs), j > 0);           // dK += dS^T(j) Q_j
+        tc_commit(&q_empty[qs]);
+        if (!has_next) tc_commit(acc_done);
+      }
+      __syncwarp();
+      if (has_next) {
+        const int dn = (j + 1) % KV_DO_STAGES;
+        mbar_wait(&do_full[dn], ((j + 1) / KV_DO_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          mma_ss_128(tdP, v_k, do_k + stage(dn));                            // dP^T(j+1), over the columns of dS^T(j)
+          tc_commit(dp_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + cS, tdP = tmem_base + lane_base + cdP;
+    const int grow = r0 + row;
+    const long long bh = ((long long)b * p.heads + h) * p.seq;
+    const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+    // statistics of inner query j * T + row, negated; finite (0) beyond the sequence so that 0 * P stays 0
+    float nl_next = row < p.seq ? -p.lse[bh + row] : 0.f;
+    float nd_next = row < p.seq ? -p.delta[bh + row] : 0.f;
+    for (int j = 0; j < n_inner; ++j) {
+      float* nlj = sNl + (j & 1) * 128;
+      float* ndj = sNd + (j & 1) * 128;
+      nlj[row] = nl_next;
+      ndj[row] = nd_next;
+      const int qn = (j + 1) * T + row;   // next tile's statistics: the loads fly under this tile's exponentials
+      nl_next = qn < p.seq ? -p.lse[bh + qn] : 0.f;
+      nd_next = qn < p.seq ? -p.delta[bh + qn] : 0.f;
+      math_bar_sync();  // buffer j & 1 complete; its readers of tile j - 2 passed the barrier of tile j - 1
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t s[T];
+#pragma unroll
+      for (int i = 0; i < T / 32; ++i) tmem_ld_32x32(tS + i * 32, reinterpret_cast<uint32_t(&)[32]>(s[i * 32]));
+      tmem_ld_wait();
+      // P^T = 2^(c S^T - lse[q]), fp32 in place; published as packed bf16 over the first 64 columns of S^T
+#pragma unroll
+      for (int cidx = 0; cidx < T / 32; ++cidx) {
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int col = cidx * 32 + i;
+          const float4 nl = *reinterpret_cast<const float4*>(nlj + col);
+          const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), c2,
+                                       make_float2(nl.x, nl.y));
+          const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(s[col + 2]), __uint_as_float(s[col + 3])), c2,
+                                       make_float2(nl.z, nl.w));
+          float2 p0, p1;
+          p0.x = fast_exp2(x0.x);
+          p0.y = fast_exp2(x0.y);
+          if ((i & 4) != 0) {
+            p1 = exp2_poly2(x1);
+          } else {
+            p1.x = fast_exp2(x1.x);
+            p1.y = fast_exp2(x1.y);
+          }
+          s[col] = __float_as_uint(p0.x);
+          s[col + 1] = __float_as_uint(p0.y);
+          s[col + 2] = __float_as_uint(p1.x);
+          s[col + 3] = __float_as_uint(p1.y);
+          o[i >> 1] = pack_bf16x2(p0.x, p0.y);
+          o[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+        }
+        tmem_st_32x16(tS + cidx * 16, o);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // dS^T / scale = P^T (dP^T - delta[q]), 32 columns at a time, packed bf16 over the first 64 columns of dP^T
+      mbar_wait(dp_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cidx = 0; cidx < T / 32; ++cidx) {
+        uint32_t d[32];
+        tmem_ld_32x32(tdP + cidx * 32, d);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int col = cidx * 32 + i;
+          const float4 nd = *reinterpret_cast<const float4*>(ndj + col);
+          const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), make_float2(nd.x, nd.y));
+          const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(d[i + 2]), __uint_as_float(d[i + 3])), make_float2(nd.z, nd.w));
+          const float2 u0 = __fmul2_rn(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), t0);
+          const float2 u1 = __fmul2_rn(make_float2(__uint_as_float(s[col + 2]), __uint_as_float(s[col + 3])), t1);
+          o[i >> 1] = pack_bf16x2(u0.x, u0.y);
+          o[(i >> 1) + 1] = pack_bf16x2(u1.x, u1.y);
+        }
+        tmem_st_32x16(tdP + cidx * 16, o);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    // epilogue: dV, scale * dK -> bf16 -> global
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const bool valid_row = grow < p.seq;
+    for (int a = 0; a < 2; ++a) {
+      __nv_bfloat16* dst = a == 0 ? p.out1 : p.out0;   // accumulator 0 = dV, 1 = dK
+      const float f = a == 0 ? 1.0f : p.scale;
+      __nv_bfloat16* orow = dst + (long long)b * p.out_bs + (long long)grow * p.out_ld + h * HD;
+      const uint32_t tA = tmem_base + lane_base + (a == 0 ? cdV : cdK);
+#pragma unroll 1
+      for (int i = 0; i < HD / 32; ++i) {
+        uint32_t o[32];
+        tmem_ld_32x32(tA + i * 32, o);
+        tmem_ld_wait();
+        if (valid_row) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack_bf16x2(f * __uint_as_float(o[g * 8 + 0]), f * __uint_as_float(o[g * 8 + 1]));
+            w.y = pack_bf16x2(f * __uint_as_float(o[g * 8 + 2]), f * __uint_as_float(o[g * 8 + 3]));
+            w.z = pack_bf16x2(f * __uint_as_float(o[g * 8 + 4]), f * __uint_as_float(o[g * 8 + 5]));
+            w.w = pack_bf16x2(f * __uint_as_float(o[g * 8 + 6]), f * __uint_as_float(o[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(orow + i * 32 + g * 8) = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int make_view_map(CUtensorMap* tm, const void* ptr, int64_t ld, int64_t bs, int batch, int seq, int heads) {
   const uint64_t dims[3] = {uint64_t(heads) * HD, uint64_t(seq), uint64_t(batch)};
   const uint64_t bstride = batch > 1 ? uint64_t(bs) : uint64_t(seq) * uint64_t(ld);
@@ -532,6 +814,7 @@ int attention_backward_launch(const afb_attn_bwd_desc* d, cudaStream_t stream) {
   if (!attr_set) {
     AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DQ_SMEM_BYTES)));
     AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BWD_SMEM_BYTES)));
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DKDV_SMEM_BYTES)));
     attr_set = true;
   }
   dim3 grid((d->seq + T - 1) / T, d->heads, d->batch);
@@ -541,7 +824,14 @@ int attention_backward_launch(const afb_attn_bwd_desc* d, cudaStream_t stream) {
   AFB_CHECK_CUDA(cudaGetLastError());
   p.out0 = static_cast<__nv_bfloat16*>(d->dk);
   p.out1 = static_cast<__nv_bfloat16*>(d->dv);
-  attention_bwd_kernel<1><<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+  static const bool legacy = [] {
+    const char* e = getenv("AFB_ATTN_BWD_LEGACY");   // developer A/B: the un-overlapped dK/dV kernel
+    return e != nullptr && e[0] == '1';
+  }();
+  if (legacy)
+    attention_bwd_kernel<1><<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+  else
+    attention_bwd_dkdv_kernel<<<grid, BWD_THREADS, DKDV_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
   return AFB_OK;
