@@ -145,6 +145,11 @@ class AdamwArgs(C.Structure):
                 ("lr_mult_begin", C.c_int64), ("lr_mult_end", C.c_int64), ("lr_mult", C.c_float), ("skip_norm", C.c_float)]
 
 
+class Adamw8bitArgs(C.Structure):
+    _fields_ = [("base", AdamwArgs), ("state1", _P), ("state2", _P), ("absmax1", _P), ("absmax2", _P), ("qmap1", _P),
+                ("qmap2", _P), ("blocksize", C.c_int32), ("reserved0", C.c_int32)]
+
+
 class DoubleBlockGrads(C.Structure):
     _fields_ = [(n, _P) for n in ("img_up_la", "img_up_lb", "img_down_la", "img_down_lb",
                                   "txt_up_la", "txt_up_lb", "txt_down_la", "txt_down_lb")]
@@ -234,6 +239,7 @@ SIGNATURES = {
     "afb_grad_norm_scratch_floats": (C.c_int, []),
     "afb_grad_norm_sq_ws": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P]),
     "afb_adamw_ema_step": (C.c_int, [C.POINTER(AdamwArgs), _P]),
+    "afb_adamw8bit_ema_step": (C.c_int, [C.POINTER(Adamw8bitArgs), _P]),
     "afb_axpy_rows": (C.c_int, [_P, _P, C.POINTER(C.c_float), _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),
     "afb_mse_rows": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),
     "afb_engine_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_P)]),

@@ -54,6 +54,7 @@ int rmsnorm_rope_bwd_launch(void* dqkv, const void* raw, int64_t ld, int64_t bs,
                             int heads, int txt_rows, const void* wq_txt, const void* wk_txt, const void* wq_img,
                             const void* wk_img, const float* cos_tab, const float* sin_tab, float eps, cudaStream_t stream);
 int adamw_ema_launch(const afb_adamw_args* a, cudaStream_t stream);
+int adamw8bit_ema_launch(const afb_adamw8bit_args* a, cudaStream_t stream);
 int gemm_tn_launch(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t out_ld, int64_t tokens,
                    int m, int n, cudaStream_t stream);
 int ln_mod_param_grad_launch(const void* x, int64_t x_bs, const void* dy, int64_t dy_bs, float* stats_ws, float* dscale,
@@ -205,6 +206,9 @@ int afb_grad_norm_sq_ws(const float* grads, int64_t n, float* out, float* scratc
 }
 int afb_adamw_ema_step(const afb_adamw_args* args, void* stream) {
   return afb::adamw_ema_launch(args, static_cast<cudaStream_t>(stream));
+}
+int afb_adamw8bit_ema_step(const afb_adamw8bit_args* args, void* stream) {
+  return afb::adamw8bit_ema_launch(args, static_cast<cudaStream_t>(stream));
 }
 int afb_axpy_rows(const float* x, const void* u, const float* coef, float* out, void* out_bf16, int32_t batch,
                   int64_t per_sample, int32_t u_is_f32, void* stream) {

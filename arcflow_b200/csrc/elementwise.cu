@@ -737,8 +737,11 @@ rowlinear_param_grad_kernel(const float* __restrict__ de, long long de_ld, const
 
 // ================================================================================================
 // LoRA input dropout (peft lora_dropout = 0.05, train only: result = base(x) + B(A(dropout(x)))).
-// Counter-based: keep(element) = hash(key, logical index) >= p * 2^32, so the checkpointed recompute and the backward
-// regenerate the same mask from (seed, layer id) with no stored mask. The hash is restated in numpy by the oracle.
+// Counter-based: one 32-bit hash per PAIR of consecutive logical elements, 16 bits each:
+//   keep(idx) = half16(lowbias32(uint32(idx >> 1) ^ key ^ hi(idx)), idx & 1) >= round(p * 2^16)
+// so the checkpointed recompute and the backward regenerate the same mask from (seed, layer id) with no stored mask. The
+// hash is restated in numpy by the oracle. (Round 1 hashed every element twice: ~22 integer instructions per element made
+// this kernel ALU-bound at a quarter of the HBM rate; a pair per hash is ~9.)
 // ================================================================================================
 __device__ __forceinline__ uint32_t lowbias32(uint32_t h) {
   h ^= h >> 16;
@@ -748,11 +751,14 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t h) {
   h ^= h >> 16;
   return h;
 }
-__device__ __forceinline__ bool dropout_keep(uint32_t key, unsigned long long idx, uint32_t thresh) {
-  uint32_t h = lowbias32(uint32_t(idx) ^ key);
-  h = lowbias32(h + uint32_t(idx >> 32) * 0x9E3779B1U + 0x85EBCA77U);
-  return h >= thresh;
+__device__ __forceinline__ uint32_t dropout_pair_bits(uint32_t key, unsigned long long pair) {
+  return lowbias32(uint32_t(pair) ^ key ^ (uint32_t(pair >> 32) * 0x9E3779B1U));
 }
+__device__ __forceinline__ bool dropout_keep(uint32_t key, unsigned long long idx, uint32_t thresh16) {
+  const uint32_t h = dropout_pair_bits(key, idx >> 1);
+  return ((idx & 1ull) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) { return uint32_t(double(p) * 65536.0 + 0.5); }
 
 struct DropParams {
   int rows_per_batch, cols, logical_cols, col0;
@@ -776,13 +782,19 @@ dropout_rows_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, long lo
   unpack8(*reinterpret_cast<const uint4*>(x + (long long)b * x_bs + r * x_ld + c), v);
   __nv_bfloat16* op = out + (long long)b * out_bs + r * out_ld + c;
   if (p.accumulate) unpack8(*reinterpret_cast<const uint4*>(op), o);
-  const unsigned long long base = (unsigned long long)row * p.logical_cols + p.col0 + c;
+  const unsigned long long pair0 = ((unsigned long long)row * p.logical_cols + p.col0 + c) >> 1;  // even: all three are
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float a = v[k];
-    if (p.silu_in) a = round_bf16(silu(a));
-    const float m = dropout_keep(p.key, base + k, p.thresh) ? a * p.inv_keep : 0.f;
-    o[k] = p.accumulate ? o[k] + m : m;
+  for (int k = 0; k < 8; k += 2) {
+    const uint32_t h = dropout_pair_bits(p.key, pair0 + (k >> 1));
+    float a0 = v[k], a1 = v[k + 1];
+    if (p.silu_in) {
+      a0 = round_bf16(silu(a0));
+      a1 = round_bf16(silu(a1));
+    }
+    const float m0 = (h & 0xFFFFu) >= p.thresh ? a0 * p.inv_keep : 0.f;
+    const float m1 = (h >> 16) >= p.thresh ? a1 * p.inv_keep : 0.f;
+    o[k] = p.accumulate ? o[k] + m0 : m0;
+    o[k + 1] = p.accumulate ? o[k + 1] + m1 : m1;
   }
   *reinterpret_cast<uint4*>(op) = pack8(o);
 }
@@ -1577,14 +1589,15 @@ int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, in
                         int silu_in, int accumulate, cudaStream_t stream) {
   AFB_REQUIRE(x && out && batches >= 1 && rows_per_batch >= 1 && cols % 8 == 0 && x_ld % 8 == 0 && out_ld % 8 == 0,
               "dropout_rows: bad arguments");
-  AFB_REQUIRE(p >= 0.f && p < 1.f && logical_cols >= col0 + cols, "dropout_rows: bad p / logical layout");
+  AFB_REQUIRE(p >= 0.f && p < 1.f && logical_cols >= col0 + cols && logical_cols % 2 == 0 && col0 % 2 == 0,
+              "dropout_rows: bad p / logical layout");
   DropParams dp{};
   dp.rows_per_batch = rows_per_batch;
   dp.cols = cols;
   dp.logical_cols = logical_cols;
   dp.col0 = col0;
   dp.key = dropout_layer_key(seed, layer_id);
-  dp.thresh = uint32_t(double(p) * 4294967296.0);
+  dp.thresh = dropout_thresh16(p);
   dp.inv_keep = 1.0f / (1.0f - p);
   dp.silu_in = silu_in;
   dp.accumulate = accumulate;
@@ -1610,7 +1623,7 @@ int dropout_f32_add_launch(const float* src, int64_t src_ld, float* dst, int64_t
   AFB_REQUIRE(src && dst && rows >= 1 && cols >= 1 && p >= 0.f && p < 1.f, "dropout_f32_add: bad arguments");
   dim3 grid((cols + 255) / 256, rows);
   dropout_f32_add_kernel<<<grid, 256, 0, stream>>>(src, src_ld, dst, dst_ld, rows, cols, dropout_layer_key(seed, layer_id),
-                                                   uint32_t(double(p) * 4294967296.0), 1.0f / (1.0f - p));
+                                                   dropout_thresh16(p), 1.0f / (1.0f - p));
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;

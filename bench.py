@@ -732,7 +732,7 @@ def run_train(args):
     torch.cuda.empty_cache()
     teacher = FluxTeacherEngine(student, make_flux_teacher_extras(cfg, 99, dev))
     student.set_activation_stash("auto")
-    trainer = ArcFlowTrainer(student, teacher)       # configs/flux: lr 1e-4, betas (.9, .95), clip 50 from iter 100, Karras EMA
+    trainer = ArcFlowTrainer(student, teacher, state_bits=8)   # configs/flux: AdamW8bit lr 1e-4, betas (.9, .95), clip 50 from iter 100, Karras EMA
     x, txt, pooled = make_flux_inputs(cfg, B, px, px, 512, 42 + rank, dev)     # --diff_seed: per-rank noise / prompts
     g = torch.Generator().manual_seed(rank)
     rands = [draw_rollout_randoms(B, 4, 16, g) for _ in range(2)]
@@ -799,7 +799,7 @@ def run_train(args):
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": f"ArcFlow-FLUX trajectory-distillation iteration, batch {B}/GPU, latent 16x{px // 8}x{px // 8} "
                                       f"(S = {512 + grid[0] * grid[1]}): 2 student + 8 teacher forwards, data-free roll-out, adapter-only "
-                                      f"backward, flat-arena all-reduce, clip + AdamW + Karras EMA (BASELINE.json configs[3])",
+                                      f"backward, flat-arena all-reduce, clip + AdamW8bit (block-wise 8-bit moments) + Karras EMA (BASELINE.json configs[3])",
                           "global_batch": B * world, "parallelism": f"ddp{world}: per-rank noise/prompts, one fp32 all-reduce of "
                                                                     f"the {trainer.opt.n * 4 / 1e9:.2f} GB gradient arena per iteration",
                           "activation_stash": bool(student.activation_stash), "trainable_params": int(trainer.opt.n),

@@ -48,7 +48,7 @@ workflow = [('train', save_interval)]
 # lr_config :27-31, runner :32-38; only the keys this build consumes) ----
 train_cfg.update(diffusion_grad_clip=50.0, diffusion_grad_clip_begin_iter=100)
 optimizer = dict(diffusion=dict(
-    type='AdamW8bit',   # moments are kept in fp32 here: same update rule, no 8-bit state
+    type='AdamW8bit',   # block-wise 8-bit moments as in bitsandbytes (arcflow_b200/optim.py); optim_bits=32 keeps fp32 moments
     lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0,
     paramwise_cfg=dict(custom_keys=dict(proj_out_loggamma=dict(lr_mult=0.1)))))
 lr_config = dict(policy='fixed', warmup='linear', warmup_iters=100, warmup_ratio=0.001)

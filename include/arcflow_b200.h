@@ -364,6 +364,28 @@ typedef struct afb_adamw_args {
 } afb_adamw_args;
 int afb_adamw_ema_step(const afb_adamw_args* args, void* stream);
 
+/* AdamW with block-wise 8-bit moment state — what `optimizer=dict(type='AdamW8bit')` (configs/flux/_ddp_train.py:18-26,
+ * registered from bitsandbytes.optim by lakonlab/runner/optimizer/builder.py:11-24) keeps per tensor of >= 4096 elements:
+ * both moments as one byte per element indexing a 256-entry "dynamic" code book (signed for exp_avg, unsigned for
+ * exp_avg_sq) times one fp32 absmax per block of `blocksize` consecutive elements. Per block and step: de-quantise,
+ * update the moments in fp32, take the new absmax, update the parameter, re-quantise to the nearest code (exp_avg keeps its
+ * sign). bitsandbytes is not vendored and its version is not pinned by the reference (requirements.txt:11): this restates
+ * the published block-wise algorithm (Dettmers et al., "8-bit Optimizers via Block-wise Quantization", and the
+ * kOptimizerStatic8bit2StateBlockwise kernel of bitsandbytes >= 0.44: block size 256). Clip / skip / EMA / bf16 shadow are
+ * the same as afb_adamw_ema_step. `n` must be a multiple of `blocksize` (the host pads every tensor's slot). */
+typedef struct afb_adamw8bit_args {
+  afb_adamw_args base;     /* exp_avg / exp_avg_sq ignored */
+  uint8_t* state1;         /* [n] codes of exp_avg */
+  uint8_t* state2;         /* [n] codes of exp_avg_sq */
+  float* absmax1;          /* [n / blocksize] */
+  float* absmax2;          /* [n / blocksize] */
+  const float* qmap1;      /* [256] ascending signed code book */
+  const float* qmap2;      /* [256] ascending unsigned code book */
+  int32_t blocksize;       /* 256 */
+  int32_t reserved0;
+} afb_adamw8bit_args;
+int afb_adamw8bit_ema_step(const afb_adamw8bit_args* args, void* stream);
+
 /* fp32 -> bf16 cast of a contiguous buffer. */
 int afb_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
 
@@ -514,7 +536,8 @@ typedef struct afb_backward_args {
 } afb_backward_args;
 /* peft lora_dropout (configs/flux/arcflux_2nfe_k16.py:40-48: 0.05, train only): the LoRA branches of
  * afb_engine_forward_train / afb_engine_backward(_embed) see dropout(x) with the keep mask
- *   hash(seed, layer id, logical element index) >= p * 2^32   (counter-based: recompute and backward regenerate it).
+ *   16 bits of hash(seed, layer id, logical element index / 2) >= round(p * 2^16): the low half of the 32-bit hash for the
+ *   even element of a pair, the high half for the odd one   (counter-based: recompute and backward regenerate it).
  * Set a fresh seed before every afb_engine_forward_train; p = 0 (default) disables it. afb_engine_forward / _denoise
  * never drop. */
 int afb_engine_set_lora_dropout(afb_engine* e, float p, uint64_t seed);

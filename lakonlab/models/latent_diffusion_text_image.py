@@ -45,7 +45,9 @@ class LatentDiffusionTextImage:
                   clip_skip_ratio=self.train_cfg.get("diffusion_grad_clip_skip_ratio", 0.0),
                   warmup_iters=lr.get("warmup_iters", 0) if lr.get("warmup") else 0,
                   warmup_ratio=lr.get("warmup_ratio", 1.0),
-                  ema_gamma=(ema.get("momentum_cfg") or {}).get("gamma", 7.0), ema_start_iter=ema.get("start_iter", 0))
+                  ema_gamma=(ema.get("momentum_cfg") or {}).get("gamma", 7.0), ema_start_iter=ema.get("start_iter", 0),
+                  # bitsandbytes' AdamW8bit keeps block-wise 8-bit moments; `optim_bits=32` is its own switch back to fp32 state
+                  state_bits=int(o.get("optim_bits", 8 if o.get("type", "AdamW8bit") == "AdamW8bit" else 32)))
         step_cfg = {k: v for k, v in self.train_cfg.items() if not k.startswith("diffusion_grad_clip")}
         self.trainer = ArcFlowTrainer(self.diffusion, self.teacher, step_cfg, self.shift, self.loss_scale, **kw)
         return {"diffusion": self.trainer.opt}

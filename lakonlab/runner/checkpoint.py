@@ -3,8 +3,9 @@ writes (`ckpt_trainable_only`, `ckpt_fp16`, `ckpt_fp16_ema`: configs/*/_ddp_trai
 lakonlab/runner/checkpoint.py:491-534, dynamic_iter_based_runner.py:110-160).
 
 Layout: `dict(meta=dict(iter=, epoch=, ...), state_dict={'diffusion.denoising.<adapter key>': bf16, 'diffusion_ema.…': bf16},
-optimizer={'diffusion': dict(params, exp_avg, exp_avg_sq, ema : fp32 flat arenas, layout, steps_taken)})`.
-The frozen base is never saved. The flat fp32 arenas make resume bit-exact.
+optimizer={'diffusion': dict(params, exp_avg, exp_avg_sq, ema : fp32 flat arenas, layout, steps_taken; with AdamW8bit also
+state1, state2 : uint8 code arenas and absmax1, absmax2 : fp32 per 256-element block)})`.
+The frozen base is never saved. The flat arenas make resume bit-exact.
 """
 from __future__ import annotations
 

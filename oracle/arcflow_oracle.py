@@ -154,7 +154,8 @@ def lora_layer_id(name: str, num_double: int) -> int:
 
 
 def lora_dropout_mask(seed: int, layer_id: int, shape, p: float) -> Tensor:
-    """keep[idx] = hash(key(seed, layer), idx) >= floor(p * 2^32), idx = row-major index into `shape` (bool tensor)."""
+    """keep[idx] = 16 bits of hash(key(seed, layer), idx >> 1) >= round(p * 2^16) — the low half for even idx, the high half
+    for odd idx; idx = row-major index into `shape` (bool tensor). One 32-bit hash serves a pair of elements."""
     import numpy as np
     m = np.uint64(0xFFFFFFFF)
     with np.errstate(over="ignore"):
@@ -164,9 +165,11 @@ def lora_dropout_mask(seed: int, layer_id: int, shape, p: float) -> Tensor:
         for d in shape:
             n *= int(d)
         idx = np.arange(n, dtype=np.uint64)
-        h = _lowbias32(((idx & m) ^ key) & m)
-        h = _lowbias32((h + (idx >> np.uint64(32)) * np.uint64(0x9E3779B1) + np.uint64(0x85EBCA77)) & m)
-    keep = h >= np.uint64(int(float(p) * 4294967296.0))
+        pair = idx >> np.uint64(1)
+        hi = ((pair >> np.uint64(32)) * np.uint64(0x9E3779B1)) & m
+        h = _lowbias32(((pair & m) ^ key ^ hi) & m)
+        bits = np.where((idx & np.uint64(1)) != 0, h >> np.uint64(16), h & np.uint64(0xFFFF))
+    keep = bits >= np.uint64(int(float(np.float32(p)) * 65536.0 + 0.5))
     return torch.from_numpy(keep).reshape(tuple(shape))
 
 

@@ -1,7 +1,9 @@
 """Times the native train iteration at the reference's training shape: FLUX, bs 4 per GPU, latent 16x128x128
 (S_img = 4096, S_txt = 512) — BASELINE.json configs[3]: 2 student + 8 teacher forwards, roll-out kernels, the full
 adapter backward (per-block recompute), grad clip + AdamW + EMA and the bf16 write-back.
-Usage: python tools/train_step_time.py [batch] [--profile] [--no-stash]
+Usage: python tools/train_step_time.py [batch] [--profile] [--no-stash] [--kineto] [--bits8]
+       --kineto: per-kernel time of ONE iteration from torch.profiler's CUPTI activity records (sees the library's kernels
+                 too; concurrent timing, unlike ncu's serialised replay), aggregated by kernel name
    or: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step_time.py [batch]
        (DDP: per-rank noise, ONE NCCL all-reduce of the flat gradient arena per iteration; time = max over ranks)"""
 import json
@@ -21,6 +23,8 @@ from arcflow_b200.train import ArcFlowTrainer, draw_rollout_randoms  # noqa: E40
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 B = int(args[0]) if args else 4
 profile = "--profile" in sys.argv
+kineto = "--kineto" in sys.argv
+bits8 = "--bits8" in sys.argv
 no_stash = "--no-stash" in sys.argv   # per-block recompute in the backward instead of the activation stash
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -35,7 +39,7 @@ del sd
 teacher = FluxTeacherEngine(student, make_flux_teacher_extras(cfg, 99, dev))
 x, txt, pooled = make_flux_inputs(cfg, B, 1024, 1024, 512, 42 + rank, dev)
 student.set_activation_stash(False if no_stash else "auto")
-trainer = ArcFlowTrainer(student, teacher)
+trainer = ArcFlowTrainer(student, teacher, state_bits=8 if bits8 else 32)
 step = trainer.distill
 g = torch.Generator().manual_seed(rank)
 rands = [draw_rollout_randoms(B, 4, 16, g) for _ in range(2)]
@@ -74,6 +78,23 @@ if profile:
     trainer.train_step(txt, pooled, (64, 64), x, rands, iteration=500)
     out["student_profile"] = student.read_profile()
     student.set_profiling(False)
+if kineto and rank == 0:
+    import re
+    from collections import defaultdict
+    from torch.profiler import ProfilerActivity, profile as tprofile
+    with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
+        trainer.train_step(txt, pooled, (64, 64), x, rands, iteration=500)
+        torch.cuda.synchronize()
+    agg, cnt = defaultdict(float), defaultdict(int)
+    for ev in prof.events():
+        if ev.device_type is not None and "cuda" in str(ev.device_type).lower() and ev.device_time > 0:
+            name = re.sub(r"\(anonymous namespace\)::|afb::|<unnamed>::|void ", "", ev.name)
+            name = re.sub(r"\(.*$", "", name)[:70]
+            agg[name] += ev.device_time / 1e3
+            cnt[name] += 1
+    total = sum(agg.values())
+    out["kineto"] = dict(total_kernel_ms=total, kernels=[dict(name=k, ms=round(v, 3), share=round(v / total, 4), launches=cnt[k])
+                                                         for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:40]])
 if world > 1:   # DDP invariant: every rank holds the same parameters after the step
     chk = trainer.opt.params.double().sum().reshape(1)
     lo, hi = chk.clone(), chk.clone()
