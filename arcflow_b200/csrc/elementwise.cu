@@ -768,35 +768,51 @@ struct DropParams {
   int accumulate;   // backward: out += mask * x / keep instead of out = ...
 };
 
+// grid = (column blocks of 256 chunks x 8 elements, groups of DROP_ROWS rows): no per-thread index division (the first
+// version derived row and column from a flat 64-bit index with two 64-bit divisions per 16-byte chunk, which cost more than
+// its memory traffic), and DROP_ROWS independent 16-byte loads in flight per thread.
+constexpr int DROP_ROWS = 4;
 __global__ void __launch_bounds__(256)
 dropout_rows_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, long long x_bs, __nv_bfloat16* __restrict__ out,
-                    long long out_ld, long long out_bs, long long total_chunks, const DropParams p) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_chunks) return;
-  const int cpr = p.cols / 8;
-  const long long row = i / cpr;
-  const int c = int(i - row * cpr) * 8;
-  const int b = int(row / p.rows_per_batch);
-  const long long r = row - (long long)b * p.rows_per_batch;
-  float v[8], o[8];
-  unpack8(*reinterpret_cast<const uint4*>(x + (long long)b * x_bs + r * x_ld + c), v);
-  __nv_bfloat16* op = out + (long long)b * out_bs + r * out_ld + c;
-  if (p.accumulate) unpack8(*reinterpret_cast<const uint4*>(op), o);
-  const unsigned long long pair0 = ((unsigned long long)row * p.logical_cols + p.col0 + c) >> 1;  // even: all three are
+                    long long out_ld, long long out_bs, int total_rows, const DropParams p) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c >= p.cols) return;
+  for (int row0 = blockIdx.y * DROP_ROWS; row0 < total_rows; row0 += gridDim.y * DROP_ROWS) {
+    uint4 xin[DROP_ROWS], acc[DROP_ROWS];
+    __nv_bfloat16* op[DROP_ROWS];
 #pragma unroll
-  for (int k = 0; k < 8; k += 2) {
-    const uint32_t h = dropout_pair_bits(p.key, pair0 + (k >> 1));
-    float a0 = v[k], a1 = v[k + 1];
-    if (p.silu_in) {
-      a0 = round_bf16(silu(a0));
-      a1 = round_bf16(silu(a1));
+    for (int q = 0; q < DROP_ROWS; ++q) {
+      const int row = min(row0 + q, total_rows - 1);   // clamped: the surplus rows of the last group are loaded, not stored
+      const int b = row / p.rows_per_batch;
+      const int r = row - b * p.rows_per_batch;
+      xin[q] = *reinterpret_cast<const uint4*>(x + (long long)b * x_bs + (long long)r * x_ld + c);
+      op[q] = out + (long long)b * out_bs + (long long)r * out_ld + c;
+      if (p.accumulate) acc[q] = *reinterpret_cast<const uint4*>(op[q]);
     }
-    const float m0 = (h & 0xFFFFu) >= p.thresh ? a0 * p.inv_keep : 0.f;
-    const float m1 = (h >> 16) >= p.thresh ? a1 * p.inv_keep : 0.f;
-    o[k] = p.accumulate ? o[k] + m0 : m0;
-    o[k + 1] = p.accumulate ? o[k + 1] + m1 : m1;
+#pragma unroll
+    for (int q = 0; q < DROP_ROWS; ++q) {
+      const int row = row0 + q;
+      if (row >= total_rows) break;
+      float v[8], o[8];
+      unpack8(xin[q], v);
+      if (p.accumulate) unpack8(acc[q], o);
+      const unsigned long long pair0 = ((unsigned long long)row * p.logical_cols + p.col0 + c) >> 1;  // even: all three are
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const uint32_t h = dropout_pair_bits(p.key, pair0 + (k >> 1));
+        float a0 = v[k], a1 = v[k + 1];
+        if (p.silu_in) {
+          a0 = round_bf16(silu(a0));
+          a1 = round_bf16(silu(a1));
+        }
+        const float m0 = (h & 0xFFFFu) >= p.thresh ? a0 * p.inv_keep : 0.f;
+        const float m1 = (h >> 16) >= p.thresh ? a1 * p.inv_keep : 0.f;
+        o[k] = p.accumulate ? o[k] + m0 : m0;
+        o[k + 1] = p.accumulate ? o[k + 1] + m1 : m1;
+      }
+      *reinterpret_cast<uint4*>(op[q]) = pack8(o);
+    }
   }
-  *reinterpret_cast<uint4*>(op) = pack8(o);
 }
 
 // ================================================================================================
@@ -836,13 +852,14 @@ gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, long long dh_bs, const __n
 __global__ void __launch_bounds__(256)
 gate_res_kernel(const __nv_bfloat16* __restrict__ res, long long res_bs, const __nv_bfloat16* __restrict__ u, long long u_bs,
                 const __nv_bfloat16* __restrict__ gate, long long gate_bs, __nv_bfloat16* __restrict__ out, long long out_bs,
-                int rows_per_batch, int cols, long long total_chunks) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                int rows_per_batch, int cols, unsigned total_chunks) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit index math (launcher checks the range): one cheap division
   if (i >= total_chunks) return;
-  const int cpr = cols / 8;
-  const long long row = i / cpr;
-  const int c = int(i - row * cpr) * 8;
-  const int b = int(row / rows_per_batch);
+  const unsigned cpr = unsigned(cols) / 8u;
+  const unsigned row32 = i / cpr;
+  const int c = int(i - row32 * cpr) * 8;
+  const long long row = row32;
+  const int b = int(row32 / unsigned(rows_per_batch));
   const long long r = row - (long long)b * rows_per_batch;
   float rv[8], uv[8], gv[8], o[8];
   unpack8(*reinterpret_cast<const uint4*>(res + (long long)b * res_bs + r * cols + c), rv);
@@ -972,13 +989,14 @@ ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, cons
 __global__ void __launch_bounds__(256)
 rowscale_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, long long x_bs, const __nv_bfloat16* __restrict__ vec,
                 long long vec_bs, __nv_bfloat16* __restrict__ out, long long out_ld, long long out_bs, int rows_per_batch,
-                int cols, long long total_chunks) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                int cols, unsigned total_chunks) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit index math (launcher checks the range): one cheap division
   if (i >= total_chunks) return;
-  const int cpr = cols / 8;
-  const long long row = i / cpr;
-  const int c = int(i - row * cpr) * 8;
-  const int b = int(row / rows_per_batch);
+  const unsigned cpr = unsigned(cols) / 8u;
+  const unsigned row32 = i / cpr;
+  const int c = int(i - row32 * cpr) * 8;
+  const long long row = row32;
+  const int b = int(row32 / unsigned(rows_per_batch));
   const long long r = row - (long long)b * rows_per_batch;
   float xv[8], gv[8], o[8];
   unpack8(*reinterpret_cast<const uint4*>(x + (long long)b * x_bs + r * x_ld + c), xv);
@@ -991,12 +1009,13 @@ rowscale_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, long long x
 // dpre = dm * gelu_tanh'(pre)  (in place on dm), generic leading dims, rows x cols
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(__nv_bfloat16* __restrict__ dm, long long dm_ld, const __nv_bfloat16* __restrict__ pre, long long pre_ld,
-                int cols, long long total_chunks) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                int cols, unsigned total_chunks) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit index math (launcher checks the range): one cheap division
   if (i >= total_chunks) return;
-  const int cpr = cols / 8;
-  const long long row = i / cpr;
-  const int c = int(i - row * cpr) * 8;
+  const unsigned cpr = unsigned(cols) / 8u;
+  const unsigned row32 = i / cpr;
+  const int c = int(i - row32 * cpr) * 8;
+  const long long row = row32;
   float d[8], x[8];
   unpack8(*reinterpret_cast<const uint4*>(dm + row * dm_ld + c), d);
   unpack8(*reinterpret_cast<const uint4*>(pre + row * pre_ld + c), x);
@@ -1012,12 +1031,13 @@ gelu_bwd_kernel(__nv_bfloat16* __restrict__ dm, long long dm_ld, const __nv_bflo
 // out = gelu_tanh(pre) (the recompute's copy of the GEMM's fused GELU epilogue; tanh.approx like gemm.cu)
 __global__ void __launch_bounds__(256)
 gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, long long pre_ld, __nv_bfloat16* __restrict__ out, long long out_ld,
-                int cols, long long total_chunks) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                int cols, unsigned total_chunks) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit index math (launcher checks the range): one cheap division
   if (i >= total_chunks) return;
-  const int cpr = cols / 8;
-  const long long row = i / cpr;
-  const int c = int(i - row * cpr) * 8;
+  const unsigned cpr = unsigned(cols) / 8u;
+  const unsigned row32 = i / cpr;
+  const int c = int(i - row32 * cpr) * 8;
+  const long long row = row32;
   float x[8];
   unpack8(*reinterpret_cast<const uint4*>(pre + row * pre_ld + c), x);
 #pragma unroll
@@ -1483,9 +1503,10 @@ int rowscale_launch(const void* x, int64_t x_ld, int64_t x_bs, const void* vec, 
                     int64_t out_bs, int batches, int rows_per_batch, int cols, cudaStream_t stream) {
   AFB_REQUIRE(x && vec && out && batches >= 1 && rows_per_batch >= 1 && cols % 8 == 0, "rowscale: bad arguments");
   const long long chunks = (long long)batches * rows_per_batch * (cols / 8);
+  AFB_REQUIRE(chunks < (1ll << 32) - 256, "rowscale: too many elements for one launch");
   rowscale_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), x_ld, x_bs, static_cast<const __nv_bfloat16*>(vec), vec_bs,
-      static_cast<__nv_bfloat16*>(out), out_ld, out_bs, rows_per_batch, cols, chunks);
+      static_cast<__nv_bfloat16*>(out), out_ld, out_bs, rows_per_batch, cols, unsigned(chunks));
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
@@ -1494,9 +1515,10 @@ int rowscale_launch(const void* x, int64_t x_ld, int64_t x_bs, const void* vec, 
 int gelu_bwd_launch(void* dm, int64_t dm_ld, const void* pre, int64_t pre_ld, int64_t rows, int cols, cudaStream_t stream) {
   AFB_REQUIRE(dm && pre && rows >= 1 && cols % 8 == 0, "gelu_bwd: bad arguments");
   const long long chunks = rows * (cols / 8);
+  AFB_REQUIRE(chunks < (1ll << 32) - 256, "gelu_bwd: too many elements for one launch");
   gelu_bwd_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dm), dm_ld,
                                                                      static_cast<const __nv_bfloat16*>(pre), pre_ld, cols,
-                                                                     chunks);
+                                                                     unsigned(chunks));
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
@@ -1523,9 +1545,10 @@ int gate_res_launch(const void* res, int64_t res_bs, const void* u, int64_t u_bs
                     int64_t out_bs, int batches, int rows_per_batch, int cols, cudaStream_t stream) {
   AFB_REQUIRE(res && u && gate && out && batches >= 1 && rows_per_batch >= 1 && cols % 8 == 0, "gate_res: bad arguments");
   const long long chunks = (long long)batches * rows_per_batch * (cols / 8);
+  AFB_REQUIRE(chunks < (1ll << 32) - 256, "gate_res: too many elements for one launch");
   gate_res_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(res), res_bs, static_cast<const __nv_bfloat16*>(u), u_bs,
-      static_cast<const __nv_bfloat16*>(gate), gate_bs, static_cast<__nv_bfloat16*>(out), out_bs, rows_per_batch, cols, chunks);
+      static_cast<const __nv_bfloat16*>(gate), gate_bs, static_cast<__nv_bfloat16*>(out), out_bs, rows_per_batch, cols, unsigned(chunks));
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
@@ -1601,10 +1624,12 @@ int dropout_rows_launch(const void* x, int64_t x_ld, int64_t x_bs, void* out, in
   dp.inv_keep = 1.0f / (1.0f - p);
   dp.silu_in = silu_in;
   dp.accumulate = accumulate;
-  const long long chunks = (long long)batches * rows_per_batch * (cols / 8);
-  dropout_rows_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_bs,
-                                                                         static_cast<__nv_bfloat16*>(out), out_ld, out_bs,
-                                                                         chunks, dp);
+  const long long total_rows = (long long)batches * rows_per_batch;
+  AFB_REQUIRE(total_rows < (1ll << 31), "dropout_rows: too many rows");
+  const long long groups = (total_rows + 3) / 4;   // DROP_ROWS rows per block
+  const dim3 grid(unsigned((cols / 8 + 255) / 256), unsigned(groups < 65535 ? groups : 65535));
+  dropout_rows_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_bs,
+                                                static_cast<__nv_bfloat16*>(out), out_ld, out_bs, int(total_rows), dp);
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
@@ -1632,8 +1657,9 @@ int dropout_f32_add_launch(const float* src, int64_t src_ld, float* dst, int64_t
 int gelu_fwd_launch(const void* pre, int64_t pre_ld, void* out, int64_t out_ld, int64_t rows, int cols, cudaStream_t stream) {
   AFB_REQUIRE(pre && out && rows >= 1 && cols % 8 == 0, "gelu_fwd: bad arguments");
   const long long chunks = rows * (cols / 8);
+  AFB_REQUIRE(chunks < (1ll << 32) - 256, "gelu_fwd: too many elements for one launch");
   gelu_fwd_kernel<<<unsigned((chunks + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(pre), pre_ld,
-                                                                     static_cast<__nv_bfloat16*>(out), out_ld, cols, chunks);
+                                                                     static_cast<__nv_bfloat16*>(out), out_ld, cols, unsigned(chunks));
   AFB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return AFB_OK;
