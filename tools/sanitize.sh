@@ -15,7 +15,8 @@ SAN="${COMPUTE_SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}"
 # small shapes only: one GEMM per epilogue, attention with a ragged tail, the streaming kernels, the sampler, the backward ops
 SELECT='test_gemm_parity or test_gemm_strided or test_attention_parity and not 4608 or test_attention_bounded and not 4608 or test_ln_modulate_parity or test_rmsnorm_rope_parity or test_small_linear_parity or test_sampler_step_matches or test_timestep_embed'
 FILES="tests/test_gpu_parity.py"
-BWD_SELECT='test_attention_backward_parity and not 1000 or test_gemm_transposed_weight or test_rowscale_and_gelu or test_ln_modulate_bwd'
+BWD_SELECT='test_attention_backward_parity and not 1000 or test_gemm_transposed_weight or test_rowscale_and_gelu or test_ln_modulate_bwd or test_lora_dropout_mask'
+OPT_SELECT='adamw8bit or skips'
 VAE_SELECT='test_conv3x3_implicit_gemm and not 64-48 or test_groupnorm_swish and not 64-64 or test_upsample_softmax'
 tools=("$tool")
 [ "$tool" = all ] && tools=(memcheck racecheck synccheck)
@@ -23,7 +24,8 @@ rc=0
 for t in "${tools[@]}"; do
   log="gpurun_out/sanitize_${t}.log"
   : > "$log"
-  for spec in "tests/test_gpu_parity.py|$SELECT" "tests/test_gpu_backward.py|$BWD_SELECT" "tests/test_gpu_vae.py|$VAE_SELECT"; do
+  for spec in "tests/test_gpu_parity.py|$SELECT" "tests/test_gpu_backward.py|$BWD_SELECT" "tests/test_gpu_vae.py|$VAE_SELECT" \
+              "tests/test_gpu_optim.py|$OPT_SELECT"; do
     f="${spec%%|*}"; k="${spec#*|}"
     echo "=== $t: $f -k '$k'" >> "$log"
     timeout "${SANITIZE_TIMEOUT:-900}" "$SAN" --tool "$t" --error-exitcode 66 --print-limit 20 --launch-timeout 120 \
