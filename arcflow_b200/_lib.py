@@ -14,7 +14,7 @@ AFB_OK = 0
 AFB_EPI_BIAS, AFB_EPI_BIAS_GELU, AFB_EPI_BIAS_GATE_RES, AFB_EPI_BIAS_RES, AFB_EPI_BIAS_QKNORM_ROPE = 0, 1, 2, 3, 4
 AFB_SL_SILU_IN, AFB_SL_ACCUMULATE = 1, 2
 AFB_ARCH_FLUX, AFB_ARCH_QWEN = 0, 1
-AFB_ABI_VERSION = 2
+AFB_ABI_VERSION = 3
 
 
 class AfbError(RuntimeError):
@@ -177,7 +177,8 @@ class ConvDesc(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("gemm_ms", C.c_double), ("attn_ms", C.c_double), ("gemm_flops", C.c_double),
-                ("attn_flops", C.c_double), ("gemm_launches", C.c_int64), ("attn_launches", C.c_int64)]
+                ("attn_flops", C.c_double), ("gemm_launches", C.c_int64), ("attn_launches", C.c_int64),
+                ("gemm_fused_qk_ms", C.c_double), ("gemm_fused_qk_flops", C.c_double), ("gemm_fused_qk_launches", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/arcflow_b200.h declares

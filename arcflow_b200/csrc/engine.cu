@@ -384,7 +384,7 @@ struct Gemm {
   int run(afb_engine* e, cudaStream_t s) {
     double k = 0;
     for (int i = 0; i < nseg; ++i) k += d.a_k[i];
-    ProfScope ps(e, s, 0, 2.0 * d.batches * d.rows_per_batch * double(d.n) * k);
+    ProfScope ps(e, s, d.epilogue == AFB_EPI_BIAS_QKNORM_ROPE ? 2 : 0, 2.0 * d.batches * d.rows_per_batch * double(d.n) * k);
     NvtxRange nv(d.w_transposed ? "gemm_dx" : (d.n <= 256 ? "gemm_lora_a" : "gemm"));
     int rc = afb::gemm_launch(&d, s);
     if (rc == AFB_OK) afb::count_launch(1);
@@ -1328,10 +1328,15 @@ int afb_engine_read_profile(afb_engine* e, afb_profile* out) {
   for (auto& r : e->prof) {
     float ms = 0.f;
     AFB_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
-    if (r.cls == 0) {
+    if (r.cls == 0 || r.cls == 2) {
       e->prof_acc.gemm_ms += ms;
       e->prof_acc.gemm_flops += r.flops;
       e->prof_acc.gemm_launches += 1;
+      if (r.cls == 2) {
+        e->prof_acc.gemm_fused_qk_ms += ms;
+        e->prof_acc.gemm_fused_qk_flops += r.flops;
+        e->prof_acc.gemm_fused_qk_launches += 1;
+      }
     } else {
       e->prof_acc.attn_ms += ms;
       e->prof_acc.attn_flops += r.flops;

@@ -63,7 +63,7 @@ struct GemmParams {
   int w_trans;   // W given as [K, N] row-major (dX = dY W): MN-major B operand (2-CTA kernel only)
   int nkb_w0;    // K blocks served by the first W buffer (the rest come from the second one; transposed mode)
   int tma_store; // epilogue through shared memory + TMA store (0: per-row 16-byte global stores)
-  int l2_hints;  // W loads evict_last, output stores evict_first; 2: A loads evict_first as well
+  int l2_hints;  // W loads evict_last, output stores evict_first
   int gn;        // tile raster: N tiles per column group (0 / >= num_n_tiles: plain N-fastest order)
   int bn;        // N extent of a tile: 256, or 128 for narrow outputs (CTA-pair kernel, K-major W only)
   // implicit-GEMM 3x3 convolution (CTA-pair kernel): A is an NHWC image read through a 4-D map, an M tile is a 16 x 16 pixel
@@ -118,13 +118,14 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 }
 
 // One thread = one accumulator row: 256 fp32 columns from TMEM in 8 chunks of 32.
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_base, int n_tile, bool valid,
+// `bn` (tile width) is a compile-time constant at every call site: it is an argument only so that one body serves both widths.
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int bn, uint32_t t_base, int n_tile, bool valid,
                                               __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
                                               const __nv_bfloat16* gate_b, int c_begin = 0, int c_end = 1 << 30) {
-  if (c_end > p.bn / 32) c_end = p.bn / 32;
+  if (c_end > bn / 32) c_end = bn / 32;
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
-    const int n0 = n_tile * p.bn + c * 32;
+    const int n0 = n_tile * bn + c * 32;
     if (n0 >= p.N) break;
     uint32_t v[32];
     tmem_ld_32x32(t_base + c * 32, v);
@@ -225,7 +226,8 @@ __device__ __forceinline__ void round_bf16_pair(float& a, float& b) {
 // samples of that launch sat on such a first use. Now each per-column vector is fetched ONCE per chunk as one coalesced
 // 4-byte load per lane (lane i holds columns 2 i, 2 i + 1) before the TMEM load and handed out by warp shuffles; per-row
 // data (residual, rotary pairs) is prefetched for the whole chunk.
-__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmOut, uint32_t t_base, int n_tile,
+template <bool QK>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const int bn, const CUtensorMap* tmOut, uint32_t t_base, int n_tile,
                                                   bool valid, int lane, int row0_warp, int b, uint8_t* stage,
                                                   int& buf, const __nv_bfloat16* res_row, const __nv_bfloat16* gate_b,
                                                   int conv_w0 = -1, int c_begin = 0, int c_end = 1 << 30,
@@ -235,15 +237,15 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   float qk_rstd = 0.f;
   // this row's rotary table entries (QKNORM_ROPE), afb_rope_pack layout: block of 32 positions, lane inside the block
   const long long rope_s = (long long)p.rope_row0 + row0_warp + lane;
-  const float4* rope_row = p.rope ? p.rope + (rope_s >> 5) * (2 * 16 * 32) + (rope_s & 31) : nullptr;
+  const float4* rope_row = QK ? p.rope + (rope_s >> 5) * (2 * 16 * 32) + (rope_s & 31) : nullptr;
   const bool has_res = p.epi == AFB_EPI_BIAS_RES || p.epi == AFB_EPI_BIAS_GATE_RES;
-  if (c_end > p.bn / EPI_COLS) c_end = p.bn / EPI_COLS;
+  if (c_end > bn / EPI_COLS) c_end = bn / EPI_COLS;
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
-    const int n0 = n_tile * p.bn + c * EPI_COLS;
+    const int n0 = n_tile * bn + c * EPI_COLS;
     if (n0 >= p.N) break;
     uint8_t* sbuf = stage + buf * EPI_BUF_BYTES;
-    const bool qk = p.epi == AFB_EPI_BIAS_QKNORM_ROPE && n0 < p.qk_cols;
+    const bool qk = QK && n0 < p.qk_cols;   // QK instantiation = AFB_EPI_BIAS_QKNORM_ROPE launches only
     const int ncol = n0 + 2 * lane;  // the two columns this lane fetches for the warp (N is a multiple of 8)
     if (qk && (c & 1) == 0) {
       // first 64-column chunk of a head: sum of squares over the head's 128 (bias-added, bf16-rounded) columns. The
@@ -518,9 +520,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       if (p.tma_store)
-        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b);
+        epilogue_tile_tma<false>(p, BN, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b);
       else
-        epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b);
+        epilogue_tile(p, BN, t_base, n_tile, valid, out_row, res_row, gate_b);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -554,6 +556,10 @@ constexpr int GEMM2_THREADS = 32 * (2 + 8);
 static_assert(GEMM2_SMEM_BYTES <= 232448 && GEMM_SMEM_BYTES <= 232448, "shared memory budget (227 KiB per CTA)");
 
 // 10 warps are allocated as 12 (registers go out in groups of 4 warps): 65536 / (12 x 32) = 170 -> 168 registers per thread
+// BN_T: tile width (256; 128 for outputs of <= 128 columns). CONV: implicit-GEMM 3x3 convolution producer / row mapping. QK: the
+// RMSNorm + RoPE epilogue. WT: W read as the MN-major operand (dX = dY W). The first three were runtime fields of GemmParams in the first conv / fused-epilogue versions; the runtime
+// tile width alone cost every launch 5-6 % (same-box A/B of the historical versions, profiles/r02_gemm_version_ab.json).
+template <int BN_T, bool CONV, bool QK, bool WT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -622,17 +628,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         const int b = m_tile / p.tiles_per_batch;
         const int t_in = m_tile - b * p.tiles_per_batch;
         const int r0 = t_in * (2 * BM) + int(rank) * BM;
-        const int half_n = p.bn >> 1;
-        const int n0 = n_tile * p.bn + int(rank) * half_n;
+        const int half_n = BN_T >> 1;
+        const int n0 = n_tile * BN_T + int(rank) * half_n;
         const uint32_t stage_tx = 2u * uint32_t(A_STAGE_BYTES + half_n * BK * 2);
-        const int conv_th = p.conv ? t_in / p.conv_tw : 0;
-        const int conv_w0 = p.conv ? (t_in - conv_th * p.conv_tw) * 16 : 0;
+        const int conv_th = CONV ? t_in / p.conv_tw : 0;
+        const int conv_w0 = CONV ? (t_in - conv_th * p.conv_tw) * 16 : 0;
         const int conv_h0 = conv_th * 16 + int(rank) * 8;
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
           if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
-          if (p.conv) {
+          if (CONV) {
             const int tap = kb / p.conv_cpt;
             const int cc = kb - tap * p.conv_cpt;
             const int dy = tap / 3;
@@ -657,11 +663,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             am = &tmA2;
             kk = kb - p.nk_end[1];
           }
-          if (p.l2_hints == 2)
-            tma_load_3d_2cta_hint(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b, L2_EVICT_FIRST);
-          else
-            tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
-          if (!p.w_trans) {
+          // (evict_first on the A loads was measured and rejected — profiles/r02_gemm_raster_sweep.json — and is gone)
+          tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
+          if (!WT) {
             if (p.l2_hints)
               tma_load_2d_2cta_hint(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0, L2_EVICT_LAST);
             else
@@ -682,11 +686,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (leader CTA only) ---------------------------
     if (leader) {
-      const uint32_t idesc = p.w_trans ? make_idesc_bf16(2 * BM, BN, false, true) : make_idesc_bf16(2 * BM, p.bn, false, false);
+      const uint32_t idesc = WT ? make_idesc_bf16(2 * BM, BN, false, true) : make_idesc_bf16(2 * BM, BN_T, false, false);
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 16, 1024);
       // K-major W: 16-element k step = 32 bytes; MN-major W: 64-n chunks 8 KiB apart, k step = 16 rows of 128 bytes
-      const uint64_t b_desc0 = p.w_trans ? make_sw128_desc(smem_u32(sB), HALF_N * BK, 1024) : make_sw128_desc(smem_u32(sB), 16, 1024);
-      const uint64_t b_kstep = p.w_trans ? uint64_t(2048 >> 4) : uint64_t(2);
+      const uint64_t b_desc0 = WT ? make_sw128_desc(smem_u32(sB), HALF_N * BK, 1024) : make_sw128_desc(smem_u32(sB), 16, 1024);
+      const uint64_t b_kstep = WT ? uint64_t(2048 >> 4) : uint64_t(2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -736,7 +740,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       int r = r0w + lane;
       bool valid = r < p.rows_per_batch;
       int conv_w0 = -1;
-      if (p.conv) {  // this warp's 32 accumulator rows = 2 image rows x 16 pixels of the CTA's 8 x 16 patch
+      if (CONV) {  // this warp's 32 accumulator rows = 2 image rows x 16 pixels of the CTA's 8 x 16 patch
         const int th = t_in / p.conv_tw;
         conv_w0 = (t_in - th * p.conv_tw) * 16;
         r0w = th * 16 + int(rank) * 8 + q * 2;  // first image row of the warp
@@ -753,10 +757,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       if (p.tma_store)
-        epilogue_tile_tma(p, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b, conv_w0,
-                          chalf * (p.bn / (2 * EPI_COLS)), (chalf + 1) * (p.bn / (2 * EPI_COLS)), true);
+        epilogue_tile_tma<QK>(p, BN_T, &tmOut, t_base, n_tile, valid, lane, r0w, b, stage, buf, res_row, gate_b, conv_w0,
+                          chalf * (BN_T / (2 * EPI_COLS)), (chalf + 1) * (BN_T / (2 * EPI_COLS)), true);
       else
-        epilogue_tile(p, t_base, n_tile, valid, out_row, res_row, gate_b, chalf * (p.bn / 64), (chalf + 1) * (p.bn / 64));
+        epilogue_tile(p, BN_T, t_base, n_tile, valid, out_row, res_row, gate_b, chalf * (BN_T / 64), (chalf + 1) * (BN_T / 64));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
@@ -775,6 +779,22 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   }
 }
 
+}  // namespace
+
+namespace {
+// One launch site per instantiation (each needs its own dynamic-shared-memory attribute, set once).
+template <int BN_T, bool CONV, bool QK, bool WT>
+int launch_2cta(int clusters, cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2,
+                const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& out, const GemmParams& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<BN_T, CONV, QK, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(GEMM2_SMEM_BYTES)));
+    attr_set = true;
+  }
+  gemm_bf16_2cta_kernel<BN_T, CONV, QK, WT><<<2 * clusters, GEMM2_THREADS, GEMM2_SMEM_BYTES, stream>>>(a0, a1, a2, b0, b1, out, p);
+  return AFB_OK;
+}
 }  // namespace
 
 int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
@@ -941,8 +961,6 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   if (!attr_set) {
     AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(GEMM_SMEM_BYTES)));
-    AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        int(GEMM2_SMEM_BYTES)));
     attr_set = true;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -950,8 +968,16 @@ int gemm_launch(const afb_gemm_desc* d, cudaStream_t stream) {
   if (two_cta) {
     const int max_clusters = sms / 2;
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-    gemm_bf16_2cta_kernel<<<2 * clusters, GEMM2_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2],
-                                                                                  tmB, tmB1, tmOut, p);
+    int rc;
+    if (d->w_transposed)
+      rc = launch_2cta<BN, false, false, true>(clusters, stream, tmA[0], tmA[1], tmA[2], tmB, tmB1, tmOut, p);
+    else if (d->epilogue == AFB_EPI_BIAS_QKNORM_ROPE)
+      rc = launch_2cta<BN, false, true, false>(clusters, stream, tmA[0], tmA[1], tmA[2], tmB, tmB1, tmOut, p);
+    else if (bn == BN)
+      rc = launch_2cta<BN, false, false, false>(clusters, stream, tmA[0], tmA[1], tmA[2], tmB, tmB1, tmOut, p);
+    else
+      rc = launch_2cta<BN / 2, false, false, false>(clusters, stream, tmA[0], tmA[1], tmA[2], tmB, tmB1, tmOut, p);
+    if (rc != AFB_OK) return rc;
   } else {
     const int grid = num_tiles < sms ? num_tiles : sms;
     gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmOut, p);
@@ -1024,16 +1050,12 @@ int conv3x3_launch(const afb_conv_desc* d, cudaStream_t stream) {
   p.res = static_cast<const __nv_bfloat16*>(d->res);
   p.res_ld = res_ld;
   p.res_batch_stride = int64_t(d->h) * d->w_px * res_ld;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        int(GEMM2_SMEM_BYTES)));
-    attr_set = true;
-  }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = device_sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  gemm_bf16_2cta_kernel<<<2 * clusters, GEMM2_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmA, tmA, tmB, tmB, tmOut, p);
+  const int rc = bn == BN ? launch_2cta<BN, true, false, false>(clusters, stream, tmA, tmA, tmA, tmB, tmB, tmOut, p)
+                          : launch_2cta<BN / 2, true, false, false>(clusters, stream, tmA, tmA, tmA, tmB, tmB, tmOut, p);
+  if (rc != AFB_OK) return rc;
   AFB_CHECK_CUDA(cudaGetLastError());
   return AFB_OK;
 }

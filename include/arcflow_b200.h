@@ -41,7 +41,7 @@ typedef struct afb_engine afb_engine;
 #define AFB_ERR_UNSUPPORTED (-3)
 
 /* ABI version; bumped on any incompatible change of the structs below. */
-#define AFB_ABI_VERSION 2
+#define AFB_ABI_VERSION 3
 int afb_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* afb_last_error(void);
@@ -570,6 +570,10 @@ typedef struct afb_profile {
   double gemm_ms, attn_ms;
   double gemm_flops, attn_flops;
   int64_t gemm_launches, attn_launches;
+  /* of the GEMM figures above: the launches whose epilogue also does the per-head RMSNorm + RoPE (AFB_EPI_BIAS_QKNORM_ROPE) —
+   * they carry the work of the former rmsnorm_rope kernel, so their time per FLOP is not a pure-GEMM figure */
+  double gemm_fused_qk_ms, gemm_fused_qk_flops;
+  int64_t gemm_fused_qk_launches;
 } afb_profile;
 int afb_engine_set_profiling(afb_engine* e, int32_t on);
 int afb_engine_read_profile(afb_engine* e, afb_profile* out);
