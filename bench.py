@@ -602,7 +602,7 @@ def run_ours(args):
             "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": attn_tf / peaks["bf16"],
             "launches": prof["attn_launches"], "avg_launch_ms": prof["attn_ms"] / max(prof["attn_launches"], 1),
             "algorithmic_bytes_per_launch": 4 * (512 + grid[0] * grid[1]) * 3072 * 2 * args.batch,
-            "traffic": traffic.get("attention", {}).get("dram_bytes_per_launch"),
+            "traffic": (traffic.get("attention") or {}).get("dram_bytes_per_launch"),
             "share_of_step": prof["attn_ms"] / step_ms if step_ms else None,
         },
         "step_tflops": step_flops / (step_ms * 1e9), "step_frac_of_peak": step_flops / (step_ms * 1e9) / peaks["bf16"],

@@ -1,6 +1,7 @@
 """Rebuilds profiles/r02_ncu_traffic.json (what bench.py's roofline.traffic reads) from `ncu --page raw --csv` exports, so the
 figure is derived, not typed:
-    python tools/make_ncu_traffic.py <gemm_shapes.csv> <attention.csv> <gemm_shapes_timing.json> [out.json]
+    python tools/make_ncu_traffic.py <gemm_shapes.csv> <attention.csv> <gemm_shapes_timing.json> [out.json] [attention_b8.csv]
+attention_b8.csv: ncu --set full of the bench-shape forward (batch 8, bounded scores: AFB_DIAG_BOUND=12 tools/diag_attn_time.py)
 gemm_shapes.csv : ncu --set full -k regex:gemm_bf16 -c 9 over tools/profile_gemm_shapes.py --once (launch i = entry i)
 attention.csv   : ncu --set full -k regex:attention --launch-skip 12 --launch-count 3 over tools/diag_attn_bwd_time.py
                   (forward, dQ, dK/dV in that order)
@@ -46,6 +47,7 @@ def read(path):
 def main():
     gemm_csv, attn_csv, timing_json = sys.argv[1:4]
     out_path = sys.argv[4] if len(sys.argv) > 4 else "profiles/r02_ncu_traffic.json"
+    attn_b8 = read(sys.argv[5])[0] if len(sys.argv) > 5 else None
     timing = {l["name"]: l for l in json.load(open(timing_json))["launches"]}
     g = read(gemm_csv)
     table = []
@@ -66,10 +68,16 @@ def main():
                          dram_read_bytes=top["dram_read_bytes"], dram_write_bytes=top["dram_write_bytes"],
                          algorithmic_bytes_per_launch=top["algorithmic_bytes"], ms_ncu=top["ms_ncu"]),
                gemm_launch_table=table,
-               attention=dict(kernel=a[0]["kernel"].split("(")[0], launch="batch 4 x 24 heads x S 4608, bounded scores (training shape)",
-                              dram_bytes_per_launch=a[0].get("dram_read", 0) + a[0].get("dram_write", 0),
-                              algorithmic_bytes_per_launch=4 * 4 * 4608 * 3072 * 2, ms_ncu=a[0]["time"] * 1e3,
-                              tensor_pipe_pct=a[0].get("tensor_pct", a[0].get("tensor_pct_hmma"))),
+               attention=(dict(kernel=attn_b8["kernel"].split("(")[0], launch="batch 8 x 24 heads x S 4608, bounded scores (the bench shape)",
+                               dram_bytes_per_launch=attn_b8.get("dram_read", 0) + attn_b8.get("dram_write", 0),
+                               algorithmic_bytes_per_launch=4 * 8 * 4608 * 3072 * 2, ms_ncu=attn_b8["time"] * 1e3,
+                               tensor_pipe_pct=attn_b8.get("tensor_pct", attn_b8.get("tensor_pct_hmma")), registers=attn_b8.get("regs"))
+                          if attn_b8 else None),
+               attention_training_shape=dict(kernel=a[0]["kernel"].split("(")[0],
+                                             launch="batch 4 x 24 heads x S 4608, " + ("bounded scores" if "split" in a[0]["kernel"] else "running-max kernel (no score bound passed by the timing tool)"),
+                                             dram_bytes_per_launch=a[0].get("dram_read", 0) + a[0].get("dram_write", 0),
+                                             algorithmic_bytes_per_launch=4 * 4 * 4608 * 3072 * 2, ms_ncu=a[0]["time"] * 1e3,
+                                             tensor_pipe_pct=a[0].get("tensor_pct", a[0].get("tensor_pct_hmma"))),
                attention_backward=[dict(kernel=r["kernel"].split("(")[0], ms_ncu=r["time"] * 1e3,
                                         dram_bytes_per_launch=r.get("dram_read", 0) + r.get("dram_write", 0),
                                         tensor_pipe_pct=r.get("tensor_pct", r.get("tensor_pct_hmma")), registers=r.get("regs"))
