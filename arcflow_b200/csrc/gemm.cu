@@ -619,7 +619,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
-    if (lane == 0) {
+    // The whole warp runs the loop converged and ONE elected lane issues (as the MMA warp does): with `if (lane == 0)` around
+    // the loop every TMA operand lived in a per-thread register and the compiler moved it to the uniform datapath through an
+    // elect + R2UR loop per instruction — ~75 SASS instructions per k-block in one thread, next to the 512 cycles the k-block's
+    // MMAs take, which is why a few more instructions in this loop cost whole percents (profiles/r02_gemm_version_ab.json).
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -634,51 +638,57 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         const int conv_th = CONV ? t_in / p.conv_tw : 0;
         const int conv_w0 = CONV ? (t_in - conv_th * p.conv_tw) * 16 : 0;
         const int conv_h0 = conv_th * 16 + int(rank) * 8;
-        for (int kb = 0; kb < nk; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
-          if (CONV) {
+        if (CONV) {
+          for (int kb = 0; kb < nk; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
             const int tap = kb / p.conv_cpt;
             const int cc = kb - tap * p.conv_cpt;
             const int dy = tap / 3;
             const int dx = tap - dy * 3;
-            tma_load_4d_2cta(sA + stage * A_STAGE_BYTES, &tmA0, leader_full, cc * BK, conv_w0 + dx - 1, conv_h0 + dy - 1, b);
-            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+            if (elect_one_sync()) {
+              if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+              tma_load_4d_2cta(sA + stage * A_STAGE_BYTES, &tmA0, leader_full, cc * BK, conv_w0 + dx - 1, conv_h0 + dy - 1, b);
+              tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+            }
+            __syncwarp();
             if (++stage == STAGES2) {
               stage = 0;
               phase ^= 1;
             }
-            continue;
           }
-          const CUtensorMap* am;
-          int kk;
-          if (kb < p.nk_end[0]) {
-            am = &tmA0;
-            kk = kb;
-          } else if (kb < p.nk_end[1]) {
-            am = &tmA1;
-            kk = kb - p.nk_end[0];
-          } else {
-            am = &tmA2;
-            kk = kb - p.nk_end[1];
-          }
-          // (evict_first on the A loads was measured and rejected — profiles/r02_gemm_raster_sweep.json — and is gone)
-          tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
-          if (!WT) {
-            if (p.l2_hints)
-              tma_load_2d_2cta_hint(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0, L2_EVICT_LAST);
-            else
-              tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
-          } else {  // W is [K, N] row-major: two [64 k x 64 n] boxes, N contiguous (MN-major operand)
-            const CUtensorMap* bm = kb < p.nkb_w0 ? &tmB : &tmB1;
-            const int kr = (kb < p.nkb_w0 ? kb : kb - p.nkb_w0) * BK;
-            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, bm, leader_full, n0, kr);
-            tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES + HALF_N * BK, bm, leader_full, n0 + 64, kr);
-          }
-          if (++stage == STAGES2) {
-            stage = 0;
-            phase ^= 1;
+        } else {
+          // one loop per K-segment (x | LoRA | concat): the segment's tensor map is loop-invariant
+          int kb = 0;
+#pragma unroll 1
+          for (int seg = 0; seg < 3; ++seg) {
+            const CUtensorMap* am = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+            const int kb_end = p.nk_end[seg];
+            for (int kk = 0; kb < kb_end; ++kb, ++kk) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
+              if (elect_one_sync()) {
+                if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+                // (evict_first on the A loads was measured and rejected — profiles/r02_gemm_raster_sweep.json — and is gone)
+                tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, am, leader_full, kk * BK, r0, b);
+                if (!WT) {
+                  if (p.l2_hints)
+                    tma_load_2d_2cta_hint(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0, L2_EVICT_LAST);
+                  else
+                    tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, &tmB, leader_full, kb * BK, n0);
+                } else {  // W is [K, N] row-major: two [64 k x 64 n] boxes, N contiguous (MN-major operand)
+                  const CUtensorMap* bm = kb < p.nkb_w0 ? &tmB : &tmB1;
+                  const int kr = (kb < p.nkb_w0 ? kb : kb - p.nkb_w0) * BK;
+                  tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES, bm, leader_full, n0, kr);
+                  tma_load_2d_2cta(sB + stage * B2_STAGE_BYTES + HALF_N * BK, bm, leader_full, n0 + 64, kr);
+                }
+              }
+              __syncwarp();
+              if (++stage == STAGES2) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
           }
         }
       }
