@@ -18,15 +18,20 @@
 //    leader's mbarrier; the leader's tcgen05.commit is multicast to both CTAs' "slot free" and
 //    "accumulator full" barriers; the peer's epilogue warps release the accumulator with a remote arrive.
 //  * gemm_bf16_kernel (AFB_GEMM_1CTA=1, or tiny problems): one CTA per 128 x 256 tile, 4-stage ring.
-// Roles per CTA: warp 0 TMA producer, warp 1 MMA issuer (whole warp converged, one elected lane issues),
-// warps 2..5 epilogue (tcgen05.ld 32x32b -> bias / GELU-tanh / gate*y+residual -> bf16 into a swizzled shared-memory
-// staging tile -> TMA store of whole 128-byte rows, 32 rows x 64 columns per warp and bulk group, double-buffered).
+// Roles per CTA (CTA-pair kernel): warp 0 TMA producer and warp 1 MMA issuer — both run their loops with the whole warp
+// converged and ONE elected lane issuing, so the operands live in uniform registers; each loop turns over once per k-block
+// (512 tensor cycles) and is on or near the critical path: the kernel is a template over everything those loops would
+// otherwise test at run time (tile width, convolution mode, QK epilogue, transposed W). Warps 2..9 are the epilogue, two per
+// TMEM lane quarter, each taking half of a tile's 64-column chunks (tcgen05.ld 32x32b, 32 columns at a time -> bias /
+// GELU-tanh / gate*y+residual / RMSNorm+RoPE -> bf16 into a swizzled shared-memory staging tile -> TMA store of whole
+// 128-byte rows, 32 rows x 64 columns per warp and bulk group). The 1-CTA kernel keeps 4 epilogue warps, double-buffered.
 // Per-row 16-byte global stores (the first version, still selectable with AFB_GEMM_TMA_STORE=0) touch 32 half-written
 // sectors per warp instruction; ncu showed 2x the algorithmic DRAM traffic from the resulting sector fills.
 // W loads carry an L2 evict_last policy and the output stores evict_first: the streamed output (0.6-0.9 GB per launch)
 // must not push the 57-82 MB weight, which every M tile re-reads, out of the 126 MB L2.
 // The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile i overlaps the main
-// loop of tile i+1. Tiles are walked N-fastest so A is read from HBM once and W stays L2-resident.
+// loop of tile i+1. Tiles are walked N-fastest, or in column groups for wide W (tile_coords): A is read from HBM once per
+// group and the group's W panels stay L2-resident.
 #include <stdlib.h>
 
 #include "common.cuh"
